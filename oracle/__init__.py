@@ -1,0 +1,166 @@
+"""CPU ORACLE — test infrastructure, not product code.
+
+ctypes front-end of ``oracle/cvpp_oracle.c`` (the plain-C restatement of the
+reference's decode / filter / NMS path) plus the few numpy restatements of
+init-time tables.  Only ``tests/``, ``__graft_entry__.smoke()`` and
+``bench.py``'s ``cpu_baseline`` / ``--impl reference`` legs may import this
+package; ``computervision.pytorch_b200`` never does.
+
+Parity status: the reference ships no tests or golden vectors, so the oracle is
+pinned by fixtures generated from the *real* reference functions
+(``tests/golden/make_golden.py``, run in the build container where
+``/root/reference`` is mounted) and checked in ``tests/test_oracle_golden.py``.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from typing import Sequence
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "libcvpp_oracle.so")
+_lib = None
+
+_f32p = ctypes.POINTER(ctypes.c_float)
+_i32p = ctypes.POINTER(ctypes.c_int32)
+_i64p = ctypes.POINTER(ctypes.c_int64)
+
+
+def build(force: bool = False) -> str:
+    """Compile the C oracle with gcc (oracle/Makefile)."""
+    src = os.path.join(_HERE, "cvpp_oracle.c")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.run(["make", "-C", _HERE], check=True, capture_output=True)
+    return _SO
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        build()
+        _lib = ctypes.CDLL(_SO)
+        _lib.orc_nms.restype = ctypes.c_int64
+        _lib.orc_batched_nms.restype = ctypes.c_int64
+        _lib.orc_nms_per_class.restype = ctypes.c_int64
+        _lib.orc_max_threads.restype = ctypes.c_int
+    return _lib
+
+
+def set_threads(n: int) -> None:
+    lib().orc_set_threads(ctypes.c_int(int(n)))
+
+
+def max_threads() -> int:
+    return int(lib().orc_max_threads())
+
+
+def _f32(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _ptr(a: np.ndarray, typ):
+    return a.ctypes.data_as(typ)
+
+
+# --------------------------------------------------------------------------
+# torchvision restatements
+# --------------------------------------------------------------------------
+def nms(boxes, scores, iou_threshold: float) -> np.ndarray:
+    """torchvision.ops.nms (CPU) restated; returns int64 kept indices, score-descending."""
+    boxes = _f32(boxes).reshape(-1, 4)
+    scores = _f32(scores).reshape(-1)
+    n = boxes.shape[0]
+    keep = np.empty(max(n, 1), dtype=np.int64)
+    k = lib().orc_nms(_ptr(boxes, _f32p), _ptr(scores, _f32p), ctypes.c_int64(n),
+                      ctypes.c_double(float(iou_threshold)), _ptr(keep, _i64p))
+    return keep[:k].copy()
+
+
+def batched_nms(boxes, scores, idxs, iou_threshold: float, mode: int = 0) -> np.ndarray:
+    """torchvision.ops.batched_nms (CPU) restated. mode 0=CPU rule, 1=trick, 2=vanilla."""
+    boxes = _f32(boxes).reshape(-1, 4)
+    scores = _f32(scores).reshape(-1)
+    idxs = _f32(idxs).reshape(-1)
+    n = boxes.shape[0]
+    keep = np.empty(max(n, 1), dtype=np.int64)
+    k = lib().orc_batched_nms(_ptr(boxes, _f32p), _ptr(scores, _f32p), _ptr(idxs, _f32p), ctypes.c_int64(n),
+                              ctypes.c_double(float(iou_threshold)), ctypes.c_int(mode), _ptr(keep, _i64p))
+    return keep[:k].copy()
+
+
+def nms_per_class(boxes, scores, cls, nc: int, iou_threshold: float) -> np.ndarray:
+    """Class-ascending loop of torchvision nms (YOLOv7._nms / Ssd.decode_boxes / yolo3_nms shape)."""
+    boxes = _f32(boxes).reshape(-1, 4)
+    scores = _f32(scores).reshape(-1)
+    cls = np.ascontiguousarray(cls, dtype=np.int32).reshape(-1)
+    n = boxes.shape[0]
+    keep = np.empty(max(n, 1), dtype=np.int64)
+    k = lib().orc_nms_per_class(_ptr(boxes, _f32p), _ptr(scores, _f32p), _ptr(cls, _i32p), ctypes.c_int64(n),
+                                ctypes.c_int(nc), ctypes.c_double(float(iou_threshold)), _ptr(keep, _i64p))
+    return keep[:k].copy()
+
+
+# --------------------------------------------------------------------------
+# YOLOv8
+# --------------------------------------------------------------------------
+def yolov8_decode(levels: Sequence[np.ndarray], strides: Sequence[float], nc: int, reg_max: int = 16) -> np.ndarray:
+    """Detect.forward eval tail (modules.py:434-445): list of (B,4*reg_max+nc,H,W) -> y (B,4+nc,A)."""
+    levels = [_f32(l) for l in levels]
+    B = levels[0].shape[0]
+    nl = len(levels)
+    hs = (ctypes.c_int * nl)(*[l.shape[2] for l in levels])
+    ws = (ctypes.c_int * nl)(*[l.shape[3] for l in levels])
+    st = (ctypes.c_float * nl)(*[float(s) for s in strides])
+    ptrs = (_f32p * nl)(*[_ptr(l, _f32p) for l in levels])
+    A = sum(l.shape[2] * l.shape[3] for l in levels)
+    for l in levels:
+        assert l.shape[1] == 4 * reg_max + nc, l.shape
+    y = np.empty((B, 4 + nc, A), dtype=np.float32)
+    lib().orc_yolov8_decode(ptrs, ctypes.c_int(nl), hs, ws, st, ctypes.c_int(B), ctypes.c_int(nc),
+                            ctypes.c_int(reg_max), _ptr(y, _f32p))
+    return y
+
+
+def yolov8_nms(pred: np.ndarray, conf_thres: float, iou_thres: float, max_det: int = 300, nc: int = 0,
+               max_nms: int = 30000, nms_mode: int = 0):
+    """non_max_suppression (ultralytics_ops.py:131-264), live configuration.
+
+    Returns (rows, anchors, cand_count): rows[b] is (n_b, 6) [x1,y1,x2,y2,conf,cls], anchors[b] the
+    kept anchor indices (int32) in the same order.
+    """
+    pred = _f32(pred)
+    B, ch, A = pred.shape
+    nc = nc or (ch - 4)
+    nm = ch - 4 - nc
+    det = np.zeros((B, max_det, 6), dtype=np.float32)
+    det_anchor = np.zeros((B, max_det), dtype=np.int32)
+    det_count = np.zeros((B,), dtype=np.int32)
+    cand_count = np.zeros((B,), dtype=np.int32)
+    lib().orc_yolov8_nms(_ptr(pred, _f32p), ctypes.c_int(B), ctypes.c_int(nc), ctypes.c_int(nm), ctypes.c_int64(A),
+                         ctypes.c_float(conf_thres), ctypes.c_double(float(iou_thres)), ctypes.c_int(max_det),
+                         ctypes.c_int(max_nms), ctypes.c_int(nms_mode), _ptr(det, _f32p), _ptr(det_anchor, _i32p),
+                         _ptr(det_count, _i32p), _ptr(cand_count, _i32p))
+    rows = [det[b, :det_count[b]].copy() for b in range(B)]
+    anchors = [det_anchor[b, :det_count[b]].copy() for b in range(B)]
+    return rows, anchors, cand_count
+
+
+def yolov8_candidates(pred: np.ndarray, conf_thres: float, nc: int = 0):
+    """Candidates entering NMS, in anchor order: per image (boxes xyxy, score, cls, anchor)."""
+    pred = _f32(pred)
+    B, ch, A = pred.shape
+    nc = nc or (ch - 4)
+    nm = ch - 4 - nc
+    box = np.zeros((B, A, 4), dtype=np.float32)
+    score = np.zeros((B, A), dtype=np.float32)
+    cls = np.zeros((B, A), dtype=np.int32)
+    anc = np.zeros((B, A), dtype=np.int32)
+    cnt = np.zeros((B,), dtype=np.int32)
+    lib().orc_yolov8_candidates(_ptr(pred, _f32p), ctypes.c_int(B), ctypes.c_int(nc), ctypes.c_int(nm),
+                                ctypes.c_int64(A), ctypes.c_float(conf_thres), _ptr(box, _f32p), _ptr(score, _f32p),
+                                _ptr(cls, _i32p), _ptr(anc, _i32p), _ptr(cnt, _i32p))
+    return [(box[b, :cnt[b]].copy(), score[b, :cnt[b]].copy(), cls[b, :cnt[b]].copy(), anc[b, :cnt[b]].copy())
+            for b in range(B)]

@@ -1,0 +1,498 @@
+/*
+ * cvpp_oracle.c — CPU ORACLE (test infrastructure, NOT product code).
+ *
+ * A plain-C restatement of the reference's detection post-processing path
+ * (calmiLovesAI/ComputerVision.pytorch) in IEEE fp32, one rounding per
+ * operation exactly as the reference's eager PyTorch ops perform them.
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs may load this library.  The product path
+ * (computervision/pytorch_b200) never links or calls it.
+ *
+ * Pinning: the reference ships no tests or golden vectors, so
+ * this file is pinned by the .npz fixtures under tests/golden/, produced by running the real
+ * reference functions (+ the installed torchvision 0.26.0 CPU nms) through
+ * tests/golden/make_golden.py in the build container.
+ *
+ * Third-party arithmetic restated here (not under /root/reference):
+ *   torchvision 0.26.0 (reference README pins 0.14.1; CPU behaviour identical):
+ *     torchvision/ops/boxes.py:51-120  batched_nms / _coordinate_trick / _vanilla
+ *     torchvision/csrc/ops/cpu/nms_kernel.cpp  nms_kernel_impl<float>
+ *
+ * Build: see oracle/Makefile (gcc -O2 -ffp-contract=off, no -ffast-math, so
+ * no FMA contraction and no reassociation).  Images are independent, so the
+ * batch loops run on a small pthread pool (libgomp is not in this image).
+ */
+#define _GNU_SOURCE
+#include <math.h>
+#include <pthread.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <unistd.h>
+
+#define ORC_API __attribute__((visibility("default")))
+
+ORC_API int orc_version(void) { return 1; }
+
+static int g_threads = 0; /* 0 = all online cores */
+
+ORC_API int orc_max_threads(void) {
+  if (g_threads > 0) return g_threads;
+  long n = sysconf(_SC_NPROCESSORS_ONLN);
+  return n > 0 ? (int)n : 1;
+}
+
+ORC_API void orc_set_threads(int n) { g_threads = n > 0 ? n : 0; }
+
+/* parallel-for over [0, count): dynamic scheduling, one item at a time */
+typedef void (*orc_body_fn)(int item, void* ctx);
+typedef struct {
+  orc_body_fn fn;
+  void* ctx;
+  int count;
+  int next; /* atomically incremented */
+} orc_pf;
+
+static void* orc_pf_worker(void* arg) {
+  orc_pf* pf = (orc_pf*)arg;
+  for (;;) {
+    int i = __atomic_fetch_add(&pf->next, 1, __ATOMIC_RELAXED);
+    if (i >= pf->count) break;
+    pf->fn(i, pf->ctx);
+  }
+  return NULL;
+}
+
+static void orc_parallel_for(int count, orc_body_fn fn, void* ctx) {
+  int nt = orc_max_threads();
+  if (nt > count) nt = count;
+  orc_pf pf = {fn, ctx, count, 0};
+  if (nt <= 1) {
+    orc_pf_worker(&pf);
+    return;
+  }
+  pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * (size_t)nt);
+  int started = 0;
+  for (int t = 0; t < nt - 1; ++t)
+    if (pthread_create(&th[started], NULL, orc_pf_worker, &pf) == 0) ++started;
+  orc_pf_worker(&pf);
+  for (int t = 0; t < started; ++t) pthread_join(th[t], NULL);
+  free(th);
+}
+
+/* ------------------------------------------------------------------------- */
+/* helpers                                                                   */
+/* ------------------------------------------------------------------------- */
+
+static inline float sigmoidf_ref(float x) {
+  /* torch.sigmoid on fp32: 1 / (1 + exp(-x)) */
+  return 1.0f / (1.0f + expf(-x));
+}
+
+typedef struct {
+  float score;
+  int64_t idx;
+} orc_si;
+
+/* descending score, ascending index: the total order of a *stable*
+ * descending sort (torchvision nms_kernel.cpp sorts with stable=true). */
+static int cmp_desc_stable(const void* a, const void* b) {
+  const orc_si* x = (const orc_si*)a;
+  const orc_si* y = (const orc_si*)b;
+  if (x->score > y->score) return -1;
+  if (x->score < y->score) return 1;
+  if (x->idx < y->idx) return -1;
+  if (x->idx > y->idx) return 1;
+  return 0;
+}
+
+/* order[k] = index of the k-th element in stable descending score order */
+static void argsort_desc_stable(const float* scores, int64_t n, int64_t* order) {
+  orc_si* tmp = (orc_si*)malloc(sizeof(orc_si) * (size_t)(n > 0 ? n : 1));
+  for (int64_t i = 0; i < n; ++i) {
+    tmp[i].score = scores[i];
+    tmp[i].idx = i;
+  }
+  qsort(tmp, (size_t)n, sizeof(orc_si), cmp_desc_stable);
+  for (int64_t i = 0; i < n; ++i) order[i] = tmp[i].idx;
+  free(tmp);
+}
+
+/* ------------------------------------------------------------------------- */
+/* torchvision.ops.nms — torchvision/csrc/ops/cpu/nms_kernel.cpp             */
+/*   called from: core/utils/ultralytics_ops.py:247 (via batched_nms),       */
+/*   core/utils/nms.py:69,134, core/algorithms/yolo_v7.py:407,               */
+/*   core/algorithms/ssd.py:267                                              */
+/* boxes (n,4) xyxy fp32, scores (n) fp32, thr is a C double (python float). */
+/* keep receives the kept indices in decreasing-score order; returns count.  */
+/* ------------------------------------------------------------------------- */
+ORC_API int64_t orc_nms(const float* boxes, const float* scores, int64_t n, double iou_threshold,
+                        int64_t* keep) {
+  if (n <= 0) return 0;
+  float* areas = (float*)malloc(sizeof(float) * (size_t)n);
+  int64_t* order = (int64_t*)malloc(sizeof(int64_t) * (size_t)n);
+  uint8_t* suppressed = (uint8_t*)calloc((size_t)n, 1);
+  for (int64_t i = 0; i < n; ++i) {
+    const float* b = boxes + 4 * i;
+    areas[i] = (b[2] - b[0]) * (b[3] - b[1]);
+  }
+  argsort_desc_stable(scores, n, order);
+  int64_t num_to_keep = 0;
+  for (int64_t _i = 0; _i < n; ++_i) {
+    int64_t i = order[_i];
+    if (suppressed[i]) continue;
+    keep[num_to_keep++] = i;
+    float ix1 = boxes[4 * i + 0], iy1 = boxes[4 * i + 1];
+    float ix2 = boxes[4 * i + 2], iy2 = boxes[4 * i + 3];
+    float iarea = areas[i];
+    for (int64_t _j = _i + 1; _j < n; ++_j) {
+      int64_t j = order[_j];
+      if (suppressed[j]) continue;
+      float xx1 = fmaxf(ix1, boxes[4 * j + 0]);
+      float yy1 = fmaxf(iy1, boxes[4 * j + 1]);
+      float xx2 = fminf(ix2, boxes[4 * j + 2]);
+      float yy2 = fminf(iy2, boxes[4 * j + 3]);
+      float w = fmaxf(0.0f, xx2 - xx1);
+      float h = fmaxf(0.0f, yy2 - yy1);
+      float inter = w * h;
+      float ovr = inter / (iarea + areas[j] - inter);
+      /* float ovr is promoted to double for the compare */
+      if ((double)ovr > iou_threshold) suppressed[j] = 1;
+    }
+  }
+  free(areas);
+  free(order);
+  free(suppressed);
+  return num_to_keep;
+}
+
+/* ------------------------------------------------------------------------- */
+/* torchvision.ops.batched_nms — torchvision/ops/boxes.py:51-120             */
+/* idxs are class ids stored as float (the reference passes x[:, 5]).        */
+/* mode: 0 = torchvision's CPU rule (numel > 4000 -> vanilla else trick),    */
+/*       1 = coordinate trick, 2 = vanilla.                                  */
+/* ------------------------------------------------------------------------- */
+static int cmp_float_asc(const void* a, const void* b) {
+  float x = *(const float*)a, y = *(const float*)b;
+  return (x > y) - (x < y);
+}
+
+ORC_API int64_t orc_batched_nms(const float* boxes, const float* scores, const float* idxs, int64_t n,
+                                double iou_threshold, int mode, int64_t* keep) {
+  if (n <= 0) return 0;
+  int vanilla = (mode == 2) || (mode == 0 && n * 4 > 4000);
+  if (!vanilla) {
+    /* _batched_nms_coordinate_trick (boxes.py:83-100) */
+    float maxc = boxes[0];
+    for (int64_t i = 1; i < 4 * n; ++i)
+      if (boxes[i] > maxc) maxc = boxes[i];
+    float mult = maxc + 1.0f;
+    float* shifted = (float*)malloc(sizeof(float) * 4 * (size_t)n);
+    for (int64_t i = 0; i < n; ++i) {
+      float off = idxs[i] * mult;
+      for (int k = 0; k < 4; ++k) shifted[4 * i + k] = boxes[4 * i + k] + off;
+    }
+    int64_t r = orc_nms(shifted, scores, n, iou_threshold, keep);
+    free(shifted);
+    return r;
+  }
+  /* _batched_nms_vanilla (boxes.py:103-120) */
+  uint8_t* keep_mask = (uint8_t*)calloc((size_t)n, 1);
+  float* uniq = (float*)malloc(sizeof(float) * (size_t)n);
+  memcpy(uniq, idxs, sizeof(float) * (size_t)n);
+  qsort(uniq, (size_t)n, sizeof(float), cmp_float_asc);
+  int64_t nu = 0;
+  for (int64_t i = 0; i < n; ++i)
+    if (i == 0 || uniq[i] != uniq[nu - 1]) uniq[nu++] = uniq[i];
+  float* cb = (float*)malloc(sizeof(float) * 4 * (size_t)n);
+  float* cs = (float*)malloc(sizeof(float) * (size_t)n);
+  int64_t* ci = (int64_t*)malloc(sizeof(int64_t) * (size_t)n);
+  int64_t* ck = (int64_t*)malloc(sizeof(int64_t) * (size_t)n);
+  for (int64_t u = 0; u < nu; ++u) {
+    int64_t m = 0;
+    for (int64_t i = 0; i < n; ++i)
+      if (idxs[i] == uniq[u]) {
+        memcpy(cb + 4 * m, boxes + 4 * i, sizeof(float) * 4);
+        cs[m] = scores[i];
+        ci[m] = i;
+        ++m;
+      }
+    int64_t k = orc_nms(cb, cs, m, iou_threshold, ck);
+    for (int64_t t = 0; t < k; ++t) keep_mask[ci[ck[t]]] = 1;
+  }
+  /* keep_indices[scores[keep_indices].sort(descending=True)[1]] */
+  int64_t nk = 0;
+  for (int64_t i = 0; i < n; ++i)
+    if (keep_mask[i]) ci[nk++] = i;
+  for (int64_t t = 0; t < nk; ++t) cs[t] = scores[ci[t]];
+  argsort_desc_stable(cs, nk, ck);
+  for (int64_t t = 0; t < nk; ++t) keep[t] = ci[ck[t]];
+  free(keep_mask);
+  free(uniq);
+  free(cb);
+  free(cs);
+  free(ci);
+  free(ck);
+  return nk;
+}
+
+/* ------------------------------------------------------------------------- */
+/* YOLOv8 head decode — core/models/yolov8/modules.py:434-445 (Detect tail), */
+/* DFL modules.py:80-82, make_anchors core/utils/anchor.py:126-145,          */
+/* dist2bbox core/utils/bboxes.py:213-222.                                   */
+/* levels[l]: (B, 4*reg_max + nc, H_l, W_l) contiguous NCHW.                 */
+/* y: (B, 4 + nc, A) with rows cx, cy, w, h (input pixels), sigmoid scores.  */
+/* ------------------------------------------------------------------------- */
+typedef struct {
+  const float* const* levels;
+  int num_levels;
+  const int* level_h;
+  const int* level_w;
+  const float* level_stride;
+  int nc, reg_max;
+  int64_t A;
+  float* y;
+} orc_dec8_ctx;
+
+static void orc_dec8_body(int b, void* vctx) {
+  const orc_dec8_ctx* c = (const orc_dec8_ctx*)vctx;
+  const int nc = c->nc, reg_max = c->reg_max;
+  const int64_t A = c->A;
+  const int no = 4 * reg_max + nc;
+  int64_t a0 = 0;
+  float* yb = c->y + (int64_t)b * (4 + nc) * A;
+  for (int l = 0; l < c->num_levels; ++l) {
+    const int H = c->level_h[l], W = c->level_w[l];
+    const int64_t HW = (int64_t)H * W;
+    const float* base = c->levels[l] + (int64_t)b * no * HW;
+    const float s = c->level_stride[l];
+    for (int64_t i = 0; i < HW; ++i) {
+      float d[4];
+      for (int side = 0; side < 4; ++side) {
+        /* softmax over the reg_max bins (dim=1 after the transpose), then the
+         * frozen 1x1 conv with weights arange(reg_max) */
+        const float* p = base + (int64_t)side * reg_max * HW + i;
+        float m = p[0];
+        for (int k = 1; k < reg_max; ++k) {
+          float v = p[(int64_t)k * HW];
+          if (v > m) m = v;
+        }
+        float e[64];
+        float sum = 0.0f;
+        for (int k = 0; k < reg_max; ++k) {
+          e[k] = expf(p[(int64_t)k * HW] - m);
+          sum += e[k];
+        }
+        float acc = 0.0f;
+        for (int k = 0; k < reg_max; ++k) acc += (float)k * (e[k] / sum);
+        d[side] = acc;
+      }
+      float ax = (float)(i % W) + 0.5f;
+      float ay = (float)(i / W) + 0.5f;
+      float x1 = ax - d[0], y1 = ay - d[1];
+      float x2 = ax + d[2], y2 = ay + d[3];
+      float cx = (x1 + x2) / 2.0f, cy = (y1 + y2) / 2.0f;
+      float w = x2 - x1, h = y2 - y1;
+      int64_t a = a0 + i;
+      yb[0 * A + a] = cx * s;
+      yb[1 * A + a] = cy * s;
+      yb[2 * A + a] = w * s;
+      yb[3 * A + a] = h * s;
+      const float* cl = base + (int64_t)4 * reg_max * HW + i;
+      for (int k = 0; k < nc; ++k) yb[(int64_t)(4 + k) * A + a] = sigmoidf_ref(cl[(int64_t)k * HW]);
+    }
+    a0 += HW;
+  }
+}
+
+ORC_API void orc_yolov8_decode(const float* const* levels, int num_levels, const int* level_h,
+                               const int* level_w, const float* level_stride, int B, int nc, int reg_max,
+                               float* y) {
+  orc_dec8_ctx c = {levels, num_levels, level_h, level_w, level_stride, nc, reg_max, 0, y};
+  if (reg_max > 64) return;
+  for (int l = 0; l < num_levels; ++l) c.A += (int64_t)level_h[l] * level_w[l];
+  orc_parallel_for(B, orc_dec8_body, &c);
+}
+
+/* ------------------------------------------------------------------------- */
+/* Candidate filter shared by the two YOLOv8 entry points below:             */
+/*   xc = prediction[:, 4:mi].amax(1) > conf_thres   (ultralytics_ops.py:190)*/
+/*   box = xywh2xyxy(box)                            (:220, :360-375)        */
+/*   conf, j = cls.max(1)  -> first index on ties    (:225)                  */
+/*   keep rows with conf > conf_thres                (:226)                  */
+/* Candidates come out in anchor order.  Returns the count.                  */
+/* ------------------------------------------------------------------------- */
+static int64_t yolov8_filter_image(const float* p, int nc, int64_t A, float conf_thres, float* boxes,
+                                   float* conf, int32_t* cls, int32_t* anc) {
+  int64_t n = 0;
+  for (int64_t a = 0; a < A; ++a) {
+    float best = p[(int64_t)4 * A + a];
+    int bj = 0;
+    for (int k = 1; k < nc; ++k) {
+      float v = p[(int64_t)(4 + k) * A + a];
+      if (v > best) {
+        best = v;
+        bj = k;
+      }
+    }
+    if (!(best > conf_thres)) continue;
+    float cx = p[0 * A + a], cy = p[1 * A + a], w = p[2 * A + a], h = p[3 * A + a];
+    boxes[4 * n + 0] = cx - w / 2.0f;
+    boxes[4 * n + 1] = cy - h / 2.0f;
+    boxes[4 * n + 2] = cx + w / 2.0f;
+    boxes[4 * n + 3] = cy + h / 2.0f;
+    conf[n] = best;
+    cls[n] = bj;
+    anc[n] = (int32_t)a;
+    ++n;
+  }
+  return n;
+}
+
+/* ------------------------------------------------------------------------- */
+/* non_max_suppression — core/utils/ultralytics_ops.py:131-264 for the live  */
+/* configuration (multi_label=False, labels=(), agnostic=False, merge=False, */
+/* classes=None; wall-clock abort disabled).                                 */
+/* pred: (B, 4 + nc + nm, A).  Outputs per image b (capacity max_det rows):  */
+/*   det[b][k] = x1,y1,x2,y2,conf,cls  ; det_anchor[b][k] ; det_count[b]     */
+/*   cand_count[b] = number of candidates that entered NMS (may be NULL).    */
+/* nms_mode as in orc_batched_nms.                                           */
+/* ------------------------------------------------------------------------- */
+typedef struct {
+  const float* pred;
+  int nc, nm;
+  int64_t A;
+  float conf_thres;
+  double iou_thres;
+  int max_det, max_nms, nms_mode;
+  float* det;
+  int32_t* det_anchor;
+  int32_t* det_count;
+  int32_t* cand_count;
+} orc_nms8_ctx;
+
+static void orc_nms8_body(int b, void* vctx) {
+  const orc_nms8_ctx* c = (const orc_nms8_ctx*)vctx;
+  const int64_t A = c->A;
+  const int ch = 4 + c->nc + c->nm;
+  const float* p = c->pred + (int64_t)b * ch * A;
+  float* boxes = (float*)malloc(sizeof(float) * 4 * (size_t)A);
+  float* conf = (float*)malloc(sizeof(float) * (size_t)A);
+  float* clsf = (float*)malloc(sizeof(float) * (size_t)A);
+  int32_t* cls = (int32_t*)malloc(sizeof(int32_t) * (size_t)A);
+  int32_t* anc = (int32_t*)malloc(sizeof(int32_t) * (size_t)A);
+  int64_t n = yolov8_filter_image(p, c->nc, A, c->conf_thres, boxes, conf, cls, anc);
+  c->det_count[b] = 0;
+  if (c->cand_count) c->cand_count[b] = (int32_t)n;
+  if (n > 0) {
+    /* x = x[x[:, 4].argsort(descending=True)[:max_nms]] (:240) */
+    int64_t* order = (int64_t*)malloc(sizeof(int64_t) * (size_t)n);
+    argsort_desc_stable(conf, n, order);
+    int64_t m = n < c->max_nms ? n : c->max_nms;
+    float* sb = (float*)malloc(sizeof(float) * 4 * (size_t)m);
+    float* ss = (float*)malloc(sizeof(float) * (size_t)m);
+    int32_t* sa = (int32_t*)malloc(sizeof(int32_t) * (size_t)m);
+    for (int64_t t = 0; t < m; ++t) {
+      memcpy(sb + 4 * t, boxes + 4 * order[t], sizeof(float) * 4);
+      ss[t] = conf[order[t]];
+      clsf[t] = (float)cls[order[t]]; /* j.float() (:226) */
+      sa[t] = anc[order[t]];
+    }
+    int64_t* keep = (int64_t*)malloc(sizeof(int64_t) * (size_t)m);
+    int64_t k = orc_batched_nms(sb, ss, clsf, m, c->iou_thres, c->nms_mode, keep); /* (:247) */
+    if (k > c->max_det) k = c->max_det;                                            /* (:248) */
+    for (int64_t t = 0; t < k; ++t) {
+      float* row = c->det + ((int64_t)b * c->max_det + t) * 6;
+      memcpy(row, sb + 4 * keep[t], sizeof(float) * 4);
+      row[4] = ss[keep[t]];
+      row[5] = clsf[keep[t]];
+      c->det_anchor[(int64_t)b * c->max_det + t] = sa[keep[t]];
+    }
+    c->det_count[b] = (int32_t)k;
+    free(order);
+    free(sb);
+    free(ss);
+    free(sa);
+    free(keep);
+  }
+  free(boxes);
+  free(conf);
+  free(clsf);
+  free(cls);
+  free(anc);
+}
+
+ORC_API void orc_yolov8_nms(const float* pred, int B, int nc, int nm, int64_t A, float conf_thres,
+                            double iou_thres, int max_det, int max_nms, int nms_mode, float* det,
+                            int32_t* det_anchor, int32_t* det_count, int32_t* cand_count) {
+  orc_nms8_ctx c = {pred, nc, nm, A, conf_thres, iou_thres, max_det, max_nms, nms_mode,
+                    det,  det_anchor, det_count, cand_count};
+  orc_parallel_for(B, orc_nms8_body, &c);
+}
+
+/* Candidate stage only (what the fused CUDA decode+filter kernel emits), in  */
+/* anchor order.  cand_box (B,A,4) xyxy ; cand_score/cls/anchor (B,A) ;       */
+/* cand_count (B).                                                            */
+typedef struct {
+  const float* pred;
+  int nc, nm;
+  int64_t A;
+  float conf_thres;
+  float* cand_box;
+  float* cand_score;
+  int32_t* cand_cls;
+  int32_t* cand_anchor;
+  int32_t* cand_count;
+} orc_cand8_ctx;
+
+static void orc_cand8_body(int b, void* vctx) {
+  const orc_cand8_ctx* c = (const orc_cand8_ctx*)vctx;
+  const int64_t A = c->A;
+  const float* p = c->pred + (int64_t)b * (4 + c->nc + c->nm) * A;
+  c->cand_count[b] = (int32_t)yolov8_filter_image(p, c->nc, A, c->conf_thres, c->cand_box + (int64_t)b * A * 4,
+                                                  c->cand_score + (int64_t)b * A, c->cand_cls + (int64_t)b * A,
+                                                  c->cand_anchor + (int64_t)b * A);
+}
+
+ORC_API void orc_yolov8_candidates(const float* pred, int B, int nc, int nm, int64_t A, float conf_thres,
+                                   float* cand_box, float* cand_score, int32_t* cand_cls,
+                                   int32_t* cand_anchor, int32_t* cand_count) {
+  orc_cand8_ctx c = {pred, nc, nm, A, conf_thres, cand_box, cand_score, cand_cls, cand_anchor, cand_count};
+  orc_parallel_for(B, orc_cand8_body, &c);
+}
+
+/* ------------------------------------------------------------------------- */
+/* Per-class NMS over one image's candidate list, the shape shared by        */
+/* YOLOv7._nms (core/algorithms/yolo_v7.py:396-413), Ssd.decode_boxes        */
+/* (core/algorithms/ssd.py:256-278) and yolo3_nms (core/utils/nms.py:66-76): */
+/* for each class id ascending, torchvision nms on that class's boxes (in    */
+/* candidate order), results concatenated class-major, score-descending.     */
+/* keep receives indices into the candidate list; returns count.             */
+/* ------------------------------------------------------------------------- */
+ORC_API int64_t orc_nms_per_class(const float* boxes, const float* scores, const int32_t* cls, int64_t n,
+                                  int nc, double iou_threshold, int64_t* keep) {
+  if (n <= 0) return 0;
+  float* cb = (float*)malloc(sizeof(float) * 4 * (size_t)n);
+  float* cs = (float*)malloc(sizeof(float) * (size_t)n);
+  int64_t* ci = (int64_t*)malloc(sizeof(int64_t) * (size_t)n);
+  int64_t* ck = (int64_t*)malloc(sizeof(int64_t) * (size_t)n);
+  int64_t total = 0;
+  for (int c = 0; c < nc; ++c) {
+    int64_t m = 0;
+    for (int64_t i = 0; i < n; ++i)
+      if (cls[i] == c) {
+        memcpy(cb + 4 * m, boxes + 4 * i, sizeof(float) * 4);
+        cs[m] = scores[i];
+        ci[m] = i;
+        ++m;
+      }
+    if (m == 0) continue;
+    int64_t k = orc_nms(cb, cs, m, iou_threshold, ck);
+    for (int64_t t = 0; t < k; ++t) keep[total++] = ci[ck[t]];
+  }
+  free(cb);
+  free(cs);
+  free(ci);
+  free(ck);
+  return total;
+}

@@ -1,0 +1,198 @@
+"""Seeded synthetic head tensors for the five BASELINE.json configurations.
+
+numpy-only and deterministic (PCG64 streams), so the same arrays can be regenerated on the GPU box
+from a seed instead of being committed.  Every generator post-processes its draw so that candidate
+scores are *separated* (relative gap > GAP) per image and away from the confidence thresholds: the
+reference's own sort/top-k tie order is implementation-defined, and a margin of many
+ulps keeps the order identical under any correctly-rounded-ish exp/sigmoid implementation.
+"""
+from __future__ import annotations
+
+import zlib
+from typing import List, Sequence, Tuple
+
+import numpy as np
+
+GAP = 2e-5          # minimum relative gap between two candidate scores of one image
+THR_MARGIN = 1e-4   # minimum relative distance of a score from a confidence threshold
+
+YOLOV8_SIZES = ((80, 80), (40, 40), (20, 20))
+YOLOV8_STRIDES = (8.0, 16.0, 32.0)
+
+
+def rng_for(seed: int) -> np.random.Generator:
+    return np.random.Generator(np.random.PCG64(seed))
+
+
+def checksum(arrays: Sequence[np.ndarray]) -> int:
+    """CRC of the raw bytes — lets a fixture assert that a regenerated input is bit-identical."""
+    c = 0
+    for a in arrays:
+        c = zlib.crc32(np.ascontiguousarray(a).view(np.uint8).reshape(-1), c)
+    return c
+
+
+def _sigmoid64(x):
+    return 1.0 / (1.0 + np.exp(-np.asarray(x, dtype=np.float64)))
+
+
+def _logit64(p):
+    p = np.asarray(p, dtype=np.float64)
+    return np.log(p) - np.log1p(-p)
+
+
+def separate_scores(scores: np.ndarray, thresholds: Sequence[float], lo: float, max_iter: int = 200):
+    """Return multiplicative nudges f (close to 1) such that scores*f are pairwise separated by GAP
+    (relative) among those >= lo, and at least THR_MARGIN away from each threshold.  scores: 1-D float64."""
+    s = scores.astype(np.float64).copy()
+    active = np.nonzero(s >= lo)[0]
+    for _ in range(max_iter):
+        changed = False
+        for t in thresholds:
+            near = active[np.abs(s[active] - t) < THR_MARGIN * t]
+            if near.size:
+                s[near] = t * (1.0 + 3.0 * THR_MARGIN)
+                changed = True
+        order = active[np.argsort(s[active], kind="stable")]
+        v = s[order]
+        close = np.nonzero((v[1:] - v[:-1]) < GAP * v[1:])[0]
+        if close.size:
+            # push the upper element of each close pair up by a growing amount
+            bump = 1.0 + GAP * (2.0 + (np.arange(close.size) % 7))
+            s[order[close + 1]] = np.minimum(s[order[close + 1]] * bump, 1.0 - 1e-4)
+            changed = True
+        if not changed:
+            return s
+    raise RuntimeError("separate_scores did not converge")
+
+
+# ------------------------------------------------------------------------------------------------
+# YOLOv8 (C1, C2): levels (B, 4*reg_max+nc, h, w)
+# ------------------------------------------------------------------------------------------------
+def yolov8_head(seed: int, B: int, nc: int = 80, reg_max: int = 16,
+                sizes: Sequence[Tuple[int, int]] = YOLOV8_SIZES, strides: Sequence[float] = YOLOV8_STRIDES,
+                conf_list: Sequence[float] = (0.001, 0.25), clustered: bool = False,
+                cls_mu: float = -18.19, cls_sigma: float = 4.3155) -> List[np.ndarray]:
+    """Box logits N(0,3^2), class logits N(cls_mu, cls_sigma^2) (≈2.5 k candidates/img at conf .001 and
+    ≈31 at .25 for the 8400-anchor head).  clustered=True plants ~30 objects per image whose
+    neighbouring anchors regress (noisily) the same box with a raised class logit, so NMS suppresses."""
+    rng = rng_for(seed)
+    no = 4 * reg_max + nc
+    levels = []
+    for (h, w) in sizes:
+        x = rng.standard_normal((B, no, h, w), dtype=np.float32)
+        x[:, : 4 * reg_max] *= np.float32(3.0)
+        x[:, 4 * reg_max:] *= np.float32(cls_sigma)
+        x[:, 4 * reg_max:] += np.float32(cls_mu)
+        levels.append(x)
+    if clustered:
+        _plant_objects(rng, levels, sizes, strides, nc, reg_max)
+    _separate_yolov8(levels, nc, reg_max, conf_list)
+    return levels
+
+
+def _plant_objects(rng, levels, sizes, strides, nc, reg_max, n_obj=30, radius=2.0):
+    B = levels[0].shape[0]
+    img_w = sizes[0][1] * strides[0]
+    img_h = sizes[0][0] * strides[0]
+    for b in range(B):
+        for _ in range(n_obj):
+            cls = int(rng.integers(0, nc))
+            bw, bh = rng.uniform(40.0, 0.45 * img_w), rng.uniform(40.0, 0.45 * img_h)
+            cx, cy = rng.uniform(0.15 * img_w, 0.85 * img_w), rng.uniform(0.15 * img_h, 0.85 * img_h)
+            x1, y1, x2, y2 = cx - bw / 2, cy - bh / 2, cx + bw / 2, cy + bh / 2
+            for lvl, ((h, w), s) in enumerate(zip(sizes, strides)):
+                gx, gy = cx / s - 0.5, cy / s - 0.5
+                ix0, ix1 = int(max(0, np.floor(gx - radius))), int(min(w - 1, np.ceil(gx + radius)))
+                iy0, iy1 = int(max(0, np.floor(gy - radius))), int(min(h - 1, np.ceil(gy + radius)))
+                for iy in range(iy0, iy1 + 1):
+                    for ix in range(ix0, ix1 + 1):
+                        ax, ay = ix + 0.5, iy + 0.5
+                        d = np.array([ax - x1 / s, ay - y1 / s, x2 / s - ax, y2 / s - ay])
+                        if np.any(d < 0.2) or np.any(d > reg_max - 1.2):
+                            continue
+                        d = d + rng.normal(0.0, 0.08, size=4)
+                        for side in range(4):
+                            t = float(np.clip(d[side], 0.01, reg_max - 1.01))
+                            k0 = int(np.floor(t))
+                            fr = t - k0
+                            col = rng.standard_normal(reg_max).astype(np.float32)
+                            col[k0] = np.float32(9.0 + np.log(max(1.0 - fr, 1e-3)))
+                            col[k0 + 1] = np.float32(9.0 + np.log(max(fr, 1e-3)))
+                            levels[lvl][b, side * reg_max:(side + 1) * reg_max, iy, ix] = col
+                        levels[lvl][b, 4 * reg_max + cls, iy, ix] = np.float32(rng.normal(1.5, 1.2))
+
+
+def _separate_yolov8(levels, nc, reg_max, conf_list):
+    B = levels[0].shape[0]
+    lo = 0.5 * min(conf_list)
+    for b in range(B):
+        cls_views = [l[b, 4 * reg_max:].reshape(nc, -1) for l in levels]   # views into the level arrays
+        top = np.concatenate([v.max(axis=0) for v in cls_views]).astype(np.float64)
+        arg = np.concatenate([v.argmax(axis=0) for v in cls_views])
+        s = _sigmoid64(top)
+        s2 = separate_scores(s, conf_list, lo)
+        moved = np.nonzero(s2 != s)[0]
+        off = 0
+        for v in cls_views:
+            n = v.shape[1]
+            m = moved[(moved >= off) & (moved < off + n)]
+            for a in m:
+                v[arg[a], a - off] = np.float32(_logit64(s2[a]))
+            # keep the runner-up class clearly below the winner for every candidate anchor
+            off += n
+    # second pass: verify in float32 terms (scores recomputed from the stored float32 logits)
+    for b in range(B):
+        cls_views = [l[b, 4 * reg_max:].reshape(nc, -1) for l in levels]
+        top = np.concatenate([v.max(axis=0) for v in cls_views]).astype(np.float64)
+        s = _sigmoid64(top)
+        c = np.sort(s[s >= lo])
+        if c.size > 1 and np.min((c[1:] - c[:-1]) / c[1:]) < 0.25 * GAP:
+            raise RuntimeError("yolov8_head: float32 rounding re-created a near-tie; change the seed")
+
+
+def yolov8_pred(seed: int, B: int, A: int, nc: int = 80, n_clusters: int = 40, per_cluster: int = 12,
+                background: int = 1500, img: float = 640.0, conf_lo: float = 0.001,
+                conf_list: Sequence[float] = (0.001, 0.25), nm: int = 0) -> np.ndarray:
+    """A decoded prediction tensor (B, 4+nc+nm, A) for stage-B (filter + NMS) tests: clustered,
+    overlapping boxes so that suppression really happens, scores separated."""
+    rng = rng_for(seed)
+    pred = np.zeros((B, 4 + nc + nm, A), dtype=np.float32)
+    for b in range(B):
+        # background anchors: tiny scores everywhere
+        pred[b, 4:4 + nc] = (rng.random((nc, A), dtype=np.float32) * np.float32(0.4 * conf_lo))
+        pred[b, 0] = rng.uniform(0, img, A).astype(np.float32)
+        pred[b, 1] = rng.uniform(0, img, A).astype(np.float32)
+        pred[b, 2] = rng.uniform(8, 200, A).astype(np.float32)
+        pred[b, 3] = rng.uniform(8, 200, A).astype(np.float32)
+        slots = rng.permutation(A)
+        used = 0
+        top = np.zeros(A, dtype=np.float64)
+        cls_of = np.zeros(A, dtype=np.int64)
+        for _ in range(n_clusters):
+            c = int(rng.integers(0, nc))
+            cx, cy = rng.uniform(60, img - 60, 2)
+            w, h = rng.uniform(30, 260, 2)
+            k = int(rng.integers(max(1, per_cluster // 2), per_cluster * 2))
+            for _ in range(k):
+                if used >= A:
+                    break
+                a = slots[used]
+                used += 1
+                pred[b, 0, a] = cx + rng.normal(0, 0.04 * w)
+                pred[b, 1, a] = cy + rng.normal(0, 0.04 * h)
+                pred[b, 2, a] = w * np.exp(rng.normal(0, 0.06))
+                pred[b, 3, a] = h * np.exp(rng.normal(0, 0.06))
+                top[a] = rng.uniform(0.05, 0.98)
+                # sometimes a neighbouring class on the same spot (class-awareness must keep both)
+                cls_of[a] = c if rng.random() < 0.85 else int(rng.integers(0, nc))
+        nb = min(background, A - used)
+        for a in slots[used:used + nb]:
+            top[a] = float(np.exp(rng.uniform(np.log(conf_lo * 0.5), np.log(0.6))))
+            cls_of[a] = int(rng.integers(0, nc))
+        s2 = separate_scores(top, conf_list, 0.5 * conf_lo)
+        idx = np.nonzero(top > 0)[0]
+        pred[b, 4 + cls_of[idx], idx] = s2[idx].astype(np.float32)
+        if nm:
+            pred[b, 4 + nc:] = rng.standard_normal((nm, A), dtype=np.float32)
+    return pred

@@ -1,0 +1,110 @@
+"""Pins the C oracle against fixtures produced by the REAL reference (tests/golden/make_golden.py).
+
+Integer outputs (kept indices, class ids, counts) must be bit-exact.  Stage-B float outputs are
+bit-exact too (they are pure fp32 add/sub/mul/div on identical inputs).  Decode outputs go through
+exp(), where the oracle's libm differs from torch's Sleef by <= a few ulp:
+    boxes : |d| <= 1e-5 * |ref| + 4 ulp at the 640-px input scale (2.5e-4 px)
+    scores: |d| <= 1e-5 * |ref|
+"""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+import synth
+
+BOX_RTOL, BOX_ATOL, SCORE_RTOL = 1e-5, 2.5e-4, 1e-5
+
+
+def load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name + ".npz"))
+
+
+def test_nms_known_answers(golden_dir):
+    g = load(golden_dir, "nms_kat")
+    for i in range(int(g["n_cases"])):
+        keep = oracle.nms(g[f"boxes{i}"], g[f"scores{i}"], float(g[f"thr{i}"]))
+        assert np.array_equal(keep, g[f"keep{i}"]), (i, keep, g[f"keep{i}"])
+
+
+def test_nms_random_all_branches(golden_dir):
+    g = load(golden_dir, "nms_random")
+    for i in range(int(g["n_cases"])):
+        b, s, c, t = g[f"boxes{i}"], g[f"scores{i}"], g[f"cls{i}"], float(g[f"thr{i}"])
+        assert np.array_equal(oracle.nms(b, s, t), g[f"keep_nms{i}"])
+        assert np.array_equal(oracle.batched_nms(b, s, c, t, 0), g[f"keep_auto{i}"])
+        assert np.array_equal(oracle.batched_nms(b, s, c, t, 1), g[f"keep_trick{i}"])
+        assert np.array_equal(oracle.batched_nms(b, s, c, t, 2), g[f"keep_vanilla{i}"])
+        # the suppression must be non-trivial for the bigger cases
+        if len(s) >= 300:
+            assert len(g[f"keep_nms{i}"]) < 0.8 * len(s)
+
+
+def _split(flat, counts):
+    out, o = [], 0
+    for c in counts:
+        out.append(flat[o:o + c])
+        o += c
+    return out
+
+
+def test_yolov8_small_decode_and_nms(golden_dir):
+    g = load(golden_dir, "yolov8_small")
+    levels = [g["level0"], g["level1"], g["level2"]]
+    y = oracle.yolov8_decode(levels, synth.YOLOV8_STRIDES, 80)
+    ref = g["y"]
+    assert np.all(np.abs(y[:, :4] - ref[:, :4]) <= BOX_RTOL * np.abs(ref[:, :4]) + BOX_ATOL)
+    assert np.all(np.abs(y[:, 4:] - ref[:, 4:]) <= SCORE_RTOL * np.abs(ref[:, 4:]))
+    for tag in "abc":
+        conf, iou, md = g[f"params_{tag}"]
+        rows, anchors, _ = oracle.yolov8_nms(ref, float(conf), float(iou), int(md), nc=80)
+        counts = g[f"counts_{tag}"]
+        assert [len(a) for a in anchors] == list(counts)
+        for r, a, rr, ra in zip(rows, anchors, _split(g[f"rows_{tag}"], counts), _split(g[f"anchors_{tag}"], counts)):
+            assert np.array_equal(a, ra)
+            assert np.array_equal(r, rr)          # stage B on identical fp32 inputs: bit-exact
+        assert sum(counts) > 0
+
+
+def test_yolov8_full_head(golden_dir):
+    g = load(golden_dir, "yolov8_full")
+    for tag in ("iid", "clu"):
+        seed, B, clustered = [int(v) for v in g[f"{tag}_seed"]]
+        levels = synth.yolov8_head(seed, B=B, clustered=bool(clustered))
+        assert synth.checksum(levels) == int(g[f"{tag}_crc"]), "regenerated input drifted from the fixture"
+        y = oracle.yolov8_decode(levels, synth.YOLOV8_STRIDES, 80)
+        sub = g[f"{tag}_y_sub"]
+        ys = y[:, :, ::53]
+        assert np.all(np.abs(ys[:, :4] - sub[:, :4]) <= BOX_RTOL * np.abs(sub[:, :4]) + BOX_ATOL)
+        assert np.all(np.abs(ys[:, 4:] - sub[:, 4:]) <= SCORE_RTOL * np.abs(sub[:, 4:]))
+        assert np.allclose(y.astype(np.float64).sum(axis=2), g[f"{tag}_y_sum"], rtol=1e-6, atol=1e-2)
+        # end to end (oracle decode -> oracle NMS) against the reference's kept sets
+        for ctag, conf in (("eval", 0.001), ("pred", 0.25)):
+            rows, anchors, cand = oracle.yolov8_nms(y, conf, 0.7, 300, nc=80)
+            counts = g[f"{tag}_{ctag}_counts"]
+            assert [len(a) for a in anchors] == list(counts)
+            for r, a, rr, ra in zip(rows, anchors, _split(g[f"{tag}_{ctag}_rows"], counts),
+                                    _split(g[f"{tag}_{ctag}_anchors"], counts)):
+                assert np.array_equal(a, ra)
+                assert np.array_equal(r[:, 5], rr[:, 5])
+                assert np.all(np.abs(r[:, :4] - rr[:, :4]) <= BOX_RTOL * np.abs(rr[:, :4]) + BOX_ATOL)
+                assert np.all(np.abs(r[:, 4] - rr[:, 4]) <= SCORE_RTOL * np.abs(rr[:, 4]))
+            if ctag == "eval":
+                assert np.all(cand > 1000)        # the vanilla batched_nms branch was exercised
+
+
+def test_yolov8_pred_stage_b(golden_dir):
+    g = load(golden_dir, "yolov8_pred")
+    for tag in g["tags"]:
+        seed, B, A, nc, nm, conf, iou, md = g[f"{tag}_cfg"]
+        pred = synth.yolov8_pred(int(seed), int(B), int(A), nc=int(nc), nm=int(nm))
+        assert synth.checksum([pred]) == int(g[f"{tag}_crc"])
+        rows, anchors, cand = oracle.yolov8_nms(pred, float(conf), float(iou), int(md), nc=int(nc))
+        counts = g[f"{tag}_counts"]
+        assert [len(a) for a in anchors] == list(counts)
+        for r, a, rr, ra, c in zip(rows, anchors, _split(g[f"{tag}_rows"], counts),
+                                   _split(g[f"{tag}_anchors"], counts), cand):
+            assert np.array_equal(a, ra)
+            assert np.array_equal(r, rr[:, :6])
+            assert len(a) < c                      # something was suppressed or capped
