@@ -1,0 +1,186 @@
+// cvpp_api.cu — the extern "C" surface of libcvpp.so (declared in include/cvpp.h).
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+
+#include "cvpp_common.cuh"
+
+namespace cvpp {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+  return CVPP_ERR_CUDA;
+}
+
+// launchers (one per .cu)
+int yolov8_decode_launch(const float* const* level_ptr, const int64_t* batch_stride, const int64_t* chan_stride,
+                         const int* level_h, const int* level_w, const float* level_stride, int num_levels, int B,
+                         int nc, int reg_max, float conf_thres, uint64_t* cand_key, int32_t* cand_count,
+                         float* box_dense, int max_cand, float* y, int force_generic, cudaStream_t stream);
+int pred_filter_launch(const float* pred, int B, int channels, int nc, int64_t A, float conf_thres, uint64_t* cand_key,
+                       int32_t* cand_count, float* box_dense, int max_cand, cudaStream_t stream);
+size_t segsort_workspace_bytes(int B, int max_cand);
+int segsort_launch(uint64_t* keys, int32_t* cand_count, int B, int max_cand, int rule, int max_nms, void* workspace,
+                   size_t workspace_bytes, cudaStream_t stream);
+size_t nms_workspace_bytes(int B, int max_cand);
+int nms_launch(const uint64_t* sorted_key, const int32_t* cand_count, const float* box_dense, int B, int max_cand,
+               int64_t A, int nc, double iou_thres, int rule, int order, int max_det, int max_out, float* det_box,
+               float* det_score, int32_t* det_cls, int32_t* det_anchor, int32_t* det_count, void* workspace,
+               size_t workspace_bytes, cudaStream_t stream);
+
+static int force_generic() {
+  const char* e = getenv("CVPP_FORCE_GENERIC");
+  return e && e[0] == '1';
+}
+
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+}  // namespace cvpp
+
+using namespace cvpp;
+
+extern "C" {
+
+int cvpp_version(void) { return 100; }
+
+const char* cvpp_last_error(void) { return g_err; }
+
+const char* cvpp_error_name(int code) {
+  switch (code) {
+    case CVPP_OK: return "CVPP_OK";
+    case CVPP_ERR_INVALID_ARG: return "CVPP_ERR_INVALID_ARG";
+    case CVPP_ERR_ALIGNMENT: return "CVPP_ERR_ALIGNMENT";
+    case CVPP_ERR_WORKSPACE: return "CVPP_ERR_WORKSPACE";
+    case CVPP_ERR_CUDA: return "CVPP_ERR_CUDA";
+    case CVPP_ERR_UNSUPPORTED: return "CVPP_ERR_UNSUPPORTED";
+    default: return "CVPP_ERR_UNKNOWN";
+  }
+}
+
+int cvpp_yolov8_decode_filter(const float* const* level_ptr, const int64_t* batch_stride, const int64_t* chan_stride,
+                              const int* level_h, const int* level_w, const float* level_stride, int num_levels,
+                              int B, int nc, int reg_max, float conf_thres, uint64_t* cand_key, int32_t* cand_count,
+                              float* box_dense, int max_cand, cvpp_stream_t stream) {
+  if (!(conf_thres >= 0.0f && conf_thres <= 1.0f)) {
+    set_error("Invalid Confidence threshold %f, valid values are between 0.0 and 1.0", conf_thres);
+    return CVPP_ERR_INVALID_ARG;
+  }
+  return yolov8_decode_launch(level_ptr, batch_stride, chan_stride, level_h, level_w, level_stride, num_levels, B, nc,
+                              reg_max, conf_thres, cand_key, cand_count, box_dense, max_cand, nullptr, force_generic(),
+                              (cudaStream_t)stream);
+}
+
+int cvpp_yolov8_decode_full(const float* const* level_ptr, const int64_t* batch_stride, const int64_t* chan_stride,
+                            const int* level_h, const int* level_w, const float* level_stride, int num_levels, int B,
+                            int nc, int reg_max, float* y, cvpp_stream_t stream) {
+  if (!y) {
+    set_error("yolov8_decode_full: y is NULL");
+    return CVPP_ERR_INVALID_ARG;
+  }
+  return yolov8_decode_launch(level_ptr, batch_stride, chan_stride, level_h, level_w, level_stride, num_levels, B, nc,
+                              reg_max, 0.0f, nullptr, nullptr, nullptr, 0, y, force_generic(), (cudaStream_t)stream);
+}
+
+int cvpp_pred_filter(const float* pred, int B, int channels, int nc, int64_t A, float conf_thres, uint64_t* cand_key,
+                     int32_t* cand_count, float* box_dense, int max_cand, cvpp_stream_t stream) {
+  if (!(conf_thres >= 0.0f && conf_thres <= 1.0f)) {
+    set_error("Invalid Confidence threshold %f, valid values are between 0.0 and 1.0", conf_thres);
+    return CVPP_ERR_INVALID_ARG;
+  }
+  return pred_filter_launch(pred, B, channels, nc, A, conf_thres, cand_key, cand_count, box_dense, max_cand,
+                            (cudaStream_t)stream);
+}
+
+size_t cvpp_sort_workspace_bytes(int B, int max_cand) {
+  if (B < 0 || max_cand < 1) return 0;
+  return segsort_workspace_bytes(B, max_cand);
+}
+
+int cvpp_segmented_sort(uint64_t* keys, int32_t* cand_count, int B, int max_cand, int rule, int max_nms,
+                        void* workspace, size_t workspace_bytes, cvpp_stream_t stream) {
+  return segsort_launch(keys, cand_count, B, max_cand, rule, max_nms, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+size_t cvpp_nms_workspace_bytes(int B, int max_cand) {
+  if (B < 0 || max_cand < 1) return 0;
+  return nms_workspace_bytes(B, max_cand);
+}
+
+int cvpp_nms(const uint64_t* sorted_key, const int32_t* cand_count, const float* box_dense, int B, int max_cand,
+             int64_t A, int nc, double iou_thres, int rule, int order, int max_det, int max_out, float* det_box,
+             float* det_score, int32_t* det_cls, int32_t* det_anchor, int32_t* det_count, void* workspace,
+             size_t workspace_bytes, cvpp_stream_t stream) {
+  return nms_launch(sorted_key, cand_count, box_dense, B, max_cand, A, nc, iou_thres, rule, order, max_det, max_out,
+                    det_box, det_score, det_cls, det_anchor, det_count, workspace, workspace_bytes,
+                    (cudaStream_t)stream);
+}
+
+size_t cvpp_yolov8_workspace_bytes(int B, int64_t A, int max_cand) {
+  if (B < 0 || A < 1 || max_cand < 1) return 0;
+  size_t s = 256;
+  s += align256((size_t)B * max_cand * sizeof(uint64_t));  // cand_key
+  s += align256((size_t)B * sizeof(int32_t));              // cand_count
+  s += align256((size_t)B * (size_t)A * 16);               // box_dense
+  s += align256(segsort_workspace_bytes(B, max_cand));
+  s += align256(nms_workspace_bytes(B, max_cand));
+  return s;
+}
+
+int cvpp_yolov8_postprocess(const float* const* level_ptr, const int64_t* batch_stride, const int64_t* chan_stride,
+                            const int* level_h, const int* level_w, const float* level_stride, int num_levels, int B,
+                            int nc, int reg_max, float conf_thres, double iou_thres, int rule, int max_det, int max_nms,
+                            int max_cand, float* det_box, float* det_score, int32_t* det_cls, int32_t* det_anchor,
+                            int32_t* det_count, int32_t* cand_count_out, void* workspace, size_t workspace_bytes,
+                            cvpp_stream_t stream) {
+  if (!level_h || !level_w || num_levels < 1 || num_levels > CVPP_MAX_LEVELS) {
+    set_error("yolov8_postprocess: bad level description");
+    return CVPP_ERR_INVALID_ARG;
+  }
+  int64_t A = 0;
+  for (int l = 0; l < num_levels; ++l) A += (int64_t)level_h[l] * level_w[l];
+  if (max_det < 1 || max_cand < 1) {
+    set_error("yolov8_postprocess: max_det and max_cand must be >= 1");
+    return CVPP_ERR_INVALID_ARG;
+  }
+  if (!workspace || workspace_bytes < cvpp_yolov8_workspace_bytes(B, A, max_cand)) {
+    set_error("yolov8_postprocess: workspace of %zu bytes needed, got %zu", cvpp_yolov8_workspace_bytes(B, A, max_cand),
+              workspace_bytes);
+    return CVPP_ERR_WORKSPACE;
+  }
+  uintptr_t p = (reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255;
+  uint64_t* cand_key = reinterpret_cast<uint64_t*>(p);
+  p += align256((size_t)B * max_cand * sizeof(uint64_t));
+  int32_t* cand_count = reinterpret_cast<int32_t*>(p);
+  p += align256((size_t)B * sizeof(int32_t));
+  float* box_dense = reinterpret_cast<float*>(p);
+  p += align256((size_t)B * (size_t)A * 16);
+  void* sort_ws = reinterpret_cast<void*>(p);
+  size_t sort_bytes = segsort_workspace_bytes(B, max_cand);
+  p += align256(sort_bytes);
+  void* nms_ws = reinterpret_cast<void*>(p);
+  size_t nms_bytes = nms_workspace_bytes(B, max_cand);
+
+  int rc = cvpp_yolov8_decode_filter(level_ptr, batch_stride, chan_stride, level_h, level_w, level_stride, num_levels,
+                                     B, nc, reg_max, conf_thres, cand_key, cand_count, box_dense, max_cand, stream);
+  if (rc != CVPP_OK) return rc;
+  rc = segsort_launch(cand_key, cand_count, B, max_cand, rule, max_nms, sort_ws, sort_bytes, (cudaStream_t)stream);
+  if (rc != CVPP_OK) return rc;
+  rc = nms_launch(cand_key, cand_count, box_dense, B, max_cand, A, nc, iou_thres, rule, CVPP_ORDER_SCORE_DESC, max_det,
+                  max_det, det_box, det_score, det_cls, det_anchor, det_count, nms_ws, nms_bytes, (cudaStream_t)stream);
+  if (rc != CVPP_OK) return rc;
+  if (cand_count_out && B > 0)
+    CVPP_CUDA_TRY(cudaMemcpyAsync(cand_count_out, cand_count, sizeof(int32_t) * (size_t)B, cudaMemcpyDeviceToDevice,
+                                  (cudaStream_t)stream));
+  return CVPP_OK;
+}
+
+}  // extern "C"

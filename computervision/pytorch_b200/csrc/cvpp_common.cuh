@@ -1,0 +1,141 @@
+// cvpp_common.cuh — shared device helpers for libcvpp (sm_100a).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "cvpp.h"
+
+#define CVPP_KEY_ANCHOR_BITS 21
+#define CVPP_KEY_SCORE_BITS 31
+#define CVPP_KEY_CLASS_BITS 12
+#define CVPP_MAX_ANCHORS (1 << CVPP_KEY_ANCHOR_BITS)
+#define CVPP_MAX_CLASSES (1 << CVPP_KEY_CLASS_BITS)
+#define CVPP_MAX_LEVELS 4
+
+// torchvision.ops.batched_nms on CPU switches to the per-class branch when boxes.numel() > 4000
+// (torchvision/ops/boxes.py:80), i.e. more than 1000 boxes.
+#define CVPP_TRICK_MAX_BOXES 1000
+
+namespace cvpp {
+
+// ---- error plumbing (host) -------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+#define CVPP_CUDA_TRY(expr)                                     \
+  do {                                                          \
+    cudaError_t _e = (expr);                                    \
+    if (_e != cudaSuccess) return ::cvpp::cuda_fail(_e, #expr); \
+  } while (0)
+
+// ---- candidate keys --------------------------------------------------------------------------
+// class-major packing: [class:12 | inv_score:31 | anchor:21]
+__host__ __device__ __forceinline__ uint64_t key_pack(uint32_t cls, uint32_t score_bits, uint32_t anchor) {
+  return ((uint64_t)cls << 52) | ((uint64_t)(0x7fffffffu - (score_bits & 0x7fffffffu)) << 21) | (uint64_t)anchor;
+}
+__host__ __device__ __forceinline__ uint32_t key_cls(uint64_t k) { return (uint32_t)(k >> 52); }
+__host__ __device__ __forceinline__ uint32_t key_score_bits(uint64_t k) {
+  return 0x7fffffffu - (uint32_t)((k >> 21) & 0x7fffffffu);
+}
+__host__ __device__ __forceinline__ uint32_t key_anchor(uint64_t k) { return (uint32_t)(k & 0x1fffffu); }
+// score-major packing used for the coordinate-trick branch: [inv_score:31 | anchor:21 | class:12]
+__host__ __device__ __forceinline__ uint64_t key_to_score_major(uint64_t k) {
+  return ((k & 0x000fffffffffffffull) << 12) | (k >> 52);
+}
+__host__ __device__ __forceinline__ uint64_t key_from_score_major(uint64_t k) {
+  return (k >> 12) | ((k & 0xfffull) << 52);
+}
+
+__host__ __device__ __forceinline__ bool rule_uses_trick(int rule, int n) {
+  return rule == CVPP_NMS_RULE_COORD_TRICK || (rule == CVPP_NMS_RULE_TORCHVISION_CPU && n <= CVPP_TRICK_MAX_BOXES);
+}
+
+#ifdef __CUDACC__
+// ---- exact fp32 arithmetic -------------------------------------------------------------------
+// The reference runs every step as a separate eager op: one IEEE rounding each, never fused.
+// The explicit round-to-nearest intrinsics are never contracted into FMAs by nvcc.
+__device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+
+// torch.sigmoid restated as 1 / (1 + exp(-x)) with the full-precision expf (<= 1 ulp)
+__device__ __forceinline__ float sigmoid_precise(float x) { return fdiv(1.0f, fadd(1.0f, expf(-x))); }
+
+// torchvision nms_kernel.cpp inner loop: is box j suppressed by kept box i?
+//   ovr = inter / (iarea + jarea - inter);  suppressed iff (double)ovr > thr  <=>  ovr > thr_eff
+// thr_eff = largest float <= thr (host-computed, thr in [0,1]).  inter == 0 (or NaN) gives ovr == 0 or
+// NaN, which never exceeds a non-negative threshold, so the division is skipped for disjoint boxes.
+__device__ __forceinline__ bool iou_suppresses(const float4& bi, float ai, const float4& bj, float aj, float thr_eff) {
+  float xx1 = fmaxf(bi.x, bj.x), yy1 = fmaxf(bi.y, bj.y);
+  float xx2 = fminf(bi.z, bj.z), yy2 = fminf(bi.w, bj.w);
+  float w = fmaxf(0.0f, fsub(xx2, xx1));
+  float h = fmaxf(0.0f, fsub(yy2, yy1));
+  float inter = fmul(w, h);
+  if (!(inter > 0.0f)) return false;
+  float ovr = fdiv(inter, fsub(fadd(ai, aj), inter));
+  return ovr > thr_eff;
+}
+__device__ __forceinline__ float box_area(const float4& b) { return fmul(fsub(b.z, b.x), fsub(b.w, b.y)); }
+
+// ---- mbarrier / bulk-copy (TMA engine, 1-D) wrappers -------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+// global -> shared bulk async copy; completion is signalled on `bar` in bytes.
+// dst, src and bytes must be multiples of 16.
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// ---- block-wide bitonic sort -------------------------------------------------------------------
+__host__ __device__ __forceinline__ int pow2_ceil(int n) {
+  int p = 1;
+  while (p < n) p <<= 1;
+  return p;
+}
+// ascending sort of P (power of two) keys by the whole CTA; `a` may be shared or global memory.
+// Ends with a __syncthreads().
+__device__ __forceinline__ void bitonic_sort_u64(uint64_t* a, int P) {
+  for (int k = 2; k <= P; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = threadIdx.x; t < (P >> 1); t += blockDim.x) {
+        int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        int l = i | j;
+        bool up = (i & k) == 0;
+        uint64_t x = a[i], y = a[l];
+        if ((x > y) == up) {
+          a[i] = y;
+          a[l] = x;
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+#endif  // __CUDACC__
+
+}  // namespace cvpp

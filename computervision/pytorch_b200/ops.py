@@ -1,0 +1,227 @@
+"""Thin torch-facing wrappers over the C ABI: they own the device buffers (torch tensors) and pass raw
+pointers + the current CUDA stream to libcvpp.  Nothing here computes on the CPU."""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import (ORDER_CLASS_MAJOR, ORDER_SCORE_DESC, RULE_COORD_TRICK, RULE_PER_CLASS,  # noqa: F401
+                   RULE_TORCHVISION_CPU, check)
+
+c_vp = ctypes.c_void_p
+
+
+def _stream(device) -> c_vp:
+    return c_vp(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> c_vp:
+    return c_vp(0 if t is None else t.data_ptr())
+
+
+def _require_cuda(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise ValueError(f"{what} must live on a CUDA device: libcvpp has no CPU path (got {t.device})")
+    if t.dtype != torch.float32:
+        raise ValueError(f"{what} must be float32 (got {t.dtype})")
+
+
+@dataclass
+class LevelSet:
+    """Host-side description of the head levels as the C ABI wants it."""
+    ptr: ctypes.Array
+    batch_stride: ctypes.Array
+    chan_stride: ctypes.Array
+    h: ctypes.Array
+    w: ctypes.Array
+    stride: ctypes.Array
+    n: int
+    B: int
+    C: int
+    A: int
+    device: torch.device
+    keep: tuple  # tensors kept alive
+
+
+def make_levels(levels: Sequence[torch.Tensor], strides: Sequence[float],
+                sizes: Optional[Sequence[Tuple[int, int]]] = None) -> LevelSet:
+    """levels: list of (B, C, H, W) tensors (any batch/channel strides, cells contiguous), or - with
+    `sizes` - list of (B, C, H*W) views, e.g. slices of the concatenated x_cat."""
+    n = len(levels)
+    if n < 1 or n > 4 or len(strides) != n:
+        raise ValueError("between 1 and 4 head levels with one stride each are supported")
+    keep = []
+    hs, ws = [], []
+    for i, t in enumerate(levels):
+        _require_cuda(t, f"level {i}")
+        if sizes is None:
+            if t.dim() != 4:
+                raise ValueError(f"level {i}: expected (B, C, H, W), got {tuple(t.shape)}")
+            H, W = int(t.shape[2]), int(t.shape[3])
+            if t.stride(3) != 1 or t.stride(2) != W:
+                t = t.contiguous()
+        else:
+            H, W = sizes[i]
+            if t.dim() != 3 or t.shape[2] != H * W:
+                raise ValueError(f"level {i}: expected (B, C, {H * W}), got {tuple(t.shape)}")
+            if t.stride(2) != 1:
+                t = t.contiguous()
+        hs.append(H)
+        ws.append(W)
+        keep.append(t)
+    B, C = int(keep[0].shape[0]), int(keep[0].shape[1])
+    for t in keep:
+        if t.shape[0] != B or t.shape[1] != C or t.device != keep[0].device:
+            raise ValueError("all levels must share batch size, channel count and device")
+    return LevelSet(
+        ptr=(c_vp * n)(*[t.data_ptr() for t in keep]),
+        batch_stride=(ctypes.c_int64 * n)(*[t.stride(0) for t in keep]),
+        chan_stride=(ctypes.c_int64 * n)(*[t.stride(1) for t in keep]),
+        h=(ctypes.c_int * n)(*hs), w=(ctypes.c_int * n)(*ws),
+        stride=(ctypes.c_float * n)(*[float(s) for s in strides]),
+        n=n, B=B, C=C, A=sum(h * w for h, w in zip(hs, ws)), device=keep[0].device, keep=tuple(keep))
+
+
+@dataclass
+class Candidates:
+    key: torch.Tensor        # (B, max_cand) int64 (bit pattern of the uint64 key)
+    count: torch.Tensor      # (B,) int32
+    box_dense: torch.Tensor  # (B, A, 4) float32, valid at candidate anchors only
+    max_cand: int
+    A: int
+    nc: int
+
+
+@dataclass
+class Detections:
+    box: torch.Tensor     # (B, max_out, 4) xyxy
+    score: torch.Tensor   # (B, max_out)
+    cls: torch.Tensor     # (B, max_out) int32
+    anchor: torch.Tensor  # (B, max_out) int32
+    count: torch.Tensor   # (B,) int32
+    cand_count: Optional[torch.Tensor] = None  # (B,) int32 candidates that entered NMS
+
+
+def yolov8_decode_filter(ls: LevelSet, nc: int, conf_thres: float, reg_max: int = 16,
+                         max_cand: Optional[int] = None) -> Candidates:
+    if ls.C != 4 * reg_max + nc:
+        raise ValueError(f"head has {ls.C} channels, expected 4*{reg_max}+{nc}")
+    max_cand = int(max_cand or ls.A)
+    dev = ls.device
+    key = torch.empty((ls.B, max_cand), dtype=torch.int64, device=dev)
+    count = torch.empty((ls.B,), dtype=torch.int32, device=dev)
+    box_dense = torch.empty((ls.B, ls.A, 4), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(_lib.lib().cvpp_yolov8_decode_filter(ls.ptr, ls.batch_stride, ls.chan_stride, ls.h, ls.w, ls.stride, ls.n,
+                                                   ls.B, nc, reg_max, float(conf_thres), _ptr(key), _ptr(count),
+                                                   _ptr(box_dense), max_cand, _stream(dev)))
+    return Candidates(key, count, box_dense, max_cand, ls.A, nc)
+
+
+def yolov8_decode_full(ls: LevelSet, nc: int, reg_max: int = 16) -> torch.Tensor:
+    if ls.C != 4 * reg_max + nc:
+        raise ValueError(f"head has {ls.C} channels, expected 4*{reg_max}+{nc}")
+    y = torch.empty((ls.B, 4 + nc, ls.A), dtype=torch.float32, device=ls.device)
+    with torch.cuda.device(ls.device):
+        check(_lib.lib().cvpp_yolov8_decode_full(ls.ptr, ls.batch_stride, ls.chan_stride, ls.h, ls.w, ls.stride, ls.n,
+                                                 ls.B, nc, reg_max, _ptr(y), _stream(ls.device)))
+    return y
+
+
+def pred_filter(pred: torch.Tensor, nc: int, conf_thres: float, max_cand: Optional[int] = None) -> Candidates:
+    _require_cuda(pred, "prediction")
+    if pred.dim() != 3:
+        raise ValueError(f"prediction must be (B, 4+nc+nm, A), got {tuple(pred.shape)}")
+    pred = pred.contiguous()
+    B, ch, A = (int(v) for v in pred.shape)
+    max_cand = int(max_cand or A)
+    dev = pred.device
+    key = torch.empty((B, max_cand), dtype=torch.int64, device=dev)
+    count = torch.empty((B,), dtype=torch.int32, device=dev)
+    box_dense = torch.empty((B, A, 4), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(_lib.lib().cvpp_pred_filter(_ptr(pred), B, ch, nc, A, float(conf_thres), _ptr(key), _ptr(count),
+                                          _ptr(box_dense), max_cand, _stream(dev)))
+    return Candidates(key, count, box_dense, max_cand, A, nc)
+
+
+def segmented_sort(c: Candidates, rule: int = RULE_TORCHVISION_CPU, max_nms: int = 0) -> None:
+    """Sorts c.key in place (and truncates c.count to max_nms when max_nms > 0)."""
+    l = _lib.lib()
+    B = int(c.key.shape[0])
+    dev = c.key.device
+    nbytes = int(l.cvpp_sort_workspace_bytes(B, c.max_cand))
+    ws = torch.empty((max(nbytes, 1),), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        check(l.cvpp_segmented_sort(_ptr(c.key), _ptr(c.count), B, c.max_cand, rule, int(max_nms), _ptr(ws), nbytes,
+                                    _stream(dev)))
+
+
+def nms(c: Candidates, iou_thres: float, rule: int = RULE_TORCHVISION_CPU, order: int = ORDER_SCORE_DESC,
+        max_det: int = 300, max_out: Optional[int] = None) -> Detections:
+    l = _lib.lib()
+    B = int(c.key.shape[0])
+    dev = c.key.device
+    if max_out is None:
+        max_out = max_det if (order == ORDER_SCORE_DESC and max_det > 0) else c.max_cand
+    max_out = max(int(max_out), 1)
+    nbytes = int(l.cvpp_nms_workspace_bytes(B, c.max_cand))
+    ws = torch.empty((max(nbytes, 1),), dtype=torch.uint8, device=dev)
+    det = Detections(box=torch.empty((B, max_out, 4), dtype=torch.float32, device=dev),
+                     score=torch.empty((B, max_out), dtype=torch.float32, device=dev),
+                     cls=torch.empty((B, max_out), dtype=torch.int32, device=dev),
+                     anchor=torch.empty((B, max_out), dtype=torch.int32, device=dev),
+                     count=torch.empty((B,), dtype=torch.int32, device=dev), cand_count=c.count)
+    with torch.cuda.device(dev):
+        check(l.cvpp_nms(_ptr(c.key), _ptr(c.count), _ptr(c.box_dense), B, c.max_cand, c.A, c.nc, float(iou_thres),
+                         rule, order, int(max_det), max_out, _ptr(det.box), _ptr(det.score), _ptr(det.cls),
+                         _ptr(det.anchor), _ptr(det.count), _ptr(ws), nbytes, _stream(dev)))
+    return det
+
+
+class Yolov8Postprocessor:
+    """Pre-allocated buffers + one C call (cvpp_yolov8_postprocess) per batch: decode+filter, sort, NMS."""
+
+    def __init__(self, B: int, A: int, nc: int, device, max_det: int = 300, max_cand: Optional[int] = None):
+        self.B, self.A, self.nc, self.max_det = int(B), int(A), int(nc), int(max_det)
+        self.max_cand = int(max_cand or A)
+        self.device = torch.device(device)
+        l = _lib.lib()
+        self.ws_bytes = int(l.cvpp_yolov8_workspace_bytes(self.B, self.A, self.max_cand))
+        dev = self.device
+        self.ws = torch.empty((self.ws_bytes,), dtype=torch.uint8, device=dev)
+        self.det = Detections(box=torch.empty((B, max_det, 4), dtype=torch.float32, device=dev),
+                              score=torch.empty((B, max_det), dtype=torch.float32, device=dev),
+                              cls=torch.empty((B, max_det), dtype=torch.int32, device=dev),
+                              anchor=torch.empty((B, max_det), dtype=torch.int32, device=dev),
+                              count=torch.empty((B,), dtype=torch.int32, device=dev),
+                              cand_count=torch.empty((B,), dtype=torch.int32, device=dev))
+
+    def __call__(self, ls: LevelSet, conf_thres: float, iou_thres: float, rule: int = RULE_TORCHVISION_CPU,
+                 max_nms: int = 30000, reg_max: int = 16) -> Detections:
+        if ls.B != self.B or ls.A != self.A or ls.C != 4 * reg_max + self.nc:
+            raise ValueError("level set does not match the shapes this post-processor was built for")
+        d = self.det
+        with torch.cuda.device(self.device):
+            check(_lib.lib().cvpp_yolov8_postprocess(
+                ls.ptr, ls.batch_stride, ls.chan_stride, ls.h, ls.w, ls.stride, ls.n, self.B, self.nc, reg_max,
+                float(conf_thres), float(iou_thres), rule, self.max_det, int(max_nms), self.max_cand, _ptr(d.box),
+                _ptr(d.score), _ptr(d.cls), _ptr(d.anchor), _ptr(d.count), _ptr(d.cand_count), _ptr(self.ws),
+                self.ws_bytes, _stream(self.device)))
+        return d
+
+
+def split_detections(det: Detections) -> List[Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]]:
+    """One device->host read of the counts, then per-image views (box, score, cls, anchor)."""
+    counts = det.count.tolist()
+    cap = det.box.shape[1]
+    out = []
+    for b, n in enumerate(counts):
+        if n > cap:
+            raise RuntimeError(f"image {b}: {n} detections exceed the output capacity {cap}")
+        out.append((det.box[b, :n], det.score[b, :n], det.cls[b, :n], det.anchor[b, :n]))
+    return out

@@ -1,0 +1,165 @@
+/*
+ * cvpp.h — C ABI of libcvpp.so, the B200 (sm_100a) detection post-processing library.
+ *
+ * The reference (calmiLovesAI/ComputerVision.pytorch) is pure Python and has no FFI; its
+ * "boundary" for this path is a handful of Python callables.  Each entry
+ * point below names the reference callable(s) whose arithmetic it replaces (file:line in the
+ * reference tree); INTEGRATION.md shows the ctypes stub a maintainer would add on the
+ * reference side.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller unless stated otherwise; the
+ *     library allocates nothing, keeps no global mutable state and never synchronises:
+ *     all work is enqueued on `stream` (a CUstream / cudaStream_t handle; NULL = legacy
+ *     default stream);
+ *   - returns CVPP_OK (0) or a negative CVPP_ERR_* code; cvpp_last_error() returns a
+ *     thread-local description of the last failure on the calling thread;
+ *   - fp32 tensors must be contiguous in their innermost dimension and 16-byte aligned.
+ *
+ * Candidate key (uint64), the unit the filter kernels emit and the sort orders:
+ *     [63:52] class id            (12 bits, nc <= 4096)
+ *     [51:21] 0x7fffffff - bits(score)   (score is a non-negative fp32; smaller = better)
+ *     [20: 0] anchor / prior index (21 bits)
+ * Ascending key order == class ascending, score descending, lower anchor first on ties —
+ * the order of torchvision's stable descending sort inside nms (SURVEY.md §8c tie rule).
+ */
+#ifndef CVPP_H
+#define CVPP_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* cvpp_stream_t;
+
+#if defined(__GNUC__)
+#define CVPP_API __attribute__((visibility("default")))
+#else
+#define CVPP_API
+#endif
+
+enum {
+  CVPP_OK = 0,
+  CVPP_ERR_INVALID_ARG = -1, /* bad shape / threshold / NULL pointer */
+  CVPP_ERR_ALIGNMENT = -2,   /* pointer or stride not 16-byte aligned */
+  CVPP_ERR_WORKSPACE = -3,   /* workspace too small */
+  CVPP_ERR_CUDA = -4,        /* CUDA runtime error (see cvpp_last_error) */
+  CVPP_ERR_UNSUPPORTED = -5  /* configuration outside the compiled kernels */
+};
+
+/* batched_nms arithmetic branch (torchvision/ops/boxes.py:51-120) */
+enum {
+  CVPP_NMS_RULE_TORCHVISION_CPU = 0, /* per image: n > 1000 -> per-class ("vanilla") else coordinate trick */
+  CVPP_NMS_RULE_COORD_TRICK = 1,     /* boxes + cls * (max_coord + 1), one class-agnostic pass          */
+  CVPP_NMS_RULE_PER_CLASS = 2        /* per-class nms on raw boxes (also what YOLOv7/SSD/YOLOv3 do)      */
+};
+
+/* output order of cvpp_nms */
+enum {
+  CVPP_ORDER_SCORE_DESC = 0, /* all classes merged, score descending, capped at max_det (YOLOv8)   */
+  CVPP_ORDER_CLASS_MAJOR = 1 /* class ascending then score descending, no cap (YOLOv7/SSD/YOLOv3)  */
+};
+
+CVPP_API int cvpp_version(void);
+CVPP_API const char* cvpp_last_error(void);
+CVPP_API const char* cvpp_error_name(int code);
+
+/* ---------------------------------------------------------------------------------------------
+ * YOLOv8 head decode + confidence filter, fused (kernel 1).
+ * Replaces: Detect.forward eval tail  core/models/yolov8/modules.py:434-445
+ *           DFL.forward               core/models/yolov8/modules.py:80-82
+ *           make_anchors              core/utils/anchor.py:126-145
+ *           dist2bbox                 core/utils/bboxes.py:213-222
+ *           the candidate filter of non_max_suppression  core/utils/ultralytics_ops.py:190,204,220-226
+ *           xywh2xyxy                 core/utils/ultralytics_ops.py:360-375
+ * Input: num_levels (<= 4) head levels; element (b, c, cell) of level l is
+ *        level_ptr[l][b*batch_stride[l] + c*chan_stride[l] + cell], c in [0, 4*reg_max + nc),
+ *        cell = y*W_l + x.  (NCHW level tensors: chan_stride = H*W, batch_stride = C*H*W; the
+ *        concatenated x_cat (B,C,A): chan_stride = A, batch_stride = C*A, pointers offset.)
+ *        level_ptr / batch_stride / chan_stride / level_h / level_w / level_stride are HOST arrays.
+ * Output: cand_key[b*max_cand + i], i < min(cand_count[b], max_cand): keys of the anchors whose
+ *         best class score is > conf_thres (arbitrary order); cand_count[b] counts ALL of them
+ *         (> max_cand means overflow); box_dense[(b*A + anchor)*4 ..] = x1,y1,x2,y2 in input
+ *         pixels for candidate anchors only (other entries untouched).
+ * ------------------------------------------------------------------------------------------- */
+CVPP_API int cvpp_yolov8_decode_filter(const float* const* level_ptr, const int64_t* batch_stride,
+                              const int64_t* chan_stride, const int* level_h, const int* level_w,
+                              const float* level_stride, int num_levels, int B, int nc, int reg_max,
+                              float conf_thres, uint64_t* cand_key, int32_t* cand_count, float* box_dense,
+                              int max_cand, cvpp_stream_t stream);
+
+/* Same decode, but writes the full y (B, 4+nc, A) = [cx,cy,w,h, sigmoid(cls)] like
+ * Detect.forward (modules.py:444) for callers that want the dense tensor. */
+CVPP_API int cvpp_yolov8_decode_full(const float* const* level_ptr, const int64_t* batch_stride,
+                            const int64_t* chan_stride, const int* level_h, const int* level_w,
+                            const float* level_stride, int num_levels, int B, int nc, int reg_max, float* y,
+                            cvpp_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Confidence filter on an already decoded prediction tensor (B, 4+nc+nm, A), rows
+ * cx,cy,w,h,scores...  Replaces non_max_suppression's candidate stage
+ * (core/utils/ultralytics_ops.py:190,204,220-226 + xywh2xyxy :360-375).  Outputs as above.
+ * ------------------------------------------------------------------------------------------- */
+CVPP_API int cvpp_pred_filter(const float* pred, int B, int channels, int nc, int64_t A, float conf_thres,
+                     uint64_t* cand_key, int32_t* cand_count, float* box_dense, int max_cand,
+                     cvpp_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Segmented sort of candidate keys, one segment per image (kernel 2).
+ * Replaces: x[:, 4].argsort(descending=True)[:max_nms]   core/utils/ultralytics_ops.py:240
+ *           the stable descending sort inside torchvision nms (per class)
+ *           torch.unique(class) + per-class gathers        core/algorithms/yolo_v7.py:396-400,
+ *                                                          torchvision/ops/boxes.py:112-116
+ * keys[b*max_cand ..] is sorted ascending in place over the first min(cand_count[b], max_cand)
+ * entries.  When `rule` selects the coordinate trick for an image, its keys are re-packed as
+ * [score | anchor | class] so the order is global score-descending; cvpp_nms undoes that.
+ * max_nms (>0) truncates each image's list to its max_nms best scores (ultralytics :240).
+ * workspace: cvpp_sort_workspace_bytes(B, max_cand) bytes, only touched by segments too large
+ * for shared memory.
+ * ------------------------------------------------------------------------------------------- */
+CVPP_API size_t cvpp_sort_workspace_bytes(int B, int max_cand);
+CVPP_API int cvpp_segmented_sort(uint64_t* keys, int32_t* cand_count, int B, int max_cand, int rule, int max_nms,
+                        void* workspace, size_t workspace_bytes, cvpp_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Class-aware greedy NMS + gather of the survivors (kernel 3).
+ * Replaces: torchvision.ops.batched_nms / nms (torchvision/ops/boxes.py:20-120, csrc/ops/cpu/nms_kernel.cpp)
+ *           at call sites core/utils/ultralytics_ops.py:247-248,257; core/utils/nms.py:69,134;
+ *           core/algorithms/yolo_v7.py:407; core/algorithms/ssd.py:267.
+ * Input: sorted keys (from cvpp_segmented_sort, same `rule`), counts, box_dense (B, A, 4); class ids
+ *        in the keys are < nc.
+ * Suppression test: IoU computed in fp32 exactly as torchvision's CPU kernel; j is suppressed by a
+ * kept i iff (double)iou > iou_thres.
+ * Output rows k < min(det_count[b], max_out), for image b at index b*max_out + k:
+ *   det_box (x1,y1,x2,y2), det_score, det_cls, det_anchor.  det_count[b] is the uncapped-by-max_out
+ *   number of survivors (after the max_det cap when order == CVPP_ORDER_SCORE_DESC).
+ * workspace: cvpp_nms_workspace_bytes(B, max_cand).
+ * ------------------------------------------------------------------------------------------- */
+CVPP_API size_t cvpp_nms_workspace_bytes(int B, int max_cand);
+CVPP_API int cvpp_nms(const uint64_t* sorted_key, const int32_t* cand_count, const float* box_dense, int B,
+             int max_cand, int64_t A, int nc, double iou_thres, int rule, int order, int max_det, int max_out,
+             float* det_box, float* det_score, int32_t* det_cls, int32_t* det_anchor, int32_t* det_count,
+             void* workspace, size_t workspace_bytes, cvpp_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * The whole YOLOv8 path in one call: decode+filter -> sort -> NMS (3 kernels + 1 memset on `stream`).
+ * Replaces Detect.forward eval tail + non_max_suppression as chained by YOLOv8.decode_box
+ * (core/algorithms/yolo_v8.py:222-227).  Scratch buffers are carved from `workspace`
+ * (cvpp_yolov8_workspace_bytes).  max_cand = A is always sufficient.
+ * ------------------------------------------------------------------------------------------- */
+CVPP_API size_t cvpp_yolov8_workspace_bytes(int B, int64_t A, int max_cand);
+CVPP_API int cvpp_yolov8_postprocess(const float* const* level_ptr, const int64_t* batch_stride,
+                            const int64_t* chan_stride, const int* level_h, const int* level_w,
+                            const float* level_stride, int num_levels, int B, int nc, int reg_max,
+                            float conf_thres, double iou_thres, int rule, int max_det, int max_nms,
+                            int max_cand, float* det_box, float* det_score, int32_t* det_cls,
+                            int32_t* det_anchor, int32_t* det_count, int32_t* cand_count_out,
+                            void* workspace, size_t workspace_bytes, cvpp_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CVPP_H */
