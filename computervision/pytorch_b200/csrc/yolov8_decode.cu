@@ -6,25 +6,30 @@
 // core/utils/ultralytics_ops.py:190,204,220-226 (+ xywh2xyxy :360-375).
 //
 // Memory-bound: every image reads (4*reg_max + nc) x A fp32 once (4 838 400 B for the 8400-anchor,
-// 80-class head) and writes 8 B + 16 B per surviving candidate.  Design:
-//   * persistent CTAs (one per SM) walk tiles of TILE_A consecutive cells of one level of one image;
-//   * a tile is C rows of TILE_A*4 contiguous bytes; warp 0 issues one 1-D bulk async copy
-//     (cp.async.bulk -> UBLKCP, the TMA engine) per row into a STAGES-deep shared-memory ring, each
-//     stage guarded by an mbarrier armed with the tile's byte count, so 2 tiles are always in
-//     flight while one is being consumed;
-//   * 16 consumer warps: thread (part, a) handles DFL side `part` (softmax-integral over 16 bins)
-//     and a quarter of the class logits of cell a; class argmax is done on logits (sigmoid is
-//     monotone) and sigmoid is evaluated once per cell; exact first-index tie semantics of
-//     `cls.max(1)` on the sigmoid values are restored on a (rare) slow path;
-//   * survivors are compacted with warp-aggregated atomics into the per-image key list.
+// 80-class head) and writes 8 B + 16 B per surviving candidate.  Design (v2, after the first ncu
+// capture showed the CTA-wide-barrier version stalled on barriers at 25 % of HBM peak):
+//   * one persistent CTA per SM, 14 fully independent warps; a warp owns whole tiles of 128
+//     consecutive cells of one level of one image (4 cells per lane) and never meets a CTA barrier;
+//   * a tile is streamed as chunks of 16 channel rows (one DFL side, or 16 classes) of 512 B: the
+//     warp issues one 1-D bulk async copy (cp.async.bulk -> UBLKCP, the TMA engine) per row into
+//     its private 2-stage shared-memory ring, each stage guarded by an mbarrier armed with the
+//     chunk's byte count;
+//   * a landed chunk is pulled into registers with conflict-free LDS.128, the stage is re-armed at
+//     once for the chunk after next, and the arithmetic (softmax-integral over the 16 DFL bins,
+//     running class argmax on logits) runs out of registers while two chunks are in flight;
+//   * sigmoid is evaluated once per cell (it is monotone); exact first-index tie semantics of
+//     `cls.max(1)` on sigmoid values are restored on a (rare) slow path;
+//   * survivors are compacted with one warp-aggregated atomic per tile into the per-image key list.
 #include "cvpp_common.cuh"
 
 namespace cvpp {
 
-constexpr int kTileA = 128;     // cells per tile
-constexpr int kRegMax = 16;     // DFL bins (reference hard-codes 16, modules.py:413)
-constexpr int kThreads = 512;   // 4 parts x 128 cells
-constexpr int kParts = 4;
+constexpr int kTileA = 128;      // cells per tile (4 per lane)
+constexpr int kRegMax = 16;      // DFL bins (reference hard-codes 16, modules.py:413)
+constexpr int kChunkRows = 16;   // channel rows per chunk
+constexpr int kStages = 2;       // per-warp ring depth
+constexpr int kWarps = 14;       // independent warps per CTA (14 x 16 KB rings = 224 KB)
+constexpr int kChunkFloats = kChunkRows * kTileA;
 
 struct LevelDesc {
   const float* ptr;
@@ -54,38 +59,35 @@ struct DecodeParams {
 };
 
 // ---- per-cell arithmetic (Appendix B of SURVEY.md: one fp32 rounding per reference op) ----------
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // softmax over the 16 bins followed by the arange(16) 1x1 conv: sum_k k * softmax(x)_k
-__device__ __forceinline__ float dfl_expectation(const float* col, int64_t cs) {
-  float v[kRegMax];
-#pragma unroll
-  for (int k = 0; k < kRegMax; ++k) v[k] = col[k * cs];
+__device__ __forceinline__ float dfl16(const float (&v)[kRegMax]) {
   float m = v[0];
 #pragma unroll
   for (int k = 1; k < kRegMax; ++k) m = fmaxf(m, v[k]);
+  const float kLog2e = 1.4426950408889634f;
+  const float mb = -m * kLog2e;
   float sum = 0.0f, wsum = 0.0f;
 #pragma unroll
   for (int k = 0; k < kRegMax; ++k) {
-    float e = __expf(v[k] - m);
+    float e = ex2_approx(fmaf(v[k], kLog2e, mb));  // exp(v - m)
     sum += e;
     wsum = fmaf((float)k, e, wsum);
   }
   return fdiv(wsum, sum);
 }
 
-// running (best, first-argmax, runner-up) over class logits [c0, c1)
-__device__ __forceinline__ void class_scan(const float* col, int64_t cs, int c0, int c1, float& best, int& arg,
-                                           float& sec) {
-#pragma unroll 4
-  for (int c = c0; c < c1; ++c) {
-    float x = col[(int64_t)(c - c0) * cs];
-    if (x > best) {
-      sec = best;
-      best = x;
-      arg = c;
-    } else {
-      sec = fmaxf(sec, x);
-    }
-  }
+// one step of the running (best, first-argmax, runner-up) scan over class logits
+__device__ __forceinline__ void class_step(float x, int c, float& best, int& arg, float& sec) {
+  const bool gt = x > best;
+  sec = fmaxf(sec, gt ? best : x);
+  arg = gt ? c : arg;
+  best = gt ? x : best;
 }
 
 // exact `conf, j = cls.max(1)` over sigmoid values: first index of the maximum sigmoid
@@ -153,129 +155,197 @@ __device__ __forceinline__ void tile_info(const DecodeParams& p, int g, int& b, 
   nA = min(kTileA, p.lv[l].hw - cell0);
 }
 
+// score / class / candidate decision for one cell, shared by both kernels.
+// `col` points at the cell's first class logit in GLOBAL memory (only touched on the tie path).
+__device__ __forceinline__ bool finalize_cell(float best, int arg_in, float sec, const float* col, int64_t cs, int nc,
+                                              float conf_thres, float& score, int& arg) {
+  score = sigmoid_precise(best);
+  arg = arg_in;
+  const bool cand = score > conf_thres;
+  // another class whose sigmoid rounds to the same float: the reference takes the FIRST index of
+  // the maximum sigmoid value, which need not be the first maximum logit.
+  if (cand && sigmoid_precise(sec) >= score) class_argmax_sigmoid(col, cs, nc, score, arg);
+  return cand;
+}
+
 // -----------------------------------------------------------------------------------------------
-// TMA-staged persistent kernel
+// TMA-streamed persistent kernel: independent warps, private bulk-copy rings
 // -----------------------------------------------------------------------------------------------
 template <bool FULL>
-__global__ void __launch_bounds__(kThreads, 1)
-yolov8_decode_tma_kernel(const __grid_constant__ DecodeParams p, const int stages) {
+__global__ void __launch_bounds__(kWarps * 32, 1) yolov8_decode_stream_kernel(const __grid_constant__ DecodeParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* ring = reinterpret_cast<float*>(smem_raw) + (size_t)warp * (kStages * kChunkFloats);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kWarps * kStages * kChunkFloats * sizeof(float)) +
+                  warp * kStages;
   const int nc = p.nc;
   const int C = 4 * kRegMax + nc;
-  const int tile_floats = C * kTileA;
-  float* tiles = reinterpret_cast<float*>(smem_raw);       // [stages][C][kTileA]
-  float* part_d = tiles + (size_t)stages * tile_floats;    // [4][kTileA]
-  float* part_max = part_d + kParts * kTileA;
-  float* part_sec = part_max + kParts * kTileA;
-  int* part_arg = reinterpret_cast<int*>(part_sec + kParts * kTileA);
-  uint64_t* full = reinterpret_cast<uint64_t*>(part_arg + kParts * kTileA);  // [stages]
+  const int nchunks = (C + kChunkRows - 1) / kChunkRows;
 
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int part = warp >> 2;
-  const int a = ((warp & 3) << 5) | lane;
-  const int ncq = (nc + kParts - 1) / kParts;
-
-  if (tid == 0) {
-    for (int s = 0; s < stages; ++s) mbar_init(&full[s], 1);
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) mbar_init(&bar[s], 1);
     mbar_fence_init();
   }
-  __syncthreads();
+  __syncwarp();
 
-  const int n_my = (p.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  // tiles of this warp: first, first + stride, ...  (CTA-major so small batches spread over all SMs)
+  const int stride_tiles = gridDim.x * kWarps;
+  const int first = blockIdx.x + gridDim.x * warp;
+  const int n_tiles = first < p.total_tiles ? (p.total_tiles - first + stride_tiles - 1) / stride_tiles : 0;
+  const int total_q = n_tiles * nchunks;
 
-  auto issue = [&](int i) {  // warp 0 only
-    int g = blockIdx.x + i * gridDim.x;
-    int s = i % stages;
+  auto issue = [&](int q) {
+    const int i = q / nchunks, j = q - i * nchunks;
     int b, l, cell0, nA;
-    tile_info(p, g, b, l, cell0, nA);
+    tile_info(p, first + i * stride_tiles, b, l, cell0, nA);
     const LevelDesc& L = p.lv[l];
-    const float* src = L.ptr + (int64_t)b * L.batch_stride + cell0;
+    const int rows = min(kChunkRows, C - kChunkRows * j);
     const uint32_t row_bytes = (uint32_t)nA * 4u;
-    if (lane == 0) mbar_arrive_expect_tx(&full[s], row_bytes * (uint32_t)C);
+    uint64_t* fb = &bar[q & (kStages - 1)];
+    if (lane == 0) mbar_arrive_expect_tx(fb, row_bytes * (uint32_t)rows);
     __syncwarp();
-    float* dst = tiles + (size_t)s * tile_floats;
-    for (int c = lane; c < C; c += 32) bulk_g2s(dst + c * kTileA, src + (int64_t)c * L.chan_stride, row_bytes, &full[s]);
+    if (lane < rows) {
+      float* dst = ring + (q & (kStages - 1)) * kChunkFloats + lane * kTileA;
+      const float* src = L.ptr + (int64_t)b * L.batch_stride + (int64_t)(kChunkRows * j + lane) * L.chan_stride + cell0;
+      bulk_g2s(dst, src, row_bytes, fb);
+    }
   };
 
-  if (warp == 0) {
-    int pre = n_my < stages ? n_my : stages;
-    for (int i = 0; i < pre; ++i) issue(i);
-  }
+  for (int q = 0; q < kStages && q < total_q; ++q) issue(q);
 
-  for (int i = 0; i < n_my; ++i) {
-    const int s = i % stages;
-    const uint32_t parity = (uint32_t)(i / stages) & 1u;
-    int b, l, cell0, nA;
-    tile_info(p, blockIdx.x + i * gridDim.x, b, l, cell0, nA);
-    const LevelDesc& L = p.lv[l];
-    const bool valid = a < nA;
-    const int anchor = L.anchor_off + cell0 + a;
-
-    mbar_wait(&full[s], parity);
-    const float* T = tiles + (size_t)s * tile_floats;
-
-    float d = 0.0f, best = -INFINITY, sec = -INFINITY;
-    int arg = 0;
-    if (valid) {
-      d = dfl_expectation(T + (part * kRegMax) * kTileA + a, kTileA);
-      const int c0 = part * ncq, c1 = min(nc, c0 + ncq);
-      const float* ccol = T + (4 * kRegMax + c0) * kTileA + a;
-      class_scan(ccol, kTileA, c0, c1, best, arg, sec);
-      if (FULL) {
-        float* yc = p.y + ((int64_t)b * (4 + nc) + 4 + c0) * p.A + anchor;
-        for (int c = c0; c < c1; ++c) yc[(int64_t)(c - c0) * p.A] = sigmoid_precise(ccol[(c - c0) * kTileA]);
+  // per-lane state of the current tile: 4 cells
+  float d[4][4];                       // [side][cell]
+  float best[4], sec[4];
+  int arg[4];
+  int b = 0, l = 0, cell0 = 0, nA = 0;
+  int j = 0, ti = 0;
+  for (int q = 0; q < total_q; ++q) {
+    if (j == 0) {
+      tile_info(p, first + ti * stride_tiles, b, l, cell0, nA);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        best[k] = -INFINITY;
+        sec[k] = -INFINITY;
+        arg[k] = 0;
       }
     }
-    part_d[part * kTileA + a] = d;
-    if (!FULL) {
-      part_max[part * kTileA + a] = best;
-      part_sec[part * kTileA + a] = sec;
-      part_arg[part * kTileA + a] = arg;
+    const LevelDesc& L = p.lv[l];
+    const int s = q & (kStages - 1);
+    mbar_wait(&bar[s], (uint32_t)(q / kStages) & 1u);
+    const int rows = min(kChunkRows, C - kChunkRows * j);
+    float4 v[kChunkRows];
+    {
+      const float4* src = reinterpret_cast<const float4*>(ring + s * kChunkFloats) + lane;
+#pragma unroll
+      for (int r = 0; r < kChunkRows; ++r) v[r] = src[r * (kTileA / 4)];
     }
-    __syncthreads();
+    __syncwarp();                          // every lane holds its copy: the stage may be refilled
+    if (q + kStages < total_q) issue(q + kStages);
 
-    if (part == 0) {
-      CellBox box;
-      if (valid)
-        box = cell_box(cell0 + a, L.w, L.stride, part_d[a], part_d[kTileA + a], part_d[2 * kTileA + a],
-                       part_d[3 * kTileA + a]);
+    const bool active = 4 * lane < nA;
+    const int anchor0 = L.anchor_off + cell0 + 4 * lane;
+    if (j < 4) {
+      float t[kRegMax];
+#pragma unroll
+      for (int r = 0; r < kRegMax; ++r) t[r] = v[r].x;
+      const float dx = dfl16(t);
+#pragma unroll
+      for (int r = 0; r < kRegMax; ++r) t[r] = v[r].y;
+      const float dy = dfl16(t);
+#pragma unroll
+      for (int r = 0; r < kRegMax; ++r) t[r] = v[r].z;
+      const float dz = dfl16(t);
+#pragma unroll
+      for (int r = 0; r < kRegMax; ++r) t[r] = v[r].w;
+      const float dw = dfl16(t);
+#pragma unroll
+      for (int side = 0; side < 4; ++side)
+        if (j == side) {
+          d[side][0] = dx;
+          d[side][1] = dy;
+          d[side][2] = dz;
+          d[side][3] = dw;
+        }
+    } else {
+      const int c0 = kChunkRows * (j - 4);
       if (FULL) {
-        if (valid) {
-          float* yb = p.y + (int64_t)b * (4 + nc) * p.A + anchor;
-          yb[0] = box.cx;
-          yb[(int64_t)p.A] = box.cy;
-          yb[2 * (int64_t)p.A] = box.w;
-          yb[3 * (int64_t)p.A] = box.h;
+        if (active) {
+          float* yc = p.y + ((int64_t)b * (4 + nc) + 4 + c0) * p.A + anchor0;
+#pragma unroll
+          for (int r = 0; r < kChunkRows; ++r) {
+            if (r < rows) {
+              float4 o;
+              o.x = sigmoid_precise(v[r].x);
+              o.y = sigmoid_precise(v[r].y);
+              o.z = sigmoid_precise(v[r].z);
+              o.w = sigmoid_precise(v[r].w);
+              *reinterpret_cast<float4*>(yc + (int64_t)r * p.A) = o;
+            }
+          }
         }
       } else {
-        bool cand = false;
-        float score = 0.0f;
-        if (valid) {
 #pragma unroll
-          for (int q = 1; q < kParts; ++q) {
-            float bq = part_max[q * kTileA + a];
-            if (bq > best) {
-              sec = fmaxf(sec, best);
-              best = bq;
-              arg = part_arg[q * kTileA + a];
-            } else {
-              sec = fmaxf(sec, bq);
-            }
-            sec = fmaxf(sec, part_sec[q * kTileA + a]);
+        for (int r = 0; r < kChunkRows; ++r) {
+          if (r < rows) {
+            class_step(v[r].x, c0 + r, best[0], arg[0], sec[0]);
+            class_step(v[r].y, c0 + r, best[1], arg[1], sec[1]);
+            class_step(v[r].z, c0 + r, best[2], arg[2], sec[2]);
+            class_step(v[r].w, c0 + r, best[3], arg[3], sec[3]);
           }
-          score = sigmoid_precise(best);
-          cand = score > p.conf_thres;
-          // another class whose sigmoid rounds to the same float: the reference takes the FIRST
-          // index of the maximum sigmoid value, which need not be the first maximum logit.
-          if (cand && sigmoid_precise(sec) >= score)
-            class_argmax_sigmoid(T + (4 * kRegMax) * kTileA + a, kTileA, nc, score, arg);
         }
-        uint64_t key = key_pack((uint32_t)arg, __float_as_uint(score), (uint32_t)anchor);
-        emit_candidate(cand, b, key, anchor, make_float4(box.x1, box.y1, box.x2, box.y2), p);
       }
     }
-    __syncthreads();  // every read of stage s (and of the part_* arrays) is done
-    if (warp == 0 && i + stages < n_my) issue(i + stages);
+
+    if (++j == nchunks) {  // tile complete
+      j = 0;
+      ++ti;
+      CellBox box[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) box[k] = cell_box(cell0 + 4 * lane + k, L.w, L.stride, d[0][k], d[1][k], d[2][k], d[3][k]);
+      if (FULL) {
+        if (active) {
+          float* yb = p.y + (int64_t)b * (4 + nc) * p.A + anchor0;
+          *reinterpret_cast<float4*>(yb) = make_float4(box[0].cx, box[1].cx, box[2].cx, box[3].cx);
+          *reinterpret_cast<float4*>(yb + (int64_t)p.A) = make_float4(box[0].cy, box[1].cy, box[2].cy, box[3].cy);
+          *reinterpret_cast<float4*>(yb + 2 * (int64_t)p.A) = make_float4(box[0].w, box[1].w, box[2].w, box[3].w);
+          *reinterpret_cast<float4*>(yb + 3 * (int64_t)p.A) = make_float4(box[0].h, box[1].h, box[2].h, box[3].h);
+        }
+      } else {
+        const float* col = L.ptr + (int64_t)b * L.batch_stride + (int64_t)(4 * kRegMax) * L.chan_stride + cell0 + 4 * lane;
+        bool cand[4];
+        float score[4];
+        int cls[4];
+        unsigned m[4];
+        int total = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          cand[k] = false;
+          score[k] = 0.f;
+          cls[k] = 0;
+          if (active) cand[k] = finalize_cell(best[k], arg[k], sec[k], col + k, L.chan_stride, nc, p.conf_thres, score[k], cls[k]);
+          m[k] = __ballot_sync(0xffffffffu, cand[k]);
+          total += __popc(m[k]);
+        }
+        if (total) {
+          int base = 0;
+          if (lane == 0) base = atomicAdd(p.cand_count + b, total);
+          base = __shfl_sync(0xffffffffu, base, 0);
+          const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (cand[k]) {
+              const int slot = base + __popc(m[k] & lt);
+              const int anchor = anchor0 + k;
+              if (slot < p.max_cand)
+                p.cand_key[(int64_t)b * p.max_cand + slot] = key_pack((uint32_t)cls[k], __float_as_uint(score[k]), (uint32_t)anchor);
+              p.box_dense[(int64_t)b * p.A + anchor] = make_float4(box[k].x1, box[k].y1, box[k].x2, box[k].y2);
+            }
+            base += __popc(m[k]);
+          }
+        }
+      }
+    }
   }
 }
 
@@ -304,7 +374,12 @@ __global__ void __launch_bounds__(128) yolov8_decode_generic_kernel(const __grid
     const int64_t cs = L.chan_stride;
     float d[4];
 #pragma unroll
-    for (int side = 0; side < 4; ++side) d[side] = dfl_expectation(col + (int64_t)side * kRegMax * cs, cs);
+    for (int side = 0; side < 4; ++side) {
+      float t[kRegMax];
+#pragma unroll
+      for (int k = 0; k < kRegMax; ++k) t[k] = col[(int64_t)(side * kRegMax + k) * cs];
+      d[side] = dfl16(t);
+    }
     box = cell_box(cell, L.w, L.stride, d[0], d[1], d[2], d[3]);
     const float* ccol = col + (int64_t)4 * kRegMax * cs;
     if (FULL) {
@@ -316,10 +391,9 @@ __global__ void __launch_bounds__(128) yolov8_decode_generic_kernel(const __grid
       for (int c = 0; c < nc; ++c) yb[(int64_t)(4 + c) * p.A] = sigmoid_precise(ccol[(int64_t)c * cs]);
     } else {
       float best = -INFINITY, sec = -INFINITY;
-      class_scan(ccol, cs, 0, nc, best, arg, sec);
-      score = sigmoid_precise(best);
-      cand = score > p.conf_thres;
-      if (cand && sigmoid_precise(sec) >= score) class_argmax_sigmoid(ccol, cs, nc, score, arg);
+      int a0 = 0;
+      for (int c = 0; c < nc; ++c) class_step(ccol[(int64_t)c * cs], c, best, a0, sec);
+      cand = finalize_cell(best, a0, sec, ccol, cs, nc, p.conf_thres, score, arg);
     }
   }
   if (!FULL) {
@@ -344,20 +418,12 @@ static int launch_decode(DecodeParams& p, bool tma_ok, cudaStream_t stream) {
   int sms = 0, max_smem = 0;
   int rc = sm_count_of_current_device(&sms, &max_smem);
   if (rc != CVPP_OK) return rc;
-  const int C = 4 * kRegMax + p.nc;
-  const size_t tile_bytes = (size_t)C * kTileA * sizeof(float);
-  const size_t fixed = (size_t)4 * kParts * kTileA * sizeof(float) + 8 * sizeof(uint64_t);
-  int stages = 0;
-  if (tma_ok && (size_t)max_smem > fixed + 2 * tile_bytes) {
-    stages = (int)(((size_t)max_smem - fixed) / tile_bytes);
-    if (stages > 4) stages = 4;
-  }
-  if (stages >= 2) {
-    const size_t smem = fixed + (size_t)stages * tile_bytes;
-    auto kern = yolov8_decode_tma_kernel<FULL>;
+  const size_t smem = (size_t)kWarps * kStages * kChunkFloats * sizeof(float) + (size_t)kWarps * kStages * sizeof(uint64_t);
+  if (tma_ok && smem <= (size_t)max_smem) {
+    auto kern = yolov8_decode_stream_kernel<FULL>;
     CVPP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = p.total_tiles < sms ? p.total_tiles : sms;
-    kern<<<grid, kThreads, smem, stream>>>(p, stages);
+    kern<<<grid, kWarps * 32, smem, stream>>>(p);
   } else {
     dim3 grid((p.A + 127) / 128, p.B);
     yolov8_decode_generic_kernel<FULL><<<grid, 128, 0, stream>>>(p);
