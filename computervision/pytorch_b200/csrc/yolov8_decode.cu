@@ -10,16 +10,19 @@
 // capture showed the CTA-wide-barrier version stalled on barriers at 25 % of HBM peak):
 //   * one persistent CTA per SM, 14 fully independent warps; a warp owns whole tiles of 128
 //     consecutive cells of one level of one image (4 cells per lane) and never meets a CTA barrier;
-//   * a tile is streamed as chunks of 16 channel rows (one DFL side, or 16 classes) of 512 B: the
-//     warp issues one 1-D bulk async copy (cp.async.bulk -> UBLKCP, the TMA engine) per row into
-//     its private 2-stage shared-memory ring, each stage guarded by an mbarrier armed with the
-//     chunk's byte count;
+//   * a tile is streamed as chunks of 16 channel rows (one DFL side, or 16 classes) x 128 cells:
+//     one elected lane issues ONE 3-D tensor-map TMA load (cp.async.bulk.tensor -> UTMALDG, box
+//     128 cells x 16 channels x 1 image; out-of-range cells are zero-filled by the engine) into the
+//     warp's private 2-stage shared-memory ring, each stage guarded by an mbarrier armed with the
+//     box's byte count (v3: 16 per-row UBLKCPs cost ~160 issue slots per chunk in the v2 capture);
 //   * a landed chunk is pulled into registers with conflict-free LDS.128, the stage is re-armed at
 //     once for the chunk after next, and the arithmetic (softmax-integral over the 16 DFL bins,
 //     running class argmax on logits) runs out of registers while two chunks are in flight;
 //   * sigmoid is evaluated once per cell (it is monotone); exact first-index tie semantics of
 //     `cls.max(1)` on sigmoid values are restored on a (rare) slow path;
 //   * survivors are compacted with one warp-aggregated atomic per tile into the per-image key list.
+#include <cuda.h>
+
 #include "cvpp_common.cuh"
 
 namespace cvpp {
@@ -43,6 +46,7 @@ struct LevelDesc {
 };
 
 struct DecodeParams {
+  CUtensorMap tmap[CVPP_MAX_LEVELS];  // (cell, channel, image) fp32, box 128 x 16 x 1; first: 64-byte aligned
   LevelDesc lv[CVPP_MAX_LEVELS];
   int num_levels;
   int B;
@@ -82,12 +86,14 @@ __device__ __forceinline__ float dfl16(const float (&v)[kRegMax]) {
   return fdiv(wsum, sum);
 }
 
-// one step of the running (best, first-argmax, runner-up) scan over class logits
-__device__ __forceinline__ void class_step(float x, int c, float& best, int& arg, float& sec) {
+// one step of the running class scan on logits.  `prev` is the largest logit seen BEFORE the current
+// best (= the old best at the last improvement): only an earlier index can steal the reference's
+// first-index-of-max-sigmoid when two logits round to the same sigmoid, so it is all the tie check needs.
+__device__ __forceinline__ void class_step(float x, int c, float& best, int& arg, float& prev) {
   const bool gt = x > best;
-  sec = fmaxf(sec, gt ? best : x);
+  prev = gt ? best : prev;
   arg = gt ? c : arg;
-  best = gt ? x : best;
+  best = fmaxf(best, x);
 }
 
 // exact `conf, j = cls.max(1)` over sigmoid values: first index of the maximum sigmoid
@@ -157,20 +163,27 @@ __device__ __forceinline__ void tile_info(const DecodeParams& p, int g, int& b, 
 
 // score / class / candidate decision for one cell, shared by both kernels.
 // `col` points at the cell's first class logit in GLOBAL memory (only touched on the tie path).
-__device__ __forceinline__ bool finalize_cell(float best, int arg_in, float sec, const float* col, int64_t cs, int nc,
+__device__ __forceinline__ bool finalize_cell(float best, int arg_in, float prev, const float* col, int64_t cs, int nc,
                                               float conf_thres, float& score, int& arg) {
   score = sigmoid_precise(best);
   arg = arg_in;
   const bool cand = score > conf_thres;
-  // another class whose sigmoid rounds to the same float: the reference takes the FIRST index of
+  // an EARLIER class whose sigmoid rounds to the same float: the reference takes the FIRST index of
   // the maximum sigmoid value, which need not be the first maximum logit.
-  if (cand && sigmoid_precise(sec) >= score) class_argmax_sigmoid(col, cs, nc, score, arg);
+  if (cand && sigmoid_precise(prev) >= score) class_argmax_sigmoid(col, cs, nc, score, arg);
   return cand;
 }
 
 // -----------------------------------------------------------------------------------------------
-// TMA-streamed persistent kernel: independent warps, private bulk-copy rings
+// TMA-streamed persistent kernel: independent warps, private tensor-map TMA rings
 // -----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
 template <bool FULL>
 __global__ void __launch_bounds__(kWarps * 32, 1) yolov8_decode_stream_kernel(const __grid_constant__ DecodeParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -195,53 +208,53 @@ __global__ void __launch_bounds__(kWarps * 32, 1) yolov8_decode_stream_kernel(co
   const int n_tiles = first < p.total_tiles ? (p.total_tiles - first + stride_tiles - 1) / stride_tiles : 0;
   const int total_q = n_tiles * nchunks;
 
-  auto issue = [&](int q) {
-    const int i = q / nchunks, j = q - i * nchunks;
-    int b, l, cell0, nA;
-    tile_info(p, first + i * stride_tiles, b, l, cell0, nA);
-    const LevelDesc& L = p.lv[l];
-    const int rows = min(kChunkRows, C - kChunkRows * j);
-    const uint32_t row_bytes = (uint32_t)nA * 4u;
-    uint64_t* fb = &bar[q & (kStages - 1)];
-    if (lane == 0) mbar_arrive_expect_tx(fb, row_bytes * (uint32_t)rows);
-    __syncwarp();
-    if (lane < rows) {
-      float* dst = ring + (q & (kStages - 1)) * kChunkFloats + lane * kTileA;
-      const float* src = L.ptr + (int64_t)b * L.batch_stride + (int64_t)(kChunkRows * j + lane) * L.chan_stride + cell0;
-      bulk_g2s(dst, src, row_bytes, fb);
+  // producer cursor (runs kStages chunks ahead of the consumer cursor)
+  int pq = 0, pj = 0, pg = first, pb = 0, pl = 0, pcell0 = 0;
+  auto issue = [&]() {
+    if (pj == 0) {
+      int nA_unused;
+      tile_info(p, pg, pb, pl, pcell0, nA_unused);
+    }
+    if (lane == 0) {
+      uint64_t* fb = &bar[pq & (kStages - 1)];
+      mbar_arrive_expect_tx(fb, (uint32_t)(kChunkFloats * sizeof(float)));
+      tma_load_3d(ring + (pq & (kStages - 1)) * kChunkFloats, &p.tmap[pl], pcell0, kChunkRows * pj, pb, fb);
+    }
+    ++pq;
+    if (++pj == nchunks) {
+      pj = 0;
+      pg += stride_tiles;
     }
   };
-
-  for (int q = 0; q < kStages && q < total_q; ++q) issue(q);
+  for (int q = 0; q < kStages && q < total_q; ++q) issue();
 
   // per-lane state of the current tile: 4 cells
-  float d[4][4];                       // [side][cell]
-  float best[4], sec[4];
+  float d[4][4];  // [side][cell]
+  float best[4], prev[4];
   int arg[4];
   int b = 0, l = 0, cell0 = 0, nA = 0;
-  int j = 0, ti = 0;
+  int j = 0, g = first;
   for (int q = 0; q < total_q; ++q) {
     if (j == 0) {
-      tile_info(p, first + ti * stride_tiles, b, l, cell0, nA);
+      tile_info(p, g, b, l, cell0, nA);
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         best[k] = -INFINITY;
-        sec[k] = -INFINITY;
+        prev[k] = -INFINITY;
         arg[k] = 0;
       }
     }
     const LevelDesc& L = p.lv[l];
     const int s = q & (kStages - 1);
     mbar_wait(&bar[s], (uint32_t)(q / kStages) & 1u);
-    const int rows = min(kChunkRows, C - kChunkRows * j);
     float4 v[kChunkRows];
     {
       const float4* src = reinterpret_cast<const float4*>(ring + s * kChunkFloats) + lane;
 #pragma unroll
       for (int r = 0; r < kChunkRows; ++r) v[r] = src[r * (kTileA / 4)];
     }
-    __syncwarp();                          // every lane holds its copy: the stage may be refilled
-    if (q + kStages < total_q) issue(q + kStages);
+    __syncwarp();  // every lane holds its copy: the stage may be refilled
+    if (pq < total_q) issue();
 
     const bool active = 4 * lane < nA;
     const int anchor0 = L.anchor_off + cell0 + 4 * lane;
@@ -269,6 +282,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) yolov8_decode_stream_kernel(co
         }
     } else {
       const int c0 = kChunkRows * (j - 4);
+      const int rows = min(kChunkRows, nc - c0);
       if (FULL) {
         if (active) {
           float* yc = p.y + ((int64_t)b * (4 + nc) + 4 + c0) * p.A + anchor0;
@@ -284,14 +298,22 @@ __global__ void __launch_bounds__(kWarps * 32, 1) yolov8_decode_stream_kernel(co
             }
           }
         }
+      } else if (rows == kChunkRows) {
+#pragma unroll
+        for (int r = 0; r < kChunkRows; ++r) {
+          class_step(v[r].x, c0 + r, best[0], arg[0], prev[0]);
+          class_step(v[r].y, c0 + r, best[1], arg[1], prev[1]);
+          class_step(v[r].z, c0 + r, best[2], arg[2], prev[2]);
+          class_step(v[r].w, c0 + r, best[3], arg[3], prev[3]);
+        }
       } else {
 #pragma unroll
         for (int r = 0; r < kChunkRows; ++r) {
           if (r < rows) {
-            class_step(v[r].x, c0 + r, best[0], arg[0], sec[0]);
-            class_step(v[r].y, c0 + r, best[1], arg[1], sec[1]);
-            class_step(v[r].z, c0 + r, best[2], arg[2], sec[2]);
-            class_step(v[r].w, c0 + r, best[3], arg[3], sec[3]);
+            class_step(v[r].x, c0 + r, best[0], arg[0], prev[0]);
+            class_step(v[r].y, c0 + r, best[1], arg[1], prev[1]);
+            class_step(v[r].z, c0 + r, best[2], arg[2], prev[2]);
+            class_step(v[r].w, c0 + r, best[3], arg[3], prev[3]);
           }
         }
       }
@@ -299,7 +321,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) yolov8_decode_stream_kernel(co
 
     if (++j == nchunks) {  // tile complete
       j = 0;
-      ++ti;
+      g += stride_tiles;
       CellBox box[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) box[k] = cell_box(cell0 + 4 * lane + k, L.w, L.stride, d[0][k], d[1][k], d[2][k], d[3][k]);
@@ -323,7 +345,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) yolov8_decode_stream_kernel(co
           cand[k] = false;
           score[k] = 0.f;
           cls[k] = 0;
-          if (active) cand[k] = finalize_cell(best[k], arg[k], sec[k], col + k, L.chan_stride, nc, p.conf_thres, score[k], cls[k]);
+          if (active) cand[k] = finalize_cell(best[k], arg[k], prev[k], col + k, L.chan_stride, nc, p.conf_thres, score[k], cls[k]);
           m[k] = __ballot_sync(0xffffffffu, cand[k]);
           total += __popc(m[k]);
         }
@@ -390,10 +412,10 @@ __global__ void __launch_bounds__(128) yolov8_decode_generic_kernel(const __grid
       yb[3 * (int64_t)p.A] = box.h;
       for (int c = 0; c < nc; ++c) yb[(int64_t)(4 + c) * p.A] = sigmoid_precise(ccol[(int64_t)c * cs]);
     } else {
-      float best = -INFINITY, sec = -INFINITY;
+      float best = -INFINITY, prev = -INFINITY;
       int a0 = 0;
-      for (int c = 0; c < nc; ++c) class_step(ccol[(int64_t)c * cs], c, best, a0, sec);
-      cand = finalize_cell(best, a0, sec, ccol, cs, nc, p.conf_thres, score, arg);
+      for (int c = 0; c < nc; ++c) class_step(ccol[(int64_t)c * cs], c, best, a0, prev);
+      cand = finalize_cell(best, a0, prev, ccol, cs, nc, p.conf_thres, score, arg);
     }
   }
   if (!FULL) {
@@ -413,6 +435,38 @@ static int sm_count_of_current_device(int* sms, int* max_smem) {
   return CVPP_OK;
 }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// cuTensorMapEncodeTiled through the runtime's driver entry-point lookup: no link-time libcuda dependency.
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      f = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(f);
+  }();
+  return fn;
+}
+
+// (cell, channel, image) view of one level; box = 128 cells x 16 channels x 1 image, zero fill out of range
+static bool make_level_tmap(CUtensorMap* tm, const LevelDesc& L, int C, int B) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return false;
+  cuuint64_t dims[3] = {(cuuint64_t)L.hw, (cuuint64_t)C, (cuuint64_t)B};
+  cuuint64_t strides[2] = {(cuuint64_t)L.chan_stride * 4u, (cuuint64_t)L.batch_stride * 4u};
+  cuuint32_t box[3] = {(cuuint32_t)kTileA, (cuuint32_t)kChunkRows, 1u};
+  cuuint32_t estr[3] = {1u, 1u, 1u};
+  if (B == 1) strides[1] = (cuuint64_t)L.chan_stride * 4u * (cuuint64_t)C;  // unused dimension: any valid stride
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(L.ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
 template <bool FULL>
 static int launch_decode(DecodeParams& p, bool tma_ok, cudaStream_t stream) {
   int sms = 0, max_smem = 0;
@@ -420,6 +474,12 @@ static int launch_decode(DecodeParams& p, bool tma_ok, cudaStream_t stream) {
   if (rc != CVPP_OK) return rc;
   const size_t smem = (size_t)kWarps * kStages * kChunkFloats * sizeof(float) + (size_t)kWarps * kStages * sizeof(uint64_t);
   if (tma_ok && smem <= (size_t)max_smem) {
+    const int C = 4 * kRegMax + p.nc;
+    for (int l = 0; l < p.num_levels && tma_ok; ++l) tma_ok = make_level_tmap(&p.tmap[l], p.lv[l], C, p.B);
+  } else {
+    tma_ok = false;
+  }
+  if (tma_ok) {
     auto kern = yolov8_decode_stream_kernel<FULL>;
     CVPP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = p.total_tiles < sms ? p.total_tiles : sms;
@@ -453,7 +513,7 @@ int yolov8_decode_launch(const float* const* level_ptr, const int64_t* batch_str
     set_error("yolov8 decode: NULL output / max_cand < 1");
     return CVPP_ERR_INVALID_ARG;
   }
-  DecodeParams p{};
+  alignas(64) DecodeParams p{};
   p.num_levels = num_levels;
   p.B = B;
   p.nc = nc;
