@@ -111,15 +111,16 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                : "memory");
 }
 
-// ---- block-wide bitonic sort -------------------------------------------------------------------
+// ---- block-wide sort of 64-bit keys --------------------------------------------------------------
 __host__ __device__ __forceinline__ int pow2_ceil(int n) {
   int p = 1;
   while (p < n) p <<= 1;
   return p;
 }
-// ascending sort of P (power of two) keys by the whole CTA; `a` may be shared or global memory.
-// Ends with a __syncthreads().
-__device__ __forceinline__ void bitonic_sort_u64(uint64_t* a, int P) {
+
+// Plain bitonic network through a generic pointer (shared OR global): one __syncthreads per substep.
+// Only used for segments that do not fit shared memory.  Ends with a __syncthreads().
+__device__ __forceinline__ void bitonic_sort_u64_generic(uint64_t* a, int P) {
   for (int k = 2; k <= P; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
       for (int t = threadIdx.x; t < (P >> 1); t += blockDim.x) {
@@ -134,6 +135,103 @@ __device__ __forceinline__ void bitonic_sort_u64(uint64_t* a, int P) {
       }
       __syncthreads();
     }
+  }
+}
+
+__device__ __forceinline__ void cmpswap_u64(uint64_t& a, uint64_t& b, bool up) {
+  const bool sw = (a > b) == up;
+  const uint64_t t = a;
+  a = sw ? b : a;
+  b = sw ? t : b;
+}
+
+// Substeps j = j_start, j_start/2, ..., 1 of the bitonic merge of size k on a warp-private block of
+// 32*E keys held in registers, striped: x[e] is element base + e*32 + lane.  Lane-crossing substeps
+// use shuffles, element-crossing ones stay in registers.
+template <int E>
+__device__ __forceinline__ void warp_bitonic_steps(uint64_t (&x)[E], int base, int k, int j_start) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int j = 16 * E; j >= 1; j >>= 1) {
+    if (j > j_start) continue;
+    if (j >= 32) {
+      const int je = j >> 5;
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        if ((e & je) == 0) {
+          const bool up = ((base + e * 32 + lane) & k) == 0;
+          cmpswap_u64(x[e], x[e | je], up);
+        }
+      }
+    } else {
+      const bool lower = (lane & j) == 0;
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const uint64_t o = __shfl_xor_sync(0xffffffffu, x[e], j);
+        const bool up = ((base + e * 32 + lane) & k) == 0;
+        const bool take_min = lower == up;
+        const bool o_lt = o < x[e];
+        x[e] = (take_min == o_lt) ? o : x[e];
+      }
+    }
+  }
+}
+
+// Hybrid bitonic sort of P keys in SHARED memory by the whole CTA (blockDim.x = T, P = E*T for
+// P >= T, else E = 1 and only P/32 warps work; P is a power of two >= 32).  Every merge level runs
+// its warp-local substeps (j < 32*E) in registers, so a sort of 4096 keys takes 27 block barriers
+// instead of 78.  Ends with a __syncthreads().
+template <int E>
+__device__ __forceinline__ void block_sort_smem_e(uint64_t* a, int P) {
+  constexpr int J0 = 32 * E;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nblocks = P / J0;
+  const int base = warp * J0;
+  uint64_t x[E];
+  if (warp < nblocks) {
+#pragma unroll
+    for (int e = 0; e < E; ++e) x[e] = a[base + e * 32 + lane];
+    for (int k = 2; k <= J0; k <<= 1) warp_bitonic_steps<E>(x, base, k, k >> 1);
+#pragma unroll
+    for (int e = 0; e < E; ++e) a[base + e * 32 + lane] = x[e];
+  }
+  __syncthreads();
+  for (int k = 2 * J0; k <= P; k <<= 1) {
+    for (int j = k >> 1; j >= J0; j >>= 1) {
+      for (int t = threadIdx.x; t < (P >> 1); t += blockDim.x) {
+        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        const int l = i | j;
+        const bool up = (i & k) == 0;
+        const uint64_t u = a[i], v = a[l];
+        if ((u > v) == up) {
+          a[i] = v;
+          a[l] = u;
+        }
+      }
+      __syncthreads();
+    }
+    if (warp < nblocks) {
+#pragma unroll
+      for (int e = 0; e < E; ++e) x[e] = a[base + e * 32 + lane];
+      warp_bitonic_steps<E>(x, base, k, J0 >> 1);
+#pragma unroll
+      for (int e = 0; e < E; ++e) a[base + e * 32 + lane] = x[e];
+    }
+    __syncthreads();
+  }
+}
+
+// dispatch on keys per thread; `a` MUST be a shared-memory array of P keys
+__device__ __forceinline__ void block_sort_smem(uint64_t* a, int P) {
+  const int T = blockDim.x;
+  const int E = P > T ? P / T : 1;
+  switch (E) {
+    case 1: block_sort_smem_e<1>(a, P); break;
+    case 2: block_sort_smem_e<2>(a, P); break;
+    case 4: block_sort_smem_e<4>(a, P); break;
+    case 8: block_sort_smem_e<8>(a, P); break;
+    case 16: block_sort_smem_e<16>(a, P); break;
+    default: bitonic_sort_u64_generic(a, P); break;
   }
 }
 #endif  // __CUDACC__

@@ -1,12 +1,14 @@
-// nms.cu — kernel 3: class-aware greedy NMS on sorted candidate keys + gather of survivors (sm_100a).
+// nms.cu — kernel 3: class-aware greedy NMS on score-sorted candidate keys + gather of survivors (sm_100a).
 //
 // Replaces torchvision.ops.nms / batched_nms (torchvision/ops/boxes.py:20-120,
 // csrc/ops/cpu/nms_kernel.cpp) at the reference call sites core/utils/ultralytics_ops.py:247-257,
 // core/utils/nms.py:69,134, core/algorithms/yolo_v7.py:407, core/algorithms/ssd.py:267.
 //
-// One CTA per image.  Candidates arrive sorted (class asc, score desc, anchor asc), so every class is
-// a contiguous segment already in torchvision's processing order.
-//   * suppression state is a shared-memory bitmask (`alive`, one bit per sorted position);
+// One CTA per image.  Candidates arrive in global score order (cvpp_segmented_sort).
+//   * a STABLE counting split by class (warp match_any + per-warp class counters + a scan) lays the
+//     boxes out class-major in shared memory, each class still in score order — torchvision's
+//     processing order — without a second sort;
+//   * suppression state is a shared-memory bitmask (`alive`, one bit per class-major position);
 //   * a 32-candidate word is resolved by one warp: lane j holds box j, kept boxes are broadcast with
 //     shuffles, the IoU test runs in all lanes and the verdicts are collected with __ballot_sync and
 //     cleared from the mask; survivors of a word are then applied to the later words of the segment;
@@ -15,8 +17,8 @@
 //   * IoU arithmetic reproduces torchvision's CPU kernel in fp32 op for op (cvpp_common.cuh), in
 //     both batched_nms branches: per-class on raw boxes, or class-agnostic on boxes shifted by
 //     cls * (max_coord + 1) (the "coordinate trick", taken when an image has <= 1000 candidates);
-//   * survivors are emitted in class-major order, or merged in score order (second bitonic sort in
-//     shared memory) and capped at max_det.
+//   * survivors are emitted class-major, or - through a second bitmask indexed by global score
+//     rank - in score order capped at max_det.  Both are ordered ballot/popc compactions.
 // Latency / SM-bound; the only HBM traffic is 8 B keys + gathered 16 B boxes (L2 resident).
 #include "cvpp_common.cuh"
 
@@ -45,12 +47,12 @@ struct NmsParams {
   int32_t* det_anchor;
   int32_t* det_count;
   // scratch
-  float4* ws_box;      // [B][max_cand] sorted boxes for images that do not fit shared memory
+  float4* ws_box;      // [B][max_cand] class-major boxes for images that do not fit shared memory
   float* ws_area;      // [B][max_cand]
-  uint64_t* ws_sort;   // [B][pow2(max_cand)] second sort for images that do not fit shared memory
-  int64_t ws_sort_stride;
+  int32_t* ws_rank;    // [B][max_cand] class-major position -> global score rank
   int smem_boxes;      // boxes that fit in shared memory
-  int alive_words;     // words reserved for the alive mask
+  int alive_words;     // words reserved for each of the two bitmasks
+  int count_warps;     // warps taking part in the counting split (per-warp class counters)
 };
 
 struct BoxView {  // sorted boxes + areas of one image (shared or global)
@@ -212,12 +214,16 @@ __device__ void nms_segment_cta(int s, int e, int cap, const BoxView& bv, uint32
 
 __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_constant__ NmsParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  // layout: [boxes float4 x smem_boxes][areas float x smem_boxes][alive u32 x alive_words][seg int x 2*nc]
+  // layout: [boxes float4 x N][areas float x N][rank int x N][alive u32 x W][galive u32 x W]
+  //         [seg_begin int x nc][seg_end int x nc][cnt int x count_warps x nc]
   float4* sh_box = reinterpret_cast<float4*>(smem_raw);
   float* sh_area = reinterpret_cast<float*>(sh_box + p.smem_boxes);
-  uint32_t* alive = reinterpret_cast<uint32_t*>(sh_area + p.smem_boxes);
-  int* seg_begin = reinterpret_cast<int*>(alive + p.alive_words);
+  int32_t* sh_rank = reinterpret_cast<int32_t*>(sh_area + p.smem_boxes);
+  uint32_t* alive = reinterpret_cast<uint32_t*>(sh_rank + p.smem_boxes);
+  uint32_t* galive = alive + p.alive_words;
+  int* seg_begin = reinterpret_cast<int*>(galive + p.alive_words);
   int* seg_end = seg_begin + p.nc;
+  int* cnt = seg_end + p.nc;
   __shared__ float sh_red[kNmsWarps];
   __shared__ int sh_scan[kNmsWarps];
   __shared__ int sh_running;
@@ -233,17 +239,30 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
     if (tid == 0) p.det_count[b] = 0;
     return;
   }
-  const uint64_t* keys = p.sorted_key + (int64_t)b * p.max_cand;
+  const uint64_t* keys = p.sorted_key + (int64_t)b * p.max_cand;  // score-major: [inv_score | anchor | class]
   const float4* dense = p.box_dense + (int64_t)b * p.A;
   const bool trick = rule_uses_trick(p.rule, n);
   const int nwords = (n + 31) >> 5;
+  const int nc = p.nc;
 
-  // ---- coordinate trick: offset = cls * (max over every coordinate + 1) (boxes.py:95-97) --------
-  float mult = 0.f;
+  const bool in_smem = n <= p.smem_boxes;
+  float4* wbox = in_smem ? sh_box : p.ws_box + (int64_t)b * p.max_cand;
+  float* warea = in_smem ? sh_area : p.ws_area + (int64_t)b * p.max_cand;
+  int32_t* wrank = in_smem ? sh_rank : p.ws_rank + (int64_t)b * p.max_cand;
+
+  for (int w = tid; w < nwords; w += kNmsThreads) {
+    const int rem = n - (w << 5);
+    alive[w] = rem >= 32 ? 0xffffffffu : ((1u << rem) - 1u);
+    galive[w] = 0u;
+  }
+  if (tid == 0) sh_next = 0;
+
   if (trick) {
+    // ---- coordinate trick: one class-agnostic segment in score order; boxes shifted by
+    //      cls * (max over every coordinate + 1)  (boxes.py:95-97)
     float m = -INFINITY;
     for (int r = tid; r < n; r += kNmsThreads) {
-      const float4 bx = dense[key_anchor(key_from_score_major(keys[r]))];
+      const float4 bx = dense[(uint32_t)(keys[r] >> 12) & 0x1fffffu];
       m = fmaxf(m, fmaxf(fmaxf(bx.x, bx.y), fmaxf(bx.z, bx.w)));
     }
     for (int d = 16; d > 0; d >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
@@ -251,46 +270,102 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
     __syncthreads();
     m = sh_red[0];
     for (int q = 1; q < kNmsWarps; ++q) m = fmaxf(m, sh_red[q]);
-    mult = fadd(m, 1.0f);
-  }
-
-  // ---- stage sorted boxes (+ areas), alive mask, class segments ---------------------------------
-  const bool in_smem = n <= p.smem_boxes;
-  float4* wbox = in_smem ? sh_box : p.ws_box + (int64_t)b * p.max_cand;
-  float* warea = in_smem ? sh_area : p.ws_area + (int64_t)b * p.max_cand;
-  for (int c = tid; c < p.nc; c += kNmsThreads) {
-    seg_begin[c] = 0;
-    seg_end[c] = 0;
-  }
-  for (int w = tid; w < nwords; w += kNmsThreads) {
-    const int rem = n - (w << 5);
-    alive[w] = rem >= 32 ? 0xffffffffu : ((1u << rem) - 1u);
-  }
-  __syncthreads();
-  for (int r = tid; r < n; r += kNmsThreads) {
-    uint64_t k = keys[r];
-    if (trick) k = key_from_score_major(k);
-    const int cls = (int)key_cls(k);
-    float4 bx = dense[key_anchor(k)];
-    if (trick) {
-      const float off = fmul((float)cls, mult);
+    const float mult = fadd(m, 1.0f);
+    for (int r = tid; r < n; r += kNmsThreads) {
+      const uint64_t k = keys[r];
+      const float off = fmul((float)(uint32_t)(k & 0xfffu), mult);
+      float4 bx = dense[(uint32_t)(k >> 12) & 0x1fffffu];
       bx.x = fadd(bx.x, off);
       bx.y = fadd(bx.y, off);
       bx.z = fadd(bx.z, off);
       bx.w = fadd(bx.w, off);
-    } else if (cls < p.nc) {
-      const int prev = r > 0 ? (int)key_cls(keys[r - 1]) : -1;
-      if (prev != cls) {
-        seg_begin[cls] = r;
-        if (prev >= 0 && prev < p.nc) seg_end[prev] = r;
-      }
-      if (r == n - 1) seg_end[cls] = n;
+      wbox[r] = bx;
+      warea[r] = box_area(bx);
     }
-    wbox[r] = bx;
-    warea[r] = box_area(bx);
+    __syncthreads();
+  } else {
+    // ---- stable counting split by class: position = class start + #earlier ranks of that class
+    const int cw = p.count_warps;
+    for (int i = tid; i < cw * nc; i += kNmsThreads) cnt[i] = 0;
+    __syncthreads();
+    const int per_warp = (((n + cw - 1) / cw) + 31) & ~31;  // contiguous rank range per counting warp
+    const int r_begin = warp * per_warp, r_end = min(n, r_begin + per_warp);
+    if (warp < cw) {
+      int* my = cnt + warp * nc;
+      for (int r0 = r_begin; r0 < r_end; r0 += 32) {
+        const int r = r0 + lane;
+        const bool v = r < r_end;
+        const int c = v ? (int)(keys[r] & 0xfffu) : -1 - lane;  // invalid lanes match nobody
+        const unsigned peers = __match_any_sync(0xffffffffu, c);
+        if (v && c < nc && (peers & ((1u << lane) - 1u)) == 0) my[c] += __popc(peers);
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    // per class: exclusive offsets over the counting warps, class totals into seg_end (temporarily)
+    for (int c = tid; c < nc; c += kNmsThreads) {
+      int run = 0;
+      for (int w = 0; w < cw; ++w) {
+        const int t = cnt[w * nc + c];
+        cnt[w * nc + c] = run;
+        run += t;
+      }
+      seg_end[c] = run;
+    }
+    __syncthreads();
+    if (warp == 0) {  // exclusive scan of the class totals -> segment starts
+      int running = 0;
+      for (int c0 = 0; c0 < nc; c0 += 32) {
+        const int c = c0 + lane;
+        const int t = c < nc ? seg_end[c] : 0;
+        int incl = t;
+        for (int d = 1; d < 32; d <<= 1) {
+          const int v = __shfl_up_sync(0xffffffffu, incl, d);
+          if (lane >= d) incl += v;
+        }
+        if (c < nc) {
+          seg_begin[c] = running + incl - t;
+          seg_end[c] = running + incl;
+        }
+        running += __shfl_sync(0xffffffffu, incl, 31);
+      }
+      if (lane == 0) sh_kept = running;  // candidates with a class id < nc (all of them, by contract)
+    }
+    __syncthreads();
+    {
+      const int nvalid = sh_kept;
+      if (nvalid < n)
+        for (int w = tid; w < nwords; w += kNmsThreads) {
+          const int rem = nvalid - (w << 5);
+          if (rem < 32) alive[w] &= rem <= 0 ? 0u : ((1u << rem) - 1u);
+        }
+    }
+    if (warp < cw) {
+      int* my = cnt + warp * nc;
+      for (int r0 = r_begin; r0 < r_end; r0 += 32) {
+        const int r = r0 + lane;
+        const bool v = r < r_end;
+        uint64_t k = 0;
+        int c = -1 - lane;
+        if (v) {
+          k = keys[r];
+          c = (int)(k & 0xfffu);
+        }
+        const unsigned peers = __match_any_sync(0xffffffffu, c);
+        if (v && c < nc) {
+          const int pos = seg_begin[c] + my[c] + __popc(peers & ((1u << lane) - 1u));
+          const float4 bx = dense[(uint32_t)(k >> 12) & 0x1fffffu];
+          wbox[pos] = bx;
+          warea[pos] = box_area(bx);
+          wrank[pos] = r;
+        }
+        __syncwarp();
+        if (v && c < nc && (peers & ((1u << lane) - 1u)) == 0) my[c] += __popc(peers);
+        __syncwarp();
+      }
+    }
+    __syncthreads();
   }
-  if (tid == 0) sh_next = 0;
-  __syncthreads();
   BoxView bv{wbox, warea};
 
   // ---- greedy suppression -------------------------------------------------------------------
@@ -308,14 +383,14 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
       int c = 0;
       if (lane == 0) c = atomicAdd(&sh_next, 1);
       c = __shfl_sync(0xffffffffu, c, 0);
-      if (c >= p.nc) break;
+      if (c >= nc) break;
       const int s = seg_begin[c], e = seg_end[c];
       if (e <= s) continue;
       if (((e - 1) >> 5) - (s >> 5) + 1 > kCoopMinWords) continue;
       nms_segment_warp(s, e, cap, bv, alive, p.thr_eff);
     }
     __syncthreads();
-    for (int c = 0; c < p.nc; ++c) {
+    for (int c = 0; c < nc; ++c) {
       const int s = seg_begin[c], e = seg_end[c];
       if (e <= s) continue;
       if (((e - 1) >> 5) - (s >> 5) + 1 <= kCoopMinWords) continue;
@@ -325,39 +400,37 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
   __syncthreads();
 
   // ---- ordered compaction of the survivors ----------------------------------------------------
-  // class-major (or trick: already global score order): emit directly.  Otherwise collect the
-  // survivors' keys in score-major packing, sort them, emit the best max_det.
-  const bool resort = (p.order == CVPP_ORDER_SCORE_DESC) && !trick;
-  uint64_t* sortbuf = nullptr;
-  int P2 = 0;
-  if (resort) {
-    P2 = pow2_ceil(n < 2 ? 2 : n);
-    // the box staging area is dead now; reuse it when the keys fit
-    sortbuf = ((size_t)P2 * sizeof(uint64_t) <= (size_t)p.smem_boxes * (sizeof(float4) + sizeof(float)))
-                  ? reinterpret_cast<uint64_t*>(smem_raw)
-                  : p.ws_sort + (int64_t)b * p.ws_sort_stride;
+  // The bitmask to compact is `alive` itself when its positions are already in output order
+  // (trick: global score order; class-major output), otherwise the survivors are first scattered
+  // into `galive`, indexed by global score rank.
+  const bool by_rank = (p.order == CVPP_ORDER_SCORE_DESC) && !trick;
+  if (by_rank) {
+    for (int w = tid; w < nwords; w += kNmsThreads) {
+      uint32_t m = alive[w];
+      while (m) {
+        const int bit = __ffs(m) - 1;
+        m &= m - 1;
+        const int r = wrank[(w << 5) + bit];
+        atomicOr(&galive[r >> 5], 1u << (r & 31));
+      }
+    }
+    __syncthreads();
   }
+  const uint32_t* mask = by_rank ? galive : alive;
+  const bool pos_is_rank = by_rank || trick;
   float4* ob = p.det_box + (int64_t)b * p.max_out;
   float* os = p.det_score + (int64_t)b * p.max_out;
   int32_t* oc = p.det_cls + (int64_t)b * p.max_out;
   int32_t* oa = p.det_anchor + (int64_t)b * p.max_out;
-
-  auto emit = [&](int pos, uint64_t k_class_major) {
-    if (pos >= p.max_out) return;
-    const uint32_t anchor = key_anchor(k_class_major);
-    ob[pos] = dense[anchor];
-    os[pos] = __uint_as_float(key_score_bits(k_class_major));
-    oc[pos] = (int32_t)key_cls(k_class_major);
-    oa[pos] = (int32_t)anchor;
-  };
+  const int out_cap = (p.order == CVPP_ORDER_SCORE_DESC && p.max_det > 0 && p.max_det < p.max_out) ? p.max_det : p.max_out;
 
   if (tid == 0) sh_running = 0;
   __syncthreads();
   for (int base = 0; base < nwords; base += kNmsThreads) {
     const int wi = base + tid;
-    uint32_t m = wi < nwords ? alive[wi] : 0u;
-    const int cnt = __popc(m);
-    int incl = cnt;
+    uint32_t m = wi < nwords ? mask[wi] : 0u;
+    const int c = __popc(m);
+    int incl = c;
     for (int d = 1; d < 32; d <<= 1) {
       int v = __shfl_up_sync(0xffffffffu, incl, d);
       if (lane >= d) incl += v;
@@ -370,45 +443,32 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
       if (q < warp) woff += v;
       total += v;
     }
-    int pos = sh_running + woff + incl - cnt;
-    while (m) {
+    int pos = sh_running + woff + incl - c;
+    while (m && pos < out_cap) {
       const int bit = __ffs(m) - 1;
       m &= m - 1;
-      uint64_t k = keys[(wi << 5) + bit];
-      if (resort) {
-        sortbuf[pos] = key_to_score_major(k);
-      } else {
-        emit(pos, trick ? key_from_score_major(k) : k);
-      }
+      const int at = (wi << 5) + bit;
+      const uint64_t k = keys[pos_is_rank ? at : wrank[at]];
+      const uint32_t anchor = (uint32_t)(k >> 12) & 0x1fffffu;
+      ob[pos] = dense[anchor];
+      os[pos] = __uint_as_float(0x7fffffffu - (uint32_t)(k >> 33));
+      oc[pos] = (int32_t)(k & 0xfffu);
+      oa[pos] = (int32_t)anchor;
       ++pos;
     }
     __syncthreads();
     if (tid == 0) sh_running += total;
     __syncthreads();
   }
-  const int n_kept = sh_running;
-  if (!resort) {
-    if (tid == 0) p.det_count[b] = n_kept;
-    return;
+  if (tid == 0) {
+    int n_kept = sh_running;
+    if (p.order == CVPP_ORDER_SCORE_DESC && p.max_det > 0 && n_kept > p.max_det) n_kept = p.max_det;
+    p.det_count[b] = n_kept;
   }
-  // NOTE: sortbuf may alias the box staging area: every warp passed the barrier above, boxes are dead.
-  const int P3 = pow2_ceil(n_kept < 2 ? 2 : n_kept);
-  for (int i = n_kept + tid; i < P3; i += kNmsThreads) sortbuf[i] = ~0ull;
-  __syncthreads();
-  bitonic_sort_u64(sortbuf, P3);
-  const int n_out = (p.max_det > 0 && n_kept > p.max_det) ? p.max_det : n_kept;
-  for (int i = tid; i < n_out; i += kNmsThreads) emit(i, key_from_score_major(sortbuf[i]));
-  if (tid == 0) p.det_count[b] = n_out;
-}
-
-static int pow2_ceil_host(int n) {
-  int p = 2;
-  while (p < n) p <<= 1;
-  return p;
 }
 
 size_t nms_workspace_bytes(int B, int max_cand) {
-  size_t per = (size_t)max_cand * (sizeof(float4) + sizeof(float)) + (size_t)pow2_ceil_host(max_cand) * sizeof(uint64_t);
+  size_t per = (size_t)max_cand * (sizeof(float4) + sizeof(float) + sizeof(int32_t));
   per = (per + 255) & ~(size_t)255;
   return per * (size_t)B + 256;
 }
@@ -471,22 +531,26 @@ int nms_launch(const uint64_t* sorted_key, const int32_t* cand_count, const floa
   uintptr_t base = (reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255;
   p.ws_box = reinterpret_cast<float4*>(base);
   p.ws_area = reinterpret_cast<float*>(base + (size_t)B * max_cand * sizeof(float4));
-  uintptr_t sort_base = (base + (size_t)B * max_cand * (sizeof(float4) + sizeof(float)) + 15) & ~(uintptr_t)15;
-  p.ws_sort = reinterpret_cast<uint64_t*>(sort_base);
-  p.ws_sort_stride = pow2_ceil_host(max_cand);
-  // shared memory: boxes+areas (<= 8192), alive mask, class segments
+  p.ws_rank = reinterpret_cast<int32_t*>(base + (size_t)B * max_cand * (sizeof(float4) + sizeof(float)));
+  // shared memory: two bitmasks, class segments, per-warp class counters (<= 32 KB), then as many
+  // box slots (24 B each) as fit, capped at max_cand
   p.alive_words = (max_cand + 31) / 32;
-  size_t fixed = (size_t)p.alive_words * 4 + (size_t)nc * 8 + 64;
-  int smem_boxes = max_cand < 8192 ? max_cand : 8192;
-  smem_boxes = (smem_boxes + 3) & ~3;
-  while (smem_boxes > 0 && fixed + (size_t)smem_boxes * 20 > (size_t)max_smem - 1024) smem_boxes -= 256;
-  if (smem_boxes < 0) smem_boxes = 0;
-  if (fixed > (size_t)max_smem - 1024) {
+  int cw = (int)((32 * 1024) / ((size_t)nc * 4));
+  if (cw > kNmsWarps) cw = kNmsWarps;
+  if (cw < 1) cw = 1;
+  p.count_warps = cw;
+  size_t fixed = (size_t)p.alive_words * 8 + (size_t)nc * 8 + (size_t)cw * nc * 4 + 64;
+  if (fixed + 4096 > (size_t)max_smem) {
     set_error("nms: max_cand=%d / nc=%d need more shared memory than the device has", max_cand, nc);
     return CVPP_ERR_UNSUPPORTED;
   }
+  size_t avail = (size_t)max_smem - fixed - 1024;
+  int smem_boxes = (int)(avail / 24);
+  if (smem_boxes > max_cand) smem_boxes = max_cand;
+  smem_boxes = (smem_boxes + 3) & ~3;
+  if ((size_t)smem_boxes * 24 > avail) smem_boxes -= 4;
   p.smem_boxes = smem_boxes;
-  size_t smem = fixed + (size_t)smem_boxes * 20;
+  size_t smem = fixed + (size_t)smem_boxes * 24;
   CVPP_CUDA_TRY(cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   nms_kernel<<<B, kNmsThreads, smem, stream>>>(p);
   CVPP_CUDA_TRY(cudaGetLastError());

@@ -5,10 +5,13 @@
 // per-class partition done with torch.unique / boolean gathers (torchvision/ops/boxes.py:112-116,
 // core/algorithms/yolo_v7.py:396-400, core/algorithms/ssd.py:256-264, core/utils/nms.py:66-68).
 //
-// One CTA per image.  The 64-bit key already encodes (class, score desc, anchor asc), so a single
-// ascending sort yields every ordering the path needs.  Segments that fit are sorted by a bitonic
-// network in shared memory (<= 16384 keys, 128 KB); larger ones use the same network on a global
-// scratch row (L2-resident).  Latency-bound, not bandwidth-bound: ~8 B per candidate of traffic.
+// One CTA per image.  Keys are re-packed score-major ([inv_score | anchor | class]) and sorted
+// ascending = score descending, lower anchor first on ties: the one global order every consumer needs
+// (max_nms cut, trick-branch NMS, final score-ordered output); the per-class partition is a stable
+// counting split inside the NMS kernel.  Segments that fit shared memory (<= 16384 keys, 128 KB) use
+// a hybrid bitonic network whose warp-local substeps run in registers with shuffles (27 block
+// barriers for 4096 keys instead of 78); larger ones run a plain network on a global scratch row.
+// Latency-bound, not bandwidth-bound: ~16 B per candidate of traffic.
 #include "cvpp_common.cuh"
 
 namespace cvpp {
@@ -16,7 +19,7 @@ namespace cvpp {
 constexpr int kSortThreads = 1024;
 
 __global__ void __launch_bounds__(kSortThreads, 1)
-segsort_kernel(uint64_t* __restrict__ keys, int32_t* __restrict__ count, int max_cand, int rule, int max_nms,
+segsort_kernel(uint64_t* __restrict__ keys, int32_t* __restrict__ count, int max_cand, int max_nms,
                uint64_t* __restrict__ ws, int64_t ws_stride, int smem_elems) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint64_t* sbuf = reinterpret_cast<uint64_t*>(smem_raw);
@@ -25,41 +28,23 @@ segsort_kernel(uint64_t* __restrict__ keys, int32_t* __restrict__ count, int max
   if (n > max_cand) n = max_cand;
   if (n <= 0) return;
   uint64_t* kb = keys + (int64_t)b * max_cand;
-
+  const int P = pow2_ceil(n < 32 ? 32 : n);
+  const bool in_smem = P <= smem_elems;
+  uint64_t* a = in_smem ? sbuf : (ws + (int64_t)b * ws_stride);
+  for (int i = threadIdx.x; i < P; i += blockDim.x) a[i] = i < n ? key_to_score_major(kb[i]) : ~0ull;
+  __syncthreads();
+  if (in_smem)
+    block_sort_smem(a, P);
+  else
+    bitonic_sort_u64_generic(a, P);
   // ultralytics :240 keeps only the max_nms best scores (over all classes) before batched_nms
-  const bool truncate = max_nms > 0 && n > max_nms;
-  const int n_final = truncate ? max_nms : n;
-  const bool trick = rule_uses_trick(rule, n_final);
-
-  // pass 0 (only when truncating and the final order is class-major): score-major sort, cut.
-  // pass 1: final order.
-  for (int pass = (truncate && !trick) ? 0 : 1; pass < 2; ++pass) {
-    const bool score_major = (pass == 0) || trick;
-    const int m = (pass == 1 && truncate && !trick) ? n_final : n;  // pass 1 after a cut sees n_final keys
-    const int P = pow2_ceil(m < 2 ? 2 : m);
-    uint64_t* a = (P <= smem_elems) ? sbuf : (ws + (int64_t)b * ws_stride);
-    for (int i = threadIdx.x; i < P; i += blockDim.x) {
-      uint64_t k = ~0ull;
-      if (i < m) {
-        k = kb[i];
-        if (score_major) k = key_to_score_major(k);
-      }
-      a[i] = k;
-    }
-    __syncthreads();
-    bitonic_sort_u64(a, P);
-    for (int i = threadIdx.x; i < n_final; i += blockDim.x) {
-      uint64_t k = a[i];
-      if (pass == 0) k = key_from_score_major(k);  // back to class-major packing for pass 1
-      kb[i] = k;
-    }
-    __syncthreads();
-  }
-  if (truncate && threadIdx.x == 0) count[b] = n_final;
+  const int n_final = (max_nms > 0 && n > max_nms) ? max_nms : n;
+  for (int i = threadIdx.x; i < n_final; i += blockDim.x) kb[i] = a[i];
+  if (n_final != n && threadIdx.x == 0) count[b] = n_final;
 }
 
 size_t segsort_workspace_bytes(int B, int max_cand) {
-  int P = 2;
+  int P = 32;
   while (P < max_cand) P <<= 1;
   return (size_t)B * (size_t)P * sizeof(uint64_t);
 }
@@ -70,12 +55,9 @@ int segsort_launch(uint64_t* keys, int32_t* cand_count, int B, int max_cand, int
     set_error("segmented_sort: NULL pointer or bad sizes (B=%d, max_cand=%d)", B, max_cand);
     return CVPP_ERR_INVALID_ARG;
   }
-  if (rule < 0 || rule > 2) {
-    set_error("segmented_sort: unknown nms rule %d", rule);
-    return CVPP_ERR_INVALID_ARG;
-  }
+  (void)rule;  // the sort order no longer depends on the batched_nms branch
   if (B == 0) return CVPP_OK;
-  int P = 2;
+  int P = 32;
   while (P < max_cand) P <<= 1;
   int dev = 0, max_smem = 0;
   CVPP_CUDA_TRY(cudaGetDevice(&dev));
@@ -92,7 +74,7 @@ int segsort_launch(uint64_t* keys, int32_t* cand_count, int B, int max_cand, int
   }
   size_t smem = (size_t)smem_elems * sizeof(uint64_t);
   CVPP_CUDA_TRY(cudaFuncSetAttribute(segsort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  segsort_kernel<<<B, kSortThreads, smem, stream>>>(keys, cand_count, max_cand, rule, max_nms,
+  segsort_kernel<<<B, kSortThreads, smem, stream>>>(keys, cand_count, max_cand, max_nms,
                                                     reinterpret_cast<uint64_t*>(workspace), (int64_t)P, smem_elems);
   CVPP_CUDA_TRY(cudaGetLastError());
   return CVPP_OK;
