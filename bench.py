@@ -216,8 +216,16 @@ def run_ours(args):
         gather_out = torch.empty((world, BS, MAX_DET, 7), dtype=torch.float32, device=dev)
         cnt_out = torch.empty((world, BS), dtype=torch.int32, device=dev)
 
+    graphed = None
+    if not args.no_graph:
+        try:
+            graphed = post.capture(ls, CONF, IOU)
+        except Exception as e:  # report, fall back to the eager C call
+            print(f"[bench] CUDA graph capture failed ({e}); using eager launches", file=sys.stderr)
+            graphed = None
+
     def step():
-        det = post(ls, CONF, IOU)
+        det = graphed.replay() if graphed is not None else post(ls, CONF, IOU)
         if world > 1:
             pack[..., :4] = det.box
             pack[..., 4] = det.score
@@ -271,25 +279,33 @@ def run_ours(args):
     cand_mean = float(det.cand_count.float().mean().item())
     kept_mean = float(det.count.float().mean().item())
 
-    # ---- roofline of the dominant kernel (decode+filter), timed alone on the launching stream
-    def decode_only():
-        ops.yolov8_decode_filter(ls, NC, CONF)
-    for _ in range(3):
-        decode_only()
-    ms_dec = timed(decode_only, K) / K
-    # per-stage split (separate calls, events around each)
-    c = ops.yolov8_decode_filter(ls, NC, CONF)
+    # ---- roofline of the dominant kernel (decode+filter): CUDA events around every stage of the
+    #      three-call pipeline (same kernels as the fused call), accumulated over K in-situ iterations
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(K)]
 
-    def sort_only():
-        ops.segmented_sort(c)
-    # sorting sorted keys costs the same as unsorted ones for a bitonic network
-    sort_only()
-    ms_sort = timed(sort_only, K) / K
-
-    def nms_only():
+    def staged(i):
+        e = ev[i]
+        e[0].record()
+        c = ops.yolov8_decode_filter(ls, NC, CONF)
+        e[1].record()
+        ops.segmented_sort(c, max_nms=30000)
+        e[2].record()
         ops.nms(c, IOU, max_det=MAX_DET)
-    nms_only()
-    ms_nms = timed(nms_only, K) / K
+        e[3].record()
+
+    for i in range(min(3, K)):
+        staged(i)
+    barrier()
+    for i in range(K):
+        staged(i)
+    barrier()
+    ms_dec = sum(e[0].elapsed_time(e[1]) for e in ev) / K
+    ms_sort = sum(e[1].elapsed_time(e[2]) for e in ev) / K
+    ms_nms = sum(e[2].elapsed_time(e[3]) for e in ev) / K
+    if world > 1:
+        t = torch.tensor([ms_dec, ms_sort, ms_nms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_dec, ms_sort, ms_nms = (float(v) for v in t.tolist())
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- e2e: pinned host buffers -> device -> kernels -> host
@@ -356,6 +372,7 @@ def run_ours(args):
             "dtype": "f32", "data": "synthetic",
             "config": dict(CONFIG, candidates_per_image=cand_mean, kept_per_image=kept_mean,
                            all_gather="detections (B,300,7) fp32 + counts per step" if world > 1 else "none (1 GPU)",
+                           launch="CUDA graph replay of cvpp_yolov8_postprocess" if graphed is not None else "eager C call",
                            timing=f"median of {len(ms_runs)} back-to-back {K}-step CUDA-event measurements"),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "kernel": "yolov8_decode_tma_kernel<false> (decode+filter)",
@@ -380,6 +397,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-graph", action="store_true", help="launch the three kernels eagerly instead of replaying a CUDA graph")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     args = ap.parse_args()
     if args.impl == "reference":

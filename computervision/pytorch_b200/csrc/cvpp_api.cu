@@ -21,6 +21,35 @@ int cuda_fail(cudaError_t e, const char* what) {
   return CVPP_ERR_CUDA;
 }
 
+int device_info(DeviceInfo* out) {
+  static DeviceInfo cache[64];
+  static bool have[64] = {};
+  int dev = 0;
+  CVPP_CUDA_TRY(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64 && have[dev]) {
+    *out = cache[dev];
+    return CVPP_OK;
+  }
+  DeviceInfo d;
+  d.device = dev;
+  CVPP_CUDA_TRY(cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev));
+  CVPP_CUDA_TRY(cudaDeviceGetAttribute(&d.max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  if (dev >= 0 && dev < 64) {
+    cache[dev] = d;  // benign race: every thread writes the same values
+    have[dev] = true;
+  }
+  *out = d;
+  return CVPP_OK;
+}
+
+int ensure_smem_attr(const void* func, int bytes, int device, unsigned long long* done) {
+  const unsigned long long bit = (device >= 0 && device < 64) ? (1ull << device) : 0ull;
+  if (bit && (__atomic_load_n(done, __ATOMIC_ACQUIRE) & bit)) return CVPP_OK;
+  CVPP_CUDA_TRY(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  if (bit) __atomic_fetch_or(done, bit, __ATOMIC_RELEASE);
+  return CVPP_OK;
+}
+
 // launchers (one per .cu)
 int yolov8_decode_launch(const float* const* level_ptr, const int64_t* batch_stride, const int64_t* chan_stride,
                          const int* level_h, const int* level_w, const float* level_stride, int num_levels, int B,
@@ -31,7 +60,7 @@ int pred_filter_launch(const float* pred, int B, int channels, int nc, int64_t A
 size_t segsort_workspace_bytes(int B, int max_cand);
 int segsort_launch(uint64_t* keys, int32_t* cand_count, int B, int max_cand, int rule, int max_nms, void* workspace,
                    size_t workspace_bytes, cudaStream_t stream);
-size_t nms_workspace_bytes(int B, int max_cand);
+size_t nms_workspace_bytes(int B, int max_cand, int nc);
 int nms_launch(const uint64_t* sorted_key, const int32_t* cand_count, const float* box_dense, int B, int max_cand,
                int64_t A, int nc, double iou_thres, int rule, int order, int max_det, int max_out, float* det_box,
                float* det_score, int32_t* det_cls, int32_t* det_anchor, int32_t* det_count, void* workspace,
@@ -110,9 +139,9 @@ int cvpp_segmented_sort(uint64_t* keys, int32_t* cand_count, int B, int max_cand
   return segsort_launch(keys, cand_count, B, max_cand, rule, max_nms, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
-size_t cvpp_nms_workspace_bytes(int B, int max_cand) {
-  if (B < 0 || max_cand < 1) return 0;
-  return nms_workspace_bytes(B, max_cand);
+size_t cvpp_nms_workspace_bytes(int B, int max_cand, int nc) {
+  if (B < 0 || max_cand < 1 || nc < 1) return 0;
+  return nms_workspace_bytes(B, max_cand, nc);
 }
 
 int cvpp_nms(const uint64_t* sorted_key, const int32_t* cand_count, const float* box_dense, int B, int max_cand,
@@ -124,14 +153,14 @@ int cvpp_nms(const uint64_t* sorted_key, const int32_t* cand_count, const float*
                     (cudaStream_t)stream);
 }
 
-size_t cvpp_yolov8_workspace_bytes(int B, int64_t A, int max_cand) {
-  if (B < 0 || A < 1 || max_cand < 1) return 0;
+size_t cvpp_yolov8_workspace_bytes(int B, int64_t A, int max_cand, int nc) {
+  if (B < 0 || A < 1 || max_cand < 1 || nc < 1) return 0;
   size_t s = 256;
   s += align256((size_t)B * max_cand * sizeof(uint64_t));  // cand_key
   s += align256((size_t)B * sizeof(int32_t));              // cand_count
   s += align256((size_t)B * (size_t)A * 16);               // box_dense
   s += align256(segsort_workspace_bytes(B, max_cand));
-  s += align256(nms_workspace_bytes(B, max_cand));
+  s += align256(nms_workspace_bytes(B, max_cand, nc));
   return s;
 }
 
@@ -151,8 +180,8 @@ int cvpp_yolov8_postprocess(const float* const* level_ptr, const int64_t* batch_
     set_error("yolov8_postprocess: max_det and max_cand must be >= 1");
     return CVPP_ERR_INVALID_ARG;
   }
-  if (!workspace || workspace_bytes < cvpp_yolov8_workspace_bytes(B, A, max_cand)) {
-    set_error("yolov8_postprocess: workspace of %zu bytes needed, got %zu", cvpp_yolov8_workspace_bytes(B, A, max_cand),
+  if (!workspace || workspace_bytes < cvpp_yolov8_workspace_bytes(B, A, max_cand, nc)) {
+    set_error("yolov8_postprocess: workspace of %zu bytes needed, got %zu", cvpp_yolov8_workspace_bytes(B, A, max_cand, nc),
               workspace_bytes);
     return CVPP_ERR_WORKSPACE;
   }
@@ -167,7 +196,7 @@ int cvpp_yolov8_postprocess(const float* const* level_ptr, const int64_t* batch_
   size_t sort_bytes = segsort_workspace_bytes(B, max_cand);
   p += align256(sort_bytes);
   void* nms_ws = reinterpret_cast<void*>(p);
-  size_t nms_bytes = nms_workspace_bytes(B, max_cand);
+  size_t nms_bytes = nms_workspace_bytes(B, max_cand, nc);
 
   int rc = cvpp_yolov8_decode_filter(level_ptr, batch_stride, chan_stride, level_h, level_w, level_stride, num_levels,
                                      B, nc, reg_max, conf_thres, cand_key, cand_count, box_dense, max_cand, stream);

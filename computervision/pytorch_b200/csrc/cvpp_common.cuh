@@ -22,6 +22,16 @@ namespace cvpp {
 // ---- error plumbing (host) -------------------------------------------------------------------
 void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what);
+// cached per-device facts (SM count, opt-in shared memory); returns CVPP_OK or CVPP_ERR_CUDA
+struct DeviceInfo {
+  int device;
+  int sms;
+  int max_smem;
+};
+int device_info(DeviceInfo* out);
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device): `done` is a per-kernel bitmask
+int ensure_smem_attr(const void* func, int bytes, int device, unsigned long long* done);
+
 #define CVPP_CUDA_TRY(expr)                                     \
   do {                                                          \
     cudaError_t _e = (expr);                                    \

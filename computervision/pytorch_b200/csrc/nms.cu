@@ -7,27 +7,33 @@
 // One CTA per image.  Candidates arrive in global score order (cvpp_segmented_sort).
 //   * a STABLE counting split by class (warp match_any + per-warp class counters + a scan) lays the
 //     boxes out class-major in shared memory, each class still in score order — torchvision's
-//     processing order — without a second sort;
+//     processing order — without a second sort; every class starts on a 32-position boundary so a
+//     typical (~30 box) class is exactly one word;
 //   * suppression state is a shared-memory bitmask (`alive`, one bit per class-major position);
-//   * a 32-candidate word is resolved by one warp: lane j holds box j, kept boxes are broadcast with
-//     shuffles, the IoU test runs in all lanes and the verdicts are collected with __ballot_sync and
-//     cleared from the mask; survivors of a word are then applied to the later words of the segment;
+//   * a 32-candidate word is resolved by one warp: lane i builds the bitmask of later boxes it would
+//     suppress (independent IoU tests against boxes broadcast from shared memory), then the greedy
+//     order is replayed with one shuffle + two logic ops per surviving box; survivors of a word are
+//     applied to the later words of the segment (ballot collects the verdicts);
 //   * small segments are handled one per warp (classes in parallel), large ones by the whole CTA
 //     (word resolve by warp 0, application to later words spread over all warps);
-//   * IoU arithmetic reproduces torchvision's CPU kernel in fp32 op for op (cvpp_common.cuh), in
-//     both batched_nms branches: per-class on raw boxes, or class-agnostic on boxes shifted by
-//     cls * (max_coord + 1) (the "coordinate trick", taken when an image has <= 1000 candidates);
+//   * the suppression test is bit-identical to torchvision's CPU kernel, `(double)(inter / union) >
+//     thr` with the fp32 division rounded to nearest, but evaluated without the division: it is
+//     equivalent to comparing inter against (midpoint of thr_eff and the next float) * union, which
+//     is exact in fp64 (24-bit x 25-bit significands); both batched_nms branches are implemented:
+//     per-class on raw boxes, or class-agnostic on boxes shifted by cls * (max_coord + 1) (the
+//     "coordinate trick", taken when an image has <= 1000 candidates);
 //   * survivors are emitted class-major, or - through a second bitmask indexed by global score
-//     rank - in score order capped at max_det.  Both are ordered ballot/popc compactions.
+//     rank - in score order capped at max_det.  Both are ordered popc/scan compactions.
 // Latency / SM-bound; the only HBM traffic is 8 B keys + gathered 16 B boxes (L2 resident).
+#include <cstring>
+
 #include "cvpp_common.cuh"
 
 namespace cvpp {
 
 constexpr int kNmsThreads = 512;
 constexpr int kNmsWarps = kNmsThreads / 32;
-constexpr int kCoopMinWords = 12;  // segments spanning more words than this use the whole CTA
-
+constexpr int kCoopMinWords = 8;  // segments spanning more words than this use the whole CTA
 
 struct NmsParams {
   const uint64_t* sorted_key;
@@ -36,7 +42,9 @@ struct NmsParams {
   int max_cand;
   int64_t A;
   int nc;
-  float thr_eff;
+  float thr_eff;   // largest float <= iou_thres
+  double thr_mid;  // midpoint of thr_eff and the next float above it
+  int tie_up;      // a quotient exactly at thr_mid rounds (to even) to the float ABOVE thr_eff
   int rule;
   int order;
   int max_det;
@@ -46,105 +54,64 @@ struct NmsParams {
   int32_t* det_cls;
   int32_t* det_anchor;
   int32_t* det_count;
-  // scratch
-  float4* ws_box;      // [B][max_cand] class-major boxes for images that do not fit shared memory
-  float* ws_area;      // [B][max_cand]
-  int32_t* ws_rank;    // [B][max_cand] class-major position -> global score rank
-  int smem_boxes;      // boxes that fit in shared memory
-  int alive_words;     // words reserved for each of the two bitmasks
-  int count_warps;     // warps taking part in the counting split (per-warp class counters)
+  // scratch for images whose padded class-major layout does not fit shared memory
+  float4* ws_box;    // [B][pos_cap]
+  float* ws_area;    // [B][pos_cap]
+  int32_t* ws_rank;  // [B][pos_cap] class-major position -> global score rank
+  int pos_cap;       // max_cand + 32 * nc (class starts are 32-aligned)
+  int smem_boxes;    // positions that fit in shared memory
+  int mask_words;    // words reserved for each of the two bitmasks
+  int count_warps;   // warps taking part in the counting split (per-warp class counters)
 };
 
-struct BoxView {  // sorted boxes + areas of one image (shared or global)
+struct SupTest {
+  float thr_eff;
+  double thr_mid;
+  bool tie_up;
+};
+
+// class-major boxes + areas of one image: shared memory (explicit LDS) or a global scratch row
+template <bool SMEM>
+struct BoxView;
+template <>
+struct BoxView<true> {
+  uint32_t box, area;  // shared-window byte addresses
+  __device__ __forceinline__ float4 load_box(int i) const {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(box + 16u * (uint32_t)i));
+    return v;
+  }
+  __device__ __forceinline__ float load_area(int i) const {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(area + 4u * (uint32_t)i));
+    return v;
+  }
+};
+template <>
+struct BoxView<false> {
   const float4* box;
   const float* area;
+  __device__ __forceinline__ float4 load_box(int i) const { return box[i]; }
+  __device__ __forceinline__ float load_area(int i) const { return area[i]; }
 };
 
-__device__ __forceinline__ float4 shfl_box(const float4& b, int src) {
-  float4 o;
-  o.x = __shfl_sync(0xffffffffu, b.x, src);
-  o.y = __shfl_sync(0xffffffffu, b.y, src);
-  o.z = __shfl_sync(0xffffffffu, b.z, src);
-  o.w = __shfl_sync(0xffffffffu, b.w, src);
-  return o;
-}
-
-// keep only the lowest `room` set bits of m
-__device__ __forceinline__ uint32_t lowest_bits(uint32_t m, int room) {
-  uint32_t o = 0;
-  while (m && room > 0) {
-    uint32_t low = m & (0u - m);
-    o |= low;
-    m ^= low;
-    --room;
-  }
-  return o;
-}
-
-// Resolve word w of segment [s, e): returns the kept mask (identical in all lanes).  All 32 lanes call.
-__device__ __forceinline__ uint32_t resolve_word(int w, int s, int e, const BoxView& bv, uint32_t* alive,
-                                                 float thr_eff, float4& box, float& area) {
-  const int lane = threadIdx.x & 31;
-  const int r = (w << 5) + lane;
-  const bool in = r >= s && r < e;
-  const uint32_t aw = alive[w];
-  bool my_alive = in && ((aw >> lane) & 1u);
-  box = make_float4(0.f, 0.f, 0.f, 0.f);
-  area = 0.f;
-  if (in) {
-    box = bv.box[r];
-    area = bv.area[r];
-  }
-  uint32_t am = __ballot_sync(0xffffffffu, my_alive);
-  uint32_t rem = am;
-  while (rem) {
-    const int i = __ffs(rem) - 1;
-    rem &= rem - 1;
-    const float4 bi = shfl_box(box, i);
-    const float ai = __shfl_sync(0xffffffffu, area, i);
-    const bool sup = my_alive && lane > i && iou_suppresses(bi, ai, box, area, thr_eff);
-    const uint32_t sm = __ballot_sync(0xffffffffu, sup);
-    am &= ~sm;
-    rem &= ~sm;
-    if (sup) my_alive = false;
-  }
-  return am;
-}
-
-// Apply the kept boxes `am` of word w (lane i of the calling warp holds box i in box/area when
-// from_regs, otherwise they are read from bv) to word w2 of the same segment.
-template <bool FROM_REGS>
-__device__ __forceinline__ void apply_word(uint32_t am, int w, int w2, int e, const BoxView& bv, uint32_t* alive,
-                                           float thr_eff, const float4& box, float area) {
-  const int lane = threadIdx.x & 31;
-  const int r2 = (w2 << 5) + lane;
-  const uint32_t aw2 = alive[w2];
-  const bool al2 = r2 < e && ((aw2 >> lane) & 1u);
-  if (!__any_sync(0xffffffffu, al2)) return;
-  float4 b2 = make_float4(0.f, 0.f, 0.f, 0.f);
-  float a2 = 0.f;
-  if (al2) {
-    b2 = bv.box[r2];
-    a2 = bv.area[r2];
-  }
-  bool sup2 = false;
-  uint32_t km = am;
-  while (km) {
-    const int i = __ffs(km) - 1;
-    km &= km - 1;
-    float4 bi;
-    float ai;
-    if (FROM_REGS) {
-      bi = shfl_box(box, i);
-      ai = __shfl_sync(0xffffffffu, area, i);
-    } else {
-      bi = bv.box[(w << 5) + i];
-      ai = bv.area[(w << 5) + i];
-    }
-    if (al2 && !sup2) sup2 = iou_suppresses(bi, ai, b2, a2, thr_eff);
-  }
-  const uint32_t sm2 = __ballot_sync(0xffffffffu, sup2);
-  if (lane == 0 && sm2) atomicAnd(&alive[w2], ~sm2);
+// Is box j suppressed by kept box i (symmetric in i, j)?  torchvision: ovr = inter / (iarea + jarea -
+// inter) in fp32, suppressed iff (double)ovr > thr.  RN(inter/uni) > thr_eff  <=>  inter/uni > thr_mid
+// (>= when the tie rounds up), and inter vs thr_mid*uni is exact in fp64.  Branch-free on the common
+// path; degenerate unions (<= 0, inf, NaN) fall back to the division.
+__device__ __forceinline__ bool suppresses(const float4& bi, float ai, const float4& bj, float aj, const SupTest& t) {
+  const float xx1 = fmaxf(bi.x, bj.x), yy1 = fmaxf(bi.y, bj.y);
+  const float xx2 = fminf(bi.z, bj.z), yy2 = fminf(bi.w, bj.w);
+  const float w = fmaxf(0.0f, fsub(xx2, xx1));
+  const float h = fmaxf(0.0f, fsub(yy2, yy1));
+  const float inter = fmul(w, h);
+  const float uni = fsub(fadd(ai, aj), inter);
+  const double lhs = (double)inter, rhs = t.thr_mid * (double)uni;
+  const bool cmp = t.tie_up ? lhs >= rhs : lhs > rhs;
+  const bool regular = uni > 0.0f && uni < INFINITY && inter < INFINITY;
+  bool sup = inter > 0.0f && regular && cmp;  // inter == 0 / NaN: ovr is 0 or NaN, never above thr
+  if (inter > 0.0f && !regular) sup = fdiv(inter, uni) > t.thr_eff;
+  return sup;
 }
 
 __device__ __forceinline__ uint32_t seg_mask_of_word(int w, int s, int e) {
@@ -154,15 +121,116 @@ __device__ __forceinline__ uint32_t seg_mask_of_word(int w, int s, int e) {
   return upto_hi & ~((1u << lo) - 1u);
 }
 
+// keep only the lowest `room` set bits of m
+__device__ __forceinline__ uint32_t lowest_bits(uint32_t m, int room) {
+  if (__popc(m) <= room) return m;
+  uint32_t o = 0;
+  while (m && room > 0) {
+    const uint32_t low = m & (0u - m);
+    o |= low;
+    m ^= low;
+    --room;
+  }
+  return o;
+}
+
+// Resolve word w of segment [s, e): returns the kept mask (identical in all lanes).  All 32 lanes call.
+// Pair (i, j) of the word is tested once, by lane i at rotation t = (j - i) mod 32, t = 1..16, so the
+// 496 pairs cost 16 rounds of 32 parallel tests; a ballot per round routes each verdict to the
+// column mask of the pair's EARLIER box.
+template <bool SMEM>
+__device__ __forceinline__ uint32_t resolve_word(int w, int s, int e, const BoxView<SMEM>& bv, const uint32_t* alive,
+                                                 const SupTest& t) {
+  const int lane = threadIdx.x & 31;
+  const int base = w << 5;
+  const uint32_t inmask = seg_mask_of_word(w, s, e);
+  uint32_t am = alive[w] & inmask;
+  if (am == 0 || (am & (am - 1)) == 0) return am;  // zero or one live box: nothing to resolve
+  const float4 bi = bv.load_box(base + lane);
+  const float ai = bv.load_area(base + lane);
+  const bool me = (am >> lane) & 1u;
+  // pairs are at most `span` lanes apart; rotations beyond min(span, 16) have nothing to test
+  const int span = (31 - __clz(am)) - (__ffs(am) - 1);
+  const int rounds = span < 16 ? span : 16;
+  uint32_t col = 0;  // which LATER live boxes of this word box `lane` suppresses
+  for (int r = 1; r <= rounds; ++r) {
+    const int j = (lane + r) & 31;
+    const bool pair = me && ((am >> j) & 1u) && (r < 16 || lane < 16);
+    bool sup = false;
+    if (pair) sup = suppresses(bi, ai, bv.load_box(base + j), bv.load_area(base + j), t);
+    const uint32_t v = __ballot_sync(0xffffffffu, sup);
+    // verdicts owned by this lane as the earlier box: (lane, lane + r) tested here if lane + r < 32,
+    // (lane, lane - r + 32) tested by lane' = lane - r + 32 if that is a later lane
+    if (lane + r < 32) col |= ((v >> lane) & 1u) << (lane + r);
+    const int k = lane - r + 32;
+    if (k < 32 && (r < 16 || k < 16)) col |= ((v >> k) & 1u) << k;
+  }
+  // replay the greedy order on bitmasks: a live box kills the later boxes in its column mask
+  uint32_t rem = am;
+  while (rem) {
+    const int i = __ffs(rem) - 1;
+    rem &= rem - 1;
+    const uint32_t c = __shfl_sync(0xffffffffu, col, i);
+    am &= ~c;
+    rem &= ~c;
+  }
+  return am;
+}
+
+// Apply the kept boxes `am` of word w to word w2 of the same segment (all 32 lanes call).
+// Lanes take the side with more boxes and loop over the other one, so a nearly empty word costs a
+// few rounds instead of 32.
+template <bool SMEM>
+__device__ __forceinline__ void apply_word(uint32_t am, int w, int w2, int e, const BoxView<SMEM>& bv, uint32_t* alive,
+                                           const SupTest& t) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t live2 = alive[w2] & seg_mask_of_word(w2, 0, e);
+  if (live2 == 0) return;
+  uint32_t sm2 = 0;
+  if (__popc(live2) >= __popc(am)) {
+    // lane = candidate of w2, loop over the kept boxes of w
+    const bool al2 = (live2 >> lane) & 1u;
+    bool sup2 = false;
+    if (al2) {
+      const float4 b2 = bv.load_box((w2 << 5) + lane);
+      const float a2 = bv.load_area((w2 << 5) + lane);
+      uint32_t km = am;
+      while (km && !sup2) {
+        const int i = __ffs(km) - 1;
+        km &= km - 1;
+        sup2 = suppresses(bv.load_box((w << 5) + i), bv.load_area((w << 5) + i), b2, a2, t);
+      }
+    }
+    sm2 = __ballot_sync(0xffffffffu, sup2);
+  } else {
+    // lane = kept box of w, loop over the candidates of w2
+    const bool kept = (am >> lane) & 1u;
+    float4 bi = make_float4(0.f, 0.f, 0.f, 0.f);
+    float ai = 0.f;
+    if (kept) {
+      bi = bv.load_box((w << 5) + lane);
+      ai = bv.load_area((w << 5) + lane);
+    }
+    uint32_t lm = live2;
+    while (lm) {
+      const int j = __ffs(lm) - 1;
+      lm &= lm - 1;
+      bool sup = false;
+      if (kept) sup = suppresses(bi, ai, bv.load_box((w2 << 5) + j), bv.load_area((w2 << 5) + j), t);
+      if (__any_sync(0xffffffffu, sup)) sm2 |= 1u << j;
+    }
+  }
+  if (lane == 0 && sm2) atomicAnd(&alive[w2], ~sm2);
+}
+
 // One warp runs greedy NMS over segment [s, e).  cap > 0 stops after `cap` survivors.
-__device__ void nms_segment_warp(int s, int e, int cap, const BoxView& bv, uint32_t* alive, float thr_eff) {
+template <bool SMEM>
+__device__ void nms_segment_warp(int s, int e, int cap, const BoxView<SMEM>& bv, uint32_t* alive, const SupTest& t) {
   const int lane = threadIdx.x & 31;
   const int w0 = s >> 5, w1 = (e - 1) >> 5;
   int kept_total = 0;
   for (int w = w0; w <= w1; ++w) {
-    float4 box;
-    float area;
-    uint32_t am = resolve_word(w, s, e, bv, alive, thr_eff, box, area);
+    uint32_t am = resolve_word(w, s, e, bv, alive, t);
     if (cap > 0) am = lowest_bits(am, cap - kept_total);
     kept_total += __popc(am);
     const uint32_t inmask = seg_mask_of_word(w, s, e);
@@ -172,13 +240,14 @@ __device__ void nms_segment_warp(int s, int e, int cap, const BoxView& bv, uint3
       break;
     }
     if (am)
-      for (int w2 = w + 1; w2 <= w1; ++w2) apply_word<true>(am, w, w2, e, bv, alive, thr_eff, box, area);
+      for (int w2 = w + 1; w2 <= w1; ++w2) apply_word(am, w, w2, e, bv, alive, t);
     __syncwarp();
   }
 }
 
 // The whole CTA runs greedy NMS over one (large) segment.  All threads call.
-__device__ void nms_segment_cta(int s, int e, int cap, const BoxView& bv, uint32_t* alive, float thr_eff,
+template <bool SMEM>
+__device__ void nms_segment_cta(int s, int e, int cap, const BoxView<SMEM>& bv, uint32_t* alive, const SupTest& t,
                                 uint32_t* sh_mask, int* sh_kept) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int w0 = s >> 5, w1 = (e - 1) >> 5;
@@ -186,12 +255,11 @@ __device__ void nms_segment_cta(int s, int e, int cap, const BoxView& bv, uint32
   __syncthreads();
   for (int w = w0; w <= w1; ++w) {
     if (warp == 0) {
-      float4 box;
-      float area;
-      uint32_t am = resolve_word(w, s, e, bv, alive, thr_eff, box, area);
-      int kept_total = *sh_kept;
+      uint32_t am = resolve_word(w, s, e, bv, alive, t);
+      const int kept_total = *sh_kept;
       if (cap > 0) am = lowest_bits(am, cap - kept_total);
       const uint32_t inmask = seg_mask_of_word(w, s, e);
+      __syncwarp();
       if (lane == 0) {
         atomicAnd(&alive[w], ~(inmask & ~am));
         *sh_mask = am;
@@ -204,11 +272,45 @@ __device__ void nms_segment_cta(int s, int e, int cap, const BoxView& bv, uint32
     if (done) {
       for (int w2 = w + 1 + threadIdx.x; w2 <= w1; w2 += blockDim.x) atomicAnd(&alive[w2], ~seg_mask_of_word(w2, s, e));
     } else if (am) {
-      float4 dummy = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int w2 = w + 1 + warp; w2 <= w1; w2 += kNmsWarps) apply_word<false>(am, w, w2, e, bv, alive, thr_eff, dummy, 0.f);
+      for (int w2 = w + 1 + warp; w2 <= w1; w2 += kNmsWarps) apply_word(am, w, w2, e, bv, alive, t);
     }
     __syncthreads();
     if (done) break;
+  }
+}
+
+// greedy suppression over every segment of the image (all threads call)
+template <bool SMEM>
+__device__ void suppress_all(const BoxView<SMEM>& bv, bool trick, int n, int nwords, int nc, int cap, uint32_t* alive,
+                             const int* seg_begin, const int* seg_end, const SupTest& st, int* sh_next,
+                             uint32_t* sh_mask, int* sh_kept) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (trick) {
+    if (nwords > kCoopMinWords) {
+      nms_segment_cta(0, n, cap, bv, alive, st, sh_mask, sh_kept);
+    } else {
+      if (warp == 0) nms_segment_warp(0, n, cap, bv, alive, st);
+      __syncthreads();
+    }
+    return;
+  }
+  // small segments: one warp each, classes claimed dynamically; large ones afterwards by the CTA
+  for (;;) {
+    int c = 0;
+    if (lane == 0) c = atomicAdd(sh_next, 1);
+    c = __shfl_sync(0xffffffffu, c, 0);
+    if (c >= nc) break;
+    const int s = seg_begin[c], e = seg_end[c];
+    if (e <= s) continue;
+    if (((e - 1) >> 5) - (s >> 5) + 1 > kCoopMinWords) continue;
+    nms_segment_warp(s, e, cap, bv, alive, st);
+  }
+  __syncthreads();
+  for (int c = 0; c < nc; ++c) {
+    const int s = seg_begin[c], e = seg_end[c];
+    if (e <= s) continue;
+    if (((e - 1) >> 5) - (s >> 5) + 1 <= kCoopMinWords) continue;
+    nms_segment_cta(s, e, cap, bv, alive, st, sh_mask, sh_kept);
   }
 }
 
@@ -220,8 +322,8 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
   float* sh_area = reinterpret_cast<float*>(sh_box + p.smem_boxes);
   int32_t* sh_rank = reinterpret_cast<int32_t*>(sh_area + p.smem_boxes);
   uint32_t* alive = reinterpret_cast<uint32_t*>(sh_rank + p.smem_boxes);
-  uint32_t* galive = alive + p.alive_words;
-  int* seg_begin = reinterpret_cast<int*>(galive + p.alive_words);
+  uint32_t* galive = alive + p.mask_words;
+  int* seg_begin = reinterpret_cast<int*>(galive + p.mask_words);
   int* seg_end = seg_begin + p.nc;
   int* cnt = seg_end + p.nc;
   __shared__ float sh_red[kNmsWarps];
@@ -230,6 +332,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
   __shared__ uint32_t sh_mask;
   __shared__ int sh_kept;
   __shared__ int sh_next;
+  __shared__ int sh_npos;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.x;
@@ -242,24 +345,30 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
   const uint64_t* keys = p.sorted_key + (int64_t)b * p.max_cand;  // score-major: [inv_score | anchor | class]
   const float4* dense = p.box_dense + (int64_t)b * p.A;
   const bool trick = rule_uses_trick(p.rule, n);
-  const int nwords = (n + 31) >> 5;
   const int nc = p.nc;
+  const SupTest st{p.thr_eff, p.thr_mid, p.tie_up != 0};
+  const int rank_words = (n + 31) >> 5;
 
-  const bool in_smem = n <= p.smem_boxes;
-  float4* wbox = in_smem ? sh_box : p.ws_box + (int64_t)b * p.max_cand;
-  float* warea = in_smem ? sh_area : p.ws_area + (int64_t)b * p.max_cand;
-  int32_t* wrank = in_smem ? sh_rank : p.ws_rank + (int64_t)b * p.max_cand;
+  float4* wbox;
+  float* warea;
+  int32_t* wrank;
+  int npos;  // size of the position space (== n for the trick branch, 32-aligned class segments otherwise)
 
-  for (int w = tid; w < nwords; w += kNmsThreads) {
-    const int rem = n - (w << 5);
-    alive[w] = rem >= 32 ? 0xffffffffu : ((1u << rem) - 1u);
+  for (int w = tid; w < p.mask_words; w += kNmsThreads) {
+    alive[w] = 0u;
     galive[w] = 0u;
   }
   if (tid == 0) sh_next = 0;
+  __syncthreads();
 
   if (trick) {
     // ---- coordinate trick: one class-agnostic segment in score order; boxes shifted by
     //      cls * (max over every coordinate + 1)  (boxes.py:95-97)
+    npos = n;
+    const bool in_smem = npos <= p.smem_boxes;
+    wbox = in_smem ? sh_box : p.ws_box + (int64_t)b * p.pos_cap;
+    warea = in_smem ? sh_area : p.ws_area + (int64_t)b * p.pos_cap;
+    wrank = in_smem ? sh_rank : p.ws_rank + (int64_t)b * p.pos_cap;
     float m = -INFINITY;
     for (int r = tid; r < n; r += kNmsThreads) {
       const float4 bx = dense[(uint32_t)(keys[r] >> 12) & 0x1fffffu];
@@ -281,6 +390,10 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
       bx.w = fadd(bx.w, off);
       wbox[r] = bx;
       warea[r] = box_area(bx);
+    }
+    for (int w = tid; w < rank_words; w += kNmsThreads) {
+      const int rem = n - (w << 5);
+      alive[w] = rem >= 32 ? 0xffffffffu : ((1u << rem) - 1u);
     }
     __syncthreads();
   } else {
@@ -313,33 +426,36 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
       seg_end[c] = run;
     }
     __syncthreads();
-    if (warp == 0) {  // exclusive scan of the class totals -> segment starts
+    if (warp == 0) {  // scan of the 32-aligned class sizes -> segment starts
       int running = 0;
       for (int c0 = 0; c0 < nc; c0 += 32) {
         const int c = c0 + lane;
         const int t = c < nc ? seg_end[c] : 0;
-        int incl = t;
+        const int ta = (t + 31) & ~31;
+        int incl = ta;
         for (int d = 1; d < 32; d <<= 1) {
           const int v = __shfl_up_sync(0xffffffffu, incl, d);
           if (lane >= d) incl += v;
         }
         if (c < nc) {
-          seg_begin[c] = running + incl - t;
-          seg_end[c] = running + incl;
+          const int s0 = running + incl - ta;
+          seg_begin[c] = s0;
+          seg_end[c] = s0 + t;
+          for (int w = 0; w < (ta >> 5); ++w) {  // live bits of this class
+            const int rem = t - (w << 5);
+            alive[(s0 >> 5) + w] = rem >= 32 ? 0xffffffffu : ((1u << rem) - 1u);
+          }
         }
         running += __shfl_sync(0xffffffffu, incl, 31);
       }
-      if (lane == 0) sh_kept = running;  // candidates with a class id < nc (all of them, by contract)
+      if (lane == 0) sh_npos = running;
     }
     __syncthreads();
-    {
-      const int nvalid = sh_kept;
-      if (nvalid < n)
-        for (int w = tid; w < nwords; w += kNmsThreads) {
-          const int rem = nvalid - (w << 5);
-          if (rem < 32) alive[w] &= rem <= 0 ? 0u : ((1u << rem) - 1u);
-        }
-    }
+    npos = sh_npos;
+    const bool in_smem = npos <= p.smem_boxes;
+    wbox = in_smem ? sh_box : p.ws_box + (int64_t)b * p.pos_cap;
+    warea = in_smem ? sh_area : p.ws_area + (int64_t)b * p.pos_cap;
+    wrank = in_smem ? sh_rank : p.ws_rank + (int64_t)b * p.pos_cap;
     if (warp < cw) {
       int* my = cnt + warp * nc;
       for (int r0 = r_begin; r0 < r_end; r0 += 32) {
@@ -366,36 +482,16 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
     }
     __syncthreads();
   }
-  BoxView bv{wbox, warea};
+  const int nwords = (npos + 31) >> 5;
 
   // ---- greedy suppression -------------------------------------------------------------------
   const int cap = (p.order == CVPP_ORDER_SCORE_DESC && p.max_det > 0) ? p.max_det : 0;
-  if (trick) {
-    if (nwords > kCoopMinWords) {
-      nms_segment_cta(0, n, cap, bv, alive, p.thr_eff, &sh_mask, &sh_kept);
-    } else {
-      if (warp == 0) nms_segment_warp(0, n, cap, bv, alive, p.thr_eff);
-      __syncthreads();
-    }
+  if (npos <= p.smem_boxes) {
+    const BoxView<true> bv{smem_u32(sh_box), smem_u32(sh_area)};
+    suppress_all(bv, trick, n, nwords, nc, cap, alive, seg_begin, seg_end, st, &sh_next, &sh_mask, &sh_kept);
   } else {
-    // small segments: one warp each, classes claimed dynamically; large ones afterwards by the CTA
-    for (;;) {
-      int c = 0;
-      if (lane == 0) c = atomicAdd(&sh_next, 1);
-      c = __shfl_sync(0xffffffffu, c, 0);
-      if (c >= nc) break;
-      const int s = seg_begin[c], e = seg_end[c];
-      if (e <= s) continue;
-      if (((e - 1) >> 5) - (s >> 5) + 1 > kCoopMinWords) continue;
-      nms_segment_warp(s, e, cap, bv, alive, p.thr_eff);
-    }
-    __syncthreads();
-    for (int c = 0; c < nc; ++c) {
-      const int s = seg_begin[c], e = seg_end[c];
-      if (e <= s) continue;
-      if (((e - 1) >> 5) - (s >> 5) + 1 <= kCoopMinWords) continue;
-      nms_segment_cta(s, e, cap, bv, alive, p.thr_eff, &sh_mask, &sh_kept);
-    }
+    const BoxView<false> bv{wbox, warea};
+    suppress_all(bv, trick, n, nwords, nc, cap, alive, seg_begin, seg_end, st, &sh_next, &sh_mask, &sh_kept);
   }
   __syncthreads();
 
@@ -417,6 +513,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
     __syncthreads();
   }
   const uint32_t* mask = by_rank ? galive : alive;
+  const int mwords = by_rank ? rank_words : nwords;
   const bool pos_is_rank = by_rank || trick;
   float4* ob = p.det_box + (int64_t)b * p.max_out;
   float* os = p.det_score + (int64_t)b * p.max_out;
@@ -424,11 +521,13 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
   int32_t* oa = p.det_anchor + (int64_t)b * p.max_out;
   const int out_cap = (p.order == CVPP_ORDER_SCORE_DESC && p.max_det > 0 && p.max_det < p.max_out) ? p.max_det : p.max_out;
 
+  // pass 1: ordered positions -> index list (the area array is dead now and is reused for it)
+  int* out_idx = reinterpret_cast<int*>(warea);
   if (tid == 0) sh_running = 0;
   __syncthreads();
-  for (int base = 0; base < nwords; base += kNmsThreads) {
+  for (int base = 0; base < mwords; base += kNmsThreads) {
     const int wi = base + tid;
-    uint32_t m = wi < nwords ? mask[wi] : 0u;
+    uint32_t m = wi < mwords ? mask[wi] : 0u;
     const int c = __popc(m);
     int incl = c;
     for (int d = 1; d < 32; d <<= 1) {
@@ -447,28 +546,32 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
     while (m && pos < out_cap) {
       const int bit = __ffs(m) - 1;
       m &= m - 1;
-      const int at = (wi << 5) + bit;
-      const uint64_t k = keys[pos_is_rank ? at : wrank[at]];
-      const uint32_t anchor = (uint32_t)(k >> 12) & 0x1fffffu;
-      ob[pos] = dense[anchor];
-      os[pos] = __uint_as_float(0x7fffffffu - (uint32_t)(k >> 33));
-      oc[pos] = (int32_t)(k & 0xfffu);
-      oa[pos] = (int32_t)anchor;
-      ++pos;
+      out_idx[pos++] = (wi << 5) + bit;
     }
     __syncthreads();
     if (tid == 0) sh_running += total;
     __syncthreads();
   }
-  if (tid == 0) {
-    int n_kept = sh_running;
-    if (p.order == CVPP_ORDER_SCORE_DESC && p.max_det > 0 && n_kept > p.max_det) n_kept = p.max_det;
-    p.det_count[b] = n_kept;
+  int n_kept = sh_running;
+  if (p.order == CVPP_ORDER_SCORE_DESC && p.max_det > 0 && n_kept > p.max_det) n_kept = p.max_det;
+  // pass 2: one output row per thread, all gathers in flight at once
+  const int n_rows = min(n_kept, out_cap);
+  for (int o = tid; o < n_rows; o += kNmsThreads) {
+    const int at = out_idx[o];
+    const uint64_t k = keys[pos_is_rank ? at : wrank[at]];
+    const uint32_t anchor = (uint32_t)(k >> 12) & 0x1fffffu;
+    ob[o] = dense[anchor];
+    os[o] = __uint_as_float(0x7fffffffu - (uint32_t)(k >> 33));
+    oc[o] = (int32_t)(k & 0xfffu);
+    oa[o] = (int32_t)anchor;
   }
+  if (tid == 0) p.det_count[b] = n_kept;
 }
 
-size_t nms_workspace_bytes(int B, int max_cand) {
-  size_t per = (size_t)max_cand * (sizeof(float4) + sizeof(float) + sizeof(int32_t));
+static size_t pos_capacity(int max_cand, int nc) { return (size_t)max_cand + 32u * (size_t)nc; }
+
+size_t nms_workspace_bytes(int B, int max_cand, int nc) {
+  size_t per = pos_capacity(max_cand, nc) * (sizeof(float4) + sizeof(float) + sizeof(int32_t));
   per = (per + 255) & ~(size_t)255;
   return per * (size_t)B + 256;
 }
@@ -498,26 +601,31 @@ int nms_launch(const uint64_t* sorted_key, const int32_t* cand_count, const floa
     return CVPP_ERR_ALIGNMENT;
   }
   if (B == 0) return CVPP_OK;
-  if (!workspace || workspace_bytes < nms_workspace_bytes(B, max_cand)) {
-    set_error("nms: workspace of %zu bytes needed, got %zu", nms_workspace_bytes(B, max_cand), workspace_bytes);
+  if (!workspace || workspace_bytes < nms_workspace_bytes(B, max_cand, nc)) {
+    set_error("nms: workspace of %zu bytes needed, got %zu", nms_workspace_bytes(B, max_cand, nc), workspace_bytes);
     return CVPP_ERR_WORKSPACE;
   }
-  // (double)ovr > thr  <=>  ovr > largest float <= thr   (ovr is a float)
-  float thr_eff = (float)iou_thres;
-  if ((double)thr_eff > iou_thres) thr_eff = nextafterf(thr_eff, -INFINITY);
-
-  int dev = 0, max_smem = 0;
-  CVPP_CUDA_TRY(cudaGetDevice(&dev));
-  CVPP_CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  DeviceInfo di;
+  int rc = device_info(&di);
+  if (rc != CVPP_OK) return rc;
+  const int max_smem = di.max_smem;
 
   NmsParams p{};
+  // (double)ovr > thr  <=>  ovr > thr_eff := largest float <= thr   (ovr is a float)
+  float thr_eff = (float)iou_thres;
+  if ((double)thr_eff > iou_thres) thr_eff = nextafterf(thr_eff, -INFINITY);
+  const float thr_next = nextafterf(thr_eff, INFINITY);
+  p.thr_eff = thr_eff;
+  p.thr_mid = ((double)thr_eff + (double)thr_next) * 0.5;  // exact: 25 significant bits
+  uint32_t next_bits;
+  memcpy(&next_bits, &thr_next, sizeof(next_bits));
+  p.tie_up = (next_bits & 1u) == 0;  // round-half-to-even picks thr_next when its significand is even
   p.sorted_key = sorted_key;
   p.cand_count = cand_count;
   p.box_dense = reinterpret_cast<const float4*>(box_dense);
   p.max_cand = max_cand;
   p.A = A;
   p.nc = nc;
-  p.thr_eff = thr_eff;
   p.rule = rule;
   p.order = order;
   p.max_det = max_det;
@@ -528,30 +636,38 @@ int nms_launch(const uint64_t* sorted_key, const int32_t* cand_count, const floa
   p.det_anchor = det_anchor;
   p.det_count = det_count;
   // workspace carve-up
+  const size_t cap = pos_capacity(max_cand, nc);
+  p.pos_cap = (int)cap;
   uintptr_t base = (reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255;
   p.ws_box = reinterpret_cast<float4*>(base);
-  p.ws_area = reinterpret_cast<float*>(base + (size_t)B * max_cand * sizeof(float4));
-  p.ws_rank = reinterpret_cast<int32_t*>(base + (size_t)B * max_cand * (sizeof(float4) + sizeof(float)));
+  p.ws_area = reinterpret_cast<float*>(base + (size_t)B * cap * sizeof(float4));
+  p.ws_rank = reinterpret_cast<int32_t*>(base + (size_t)B * cap * (sizeof(float4) + sizeof(float)));
   // shared memory: two bitmasks, class segments, per-warp class counters (<= 32 KB), then as many
-  // box slots (24 B each) as fit, capped at max_cand
-  p.alive_words = (max_cand + 31) / 32;
+  // box slots (24 B each) as fit, capped at the padded position capacity
+  p.mask_words = (int)((cap + 31) / 32);
   int cw = (int)((32 * 1024) / ((size_t)nc * 4));
   if (cw > kNmsWarps) cw = kNmsWarps;
   if (cw < 1) cw = 1;
   p.count_warps = cw;
-  size_t fixed = (size_t)p.alive_words * 8 + (size_t)nc * 8 + (size_t)cw * nc * 4 + 64;
+  size_t fixed = (size_t)p.mask_words * 8 + (size_t)nc * 8 + (size_t)cw * nc * 4 + 64;
   if (fixed + 4096 > (size_t)max_smem) {
     set_error("nms: max_cand=%d / nc=%d need more shared memory than the device has", max_cand, nc);
     return CVPP_ERR_UNSUPPORTED;
   }
   size_t avail = (size_t)max_smem - fixed - 1024;
-  int smem_boxes = (int)(avail / 24);
-  if (smem_boxes > max_cand) smem_boxes = max_cand;
-  smem_boxes = (smem_boxes + 3) & ~3;
-  if ((size_t)smem_boxes * 24 > avail) smem_boxes -= 4;
-  p.smem_boxes = smem_boxes;
-  size_t smem = fixed + (size_t)smem_boxes * 24;
-  CVPP_CUDA_TRY(cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  size_t smem_boxes = avail / 24;
+  if (smem_boxes > cap) smem_boxes = cap;
+  smem_boxes &= ~(size_t)3;
+  p.smem_boxes = (int)smem_boxes;
+  size_t smem = fixed + smem_boxes * 24;
+  static unsigned long long attr_done = 0;
+  static int attr_bytes = 0;  // the attribute must cover the largest request seen so far
+  if ((int)smem > attr_bytes) {
+    attr_done = 0;
+    attr_bytes = (int)smem;
+  }
+  rc = ensure_smem_attr(reinterpret_cast<const void*>(nms_kernel), attr_bytes, di.device, &attr_done);
+  if (rc != CVPP_OK) return rc;
   nms_kernel<<<B, kNmsThreads, smem, stream>>>(p);
   CVPP_CUDA_TRY(cudaGetLastError());
   return CVPP_OK;

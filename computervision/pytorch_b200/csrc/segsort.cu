@@ -59,9 +59,10 @@ int segsort_launch(uint64_t* keys, int32_t* cand_count, int B, int max_cand, int
   if (B == 0) return CVPP_OK;
   int P = 32;
   while (P < max_cand) P <<= 1;
-  int dev = 0, max_smem = 0;
-  CVPP_CUDA_TRY(cudaGetDevice(&dev));
-  CVPP_CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  DeviceInfo di;
+  int rc = device_info(&di);
+  if (rc != CVPP_OK) return rc;
+  const int max_smem = di.max_smem;
   int smem_elems = 1;
   while ((size_t)smem_elems * 2 * sizeof(uint64_t) <= (size_t)max_smem && smem_elems * 2 <= 16384) smem_elems <<= 1;
   if (smem_elems > P) smem_elems = P;
@@ -73,7 +74,14 @@ int segsort_launch(uint64_t* keys, int32_t* cand_count, int B, int max_cand, int
     }
   }
   size_t smem = (size_t)smem_elems * sizeof(uint64_t);
-  CVPP_CUDA_TRY(cudaFuncSetAttribute(segsort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static unsigned long long attr_done = 0;
+  static int attr_bytes = 0;  // the attribute must cover the largest request seen so far
+  if ((int)smem > attr_bytes) {
+    attr_done = 0;
+    attr_bytes = (int)smem;
+  }
+  rc = ensure_smem_attr(reinterpret_cast<const void*>(segsort_kernel), attr_bytes, di.device, &attr_done);
+  if (rc != CVPP_OK) return rc;
   segsort_kernel<<<B, kSortThreads, smem, stream>>>(keys, cand_count, max_cand, max_nms,
                                                     reinterpret_cast<uint64_t*>(workspace), (int64_t)P, smem_elems);
   CVPP_CUDA_TRY(cudaGetLastError());

@@ -427,14 +427,6 @@ __global__ void __launch_bounds__(128) yolov8_decode_generic_kernel(const __grid
 // -----------------------------------------------------------------------------------------------
 // host launcher
 // -----------------------------------------------------------------------------------------------
-static int sm_count_of_current_device(int* sms, int* max_smem) {
-  int dev = 0;
-  CVPP_CUDA_TRY(cudaGetDevice(&dev));
-  CVPP_CUDA_TRY(cudaDeviceGetAttribute(sms, cudaDevAttrMultiProcessorCount, dev));
-  CVPP_CUDA_TRY(cudaDeviceGetAttribute(max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-  return CVPP_OK;
-}
-
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -469,9 +461,10 @@ static bool make_level_tmap(CUtensorMap* tm, const LevelDesc& L, int C, int B) {
 
 template <bool FULL>
 static int launch_decode(DecodeParams& p, bool tma_ok, cudaStream_t stream) {
-  int sms = 0, max_smem = 0;
-  int rc = sm_count_of_current_device(&sms, &max_smem);
+  DeviceInfo di;
+  int rc = device_info(&di);
   if (rc != CVPP_OK) return rc;
+  const int sms = di.sms, max_smem = di.max_smem;
   const size_t smem = (size_t)kWarps * kStages * kChunkFloats * sizeof(float) + (size_t)kWarps * kStages * sizeof(uint64_t);
   if (tma_ok && smem <= (size_t)max_smem) {
     const int C = 4 * kRegMax + p.nc;
@@ -481,7 +474,9 @@ static int launch_decode(DecodeParams& p, bool tma_ok, cudaStream_t stream) {
   }
   if (tma_ok) {
     auto kern = yolov8_decode_stream_kernel<FULL>;
-    CVPP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static unsigned long long attr_done = 0;  // one per template instantiation
+    rc = ensure_smem_attr(reinterpret_cast<const void*>(kern), (int)smem, di.device, &attr_done);
+    if (rc != CVPP_OK) return rc;
     int grid = p.total_tiles < sms ? p.total_tiles : sms;
     kern<<<grid, kWarps * 32, smem, stream>>>(p);
   } else {

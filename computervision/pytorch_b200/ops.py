@@ -169,7 +169,7 @@ def nms(c: Candidates, iou_thres: float, rule: int = RULE_TORCHVISION_CPU, order
     if max_out is None:
         max_out = max_det if (order == ORDER_SCORE_DESC and max_det > 0) else c.max_cand
     max_out = max(int(max_out), 1)
-    nbytes = int(l.cvpp_nms_workspace_bytes(B, c.max_cand))
+    nbytes = int(l.cvpp_nms_workspace_bytes(B, c.max_cand, c.nc))
     ws = torch.empty((max(nbytes, 1),), dtype=torch.uint8, device=dev)
     det = Detections(box=torch.empty((B, max_out, 4), dtype=torch.float32, device=dev),
                      score=torch.empty((B, max_out), dtype=torch.float32, device=dev),
@@ -184,14 +184,19 @@ def nms(c: Candidates, iou_thres: float, rule: int = RULE_TORCHVISION_CPU, order
 
 
 class Yolov8Postprocessor:
-    """Pre-allocated buffers + one C call (cvpp_yolov8_postprocess) per batch: decode+filter, sort, NMS."""
+    """Pre-allocated buffers + one C call (cvpp_yolov8_postprocess) per batch: decode+filter, sort, NMS.
+
+    `capture()` records that call into a CUDA graph bound to one LevelSet (fixed input buffers), so a
+    steady-state step is a single graph launch - the form to use for bs=1 latency."""
 
     def __init__(self, B: int, A: int, nc: int, device, max_det: int = 300, max_cand: Optional[int] = None):
         self.B, self.A, self.nc, self.max_det = int(B), int(A), int(nc), int(max_det)
         self.max_cand = int(max_cand or A)
         self.device = torch.device(device)
-        l = _lib.lib()
-        self.ws_bytes = int(l.cvpp_yolov8_workspace_bytes(self.B, self.A, self.max_cand))
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self._lib = _lib.lib()
+        self.ws_bytes = int(self._lib.cvpp_yolov8_workspace_bytes(self.B, self.A, self.max_cand, self.nc))
         dev = self.device
         self.ws = torch.empty((self.ws_bytes,), dtype=torch.uint8, device=dev)
         self.det = Detections(box=torch.empty((B, max_det, 4), dtype=torch.float32, device=dev),
@@ -200,19 +205,44 @@ class Yolov8Postprocessor:
                               anchor=torch.empty((B, max_det), dtype=torch.int32, device=dev),
                               count=torch.empty((B,), dtype=torch.int32, device=dev),
                               cand_count=torch.empty((B,), dtype=torch.int32, device=dev))
+        d = self.det
+        self._out_args = (_ptr(d.box), _ptr(d.score), _ptr(d.cls), _ptr(d.anchor), _ptr(d.count), _ptr(d.cand_count),
+                          _ptr(self.ws), self.ws_bytes)
 
     def __call__(self, ls: LevelSet, conf_thres: float, iou_thres: float, rule: int = RULE_TORCHVISION_CPU,
                  max_nms: int = 30000, reg_max: int = 16) -> Detections:
         if ls.B != self.B or ls.A != self.A or ls.C != 4 * reg_max + self.nc:
             raise ValueError("level set does not match the shapes this post-processor was built for")
-        d = self.det
-        with torch.cuda.device(self.device):
-            check(_lib.lib().cvpp_yolov8_postprocess(
-                ls.ptr, ls.batch_stride, ls.chan_stride, ls.h, ls.w, ls.stride, ls.n, self.B, self.nc, reg_max,
-                float(conf_thres), float(iou_thres), rule, self.max_det, int(max_nms), self.max_cand, _ptr(d.box),
-                _ptr(d.score), _ptr(d.cls), _ptr(d.anchor), _ptr(d.count), _ptr(d.cand_count), _ptr(self.ws),
-                self.ws_bytes, _stream(self.device)))
-        return d
+        dev = self.device
+        if torch.cuda.current_device() != dev.index:
+            with torch.cuda.device(dev):
+                return self.__call__(ls, conf_thres, iou_thres, rule, max_nms, reg_max)
+        check(self._lib.cvpp_yolov8_postprocess(
+            ls.ptr, ls.batch_stride, ls.chan_stride, ls.h, ls.w, ls.stride, ls.n, self.B, self.nc, reg_max,
+            float(conf_thres), float(iou_thres), rule, self.max_det, int(max_nms), self.max_cand, *self._out_args,
+            c_vp(torch.cuda.current_stream().cuda_stream)))
+        return self.det
+
+    def capture(self, ls: LevelSet, conf_thres: float, iou_thres: float, rule: int = RULE_TORCHVISION_CPU,
+                max_nms: int = 30000, reg_max: int = 16) -> "GraphedPostprocess":
+        return GraphedPostprocess(self, ls, (conf_thres, iou_thres, rule, max_nms, reg_max))
+
+
+class GraphedPostprocess:
+    """A CUDA-graph capture of Yolov8Postprocessor.__call__ on fixed input buffers."""
+
+    def __init__(self, post: Yolov8Postprocessor, ls: LevelSet, args):
+        self.post, self.ls = post, ls
+        with torch.cuda.device(post.device):
+            post(ls, *args)  # warm-up outside capture: one-time attribute / driver-entry-point work
+            torch.cuda.synchronize()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                post(ls, *args)
+
+    def replay(self) -> Detections:
+        self.graph.replay()
+        return self.post.det
 
 
 def split_detections(det: Detections) -> List[Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]]:

@@ -9,7 +9,8 @@
  *
  * Conventions
  *   - every pointer is a DEVICE pointer owned by the caller unless stated otherwise; the
- *     library allocates nothing, keeps no global mutable state and never synchronises:
+ *     library allocates nothing, keeps no state besides idempotent per-device caches (SM count,
+ *     shared-memory opt-in) and never synchronises:
  *     all work is enqueued on `stream` (a CUstream / cudaStream_t handle; NULL = legacy
  *     default stream);
  *   - returns CVPP_OK (0) or a negative CVPP_ERR_* code; cvpp_last_error() returns a
@@ -113,10 +114,12 @@ CVPP_API int cvpp_pred_filter(const float* pred, int B, int channels, int nc, in
  *           the stable descending sort inside torchvision nms (per class)
  *           torch.unique(class) + per-class gathers        core/algorithms/yolo_v7.py:396-400,
  *                                                          torchvision/ops/boxes.py:112-116
- * keys[b*max_cand ..] is sorted ascending in place over the first min(cand_count[b], max_cand)
- * entries.  When `rule` selects the coordinate trick for an image, its keys are re-packed as
- * [score | anchor | class] so the order is global score-descending; cvpp_nms undoes that.
- * max_nms (>0) truncates each image's list to its max_nms best scores (ultralytics :240).
+ * keys[b*max_cand ..] (first min(cand_count[b], max_cand) entries) are re-packed SCORE-MAJOR,
+ *     [63:33] 0x7fffffff - bits(score) | [32:12] anchor | [11:0] class,
+ * and sorted ascending in place: score descending, lower anchor first on ties - the one global order
+ * every consumer needs; the per-class partition is a stable counting split inside cvpp_nms.
+ * max_nms (>0) truncates each image's list to its max_nms best scores (ultralytics :240) and
+ * rewrites cand_count[b].  `rule` is accepted for symmetry with cvpp_nms and ignored.
  * workspace: cvpp_sort_workspace_bytes(B, max_cand) bytes, only touched by segments too large
  * for shared memory.
  * ------------------------------------------------------------------------------------------- */
@@ -129,16 +132,16 @@ CVPP_API int cvpp_segmented_sort(uint64_t* keys, int32_t* cand_count, int B, int
  * Replaces: torchvision.ops.batched_nms / nms (torchvision/ops/boxes.py:20-120, csrc/ops/cpu/nms_kernel.cpp)
  *           at call sites core/utils/ultralytics_ops.py:247-248,257; core/utils/nms.py:69,134;
  *           core/algorithms/yolo_v7.py:407; core/algorithms/ssd.py:267.
- * Input: sorted keys (from cvpp_segmented_sort, same `rule`), counts, box_dense (B, A, 4); class ids
+ * Input: score-major sorted keys (from cvpp_segmented_sort), counts, box_dense (B, A, 4); class ids
  *        in the keys are < nc.
  * Suppression test: IoU computed in fp32 exactly as torchvision's CPU kernel; j is suppressed by a
  * kept i iff (double)iou > iou_thres.
  * Output rows k < min(det_count[b], max_out), for image b at index b*max_out + k:
  *   det_box (x1,y1,x2,y2), det_score, det_cls, det_anchor.  det_count[b] is the uncapped-by-max_out
  *   number of survivors (after the max_det cap when order == CVPP_ORDER_SCORE_DESC).
- * workspace: cvpp_nms_workspace_bytes(B, max_cand).
+ * workspace: cvpp_nms_workspace_bytes(B, max_cand, nc).
  * ------------------------------------------------------------------------------------------- */
-CVPP_API size_t cvpp_nms_workspace_bytes(int B, int max_cand);
+CVPP_API size_t cvpp_nms_workspace_bytes(int B, int max_cand, int nc);
 CVPP_API int cvpp_nms(const uint64_t* sorted_key, const int32_t* cand_count, const float* box_dense, int B,
              int max_cand, int64_t A, int nc, double iou_thres, int rule, int order, int max_det, int max_out,
              float* det_box, float* det_score, int32_t* det_cls, int32_t* det_anchor, int32_t* det_count,
@@ -150,7 +153,7 @@ CVPP_API int cvpp_nms(const uint64_t* sorted_key, const int32_t* cand_count, con
  * (core/algorithms/yolo_v8.py:222-227).  Scratch buffers are carved from `workspace`
  * (cvpp_yolov8_workspace_bytes).  max_cand = A is always sufficient.
  * ------------------------------------------------------------------------------------------- */
-CVPP_API size_t cvpp_yolov8_workspace_bytes(int B, int64_t A, int max_cand);
+CVPP_API size_t cvpp_yolov8_workspace_bytes(int B, int64_t A, int max_cand, int nc);
 CVPP_API int cvpp_yolov8_postprocess(const float* const* level_ptr, const int64_t* batch_stride,
                             const int64_t* chan_stride, const int* level_h, const int* level_w,
                             const float* level_stride, int num_levels, int B, int nc, int reg_max,
