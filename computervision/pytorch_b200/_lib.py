@@ -45,6 +45,10 @@ _PROTOS = {
     "cvpp_yolov8_postprocess": (c_int, [P(c_vp), P(c_i64), P(c_i64), P(c_int), P(c_int), P(c_f32), c_int, c_int,
                                         c_int, c_int, c_f32, c_f64, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp,
                                         c_vp, c_vp, c_vp, c_vp, c_size, c_vp]),
+    "cvpp_centernet_workspace_bytes": (c_size, [c_int, c_int, c_int, c_int, c_int]),
+    "cvpp_centernet_decode": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_f32, c_int, c_int, c_f32, c_vp, c_vp,
+                                      c_vp, c_vp, c_vp, c_vp, c_vp, c_size, c_vp]),
+    "cvpp_diou_nms": (c_int, [c_vp, c_vp, c_int, c_f32, c_vp, c_vp, c_vp]),
 }
 
 _lib = None

@@ -1,0 +1,532 @@
+// centernet.cu — kernel 4: CenterNet heatmap peak extraction + top-K + box assembly + DIoU-NMS (sm_100a).
+//
+// Replaces (reference file:line): CenterNetA.decode_boxes core/algorithms/centernet.py:271-314,
+// _suppress_redundant_centers :316-326, _top_k :328-338, RegL1Loss.gather_feat
+// core/loss/centernet_loss.py:37-43, xywh_to_xyxy_torch core/utils/bboxes.py:29-49, diou_nms
+// core/utils/nms.py:9-31 (+ box_diou / box_iou core/utils/iou.py:8-64), reverse_letter_box
+// core/utils/image_process.py:100-129.
+//
+// Reference quirk kept on purpose: the reference applies MaxPool2d(3,1,1) to the
+// NHWC tensor, so the 3x3 window spans (x, class) of one image row y, not (y, x).  Rows are therefore
+// independent, which is what makes the single streaming pass below possible.
+//
+// Pass A (memory-bound, reads the (B,H,W,nc+4) tensor exactly once): persistent CTAs walk image rows;
+// a row (W*(nc+4) contiguous floats, 43 KB at 128x84) is one bulk async copy (UBLKCP) into a 2-stage
+// shared-memory ring.  Threads test each heat cell against its 8 neighbours in the LOGIT domain
+// (sigmoid is monotone; equality of rounded sigmoids is re-checked only when logits nearly tie),
+// turn peaks into 64-bit keys [inv_score | flat index] and keep those not worse than the image's
+// running K-th best key `tau` (atomicMin, only ever tightened by rows that hold >= K peaks, which
+// they sort with the hybrid bitonic network).  Each row appends at most K keys to the image's list.
+// Pass B (one CTA per image): sort the list, take K, gather reg/wh, assemble + clamp boxes, score
+// mask, optional class-agnostic DIoU-NMS (greedy, one barrier per candidate), letterbox inverse.
+#include "cvpp_common.cuh"
+
+namespace cvpp {
+
+constexpr int kCnThreads = 1024;
+
+struct CnParams {
+  const float* pred;
+  int B, H, W, nc, K;
+  unsigned long long* tau;  // [B] running upper bound of the K-th best key
+  uint64_t* list;           // [B][list_cap]
+  int32_t* list_count;      // [B]
+  int list_cap;             // H * K
+  int key_cap;              // shared key buffer (power of two >= W * nc)
+  // pass B
+  float conf;
+  int use_nms;
+  float nms_thr;
+  const float* letterbox;  // [B][5]: in_w, in_h, left, top, scale  (or NULL)
+  float4* det_box;
+  float* det_score;
+  int32_t* det_cls;
+  int32_t* det_pixel;
+  int32_t* det_count;
+  uint64_t* ws_sort;  // [B][sort_cap] for lists too large for shared memory
+  int sort_cap;
+};
+
+__device__ __forceinline__ uint64_t cn_key(float score, uint32_t flat) {
+  return ((uint64_t)(0x7fffffffu - (__float_as_uint(score) & 0x7fffffffu)) << 32) | (uint64_t)flat;
+}
+
+// ---------------------------------------------------------------------------------------------
+// pass A
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kCnThreads, 1) centernet_peaks_kernel(const __grid_constant__ CnParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int W = p.W, nc = p.nc, Cf = p.nc + 4;
+  const int row_floats = W * Cf;
+  const uint32_t row_bytes = (uint32_t)row_floats * 4u;
+  float* ring = reinterpret_cast<float*>(smem_raw);                                 // [2][row_floats]
+  uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw + (((size_t)2 * row_bytes + 127) & ~(size_t)127));
+  uint64_t* bar = keys + p.key_cap;                                                 // [2]
+  __shared__ int sh_cnt;
+  __shared__ int sh_base;
+
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int rows_total = p.B * p.H;
+  const int n_my = ((int)blockIdx.x < rows_total) ? (rows_total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+
+  if (tid == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  auto issue = [&](int i) {  // thread 0 only; rows are handed out image-fastest so that concurrently
+    const int r = blockIdx.x + i * gridDim.x;  // running CTAs work on different images
+    const int b = r % p.B, y = r / p.B;
+    mbar_arrive_expect_tx(&bar[i & 1], row_bytes);
+    bulk_g2s(ring + (size_t)(i & 1) * row_floats, p.pred + ((size_t)b * p.H + y) * row_floats, row_bytes, &bar[i & 1]);
+  };
+  if (tid == 0) {
+    if (n_my > 0) issue(0);
+    if (n_my > 1) issue(1);
+  }
+
+  for (int i = 0; i < n_my; ++i) {
+    const int r = blockIdx.x + i * gridDim.x;
+    const int b = r % p.B, y = r / p.B;
+    const float* row = ring + (size_t)(i & 1) * row_floats;
+    if (tid == 0) sh_cnt = 0;
+    const unsigned long long tau = *reinterpret_cast<volatile unsigned long long*>(p.tau + b);
+    mbar_wait(&bar[i & 1], (uint32_t)(i >> 1) & 1u);
+    __syncthreads();
+
+    const int cells = W * nc;
+    for (int e0 = 0; e0 < cells; e0 += kCnThreads) {
+      const int e = e0 + tid;
+      bool take = false;
+      uint64_t key = 0;
+      if (e < cells) {
+        const int x = e / nc, c = e - x * nc;
+        const float* q = row + x * Cf + c;
+        const float v = q[0];
+        float nmax = -INFINITY;
+        const bool xl = x > 0, xr = x + 1 < W, cl = c > 0, cr = c + 1 < nc;
+        if (cl) nmax = fmaxf(nmax, q[-1]);
+        if (cr) nmax = fmaxf(nmax, q[1]);
+        if (xl) {
+          nmax = fmaxf(nmax, q[-Cf]);
+          if (cl) nmax = fmaxf(nmax, q[-Cf - 1]);
+          if (cr) nmax = fmaxf(nmax, q[-Cf + 1]);
+        }
+        if (xr) {
+          nmax = fmaxf(nmax, q[Cf]);
+          if (cl) nmax = fmaxf(nmax, q[Cf - 1]);
+          if (cr) nmax = fmaxf(nmax, q[Cf + 1]);
+        }
+        // heatmap == maxpool(heatmap) on the rounded sigmoid values.  v >= nmax implies it; below a
+        // neighbour the rounded sigmoids can still coincide (nearly equal logits, or saturation).
+        bool peak = v >= nmax;
+        float sc = 0.f;
+        if (peak) {
+          sc = sigmoid_precise(v);
+        } else if (nmax - v < 1e-3f || v > 8.0f) {
+          sc = sigmoid_precise(v);
+          peak = sc == sigmoid_precise(nmax);
+        }
+        if (peak) {
+          key = cn_key(sc, (uint32_t)((y * W + x) * nc + c));
+          take = key <= tau;
+        }
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, take);
+      if (m) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&sh_cnt, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (take) keys[base + __popc(m & ((1u << lane) - 1u))] = key;
+      }
+    }
+    __syncthreads();  // the row has been consumed: refill this stage, and sh_cnt is final
+    if (tid == 0 && i + 2 < n_my) issue(i + 2);
+    const int n_r = sh_cnt;
+    int n_emit = n_r;
+    if (n_r > p.K) {
+      const int P = pow2_ceil(n_r < 32 ? 32 : n_r);
+      for (int t = n_r + tid; t < P; t += kCnThreads) keys[t] = ~0ull;
+      __syncthreads();
+      block_sort_smem(keys, P);
+      n_emit = p.K;
+      if (tid == 0) atomicMin(p.tau + b, (unsigned long long)keys[p.K - 1]);
+    }
+    if (tid == 0) sh_base = atomicAdd(p.list_count + b, n_emit);
+    __syncthreads();
+    const int base = sh_base;
+    uint64_t* dst = p.list + (size_t)b * p.list_cap;
+    for (int t = tid; t < n_emit; t += kCnThreads)
+      if (base + t < p.list_cap) dst[base + t] = keys[t];
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// box_diou (iou.py:41-64) of two xyxy boxes, one fp32 rounding per reference op
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float diou_exact(const float4& a, const float4& b) {
+  const float eps = 1e-6f;
+  const float area1 = fmul(fsub(a.z, a.x), fsub(a.w, a.y));
+  const float area2 = fmul(fsub(b.z, b.x), fsub(b.w, b.y));
+  const float iw = fmaxf(fsub(fminf(a.z, b.z), fmaxf(a.x, b.x)), 0.0f);
+  const float ih = fmaxf(fsub(fminf(a.w, b.w), fmaxf(a.y, b.y)), 0.0f);
+  const float inter = fmul(iw, ih);
+  const float uni = fsub(fadd(area1, area2), inter);
+  const float iou = fdiv(inter, fmaxf(uni, eps));
+  const float c1x = fmul(fadd(a.x, a.z), 0.5f), c1y = fmul(fadd(a.y, a.w), 0.5f);
+  const float c2x = fmul(fadd(b.x, b.z), 0.5f), c2y = fmul(fadd(b.y, b.w), 0.5f);
+  const float ew = fmaxf(fsub(fmaxf(a.z, b.z), fminf(a.x, b.x)), 0.0f);
+  const float eh = fmaxf(fsub(fmaxf(a.w, b.w), fminf(a.y, b.y)), 0.0f);
+  const float c_sq = fadd(fmul(ew, ew), fmul(eh, eh));
+  const float dx = fsub(c1x, c2x), dy = fsub(c1y, c2y);
+  const float d_sq = fadd(fmul(dx, dx), fmul(dy, dy));
+  return fsub(iou, fdiv(d_sq, fmaxf(c_sq, eps)));
+}
+
+// greedy DIoU-NMS over n (<= blockDim.x) score-ordered boxes in shared memory; alive[] in/out
+__device__ __forceinline__ void diou_greedy_block(const float4* box, int n, float thr, unsigned char* alive) {
+  const int j = threadIdx.x;
+  float4 mine = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (j < n) mine = box[j];
+  for (int i = 0; i < n; ++i) {
+    __syncthreads();
+    if (alive[i] && j > i && j < n && alive[j]) {
+      if (!(diou_exact(box[i], mine) <= thr)) alive[j] = 0;
+    }
+  }
+  __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------
+// pass B
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kCnThreads, 1) centernet_finalize_kernel(const __grid_constant__ CnParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);  // [key_cap]
+  __shared__ float4 sbox[kCnThreads];
+  __shared__ float sscore[kCnThreads];
+  __shared__ int scls[kCnThreads];
+  __shared__ int spix[kCnThreads];
+  __shared__ unsigned char alive[kCnThreads];
+  __shared__ int sh_cnt;
+  __shared__ int sh_warp[kCnThreads / 32];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.x;
+  const int W = p.W, H = p.H, nc = p.nc, Cf = p.nc + 4;
+  int m = p.list_count[b];
+  if (m > p.list_cap) m = p.list_cap;
+  const unsigned long long tau = p.tau[b];
+  const uint64_t* src = p.list + (size_t)b * p.list_cap;
+
+  // keep the keys that can still be among the K best, compacted into the sort buffer
+  uint64_t* buf = (p.sort_cap <= p.key_cap) ? keys : p.ws_sort + (size_t)b * p.sort_cap;
+  if (tid == 0) sh_cnt = 0;
+  __syncthreads();
+  for (int t0 = 0; t0 < m; t0 += kCnThreads) {
+    const int t = t0 + tid;
+    uint64_t k = 0;
+    bool take = false;
+    if (t < m) {
+      k = src[t];
+      take = k <= tau;
+    }
+    const unsigned mk = __ballot_sync(0xffffffffu, take);
+    if (mk) {
+      int base = 0;
+      if (lane == 0) base = atomicAdd(&sh_cnt, __popc(mk));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (take) buf[base + __popc(mk & ((1u << lane) - 1u))] = k;
+    }
+  }
+  __syncthreads();
+  const int m2 = sh_cnt;
+  const int P = pow2_ceil(m2 < 32 ? 32 : m2);
+  for (int t = m2 + tid; t < P; t += kCnThreads) buf[t] = ~0ull;
+  __syncthreads();
+  if (buf == keys)
+    block_sort_smem(buf, P);
+  else
+    bitonic_sort_u64_generic(buf, P);
+
+  // top K: decode, gather reg / wh, assemble (centernet.py:282-304)
+  const int n_top = m2 < p.K ? m2 : p.K;
+  bool pass = false;
+  if (tid < n_top) {
+    const uint64_t k = buf[tid];
+    const uint32_t flat = (uint32_t)k;
+    const float score = __uint_as_float(0x7fffffffu - (uint32_t)(k >> 32));
+    const int c = (int)(flat % (uint32_t)nc);
+    const int pixel = (int)(flat / (uint32_t)nc);
+    const int y = pixel / W, x = pixel - y * W;
+    const float* pp = p.pred + ((size_t)b * H * W + pixel) * Cf;
+    float cx = fadd((float)x, pp[nc]), cy = fadd((float)y, pp[nc + 1]);
+    float w = pp[Cf - 2], h = pp[Cf - 1];
+    cx = fdiv(cx, (float)W);
+    w = fdiv(w, (float)W);
+    cy = fdiv(cy, (float)H);
+    h = fdiv(h, (float)H);
+    cx = fminf(fmaxf(cx, 0.0f), 1.0f);
+    cy = fminf(fmaxf(cy, 0.0f), 1.0f);
+    w = fminf(fmaxf(w, 0.0f), 1.0f);
+    h = fminf(fmaxf(h, 0.0f), 1.0f);
+    const float hw = fmul(w, 0.5f), hh = fmul(h, 0.5f);
+    sbox[tid] = make_float4(fsub(cx, hw), fsub(cy, hh), fadd(cx, hw), fadd(cy, hh));
+    sscore[tid] = score;
+    scls[tid] = c;
+    spix[tid] = pixel;
+    pass = score >= p.conf;  // scores are descending: the survivors are a prefix
+  }
+  const unsigned pm = __ballot_sync(0xffffffffu, pass);
+  if (lane == 0) sh_warp[warp] = __popc(pm);
+  __syncthreads();
+  int n_conf = 0;
+  for (int q = 0; q < kCnThreads / 32; ++q) n_conf += sh_warp[q];
+  alive[tid] = tid < n_conf ? 1 : 0;
+  __syncthreads();
+  if (p.use_nms && n_conf > 1) diou_greedy_block(sbox, n_conf, p.nms_thr, alive);
+
+  // ordered compaction + letterbox inverse (xywh=False branch, image_process.py:112-129)
+  const bool keep = tid < n_conf && alive[tid];
+  const unsigned km = __ballot_sync(0xffffffffu, keep);
+  __syncthreads();
+  if (lane == 0) sh_warp[warp] = __popc(km);
+  __syncthreads();
+  int off = 0, total = 0;
+  for (int q = 0; q < kCnThreads / 32; ++q) {
+    if (q < warp) off += sh_warp[q];
+    total += sh_warp[q];
+  }
+  if (keep) {
+    const int o = off + __popc(km & ((1u << lane) - 1u));
+    float4 bx = sbox[tid];
+    if (p.letterbox) {
+      const float* L = p.letterbox + 5 * b;
+      bx.x = fmul(fsub(fmul(bx.x, L[0]), L[2]), L[4]);
+      bx.z = fmul(fsub(fmul(bx.z, L[0]), L[2]), L[4]);
+      bx.y = fmul(fsub(fmul(bx.y, L[1]), L[3]), L[4]);
+      bx.w = fmul(fsub(fmul(bx.w, L[1]), L[3]), L[4]);
+    }
+    const size_t at = (size_t)b * p.K + o;
+    p.det_box[at] = bx;
+    p.det_score[at] = sscore[tid];
+    p.det_cls[at] = scls[tid];
+    p.det_pixel[at] = spix[tid];
+  }
+  if (tid == 0) p.det_count[b] = total;
+}
+
+// ---------------------------------------------------------------------------------------------
+// standalone diou_nms(boxes, scores, thr) (core/utils/nms.py:9-31), one CTA
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kCnThreads, 1)
+diou_nms_kernel(const float4* __restrict__ boxes, const float* __restrict__ scores, int n, float thr,
+                long long* __restrict__ keep, int32_t* __restrict__ keep_count, int P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);                     // [P]
+  unsigned char* alive = reinterpret_cast<unsigned char*>(keys + P);          // [P]
+  __shared__ int sh_warp[kCnThreads / 32];
+  __shared__ int sh_running;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int t = tid; t < P; t += kCnThreads) {
+    keys[t] = t < n ? cn_key(scores[t], (uint32_t)t) : ~0ull;
+    alive[t] = t < n ? 1 : 0;
+  }
+  __syncthreads();
+  block_sort_smem(keys, P);
+  // greedy in sorted order; alive[] is indexed by sorted position
+  for (int i = 0; i < n; ++i) {
+    __syncthreads();
+    if (!alive[i]) continue;
+    const float4 bi = boxes[(uint32_t)keys[i]];
+    for (int j = i + 1 + tid; j < n; j += kCnThreads)
+      if (alive[j] && !(diou_exact(bi, boxes[(uint32_t)keys[j]]) <= thr)) alive[j] = 0;
+  }
+  __syncthreads();
+  if (tid == 0) sh_running = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += kCnThreads) {
+    const int t = base + tid;
+    const bool k = t < n && alive[t];
+    const unsigned km = __ballot_sync(0xffffffffu, k);
+    if (lane == 0) sh_warp[warp] = __popc(km);
+    __syncthreads();
+    int off = 0, total = 0;
+    for (int q = 0; q < kCnThreads / 32; ++q) {
+      if (q < warp) off += sh_warp[q];
+      total += sh_warp[q];
+    }
+    if (k) keep[sh_running + off + __popc(km & ((1u << lane) - 1u))] = (long long)(uint32_t)keys[t];
+    __syncthreads();
+    if (tid == 0) sh_running += total;
+    __syncthreads();
+  }
+  if (tid == 0) *keep_count = sh_running;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host
+// ---------------------------------------------------------------------------------------------
+static int cn_sort_cap(int H, int K) {
+  int P = 32;
+  while (P < H * K) P <<= 1;
+  return P;
+}
+
+size_t centernet_workspace_bytes(int B, int H, int W, int nc, int K) {
+  (void)W;
+  (void)nc;
+  size_t s = 256;
+  s += ((size_t)B * 8 + 255) & ~(size_t)255;                          // tau
+  s += ((size_t)B * 4 + 255) & ~(size_t)255;                          // list_count
+  s += ((size_t)B * (size_t)H * K * 8 + 255) & ~(size_t)255;          // list
+  s += ((size_t)B * (size_t)cn_sort_cap(H, K) * 8 + 255) & ~(size_t)255;  // sort scratch
+  return s;
+}
+
+int centernet_launch(const float* pred, int B, int H, int W, int nc, int K, float conf, int pool_mode, int use_nms,
+                     float nms_thr, const float* letterbox, float* det_box, float* det_score, int32_t* det_cls,
+                     int32_t* det_pixel, int32_t* det_count, void* workspace, size_t workspace_bytes,
+                     cudaStream_t stream) {
+  if (!pred || !det_box || !det_score || !det_cls || !det_pixel || !det_count) {
+    set_error("centernet: NULL pointer argument");
+    return CVPP_ERR_INVALID_ARG;
+  }
+  if (B < 0 || H < 1 || W < 1 || nc < 1 || K < 1 || (int64_t)H * W * nc >= (1ll << 32)) {
+    set_error("centernet: bad sizes (B=%d H=%d W=%d nc=%d K=%d)", B, H, W, nc, K);
+    return CVPP_ERR_INVALID_ARG;
+  }
+  if (pool_mode != 0) {
+    set_error("centernet: pool_mode %d is not compiled in (0 = the reference's (x, class) window)", pool_mode);
+    return CVPP_ERR_UNSUPPORTED;
+  }
+  if (K > kCnThreads) {
+    set_error("centernet: K=%d exceeds %d", K, kCnThreads);
+    return CVPP_ERR_UNSUPPORTED;
+  }
+  const size_t row_bytes = (size_t)W * (nc + 4) * 4;
+  if ((reinterpret_cast<uintptr_t>(pred) & 15u) || (row_bytes & 15u) || (reinterpret_cast<uintptr_t>(det_box) & 15u)) {
+    set_error("centernet: pred rows and det_box must be 16-byte aligned (W*(nc+4) %% 4 == 0)");
+    return CVPP_ERR_ALIGNMENT;
+  }
+  if (B == 0) return CVPP_OK;
+  if (!workspace || workspace_bytes < centernet_workspace_bytes(B, H, W, nc, K)) {
+    set_error("centernet: workspace of %zu bytes needed, got %zu", centernet_workspace_bytes(B, H, W, nc, K),
+              workspace_bytes);
+    return CVPP_ERR_WORKSPACE;
+  }
+  DeviceInfo di;
+  int rc = device_info(&di);
+  if (rc != CVPP_OK) return rc;
+
+  CnParams p{};
+  p.pred = pred;
+  p.B = B;
+  p.H = H;
+  p.W = W;
+  p.nc = nc;
+  p.K = K;
+  p.conf = conf;
+  p.use_nms = use_nms;
+  p.nms_thr = nms_thr;
+  p.letterbox = letterbox;
+  p.det_box = reinterpret_cast<float4*>(det_box);
+  p.det_score = det_score;
+  p.det_cls = det_cls;
+  p.det_pixel = det_pixel;
+  p.det_count = det_count;
+  p.list_cap = H * K;
+  p.sort_cap = cn_sort_cap(H, K);
+  uintptr_t w = (reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255;
+  p.tau = reinterpret_cast<unsigned long long*>(w);
+  w += ((size_t)B * 8 + 255) & ~(size_t)255;
+  p.list_count = reinterpret_cast<int32_t*>(w);
+  w += ((size_t)B * 4 + 255) & ~(size_t)255;
+  p.list = reinterpret_cast<uint64_t*>(w);
+  w += ((size_t)B * (size_t)H * K * 8 + 255) & ~(size_t)255;
+  p.ws_sort = reinterpret_cast<uint64_t*>(w);
+
+  CVPP_CUDA_TRY(cudaMemsetAsync(p.tau, 0xff, sizeof(unsigned long long) * (size_t)B, stream));
+  CVPP_CUDA_TRY(cudaMemsetAsync(p.list_count, 0, sizeof(int32_t) * (size_t)B, stream));
+
+  // pass A shared memory: 2 row stages + key buffer (power of two >= W*nc) + 2 barriers
+  int key_cap = 32;
+  while (key_cap < W * nc) key_cap <<= 1;
+  const size_t smem_a = ((2 * row_bytes + 127) & ~(size_t)127) + (size_t)key_cap * 8 + 16;
+  if (smem_a > (size_t)di.max_smem || key_cap > 16384) {
+    set_error("centernet: a row of %d x %d cells does not fit the shared-memory pipeline", W, nc + 4);
+    return CVPP_ERR_UNSUPPORTED;
+  }
+  p.key_cap = key_cap;
+  static unsigned long long done_a = 0;
+  static int bytes_a = 0;
+  if ((int)smem_a > bytes_a) {
+    done_a = 0;
+    bytes_a = (int)smem_a;
+  }
+  rc = ensure_smem_attr(reinterpret_cast<const void*>(centernet_peaks_kernel), bytes_a, di.device, &done_a);
+  if (rc != CVPP_OK) return rc;
+  const int rows = B * H;
+  const int grid_a = rows < di.sms ? rows : di.sms;
+  centernet_peaks_kernel<<<grid_a, kCnThreads, smem_a, stream>>>(p);
+  CVPP_CUDA_TRY(cudaGetLastError());
+
+  // pass B shared memory: sort buffer when it fits (<= 16384 keys), else the global scratch rows
+  CnParams pb = p;
+  pb.key_cap = p.sort_cap <= 16384 ? p.sort_cap : 32;
+  const size_t smem_b = (size_t)pb.key_cap * 8;
+  static unsigned long long done_b = 0;
+  static int bytes_b = 0;
+  if ((int)smem_b > bytes_b) {
+    done_b = 0;
+    bytes_b = (int)smem_b;
+  }
+  rc = ensure_smem_attr(reinterpret_cast<const void*>(centernet_finalize_kernel), bytes_b, di.device, &done_b);
+  if (rc != CVPP_OK) return rc;
+  centernet_finalize_kernel<<<B, kCnThreads, smem_b, stream>>>(pb);
+  CVPP_CUDA_TRY(cudaGetLastError());
+  return CVPP_OK;
+}
+
+int diou_nms_launch(const float* boxes, const float* scores, int n, float thr, long long* keep, int32_t* keep_count,
+                    cudaStream_t stream) {
+  if (!keep_count || n < 0 || (n > 0 && (!boxes || !scores || !keep))) {
+    set_error("diou_nms: NULL pointer or negative n");
+    return CVPP_ERR_INVALID_ARG;
+  }
+  if (n == 0) {
+    CVPP_CUDA_TRY(cudaMemsetAsync(keep_count, 0, sizeof(int32_t), stream));
+    return CVPP_OK;
+  }
+  if (reinterpret_cast<uintptr_t>(boxes) & 15u) {
+    set_error("diou_nms: boxes must be 16-byte aligned");
+    return CVPP_ERR_ALIGNMENT;
+  }
+  int P = 32;
+  while (P < n) P <<= 1;
+  if (P > 16384) {
+    set_error("diou_nms: n=%d exceeds the 16384-box single-CTA limit", n);
+    return CVPP_ERR_UNSUPPORTED;
+  }
+  DeviceInfo di;
+  int rc = device_info(&di);
+  if (rc != CVPP_OK) return rc;
+  const size_t smem = (size_t)P * 9;
+  static unsigned long long done = 0;
+  static int bytes = 0;
+  if ((int)smem > bytes) {
+    done = 0;
+    bytes = (int)smem;
+  }
+  rc = ensure_smem_attr(reinterpret_cast<const void*>(diou_nms_kernel), bytes, di.device, &done);
+  if (rc != CVPP_OK) return rc;
+  diou_nms_kernel<<<1, kCnThreads, smem, stream>>>(reinterpret_cast<const float4*>(boxes), scores, n, thr, keep,
+                                                 keep_count, P);
+  CVPP_CUDA_TRY(cudaGetLastError());
+  return CVPP_OK;
+}
+
+}  // namespace cvpp

@@ -66,6 +66,14 @@ int nms_launch(const uint64_t* sorted_key, const int32_t* cand_count, const floa
                float* det_score, int32_t* det_cls, int32_t* det_anchor, int32_t* det_count, void* workspace,
                size_t workspace_bytes, cudaStream_t stream);
 
+size_t centernet_workspace_bytes(int B, int H, int W, int nc, int K);
+int centernet_launch(const float* pred, int B, int H, int W, int nc, int K, float conf, int pool_mode, int use_nms,
+                     float nms_thr, const float* letterbox, float* det_box, float* det_score, int32_t* det_cls,
+                     int32_t* det_pixel, int32_t* det_count, void* workspace, size_t workspace_bytes,
+                     cudaStream_t stream);
+int diou_nms_launch(const float* boxes, const float* scores, int n, float thr, long long* keep, int32_t* keep_count,
+                    cudaStream_t stream);
+
 static int force_generic() {
   const char* e = getenv("CVPP_FORCE_GENERIC");
   return e && e[0] == '1';
@@ -210,6 +218,24 @@ int cvpp_yolov8_postprocess(const float* const* level_ptr, const int64_t* batch_
     CVPP_CUDA_TRY(cudaMemcpyAsync(cand_count_out, cand_count, sizeof(int32_t) * (size_t)B, cudaMemcpyDeviceToDevice,
                                   (cudaStream_t)stream));
   return CVPP_OK;
+}
+
+size_t cvpp_centernet_workspace_bytes(int B, int H, int W, int nc, int K) {
+  if (B < 0 || H < 1 || W < 1 || nc < 1 || K < 1) return 0;
+  return centernet_workspace_bytes(B, H, W, nc, K);
+}
+
+int cvpp_centernet_decode(const float* pred, int B, int H, int W, int nc, int K, float conf_thres, int pool_mode,
+                          int use_nms, float nms_thres, const float* letterbox, float* det_box, float* det_score,
+                          int32_t* det_cls, int32_t* det_pixel, int32_t* det_count, void* workspace,
+                          size_t workspace_bytes, cvpp_stream_t stream) {
+  return centernet_launch(pred, B, H, W, nc, K, conf_thres, pool_mode, use_nms, nms_thres, letterbox, det_box,
+                          det_score, det_cls, det_pixel, det_count, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int cvpp_diou_nms(const float* boxes, const float* scores, int n, float thr, int64_t* keep, int32_t* keep_count,
+                  cvpp_stream_t stream) {
+  return diou_nms_launch(boxes, scores, n, thr, reinterpret_cast<long long*>(keep), keep_count, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -245,6 +245,71 @@ class GraphedPostprocess:
         return self.post.det
 
 
+def letterbox_params(image_hw: Sequence[Tuple[int, int]], input_hw: Sequence[int], device) -> torch.Tensor:
+    """(B, 5) fp32 rows in_w, in_h, left, top, scale: the scalars of reverse_letter_box
+    (image_process.py:115-121) computed in Python doubles exactly like the reference, then cast."""
+    rows = []
+    for (h, w) in image_hw:
+        scale = max(h / input_hw[0], w / input_hw[1])
+        top = (input_hw[0] - h / scale) // 2
+        left = (input_hw[1] - w / scale) // 2
+        rows.append([float(input_hw[1]), float(input_hw[0]), left, top, scale])
+    return torch.tensor(rows, dtype=torch.float64).to(torch.float32).to(device)
+
+
+@dataclass
+class CenterDetections:
+    box: torch.Tensor     # (B, K, 4) xyxy (normalised, or original-image pixels with a letterbox)
+    score: torch.Tensor   # (B, K)
+    cls: torch.Tensor     # (B, K) int32
+    pixel: torch.Tensor   # (B, K) int32  y*W + x of the peak
+    count: torch.Tensor   # (B,) int32
+
+
+def centernet_decode(pred: torch.Tensor, K: int, conf_thres: float, use_nms: bool = False, nms_thres: float = 0.5,
+                     letterbox: Optional[torch.Tensor] = None, pool_mode: int = 0) -> CenterDetections:
+    """pred (B, H, W, nc+4) NHWC -> per-image top-K peaks as boxes (cvpp_centernet_decode)."""
+    _require_cuda(pred, "pred")
+    if pred.dim() != 4 or pred.shape[3] < 5:
+        raise ValueError(f"pred must be (B, H, W, nc+4), got {tuple(pred.shape)}")
+    pred = pred.contiguous()
+    B, H, W, Cf = (int(v) for v in pred.shape)
+    nc = Cf - 4
+    dev = pred.device
+    l = _lib.lib()
+    nbytes = int(l.cvpp_centernet_workspace_bytes(B, H, W, nc, K))
+    ws = torch.empty((max(nbytes, 1),), dtype=torch.uint8, device=dev)
+    out = CenterDetections(box=torch.empty((B, K, 4), dtype=torch.float32, device=dev),
+                           score=torch.empty((B, K), dtype=torch.float32, device=dev),
+                           cls=torch.empty((B, K), dtype=torch.int32, device=dev),
+                           pixel=torch.empty((B, K), dtype=torch.int32, device=dev),
+                           count=torch.empty((B,), dtype=torch.int32, device=dev))
+    if letterbox is not None:
+        letterbox = letterbox.to(device=dev, dtype=torch.float32).contiguous()
+        if tuple(letterbox.shape) != (B, 5):
+            raise ValueError("letterbox must be (B, 5)")
+    with torch.cuda.device(dev):
+        check(l.cvpp_centernet_decode(_ptr(pred), B, H, W, nc, int(K), float(conf_thres), int(pool_mode), int(use_nms),
+                                      float(nms_thres), _ptr(letterbox), _ptr(out.box), _ptr(out.score), _ptr(out.cls),
+                                      _ptr(out.pixel), _ptr(out.count), _ptr(ws), nbytes, _stream(dev)))
+    return out
+
+
+def diou_nms(boxes: torch.Tensor, scores: torch.Tensor, thr: float) -> torch.Tensor:
+    """cvpp_diou_nms: int64 kept indices in descending score order."""
+    _require_cuda(boxes, "boxes")
+    _require_cuda(scores, "scores")
+    boxes = boxes.reshape(-1, 4).contiguous()
+    scores = scores.reshape(-1).contiguous()
+    n = int(boxes.shape[0])
+    dev = boxes.device
+    keep = torch.empty((max(n, 1),), dtype=torch.int64, device=dev)
+    cnt = torch.empty((1,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        check(_lib.lib().cvpp_diou_nms(_ptr(boxes), _ptr(scores), n, float(thr), _ptr(keep), _ptr(cnt), _stream(dev)))
+    return keep[: int(cnt.item())]
+
+
 def split_detections(det: Detections) -> List[Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]]:
     """One device->host read of the counts, then per-image views (box, score, cls, anchor)."""
     counts = det.count.tolist()

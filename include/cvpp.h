@@ -162,6 +162,37 @@ CVPP_API int cvpp_yolov8_postprocess(const float* const* level_ptr, const int64_
                             int32_t* det_anchor, int32_t* det_count, int32_t* cand_count_out,
                             void* workspace, size_t workspace_bytes, cvpp_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * CenterNet decode (kernel 4): heatmap peaks + top-K + box assembly + score mask + optional
+ * class-agnostic DIoU-NMS + letterbox inverse, per image.
+ * Replaces: CenterNetA.decode_boxes        core/algorithms/centernet.py:271-314
+ *           _suppress_redundant_centers    core/algorithms/centernet.py:316-326
+ *           _top_k                         core/algorithms/centernet.py:328-338
+ *           RegL1Loss.gather_feat          core/loss/centernet_loss.py:37-43
+ *           xywh_to_xyxy_torch             core/utils/bboxes.py:29-49
+ *           diou_nms / box_diou / box_iou  core/utils/nms.py:9-31, core/utils/iou.py:8-64
+ *           reverse_letter_box             core/utils/image_process.py:100-129
+ * pred: (B, H, W, nc + 4) NHWC = heat logits | reg (2) | wh (2).  pool_mode 0 reproduces the
+ * reference, whose MaxPool2d runs on the NHWC tensor and therefore pools over (x, class).
+ * Equal scores are ordered by the lower flat index (y*W + x)*nc + c.  Suppressed cells are never
+ * emitted, so with conf_thres <= 0 and fewer than K peaks the reference's zero-score filler rows are
+ * absent.  letterbox: NULL or (B, 5) fp32 rows in_w, in_h, left, top, scale (host-computed in double
+ * like the reference, then cast).  Outputs: capacity K rows per image, det_count[b] valid.
+ * det_box is normalised xyxy in [0,1] when letterbox is NULL.
+ * ------------------------------------------------------------------------------------------- */
+CVPP_API size_t cvpp_centernet_workspace_bytes(int B, int H, int W, int nc, int K);
+CVPP_API int cvpp_centernet_decode(const float* pred, int B, int H, int W, int nc, int K, float conf_thres,
+                                   int pool_mode, int use_nms, float nms_thres, const float* letterbox,
+                                   float* det_box, float* det_score, int32_t* det_cls, int32_t* det_pixel,
+                                   int32_t* det_count, void* workspace, size_t workspace_bytes,
+                                   cvpp_stream_t stream);
+
+/* diou_nms(boxes, scores, iou_threshold) (core/utils/nms.py:9-31): greedy, class-agnostic, a later box
+ * survives a kept one iff DIoU <= thr (fp32).  keep receives int64 indices in descending score order
+ * (ties: lower index first); n <= 16384. */
+CVPP_API int cvpp_diou_nms(const float* boxes, const float* scores, int n, float thr, int64_t* keep,
+                           int32_t* keep_count, cvpp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -164,3 +164,51 @@ def yolov8_candidates(pred: np.ndarray, conf_thres: float, nc: int = 0):
                                 _ptr(cls, _i32p), _ptr(anc, _i32p), _ptr(cnt, _i32p))
     return [(box[b, :cnt[b]].copy(), score[b, :cnt[b]].copy(), cls[b, :cnt[b]].copy(), anc[b, :cnt[b]].copy())
             for b in range(B)]
+
+
+# --------------------------------------------------------------------------
+# CenterNet
+# --------------------------------------------------------------------------
+def letterbox_params(image_hw, input_hw) -> np.ndarray:
+    """(in_w, in_h, left, top, scale) as float32, computed in Python doubles like
+    reverse_letter_box (image_process.py:115-121)."""
+    out = []
+    for (h, w) in image_hw:
+        scale = max(h / input_hw[0], w / input_hw[1])
+        top = (input_hw[0] - h / scale) // 2
+        left = (input_hw[1] - w / scale) // 2
+        out.append([input_hw[1], input_hw[0], left, top, scale])
+    return np.asarray(out, dtype=np.float32)
+
+
+def diou_nms(boxes, scores, thr: float) -> np.ndarray:
+    """core/utils/nms.py:9-31 restated; kept indices in descending score order."""
+    boxes = _f32(boxes).reshape(-1, 4)
+    scores = _f32(scores).reshape(-1)
+    n = boxes.shape[0]
+    keep = np.empty(max(n, 1), dtype=np.int64)
+    lib().orc_diou_nms.restype = ctypes.c_int64
+    k = lib().orc_diou_nms(_ptr(boxes, _f32p), _ptr(scores, _f32p), ctypes.c_int64(n), ctypes.c_float(thr),
+                           _ptr(keep, _i64p))
+    return keep[:k].copy()
+
+
+def centernet_decode(pred, K: int, conf: float, pool_mode: int = 0, use_nms: bool = False, nms_thr: float = 0.5,
+                     letterbox=None):
+    """CenterNetA.decode_boxes (centernet.py:271-314) per image. pred (B,H,W,nc+4) NHWC.
+    Returns per image (boxes (n,4), scores (n,), classes (n,) int32, pixel (n,) int32)."""
+    pred = _f32(pred)
+    B, H, W, Cf = pred.shape
+    nc = Cf - 4
+    box = np.zeros((B, K, 4), np.float32)
+    score = np.zeros((B, K), np.float32)
+    cls = np.zeros((B, K), np.int32)
+    pix = np.zeros((B, K), np.int32)
+    cnt = np.zeros((B,), np.int32)
+    lb = None if letterbox is None else _f32(letterbox)
+    lib().orc_centernet_decode(_ptr(pred, _f32p), ctypes.c_int(B), ctypes.c_int(H), ctypes.c_int(W), ctypes.c_int(nc),
+                               ctypes.c_int(K), ctypes.c_float(conf), ctypes.c_int(pool_mode), ctypes.c_int(int(use_nms)),
+                               ctypes.c_float(nms_thr), None if lb is None else _ptr(lb, _f32p), _ptr(box, _f32p),
+                               _ptr(score, _f32p), _ptr(cls, _i32p), _ptr(pix, _i32p), _ptr(cnt, _i32p))
+    return [(box[b, :cnt[b]].copy(), score[b, :cnt[b]].copy(), cls[b, :cnt[b]].copy(), pix[b, :cnt[b]].copy())
+            for b in range(B)]

@@ -496,3 +496,208 @@ ORC_API int64_t orc_nms_per_class(const float* boxes, const float* scores, const
   free(ck);
   return total;
 }
+
+/* ========================================================================= */
+/* CenterNet — core/algorithms/centernet.py:271-338, core/utils/nms.py:9-31, */
+/* core/utils/iou.py:8-64, core/loss/centernet_loss.py:37-43,                */
+/* core/utils/image_process.py:100-129                                       */
+/* ========================================================================= */
+
+/* box_diou(boxes1, boxes2) (iou.py:41-64) on two xyxy boxes, op for op in fp32 */
+static float diou_ref(const float* a, const float* b) {
+  const float eps = 1e-6f;
+  float area1 = (a[2] - a[0]) * (a[3] - a[1]);
+  float area2 = (b[2] - b[0]) * (b[3] - b[1]);
+  float iw = fminf(a[2], b[2]) - fmaxf(a[0], b[0]);
+  float ih = fminf(a[3], b[3]) - fmaxf(a[1], b[1]);
+  if (iw < 0.0f) iw = 0.0f; /* clamp(min=0) */
+  if (ih < 0.0f) ih = 0.0f;
+  float inter = iw * ih;
+  float uni = area1 + area2 - inter;
+  float iou = inter / (uni < eps ? eps : uni);
+  float c1x = (a[0] + a[2]) / 2.0f, c1y = (a[1] + a[3]) / 2.0f;
+  float c2x = (b[0] + b[2]) / 2.0f, c2y = (b[1] + b[3]) / 2.0f;
+  float ew = fmaxf(a[2], b[2]) - fminf(a[0], b[0]);
+  float eh = fmaxf(a[3], b[3]) - fminf(a[1], b[1]);
+  if (ew < 0.0f) ew = 0.0f;
+  if (eh < 0.0f) eh = 0.0f;
+  float c_sq = ew * ew + eh * eh;
+  float dx = c1x - c2x, dy = c1y - c2y;
+  float d_sq = dx * dx + dy * dy;
+  return iou - d_sq / (c_sq < eps ? eps : c_sq);
+}
+
+/* diou_nms (nms.py:9-31): greedy in descending score order (ties: lower index first), a later box */
+/* survives a kept one iff diou <= thr (fp32 compare).  Returns the kept indices in that order.   */
+ORC_API int64_t orc_diou_nms(const float* boxes, const float* scores, int64_t n, float thr, int64_t* keep) {
+  if (n <= 0) return 0;
+  int64_t* order = (int64_t*)malloc(sizeof(int64_t) * (size_t)n);
+  uint8_t* dead = (uint8_t*)calloc((size_t)n, 1);
+  argsort_desc_stable(scores, n, order);
+  int64_t k = 0;
+  for (int64_t _i = 0; _i < n; ++_i) {
+    int64_t i = order[_i];
+    if (dead[i]) continue;
+    keep[k++] = i;
+    for (int64_t _j = _i + 1; _j < n; ++_j) {
+      int64_t j = order[_j];
+      if (dead[j]) continue;
+      if (!(diou_ref(boxes + 4 * i, boxes + 4 * j) <= thr)) dead[j] = 1;
+    }
+  }
+  free(order);
+  free(dead);
+  return k;
+}
+
+typedef struct {
+  float score;
+  int64_t idx;
+} orc_peak;
+
+static int cmp_peak(const void* a, const void* b) {
+  const orc_peak* x = (const orc_peak*)a;
+  const orc_peak* y = (const orc_peak*)b;
+  if (x->score > y->score) return -1;
+  if (x->score < y->score) return 1;
+  return (x->idx > y->idx) - (x->idx < y->idx);
+}
+
+/* One image of CenterNetA.decode_boxes up to (and including) the score mask (:274-304).             */
+/* pred: (H, W, nc + 4) NHWC.  pool_mode 0 = the reference's behaviour (MaxPool2d applied to the      */
+/* NHWC tensor, i.e. a 3x3 window over (x, class)), 1 = spatial 3x3 over (y, x).      */
+/* Outputs (capacity K): box xyxy normalised+clamped, score, cls, pixel index y*W+x.  Returns count.  */
+static int centernet_image(const float* pred, int H, int W, int nc, int K, float conf, int pool_mode, float* box,
+                           float* score, int32_t* cls, int32_t* pix) {
+  const int Cf = nc + 4;
+  const int64_t total = (int64_t)H * W * nc;
+  float* s = (float*)malloc(sizeof(float) * (size_t)total);
+  for (int64_t p = 0; p < (int64_t)H * W; ++p)
+    for (int c = 0; c < nc; ++c) s[p * nc + c] = sigmoidf_ref(pred[p * Cf + c]);
+  orc_peak* peaks = (orc_peak*)malloc(sizeof(orc_peak) * (size_t)total);
+  int64_t np_ = 0;
+  for (int y = 0; y < H; ++y)
+    for (int x = 0; x < W; ++x)
+      for (int c = 0; c < nc; ++c) {
+        const int64_t idx = ((int64_t)y * W + x) * nc + c;
+        const float v = s[idx];
+        float m = v;
+        for (int d0 = -1; d0 <= 1; ++d0)
+          for (int d1 = -1; d1 <= 1; ++d1) {
+            int yy = y, xx = x, cc = c;
+            if (pool_mode == 0) {
+              xx = x + d0;
+              cc = c + d1;
+            } else {
+              yy = y + d0;
+              xx = x + d1;
+            }
+            if (yy < 0 || yy >= H || xx < 0 || xx >= W || cc < 0 || cc >= nc) continue; /* -inf padding */
+            float t = s[((int64_t)yy * W + xx) * nc + cc];
+            if (t > m) m = t;
+          }
+        /* heatmap * (heatmap == hmax): non-peaks become 0 and still take part in topk */
+        peaks[np_].score = (v == m) ? v : 0.0f;
+        peaks[np_].idx = idx;
+        ++np_;
+      }
+  /* topk(k, largest, sorted): descending score, ties resolved by lower flat index (our stated rule) */
+  qsort(peaks, (size_t)np_, sizeof(orc_peak), cmp_peak);
+  int n = 0;
+  for (int k = 0; k < K && k < np_; ++k) {
+    const int64_t idx = peaks[k].idx;
+    const int c = (int)(idx % nc);
+    const int64_t pixel = idx / nc;
+    const int y = (int)(pixel / W), x = (int)(pixel % W);
+    const float* pp = pred + pixel * Cf;
+    float cx = (float)x + pp[nc], cy = (float)y + pp[nc + 1]; /* xs + reg[...,0], ys + reg[...,1] */
+    float w = pp[Cf - 2], h = pp[Cf - 1];                     /* wh = pred[..., -2:] */
+    cx = cx / (float)W;
+    w = w / (float)W;
+    cy = cy / (float)H;
+    h = h / (float)H;
+    cx = fminf(fmaxf(cx, 0.0f), 1.0f);
+    cy = fminf(fmaxf(cy, 0.0f), 1.0f);
+    w = fminf(fmaxf(w, 0.0f), 1.0f);
+    h = fminf(fmaxf(h, 0.0f), 1.0f);
+    if (!(peaks[k].score >= conf)) continue; /* score mask (:300) */
+    box[4 * n + 0] = cx - w / 2.0f;
+    box[4 * n + 1] = cy - h / 2.0f;
+    box[4 * n + 2] = cx + w / 2.0f;
+    box[4 * n + 3] = cy + h / 2.0f;
+    score[n] = peaks[k].score;
+    cls[n] = c;
+    pix[n] = (int32_t)pixel;
+    ++n;
+  }
+  free(s);
+  free(peaks);
+  return n;
+}
+
+typedef struct {
+  const float* pred;
+  int H, W, nc, K, pool_mode, use_nms;
+  float conf, nms_thr;
+  const float* letterbox; /* per image: in_w, in_h, left, top, scale (already fp32) or NULL */
+  float* box;
+  float* score;
+  int32_t* cls;
+  int32_t* pix;
+  int32_t* count;
+} orc_cn_ctx;
+
+static void orc_cn_body(int b, void* vctx) {
+  const orc_cn_ctx* c = (const orc_cn_ctx*)vctx;
+  const int K = c->K;
+  float* box = c->box + (int64_t)b * K * 4;
+  float* score = c->score + (int64_t)b * K;
+  int32_t* cls = c->cls + (int64_t)b * K;
+  int32_t* pix = c->pix + (int64_t)b * K;
+  int n = centernet_image(c->pred + (int64_t)b * c->H * c->W * (c->nc + 4), c->H, c->W, c->nc, K, c->conf,
+                          c->pool_mode, box, score, cls, pix);
+  if (c->use_nms && n > 0) {
+    int64_t* keep = (int64_t*)malloc(sizeof(int64_t) * (size_t)n);
+    int64_t k = orc_diou_nms(box, score, n, c->nms_thr, keep);
+    float* tb = (float*)malloc(sizeof(float) * 4 * (size_t)k);
+    float* ts = (float*)malloc(sizeof(float) * (size_t)k);
+    int32_t* tc = (int32_t*)malloc(sizeof(int32_t) * (size_t)k);
+    int32_t* tp = (int32_t*)malloc(sizeof(int32_t) * (size_t)k);
+    for (int64_t t = 0; t < k; ++t) {
+      memcpy(tb + 4 * t, box + 4 * keep[t], sizeof(float) * 4);
+      ts[t] = score[keep[t]];
+      tc[t] = cls[keep[t]];
+      tp[t] = pix[keep[t]];
+    }
+    memcpy(box, tb, sizeof(float) * 4 * (size_t)k);
+    memcpy(score, ts, sizeof(float) * (size_t)k);
+    memcpy(cls, tc, sizeof(int32_t) * (size_t)k);
+    memcpy(pix, tp, sizeof(int32_t) * (size_t)k);
+    free(keep);
+    free(tb);
+    free(ts);
+    free(tc);
+    free(tp);
+    n = (int)k;
+  }
+  if (c->letterbox) { /* reverse_letter_box(xywh=False) (image_process.py:112-129) */
+    const float* L = c->letterbox + 5 * b;
+    for (int i = 0; i < n; ++i) {
+      float* q = box + 4 * i;
+      q[0] = (q[0] * L[0] - L[2]) * L[4];
+      q[2] = (q[2] * L[0] - L[2]) * L[4];
+      q[1] = (q[1] * L[1] - L[3]) * L[4];
+      q[3] = (q[3] * L[1] - L[3]) * L[4];
+    }
+  }
+  c->count[b] = n;
+}
+
+/* Per-image CenterNet decode (the reference merges the images of a batch before its NMS; callers     */
+/* that need that behaviour run B = 1 or merge themselves).                                           */
+ORC_API void orc_centernet_decode(const float* pred, int B, int H, int W, int nc, int K, float conf, int pool_mode,
+                                  int use_nms, float nms_thr, const float* letterbox, float* box, float* score,
+                                  int32_t* cls, int32_t* pix, int32_t* count) {
+  orc_cn_ctx c = {pred, H, W, nc, K, pool_mode, use_nms, conf, nms_thr, letterbox, box, score, cls, pix, count};
+  orc_parallel_for(B, orc_cn_body, &c);
+}

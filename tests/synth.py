@@ -196,3 +196,55 @@ def yolov8_pred(seed: int, B: int, A: int, nc: int = 80, n_clusters: int = 40, p
         if nm:
             pred[b, 4 + nc:] = rng.standard_normal((nm, A), dtype=np.float32)
     return pred
+
+
+# ------------------------------------------------------------------------------------------------
+# CenterNet (C3): pred (B, H, W, nc + 4) NHWC = heatmap logits | reg (2) | wh (2)
+# ------------------------------------------------------------------------------------------------
+def _centernet_peaks64(logits: np.ndarray):
+    """Reference-quirk peaks of one image in float64: 3x3 max over (x, class) of the (H, W, nc) logits."""
+    pad = np.full((logits.shape[0], logits.shape[1] + 2, logits.shape[2] + 2), -np.inf)
+    pad[:, 1:-1, 1:-1] = logits
+    m = np.full(logits.shape, -np.inf)
+    for dx in range(3):
+        for dc in range(3):
+            if dx == 1 and dc == 1:
+                continue
+            m = np.maximum(m, pad[:, dx:dx + logits.shape[1], dc:dc + logits.shape[2]])
+    return m  # max over the 8 neighbours
+
+
+def centernet_pred(seed: int, B: int, H: int = 128, W: int = 128, nc: int = 80, K: int = 100,
+                   hm_mu: float = -5.0, hm_sigma: float = 1.5, conf_list: Sequence[float] = (0.001, 0.1)) -> np.ndarray:
+    """Heatmap logits N(hm_mu, hm_sigma^2), reg U(0,1), wh U(0,20).  The K+40 best peaks of
+    every image get pairwise-separated scores and a clear margin over their neighbourhood."""
+    rng = rng_for(seed)
+    pred = np.empty((B, H, W, nc + 4), dtype=np.float32)
+    pred[..., :nc] = rng.standard_normal((B, H, W, nc), dtype=np.float32) * np.float32(hm_sigma) + np.float32(hm_mu)
+    pred[..., nc:nc + 2] = rng.random((B, H, W, 2), dtype=np.float32)
+    pred[..., nc + 2:] = rng.random((B, H, W, 2), dtype=np.float32) * np.float32(20.0)
+    top = K + 40
+    for b in range(B):
+        for _ in range(60):
+            lg = pred[b, ..., :nc].astype(np.float64)
+            nmax = _centernet_peaks64(lg)
+            peak = lg >= nmax
+            flat = np.where(peak.reshape(-1), lg.reshape(-1), -np.inf)
+            idx = np.argpartition(-flat, top)[:top]
+            idx = idx[np.argsort(-flat[idx], kind="stable")]
+            s = _sigmoid64(flat[idx])
+            s2 = separate_scores(s, conf_list, 0.0)
+            margin = flat[idx] - nmax.reshape(-1)[idx]
+            changed = False
+            hm = pred[b, ..., :nc]
+            for j in np.nonzero(s2 != s)[0]:
+                hm[np.unravel_index(idx[j], hm.shape)] = np.float32(_logit64(s2[j]))
+                changed = True
+            for j in np.nonzero(margin < 1e-3)[0]:            # lift a peak clearly above its neighbourhood
+                hm[np.unravel_index(idx[j], hm.shape)] += np.float32(0.01)
+                changed = True
+            if not changed:
+                break
+        else:
+            raise RuntimeError("centernet_pred: separation did not converge; change the seed")
+    return pred

@@ -108,3 +108,25 @@ def test_yolov8_pred_stage_b(golden_dir):
             assert np.array_equal(a, ra)
             assert np.array_equal(r, rr[:, :6])
             assert len(a) < c                      # something was suppressed or capped
+
+
+def test_centernet_decode_and_diou_nms(golden_dir):
+    g = load(golden_dir, "centernet")
+    for i in range(int(g["diou_cases"])):
+        keep = oracle.diou_nms(g[f"diou_boxes{i}"], g[f"diou_scores{i}"], 0.5)
+        assert np.array_equal(keep, g[f"diou_keep{i}"])
+    assert len(g["diou_keep4"]) < 300
+    for tag in g["cases"]:
+        seed, B, H, W, nc, in_h, in_w = [int(v) for v in g[f"{tag}_cfg"]]
+        pred = synth.centernet_pred(seed, B, H, W, nc)
+        assert synth.checksum([pred]) == int(g[f"{tag}_crc"])
+        lb = oracle.letterbox_params([(480, 640)] * B, (in_h, in_w))
+        for ntag, use_nms in (("nms", True), ("raw", False)):
+            for ctag, conf in (("lo", 0.001), ("hi", 0.1)):
+                out = oracle.centernet_decode(pred, 100, conf, 0, use_nms, 0.5, lb)
+                for b, (box, score, cls, pix) in enumerate(out):
+                    k = f"{tag}_{b}_{ntag}_{ctag}"
+                    assert np.array_equal(cls, g[k + "_classes"])
+                    assert np.all(np.abs(score - g[k + "_scores"]) <= SCORE_RTOL * g[k + "_scores"])
+                    assert np.all(np.abs(box - g[k + "_boxes"]) <= BOX_RTOL * np.abs(g[k + "_boxes"]) + BOX_ATOL)
+                    assert len(cls) > 0
