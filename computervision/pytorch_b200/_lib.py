@@ -49,6 +49,8 @@ _PROTOS = {
     "cvpp_centernet_decode": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_f32, c_int, c_int, c_f32, c_vp, c_vp,
                                       c_vp, c_vp, c_vp, c_vp, c_vp, c_size, c_vp]),
     "cvpp_diou_nms": (c_int, [c_vp, c_vp, c_int, c_f32, c_vp, c_vp, c_vp]),
+    "cvpp_ssd_decode_filter": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_f32, c_vp, c_vp, c_vp, c_int, c_vp]),
+    "cvpp_ssd_parse_loc": (c_int, [c_vp, c_vp, c_int, c_int, c_vp, c_vp]),
 }
 
 _lib = None

@@ -74,6 +74,11 @@ int centernet_launch(const float* pred, int B, int H, int W, int nc, int K, floa
 int diou_nms_launch(const float* boxes, const float* scores, int n, float thr, long long* keep, int32_t* keep_count,
                     cudaStream_t stream);
 
+int ssd_decode_filter_launch(const float* loc, const float* conf, const float* priors, int B, int P, int nc,
+                             float conf_thres, uint64_t* cand_key, int32_t* cand_count, float* box_dense, int max_cand,
+                             cudaStream_t stream);
+int ssd_parse_loc_launch(const float* loc, const float* priors, int B, int P, float* out, cudaStream_t stream);
+
 static int force_generic() {
   const char* e = getenv("CVPP_FORCE_GENERIC");
   return e && e[0] == '1';
@@ -236,6 +241,17 @@ int cvpp_centernet_decode(const float* pred, int B, int H, int W, int nc, int K,
 int cvpp_diou_nms(const float* boxes, const float* scores, int n, float thr, int64_t* keep, int32_t* keep_count,
                   cvpp_stream_t stream) {
   return diou_nms_launch(boxes, scores, n, thr, reinterpret_cast<long long*>(keep), keep_count, (cudaStream_t)stream);
+}
+
+int cvpp_ssd_decode_filter(const float* loc, const float* conf, const float* priors, int B, int P, int nc,
+                           float conf_thres, uint64_t* cand_key, int32_t* cand_count, float* box_dense, int max_cand,
+                           cvpp_stream_t stream) {
+  return ssd_decode_filter_launch(loc, conf, priors, B, P, nc, conf_thres, cand_key, cand_count, box_dense, max_cand,
+                                  (cudaStream_t)stream);
+}
+
+int cvpp_ssd_parse_loc(const float* loc, const float* priors, int B, int P, float* out, cvpp_stream_t stream) {
+  return ssd_parse_loc_launch(loc, priors, B, P, out, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -1,0 +1,142 @@
+// ssd_decode.cu — SSD prior decode + softmax + per-(prior, class) confidence filter (sm_100a).
+//
+// Replaces (reference file:line): Ssd.decode_boxes core/algorithms/ssd.py:236-264 (softmax :248,
+// per-class threshold mask :256-264) and Ssd._parse_mbox_loc :290-325.  The per-class NMS that follows
+// (:267) is cvpp_segmented_sort + cvpp_nms with CVPP_NMS_RULE_PER_CLASS / CVPP_ORDER_CLASS_MAJOR.
+//
+// Memory-bound on loc (16 B) + conf (4*(nc+1) B) per prior = 100 B at nc = 20 (873 200 B per 8732-prior
+// image); the priors table (140 KB) stays L2-resident.  A CTA stages the contiguous conf rows of 256
+// priors through shared memory with coalesced loads (a prior's nc+1 logits are contiguous, so a
+// thread-per-prior global read would be strided); thread-per-prior then reads its row conflict-free
+// ((nc+1) odd), runs the softmax, decodes the box once, and emits one key per class above the threshold
+// (one ballot + warp-aggregated atomic per class with any hit).
+#include "cvpp_common.cuh"
+
+namespace cvpp {
+
+constexpr int kSsdThreads = 256;
+
+// Ssd._parse_mbox_loc for one prior: ltrb prior + (dx, dy, dw, dh) -> clamped xyxy (ssd.py:293-324)
+__device__ __forceinline__ float4 ssd_decode_box(const float4& a, const float4& l) {
+  const float v0 = 0.1f, v1 = 0.2f;  // variance[::2]
+  const float aw = fsub(a.z, a.x), ah = fsub(a.w, a.y);
+  const float acx = fmul(0.5f, fadd(a.z, a.x)), acy = fmul(0.5f, fadd(a.w, a.y));
+  const float cx = fadd(fmul(fmul(l.x, aw), v0), acx);
+  const float cy = fadd(fmul(fmul(l.y, ah), v0), acy);
+  const float w = fmul(expf(fmul(l.z, v1)), aw);
+  const float h = fmul(expf(fmul(l.w, v1)), ah);
+  const float hw = fmul(0.5f, w), hh = fmul(0.5f, h);
+  float4 o;
+  o.x = fminf(fmaxf(fsub(cx, hw), 0.0f), 1.0f);
+  o.y = fminf(fmaxf(fsub(cy, hh), 0.0f), 1.0f);
+  o.z = fminf(fmaxf(fadd(cx, hw), 0.0f), 1.0f);
+  o.w = fminf(fmaxf(fadd(cy, hh), 0.0f), 1.0f);
+  return o;
+}
+
+__global__ void __launch_bounds__(kSsdThreads)
+ssd_decode_filter_kernel(const float4* __restrict__ loc, const float* __restrict__ conf,
+                         const float4* __restrict__ priors, int P, int nc, float conf_thres,
+                         uint64_t* __restrict__ cand_key, int32_t* __restrict__ cand_count,
+                         float4* __restrict__ box_dense, int max_cand) {
+  extern __shared__ float sm[];  // [kSsdThreads][nc + 1]
+  const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
+  const int p0 = blockIdx.x * kSsdThreads;
+  const int rows = min(kSsdThreads, P - p0);
+  const int nc1 = nc + 1;
+  const float* src = conf + ((int64_t)b * P + p0) * nc1;
+  for (int i = tid; i < rows * nc1; i += kSsdThreads) sm[i] = __ldg(src + i);
+  __syncthreads();
+
+  const int pr = p0 + tid;
+  const bool valid = tid < rows;
+  const float* x = sm + tid * nc1;
+  float m = -INFINITY, sum = 1.0f;
+  if (valid) {
+    for (int k = 0; k < nc1; ++k) m = fmaxf(m, x[k]);
+    sum = 0.0f;
+    for (int k = 0; k < nc1; ++k) sum = fadd(sum, expf(fsub(x[k], m)));  // torch.softmax: exp(x - max) / sum
+  }
+  bool any = false;
+  for (int c = 1; c <= nc; ++c) {
+    float prob = 0.0f;
+    bool hit = false;
+    if (valid) {
+      prob = fdiv(expf(fsub(x[c], m)), sum);
+      hit = prob > conf_thres;
+    }
+    const unsigned mk = __ballot_sync(0xffffffffu, hit);
+    if (mk == 0) continue;
+    int base = 0;
+    if (lane == 0) base = atomicAdd(cand_count + b, __popc(mk));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (hit) {
+      const int slot = base + __popc(mk & ((1u << lane) - 1u));
+      if (slot < max_cand)
+        cand_key[(int64_t)b * max_cand + slot] = key_pack((uint32_t)(c - 1), __float_as_uint(prob), (uint32_t)pr);
+      any = true;
+    }
+  }
+  if (any) box_dense[(int64_t)b * P + pr] = ssd_decode_box(priors[pr], loc[(int64_t)b * P + pr]);
+}
+
+__global__ void __launch_bounds__(256)
+ssd_parse_loc_kernel(const float4* __restrict__ loc, const float4* __restrict__ priors, int P, int64_t total,
+                     float4* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < total) out[i] = ssd_decode_box(priors[i % P], loc[i]);
+}
+
+int ssd_decode_filter_launch(const float* loc, const float* conf, const float* priors, int B, int P, int nc,
+                             float conf_thres, uint64_t* cand_key, int32_t* cand_count, float* box_dense, int max_cand,
+                             cudaStream_t stream) {
+  if (!loc || !conf || !priors || !cand_key || !cand_count || !box_dense) {
+    set_error("ssd_decode_filter: NULL pointer argument");
+    return CVPP_ERR_INVALID_ARG;
+  }
+  if (B < 0 || P < 1 || P > CVPP_MAX_ANCHORS || nc < 1 || nc > CVPP_MAX_CLASSES || max_cand < 1) {
+    set_error("ssd_decode_filter: bad sizes (B=%d P=%d nc=%d max_cand=%d)", B, P, nc, max_cand);
+    return CVPP_ERR_INVALID_ARG;
+  }
+  if (!(conf_thres >= 0.0f && conf_thres <= 1.0f)) {
+    set_error("ssd_decode_filter: confidence threshold %f outside [0, 1]", conf_thres);
+    return CVPP_ERR_INVALID_ARG;
+  }
+  if ((reinterpret_cast<uintptr_t>(loc) | reinterpret_cast<uintptr_t>(priors) | reinterpret_cast<uintptr_t>(box_dense)) & 15u) {
+    set_error("ssd_decode_filter: loc, priors and box_dense must be 16-byte aligned");
+    return CVPP_ERR_ALIGNMENT;
+  }
+  const size_t smem = (size_t)kSsdThreads * (nc + 1) * sizeof(float);
+  if (smem > 48 * 1024) {
+    set_error("ssd_decode_filter: nc=%d needs more than 48 KB of staging shared memory", nc);
+    return CVPP_ERR_UNSUPPORTED;
+  }
+  CVPP_CUDA_TRY(cudaMemsetAsync(cand_count, 0, sizeof(int32_t) * (size_t)B, stream));
+  if (B == 0) return CVPP_OK;
+  dim3 grid((unsigned)((P + kSsdThreads - 1) / kSsdThreads), (unsigned)B);
+  ssd_decode_filter_kernel<<<grid, kSsdThreads, smem, stream>>>(
+      reinterpret_cast<const float4*>(loc), conf, reinterpret_cast<const float4*>(priors), P, nc, conf_thres, cand_key,
+      cand_count, reinterpret_cast<float4*>(box_dense), max_cand);
+  CVPP_CUDA_TRY(cudaGetLastError());
+  return CVPP_OK;
+}
+
+int ssd_parse_loc_launch(const float* loc, const float* priors, int B, int P, float* out, cudaStream_t stream) {
+  if (!loc || !priors || !out || B < 0 || P < 1) {
+    set_error("ssd_parse_loc: NULL pointer or bad sizes");
+    return CVPP_ERR_INVALID_ARG;
+  }
+  if ((reinterpret_cast<uintptr_t>(loc) | reinterpret_cast<uintptr_t>(priors) | reinterpret_cast<uintptr_t>(out)) & 15u) {
+    set_error("ssd_parse_loc: pointers must be 16-byte aligned");
+    return CVPP_ERR_ALIGNMENT;
+  }
+  const int64_t total = (int64_t)B * P;
+  if (total == 0) return CVPP_OK;
+  ssd_parse_loc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
+      reinterpret_cast<const float4*>(loc), reinterpret_cast<const float4*>(priors), P, total,
+      reinterpret_cast<float4*>(out));
+  CVPP_CUDA_TRY(cudaGetLastError());
+  return CVPP_OK;
+}
+
+}  // namespace cvpp

@@ -310,6 +310,60 @@ def diou_nms(boxes: torch.Tensor, scores: torch.Tensor, thr: float) -> torch.Ten
     return keep[: int(cnt.item())]
 
 
+def ssd_decode_filter(loc: torch.Tensor, conf: torch.Tensor, priors: torch.Tensor, conf_thres: float,
+                      max_cand: Optional[int] = None) -> Candidates:
+    """loc (B,P,4), conf (B,P,nc+1) logits, priors (P,4) -> candidate keys per (prior, class-1)."""
+    for t, name in ((loc, "loc"), (conf, "conf"), (priors, "priors")):
+        _require_cuda(t, name)
+    loc, conf, priors = loc.contiguous(), conf.contiguous(), priors.contiguous()
+    B, P = int(loc.shape[0]), int(loc.shape[1])
+    nc = int(conf.shape[2]) - 1
+    if tuple(conf.shape[:2]) != (B, P) or tuple(priors.shape) != (P, 4) or loc.shape[2] != 4:
+        raise ValueError("expected loc (B,P,4), conf (B,P,nc+1), priors (P,4)")
+    max_cand = int(max_cand or P * nc)
+    dev = loc.device
+    key = torch.empty((B, max_cand), dtype=torch.int64, device=dev)
+    count = torch.empty((B,), dtype=torch.int32, device=dev)
+    box_dense = torch.empty((B, P, 4), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(_lib.lib().cvpp_ssd_decode_filter(_ptr(loc), _ptr(conf), _ptr(priors), B, P, nc, float(conf_thres),
+                                                _ptr(key), _ptr(count), _ptr(box_dense), max_cand, _stream(dev)))
+    return Candidates(key, count, box_dense, max_cand, P, nc)
+
+
+def ssd_parse_loc(loc: torch.Tensor, priors: torch.Tensor) -> torch.Tensor:
+    """Ssd._parse_mbox_loc: loc (..., P, 4) + priors (P, 4) -> decoded, clamped xyxy of the same shape."""
+    _require_cuda(loc, "loc")
+    _require_cuda(priors, "priors")
+    shape = loc.shape
+    loc = loc.reshape(-1, shape[-2], 4).contiguous()
+    priors = priors.contiguous()
+    out = torch.empty_like(loc)
+    with torch.cuda.device(loc.device):
+        check(_lib.lib().cvpp_ssd_parse_loc(_ptr(loc), _ptr(priors), int(loc.shape[0]), int(loc.shape[1]), _ptr(out),
+                                            _stream(loc.device)))
+    return out.reshape(shape)
+
+
+def per_class_nms_rows(c: Candidates, nms_thres: float, initial_out: int = 4096):
+    """sort + per-class NMS (class-major order, no cap) and one device->host transfer.
+    Returns per image (box (n,4), score (n,), cls (n,), anchor (n,)) as torch CPU tensors; retries with a
+    larger output / candidate capacity when the first guess overflows."""
+    B = int(c.key.shape[0])
+    if int(c.count.max().item()) > c.max_cand:
+        raise OverflowError("candidate buffer overflow: re-run the filter with a larger max_cand")
+    segmented_sort(c, RULE_PER_CLASS)
+    max_out = min(c.max_cand, initial_out)
+    while True:
+        det = nms(c, nms_thres, RULE_PER_CLASS, ORDER_CLASS_MAJOR, max_det=0, max_out=max_out)
+        counts = det.count.cpu()
+        if int(counts.max()) <= max_out:
+            break
+        max_out = int(counts.max())
+    box, score, cls, anchor = det.box.cpu(), det.score.cpu(), det.cls.cpu(), det.anchor.cpu()
+    return [(box[b, :n], score[b, :n], cls[b, :n], anchor[b, :n]) for b, n in enumerate(counts.tolist())]
+
+
 def split_detections(det: Detections) -> List[Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]]:
     """One device->host read of the counts, then per-image views (box, score, cls, anchor)."""
     counts = det.count.tolist()

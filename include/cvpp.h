@@ -193,6 +193,24 @@ CVPP_API int cvpp_centernet_decode(const float* pred, int B, int H, int W, int n
 CVPP_API int cvpp_diou_nms(const float* boxes, const float* scores, int n, float thr, int64_t* keep,
                            int32_t* keep_count, cvpp_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * SSD prior decode + softmax + per-(prior, class) confidence filter.
+ * Replaces: Ssd.decode_boxes   core/algorithms/ssd.py:236-264 (softmax :248, class masks :256-264)
+ *           Ssd._parse_mbox_loc core/algorithms/ssd.py:290-325
+ * loc (B, P, 4), conf (B, P, nc + 1) logits with column 0 = background, priors (P, 4) ltrb fp32 (the
+ * table of Ssd._get_ssd_anchors, ssd.py:482-541).  One key per (prior, class >= 1) whose softmax
+ * probability is > conf_thres: class field = class - 1 (the reference's label), anchor field = prior
+ * index; box_dense (B, P, 4) holds the decoded, clamped, normalised xyxy of every prior that has a key.
+ * Follow with cvpp_segmented_sort and cvpp_nms(rule = CVPP_NMS_RULE_PER_CLASS, order =
+ * CVPP_ORDER_CLASS_MAJOR, A = P) for ssd.py:267-278.
+ * cvpp_ssd_parse_loc is _parse_mbox_loc alone: out (B, P, 4).
+ * ------------------------------------------------------------------------------------------- */
+CVPP_API int cvpp_ssd_decode_filter(const float* loc, const float* conf, const float* priors, int B, int P, int nc,
+                                    float conf_thres, uint64_t* cand_key, int32_t* cand_count, float* box_dense,
+                                    int max_cand, cvpp_stream_t stream);
+CVPP_API int cvpp_ssd_parse_loc(const float* loc, const float* priors, int B, int P, float* out,
+                                cvpp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -212,3 +212,85 @@ def centernet_decode(pred, K: int, conf: float, pool_mode: int = 0, use_nms: boo
                                _ptr(score, _f32p), _ptr(cls, _i32p), _ptr(pix, _i32p), _ptr(cnt, _i32p))
     return [(box[b, :cnt[b]].copy(), score[b, :cnt[b]].copy(), cls[b, :cnt[b]].copy(), pix[b, :cnt[b]].copy())
             for b in range(B)]
+
+
+# --------------------------------------------------------------------------
+# SSD
+# --------------------------------------------------------------------------
+def ssd_priors(input_hw=(300, 300), anchor_sizes=(30, 60, 111, 162, 213, 264, 315), feature_shapes=(38, 19, 10, 5, 3, 1),
+               aspect_ratios=((1, 2, 0.5), (1, 2, 0.5, 3, 1.0 / 3), (1, 2, 0.5, 3, 1.0 / 3), (1, 2, 0.5, 3, 1.0 / 3),
+                              (1, 2, 0.5), (1, 2, 0.5))) -> np.ndarray:
+    """Ssd._get_ssd_anchors (ssd.py:482-541) restated: float64 numpy, cast to float32 at the end."""
+    image_h, image_w = input_hw
+    out = []
+    for i, fs in enumerate(feature_shapes):
+        lo, hi = anchor_sizes[i], anchor_sizes[i + 1]
+        bw, bh = [], []
+        for ar in aspect_ratios[i]:
+            if ar == 1:
+                bw += [lo, np.sqrt(lo * hi)]
+                bh += [lo, np.sqrt(lo * hi)]
+            else:
+                bw.append(lo * np.sqrt(ar))
+                bh.append(lo / np.sqrt(ar))
+        hw_, hh_ = np.array(bw) / 2.0, np.array(bh) / 2.0
+        px = [image_h / fs, image_w / fs]
+        cx = np.linspace(0.5 * px[1], image_w - 0.5 * px[1], fs)
+        cy = np.linspace(0.5 * px[0], image_h - 0.5 * px[0], fs)
+        gx, gy = np.meshgrid(cx, cy)
+        a = np.concatenate((gx.reshape(-1, 1), gy.reshape(-1, 1)), axis=1)
+        a = np.tile(a, (1, len(bw) * 2))
+        a[:, ::4] -= hw_
+        a[:, 1::4] -= hh_
+        a[:, 2::4] += hw_
+        a[:, 3::4] += hh_
+        a[:, ::2] /= image_w
+        a[:, 1::2] /= image_h
+        out.append(np.clip(a, 0.0, 1.0).reshape(-1, 4))
+    return np.concatenate(out, axis=0).astype(np.float32)
+
+
+def ssd_decode(loc, conf, priors, conf_thres: float, nms_thres: float = 0.5, cap: int = 0):
+    """Ssd.decode_boxes (ssd.py:236-288) before the letterbox epilogue: per image rows (n, 6)
+    [x1,y1,x2,y2,label,conf] in normalised coordinates, class-ascending then score-descending, and the
+    prior index of every row."""
+    loc, conf, priors = _f32(loc), _f32(conf), _f32(priors)
+    B, P, _ = loc.shape
+    nc = conf.shape[2] - 1
+    cap = cap or P * nc
+    rows = np.zeros((B, cap, 6), np.float32)
+    prior = np.zeros((B, cap), np.int32)
+    cnt = np.zeros((B,), np.int32)
+    lib().orc_ssd_decode(_ptr(loc, _f32p), _ptr(conf, _f32p), _ptr(priors, _f32p), ctypes.c_int(B), ctypes.c_int64(P),
+                         ctypes.c_int(nc), ctypes.c_float(conf_thres), ctypes.c_double(float(nms_thres)),
+                         ctypes.c_int(cap), _ptr(rows, _f32p), _ptr(prior, _i32p), _ptr(cnt, _i32p))
+    return [(rows[b, :min(cnt[b], cap)].copy(), prior[b, :min(cnt[b], cap)].copy()) for b in range(B)]
+
+
+def yolo_correct_rows(rows: np.ndarray, input_hw, image_hw, letterbox: bool = True) -> np.ndarray:
+    """The shared epilogue of Ssd.decode_boxes (:282-287) / YOLOv7._nms (:416-421): xyxy -> (centre, size) ->
+    yolo_correct_boxes (image_process.py:161-181), float32 numpy with Python-double scalars."""
+    out = rows.copy()
+    if out.shape[0] == 0:
+        return out
+    xy = (out[:, 0:2] + out[:, 2:4]) / 2
+    wh = out[:, 2:4] - out[:, 0:2]
+    xywh = np.concatenate([xy, wh], axis=-1)
+    if letterbox:
+        nb = np.concatenate((xywh[..., 0:2] - xywh[..., 2:4] / 2, xywh[..., 0:2] + xywh[..., 2:4] / 2), axis=-1)
+        nb[..., ::2] *= input_hw[1]
+        nb[..., 1::2] *= input_hw[0]
+        scale = max(image_hw[0] / input_hw[0], image_hw[1] / input_hw[1])
+        top = (input_hw[0] - image_hw[0] / scale) // 2
+        left = (input_hw[1] - image_hw[1] / scale) // 2
+        nb[..., 0] -= left
+        nb[..., 2] -= left
+        nb[..., 1] -= top
+        nb[..., 3] -= top
+        nb *= scale
+    else:
+        nb = np.concatenate((xywh[..., 0:2] - xywh[..., 2:4] / 2, xywh[..., 0:2] + xywh[..., 2:4] / 2), axis=-1)
+        nb[:, ::2] *= image_hw[1]
+        nb[:, 1::2] *= image_hw[0]
+    out[:, :4] = nb
+    return out

@@ -701,3 +701,112 @@ ORC_API void orc_centernet_decode(const float* pred, int B, int H, int W, int nc
   orc_cn_ctx c = {pred, H, W, nc, K, pool_mode, use_nms, conf, nms_thr, letterbox, box, score, cls, pix, count};
   orc_parallel_for(B, orc_cn_body, &c);
 }
+
+/* ========================================================================= */
+/* SSD — core/algorithms/ssd.py:236-288 (decode_boxes), :290-325             */
+/* (_parse_mbox_loc).  Priors come from _get_ssd_anchors (:482-541), computed */
+/* in float64 numpy by the caller and passed in as float32.                   */
+/* ========================================================================= */
+static void ssd_parse_loc(const float* loc, const float* priors, int64_t P, float* box) {
+  const float v0 = 0.1f, v1 = 0.2f; /* variance[::2] */
+  for (int64_t i = 0; i < P; ++i) {
+    const float* a = priors + 4 * i;
+    const float* l = loc + 4 * i;
+    float aw = a[2] - a[0], ah = a[3] - a[1];
+    float acx = 0.5f * (a[2] + a[0]), acy = 0.5f * (a[3] + a[1]);
+    float cx = l[0] * aw * v0;
+    cx += acx;
+    float cy = l[1] * ah * v0;
+    cy += acy;
+    float w = expf(l[2] * v1);
+    w *= aw;
+    float h = expf(l[3] * v1);
+    h *= ah;
+    float x1 = cx - 0.5f * w, y1 = cy - 0.5f * h, x2 = cx + 0.5f * w, y2 = cy + 0.5f * h;
+    box[4 * i + 0] = fminf(fmaxf(x1, 0.0f), 1.0f);
+    box[4 * i + 1] = fminf(fmaxf(y1, 0.0f), 1.0f);
+    box[4 * i + 2] = fminf(fmaxf(x2, 0.0f), 1.0f);
+    box[4 * i + 3] = fminf(fmaxf(y2, 0.0f), 1.0f);
+  }
+}
+
+ORC_API void orc_ssd_parse_mbox_loc(const float* loc, const float* priors, int64_t P, float* box) {
+  ssd_parse_loc(loc, priors, P, box);
+}
+
+typedef struct {
+  const float* loc;
+  const float* conf;
+  const float* priors;
+  int64_t P;
+  int nc; /* foreground classes; conf has nc + 1 columns, column 0 = background */
+  float conf_thres;
+  double nms_thres;
+  int cap; /* rows per image in the outputs */
+  float* rows;        /* (B, cap, 6): x1,y1,x2,y2,label,conf (normalised coordinates) */
+  int32_t* row_prior; /* (B, cap) */
+  int32_t* count;     /* (B) true number of rows (may exceed cap) */
+} orc_ssd_ctx;
+
+static void orc_ssd_body(int b, void* vctx) {
+  const orc_ssd_ctx* c = (const orc_ssd_ctx*)vctx;
+  const int64_t P = c->P;
+  const int nc1 = c->nc + 1;
+  float* box = (float*)malloc(sizeof(float) * 4 * (size_t)P);
+  float* prob = (float*)malloc(sizeof(float) * (size_t)P * nc1);
+  ssd_parse_loc(c->loc + (int64_t)b * P * 4, c->priors, P, box);
+  const float* logits = c->conf + (int64_t)b * P * nc1;
+  for (int64_t i = 0; i < P; ++i) { /* torch.softmax(preds[1], dim=-1) (:248) */
+    const float* x = logits + i * nc1;
+    float m = x[0];
+    for (int k = 1; k < nc1; ++k)
+      if (x[k] > m) m = x[k];
+    float sum = 0.0f;
+    for (int k = 0; k < nc1; ++k) {
+      prob[i * nc1 + k] = expf(x[k] - m);
+      sum += prob[i * nc1 + k];
+    }
+    for (int k = 0; k < nc1; ++k) prob[i * nc1 + k] = prob[i * nc1 + k] / sum;
+  }
+  float* cb = (float*)malloc(sizeof(float) * 4 * (size_t)P);
+  float* cs = (float*)malloc(sizeof(float) * (size_t)P);
+  int64_t* ci = (int64_t*)malloc(sizeof(int64_t) * (size_t)P);
+  int64_t* keep = (int64_t*)malloc(sizeof(int64_t) * (size_t)P);
+  int64_t total = 0;
+  for (int cls = 1; cls <= c->nc; ++cls) { /* (:256-278) */
+    int64_t m = 0;
+    for (int64_t i = 0; i < P; ++i) {
+      float p = prob[i * nc1 + cls];
+      if (p > c->conf_thres) {
+        memcpy(cb + 4 * m, box + 4 * i, sizeof(float) * 4);
+        cs[m] = p;
+        ci[m] = i;
+        ++m;
+      }
+    }
+    if (m == 0) continue;
+    int64_t k = orc_nms(cb, cs, m, c->nms_thres, keep);
+    for (int64_t t = 0; t < k; ++t, ++total) {
+      if (total >= c->cap) continue;
+      float* row = c->rows + ((int64_t)b * c->cap + total) * 6;
+      memcpy(row, cb + 4 * keep[t], sizeof(float) * 4);
+      row[4] = (float)(cls - 1);
+      row[5] = cs[keep[t]];
+      c->row_prior[(int64_t)b * c->cap + total] = (int32_t)ci[keep[t]];
+    }
+  }
+  c->count[b] = (int32_t)total;
+  free(box);
+  free(prob);
+  free(cb);
+  free(cs);
+  free(ci);
+  free(keep);
+}
+
+ORC_API void orc_ssd_decode(const float* loc, const float* conf, const float* priors, int B, int64_t P, int nc,
+                            float conf_thres, double nms_thres, int cap, float* rows, int32_t* row_prior,
+                            int32_t* count) {
+  orc_ssd_ctx c = {loc, conf, priors, P, nc, conf_thres, nms_thres, cap, rows, row_prior, count};
+  orc_parallel_for(B, orc_ssd_body, &c);
+}

@@ -248,3 +248,42 @@ def centernet_pred(seed: int, B: int, H: int = 128, W: int = 128, nc: int = 80, 
         else:
             raise RuntimeError("centernet_pred: separation did not converge; change the seed")
     return pred
+
+
+# ------------------------------------------------------------------------------------------------
+# SSD (C4): loc (B, P, 4), conf logits (B, P, nc + 1) with column 0 = background
+# ------------------------------------------------------------------------------------------------
+def ssd_head(seed: int, B: int, P: int = 8732, nc: int = 20, conf_list: Sequence[float] = (0.001, 0.7),
+             boost_frac: float = 0.003) -> Tuple[np.ndarray, np.ndarray]:
+    """loc N(0,1); background logit N(12,1), foreground N(0,2^2), and `boost_frac` of the priors get one
+    random class raised to background + N(2,2^2) (~2 k pairs > .001 and ~19 > .7 per image).
+    Candidate probabilities are separated per image."""
+    rng = rng_for(seed)
+    loc = rng.standard_normal((B, P, 4), dtype=np.float32)
+    conf = rng.standard_normal((B, P, nc + 1), dtype=np.float32) * np.float32(2.0)
+    conf[..., 0] = rng.standard_normal((B, P), dtype=np.float32) + np.float32(12.0)
+    n_boost = max(1, int(P * boost_frac))
+    for b in range(B):
+        pri = rng.choice(P, n_boost, replace=False)
+        cls = rng.integers(1, nc + 1, n_boost)
+        conf[b, pri, cls] = conf[b, pri, 0] + rng.normal(2.0, 2.0, n_boost).astype(np.float32)
+    lo = 0.5 * min(conf_list)
+    for b in range(B):
+        for _ in range(100):
+            x = conf[b].astype(np.float64)
+            e = np.exp(x - x.max(axis=1, keepdims=True))
+            p = e / e.sum(axis=1, keepdims=True)
+            fg = p[:, 1:]
+            idx = np.nonzero(fg.reshape(-1) >= lo)[0]
+            s = fg.reshape(-1)[idx]
+            s2 = separate_scores(s, conf_list, lo)
+            moved = np.nonzero(s2 != s)[0]
+            if moved.size == 0:
+                break
+            for j in moved:
+                pr, c = divmod(int(idx[j]), nc)
+                # logit shift that moves the probability from s to s2 (other logits fixed)
+                conf[b, pr, c + 1] += np.float32(np.log(s2[j] * (1 - s[j]) / (s[j] * (1 - s2[j]))))
+        else:
+            raise RuntimeError("ssd_head: separation did not converge; change the seed")
+    return loc, conf

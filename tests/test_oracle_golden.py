@@ -130,3 +130,19 @@ def test_centernet_decode_and_diou_nms(golden_dir):
                     assert np.all(np.abs(score - g[k + "_scores"]) <= SCORE_RTOL * g[k + "_scores"])
                     assert np.all(np.abs(box - g[k + "_boxes"]) <= BOX_RTOL * np.abs(g[k + "_boxes"]) + BOX_ATOL)
                     assert len(cls) > 0
+
+
+def test_ssd_decode(golden_dir):
+    g = load(golden_dir, "ssd")
+    loc, conf = synth.ssd_head(int(g["seed"][0]), int(g["seed"][1]))
+    assert synth.checksum([loc, conf]) == int(g["crc"])
+    pri = oracle.ssd_priors()
+    assert np.array_equal(pri, load(golden_dir, "host_helpers")["ssd_priors"])
+    for ctag, thr in (("eval", 0.001), ("pred", 0.7)):
+        out = oracle.ssd_decode(loc, conf, pri, thr, 0.5)
+        for b, (rows, prior) in enumerate(out):
+            ref = g[f"rows_{b}_{ctag}"]
+            got = oracle.yolo_correct_rows(rows, (300, 300), (480, 640), True)
+            assert got.shape == ref.shape and np.array_equal(got[:, 4], ref[:, 4])
+            assert np.all(np.abs(got[:, 5] - ref[:, 5]) <= SCORE_RTOL * ref[:, 5])
+            assert np.all(np.abs(got[:, :4] - ref[:, :4]) <= BOX_RTOL * np.abs(ref[:, :4]) + BOX_ATOL * 2.2)
