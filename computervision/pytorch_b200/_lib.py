@@ -11,6 +11,8 @@ SO_PATH = os.path.join(_HERE, "libcvpp.so")
 CVPP_OK = 0
 RULE_TORCHVISION_CPU, RULE_COORD_TRICK, RULE_PER_CLASS = 0, 1, 2
 ORDER_SCORE_DESC, ORDER_CLASS_MAJOR = 0, 1
+ROWS_YOLOV8, ROWS_SSD, ROWS_YOLOV7, ROWS_FULL = 0, 1, 2, 3
+BOX_KEEP, BOX_CORRECT, BOX_NORMALISE_CORRECT = 0, 1, 2
 
 c_int, c_i64, c_f32, c_f64 = ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_double
 c_vp, c_size = ctypes.c_void_p, ctypes.c_size_t
@@ -51,6 +53,16 @@ _PROTOS = {
     "cvpp_diou_nms": (c_int, [c_vp, c_vp, c_int, c_f32, c_vp, c_vp, c_vp]),
     "cvpp_ssd_decode_filter": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_f32, c_vp, c_vp, c_vp, c_int, c_vp]),
     "cvpp_ssd_parse_loc": (c_int, [c_vp, c_vp, c_int, c_int, c_vp, c_vp]),
+    "cvpp_yolov7_decode_filter": (c_int, [P(c_vp), P(c_i64), P(c_i64), P(c_int), P(c_int), P(c_f32), c_int, c_int,
+                                          c_int, c_int, c_int, c_f32, c_vp, c_vp, c_vp, c_vp, c_int, c_vp]),
+    "cvpp_yolov7_pred_filter": (c_int, [c_vp, c_int, c_i64, c_int, c_f32, c_vp, c_vp, c_vp, c_vp, c_int, c_vp]),
+    "cvpp_yolov3_decode_filter": (c_int, [P(c_vp), P(c_i64), P(c_i64), P(c_int), P(c_int), P(c_f32), c_int, c_int,
+                                          c_int, c_int, c_int, c_f32, c_int, c_vp, c_vp, c_vp, c_int, c_vp]),
+    "cvpp_yolov3_predict_bbox": (c_int, [c_vp, c_int, c_int, c_int, c_int, P(c_f32), c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "cvpp_score_matrix_filter": (c_int, [c_vp, c_i64, c_int, c_f32, c_vp, c_vp, c_int, c_vp]),
+    "cvpp_gather_feat": (c_int, [c_vp, c_vp, c_int, c_vp, c_int, c_i64, c_int, c_int, c_vp, c_vp, c_vp]),
+    "cvpp_detection_epilogue": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_i64, c_int, c_int, c_vp,
+                                        c_vp, c_vp]),
 }
 
 _lib = None

@@ -79,6 +79,25 @@ int ssd_decode_filter_launch(const float* loc, const float* conf, const float* p
                              cudaStream_t stream);
 int ssd_parse_loc_launch(const float* loc, const float* priors, int B, int P, float* out, cudaStream_t stream);
 
+int yolo_anchor_decode_launch(int mode, const float* const* level_ptr, const int64_t* batch_stride,
+                              const int64_t* chan_stride, const int* level_h, const int* level_w,
+                              const float* level_anchors, int num_levels, int B, int nc, int input_h, int input_w,
+                              float conf_thres, int merge_batch, uint64_t* cand_key, int32_t* cand_count, float* box_dense,
+                              float* aux_dense, int max_cand, int force_generic, cudaStream_t stream);
+int yolov3_predict_bbox_launch(const float* feature, int B, int nc, int H, int W, const float* anchors, float* box_xy,
+                               float* box_wh, float* confidence, float* class_prob, cudaStream_t stream);
+int yolov7_pred_filter_launch(const float* pred, int B, int64_t A, int nc, float conf_thres, uint64_t* cand_key,
+                              int32_t* cand_count, float* box_dense, float* aux_dense, int max_cand,
+                              cudaStream_t stream);
+int score_matrix_filter_launch(const float* scores, int64_t M, int nc, float conf_thres, uint64_t* cand_key,
+                               int32_t* cand_count, int max_cand, cudaStream_t stream);
+int gather_feat_launch(const float* feat, const void* ind, int ind_is_int64, const int32_t* count, int B, int64_t N, int C,
+                       int K, float* out, int32_t* err_flag, cudaStream_t stream);
+int detection_epilogue_launch(const float* det_box, const float* det_score, const int32_t* det_cls,
+                              const int32_t* det_anchor, const int32_t* det_count, const float* aux_dense, int B,
+                              int max_out, int64_t A, int layout, int box_mode, const float* letterbox, float* rows,
+                              cudaStream_t stream);
+
 static int force_generic() {
   const char* e = getenv("CVPP_FORCE_GENERIC");
   return e && e[0] == '1';
@@ -252,6 +271,56 @@ int cvpp_ssd_decode_filter(const float* loc, const float* conf, const float* pri
 
 int cvpp_ssd_parse_loc(const float* loc, const float* priors, int B, int P, float* out, cvpp_stream_t stream) {
   return ssd_parse_loc_launch(loc, priors, B, P, out, (cudaStream_t)stream);
+}
+
+int cvpp_yolov7_decode_filter(const float* const* level_ptr, const int64_t* batch_stride, const int64_t* chan_stride,
+                              const int* level_h, const int* level_w, const float* level_anchors, int num_levels, int B,
+                              int nc, int input_h, int input_w, float conf_thres, uint64_t* cand_key,
+                              int32_t* cand_count, float* box_dense, float* aux_dense, int max_cand,
+                              cvpp_stream_t stream) {
+  return yolo_anchor_decode_launch(0, level_ptr, batch_stride, chan_stride, level_h, level_w, level_anchors, num_levels, B,
+                                   nc, input_h, input_w, conf_thres, 0, cand_key, cand_count, box_dense, aux_dense,
+                                   max_cand, force_generic(), (cudaStream_t)stream);
+}
+
+int cvpp_yolov7_pred_filter(const float* pred, int B, int64_t A, int nc, float conf_thres, uint64_t* cand_key,
+                            int32_t* cand_count, float* box_dense, float* aux_dense, int max_cand,
+                            cvpp_stream_t stream) {
+  return yolov7_pred_filter_launch(pred, B, A, nc, conf_thres, cand_key, cand_count, box_dense, aux_dense, max_cand,
+                                   (cudaStream_t)stream);
+}
+
+int cvpp_yolov3_decode_filter(const float* const* level_ptr, const int64_t* batch_stride, const int64_t* chan_stride,
+                              const int* level_h, const int* level_w, const float* level_anchors, int num_levels, int B,
+                              int nc, int input_h, int input_w, float conf_thres, int merge_batch, uint64_t* cand_key,
+                              int32_t* cand_count, float* box_dense, int max_cand, cvpp_stream_t stream) {
+  return yolo_anchor_decode_launch(1, level_ptr, batch_stride, chan_stride, level_h, level_w, level_anchors, num_levels, B,
+                                   nc, input_h, input_w, conf_thres, merge_batch, cand_key, cand_count, box_dense, nullptr,
+                                   max_cand, force_generic(), (cudaStream_t)stream);
+}
+
+int cvpp_yolov3_predict_bbox(const float* feature, int B, int nc, int H, int W, const float* anchors, float* box_xy,
+                             float* box_wh, float* confidence, float* class_prob, cvpp_stream_t stream) {
+  return yolov3_predict_bbox_launch(feature, B, nc, H, W, anchors, box_xy, box_wh, confidence, class_prob,
+                                    (cudaStream_t)stream);
+}
+
+int cvpp_score_matrix_filter(const float* scores, int64_t M, int nc, float conf_thres, uint64_t* cand_key,
+                             int32_t* cand_count, int max_cand, cvpp_stream_t stream) {
+  return score_matrix_filter_launch(scores, M, nc, conf_thres, cand_key, cand_count, max_cand, (cudaStream_t)stream);
+}
+
+int cvpp_gather_feat(const float* feat, const void* ind, int ind_is_int64, const int32_t* count, int B, int64_t N, int C,
+                     int K, float* out, int32_t* err_flag, cvpp_stream_t stream) {
+  return gather_feat_launch(feat, ind, ind_is_int64, count, B, N, C, K, out, err_flag, (cudaStream_t)stream);
+}
+
+int cvpp_detection_epilogue(const float* det_box, const float* det_score, const int32_t* det_cls,
+                            const int32_t* det_anchor, const int32_t* det_count, const float* aux_dense, int B,
+                            int max_out, int64_t A, int layout, int box_mode, const float* letterbox, float* rows,
+                            cvpp_stream_t stream) {
+  return detection_epilogue_launch(det_box, det_score, det_cls, det_anchor, det_count, aux_dense, B, max_out, A, layout,
+                                   box_mode, letterbox, rows, (cudaStream_t)stream);
 }
 
 }  // extern "C"

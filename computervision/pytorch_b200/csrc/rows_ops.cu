@@ -1,0 +1,324 @@
+// rows_ops.cu — row-layout helpers around the NMS kernel (sm_100a):
+//
+//   yolov7_pred_filter  candidate stage of YOLOv7._nms / yolo7_nms on an already decoded (B, A, 5 + nc)
+//                       tensor: core/algorithms/yolo_v7.py:361-377 == core/utils/nms.py:93-113
+//                       (xywh_to_xyxy_torch core/utils/bboxes.py:29-49; class max first index; obj *
+//                       class_conf >= conf).
+//   gather_feat         RegL1Loss.gather_feat core/loss/centernet_loss.py:37-43 and the row gathers after
+//                       NMS (gather_op core/utils/nms.py:34-51, `detections_class[keep]` yolo_v7.py:410).
+//   detection_epilogue  what every decoder does with the kept rows before handing them to the caller:
+//                       row assembly (ultralytics_ops.py:226,257; yolo_v7.py:391; ssd.py:275-278),
+//                       YOLOv8's normalisation (yolo_v8.py:233-234), centre/size round trip
+//                       (yolo_v8.py:237-238, yolo_v7.py:416-417, ssd.py:284-285) and yolo_correct_boxes /
+//                       reverse_letter_box_numpy (core/utils/image_process.py:69-97,161-181), batched with
+//                       one (h, w) per image instead of one D2H + numpy pass per image.
+//
+// All three are bandwidth-trivial next to the decode kernels (<= 85 floats per anchor streamed once, or a
+// few KB of gathered rows); they exist so that no step of the path runs on the host or in eager ops.
+#include "cvpp_common.cuh"
+
+namespace cvpp {
+
+// ---------------------------------------------------------------------------------------------------
+// yolov7_pred_filter: rows are contiguous (5 + nc floats per anchor), so a CTA stages 128 rows with
+// coalesced loads and each thread then scans its own row from shared memory (row pitch odd or padded to
+// odd -> conflict-free).
+// ---------------------------------------------------------------------------------------------------
+constexpr int kRowThreads = 128;
+
+__global__ void __launch_bounds__(kRowThreads)
+yolov7_pred_filter_kernel(const float* __restrict__ pred, int64_t A, int nc, float conf_thres,
+                          uint64_t* __restrict__ cand_key, int32_t* __restrict__ cand_count,
+                          float4* __restrict__ box_dense, float2* __restrict__ aux_dense, int max_cand, int pitch) {
+  extern __shared__ float sm[];
+  const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
+  const int attrs = 5 + nc;
+  const int64_t a0 = (int64_t)blockIdx.x * kRowThreads;
+  const int rows = (int)min((int64_t)kRowThreads, A - a0);
+  const float* src = pred + ((int64_t)b * A + a0) * attrs;
+  for (int i = tid; i < rows * attrs; i += kRowThreads) {
+    const int r = i / attrs, c = i - r * attrs;
+    sm[r * pitch + c] = __ldg(src + i);
+  }
+  __syncthreads();
+  bool cand = false;
+  float best = 0.0f, obj = 0.0f, score = 0.0f;
+  int arg = 0;
+  const float* x = sm + tid * pitch;
+  if (tid < rows) {
+    best = x[5];
+    for (int k = 1; k < nc; ++k) {
+      const float v = x[5 + k];
+      if (v > best) {  // strict: first index wins ties, like torch.max(dim)
+        best = v;
+        arg = k;
+      }
+    }
+    obj = x[4];
+    score = fmul(obj, best);
+    cand = score >= conf_thres;
+  }
+  const unsigned mask = __ballot_sync(0xffffffffu, cand);
+  if (mask == 0) return;
+  int base = 0;
+  if (lane == 0) base = atomicAdd(cand_count + b, __popc(mask));
+  base = __shfl_sync(0xffffffffu, base, 0);
+  if (cand) {
+    const int64_t a = a0 + tid;
+    const float hw = fmul(x[2], 0.5f), hh = fmul(x[3], 0.5f);
+    const int slot = base + __popc(mask & ((1u << lane) - 1u));
+    if (slot < max_cand) cand_key[(int64_t)b * max_cand + slot] = key_pack((uint32_t)arg, __float_as_uint(score), (uint32_t)a);
+    box_dense[(int64_t)b * A + a] = make_float4(fsub(x[0], hw), fsub(x[1], hh), fadd(x[0], hw), fadd(x[1], hh));
+    aux_dense[(int64_t)b * A + a] = make_float2(obj, best);
+  }
+}
+
+int yolov7_pred_filter_launch(const float* pred, int B, int64_t A, int nc, float conf_thres, uint64_t* cand_key,
+                              int32_t* cand_count, float* box_dense, float* aux_dense, int max_cand,
+                              cudaStream_t stream) {
+  if (!pred || !cand_key || !cand_count || !box_dense || !aux_dense) {
+    set_error("yolov7_pred_filter: NULL pointer argument");
+    return CVPP_ERR_INVALID_ARG;
+  }
+  if (B < 0 || nc < 1 || nc > CVPP_MAX_CLASSES || A < 1 || A > CVPP_MAX_ANCHORS || max_cand < 1) {
+    set_error("yolov7_pred_filter: bad sizes (B=%d nc=%d A=%lld max_cand=%d)", B, nc, (long long)A, max_cand);
+    return CVPP_ERR_INVALID_ARG;
+  }
+  if (!(conf_thres >= 0.0f && conf_thres <= 1.0f)) {
+    set_error("yolov7_pred_filter: confidence threshold %f outside [0, 1]", conf_thres);
+    return CVPP_ERR_INVALID_ARG;
+  }
+  if ((reinterpret_cast<uintptr_t>(box_dense) & 15u) || (reinterpret_cast<uintptr_t>(aux_dense) & 7u)) {
+    set_error("yolov7_pred_filter: box_dense / aux_dense misaligned");
+    return CVPP_ERR_ALIGNMENT;
+  }
+  CVPP_CUDA_TRY(cudaMemsetAsync(cand_count, 0, sizeof(int32_t) * (size_t)B, stream));
+  if (B == 0) return CVPP_OK;
+  const int pitch = (5 + nc) | 1;
+  const size_t smem = (size_t)kRowThreads * pitch * sizeof(float);
+  DeviceInfo di;
+  int rc = device_info(&di);
+  if (rc != CVPP_OK) return rc;
+  if (smem > (size_t)di.max_smem) {
+    set_error("yolov7_pred_filter: nc=%d needs %zu bytes of staging shared memory", nc, smem);
+    return CVPP_ERR_UNSUPPORTED;
+  }
+  static unsigned long long attr_done = 0;
+  static int attr_bytes = 0;
+  if ((int)smem > attr_bytes) {
+    attr_done = 0;
+    attr_bytes = (int)smem;
+  }
+  rc = ensure_smem_attr(reinterpret_cast<const void*>(yolov7_pred_filter_kernel), attr_bytes, di.device, &attr_done);
+  if (rc != CVPP_OK) return rc;
+  dim3 grid((unsigned)((A + kRowThreads - 1) / kRowThreads), (unsigned)B);
+  yolov7_pred_filter_kernel<<<grid, kRowThreads, smem, stream>>>(pred, A, nc, conf_thres, cand_key, cand_count,
+                                                                 reinterpret_cast<float4*>(box_dense),
+                                                                 reinterpret_cast<float2*>(aux_dense), max_cand, pitch);
+  CVPP_CUDA_TRY(cudaGetLastError());
+  return CVPP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// score_matrix_filter: the mask of yolo3_nms (core/utils/nms.py:60) on a (M, nc) score matrix:
+// one key (class c, score, row m) per element >= conf_thres.  Thread per element, coalesced.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+score_matrix_filter_kernel(const float* __restrict__ scores, int64_t total, int nc, float conf_thres,
+                           uint64_t* __restrict__ cand_key, int32_t* __restrict__ cand_count, int max_cand) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  float s = 0.0f;
+  bool hit = false;
+  if (i < total) {
+    s = __ldg(scores + i);
+    hit = s >= conf_thres;
+  }
+  const unsigned mk = __ballot_sync(0xffffffffu, hit);
+  if (mk == 0) return;
+  int base = 0;
+  if (lane == 0) base = atomicAdd(cand_count, __popc(mk));
+  base = __shfl_sync(0xffffffffu, base, 0);
+  if (hit) {
+    const int slot = base + __popc(mk & ((1u << lane) - 1u));
+    const int64_t m = i / nc;
+    const int c = (int)(i - m * nc);
+    if (slot < max_cand) cand_key[slot] = key_pack((uint32_t)c, __float_as_uint(s), (uint32_t)m);
+  }
+}
+
+int score_matrix_filter_launch(const float* scores, int64_t M, int nc, float conf_thres, uint64_t* cand_key,
+                               int32_t* cand_count, int max_cand, cudaStream_t stream) {
+  if (!scores || !cand_key || !cand_count || M < 0 || M > CVPP_MAX_ANCHORS || nc < 1 || nc > CVPP_MAX_CLASSES ||
+      max_cand < 1) {
+    set_error("score_matrix_filter: NULL pointer or bad sizes (M=%lld nc=%d max_cand=%d)", (long long)M, nc, max_cand);
+    return CVPP_ERR_INVALID_ARG;
+  }
+  CVPP_CUDA_TRY(cudaMemsetAsync(cand_count, 0, sizeof(int32_t), stream));
+  const int64_t total = M * nc;
+  if (total == 0) return CVPP_OK;
+  score_matrix_filter_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(scores, total, nc, conf_thres, cand_key,
+                                                                                 cand_count, max_cand);
+  CVPP_CUDA_TRY(cudaGetLastError());
+  return CVPP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// gather_feat: out[b, k, :] = feat[b, ind[b, k], :]   (rows of C floats; one warp per (b, k))
+// ---------------------------------------------------------------------------------------------------
+template <typename IndexT>
+__global__ void __launch_bounds__(256)
+gather_feat_kernel(const float* __restrict__ feat, const IndexT* __restrict__ ind, const int32_t* __restrict__ count,
+                   int B, int64_t N, int C, int K, float* __restrict__ out, int* __restrict__ err) {
+  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= (int64_t)B * K) return;
+  const int b = (int)(w / K), k = (int)(w - (int64_t)b * K);
+  if (count && k >= count[b]) return;
+  const int64_t i = (int64_t)ind[w];
+  if (i < 0 || i >= N) {  // torch.gather raises; report instead of reading out of bounds
+    if (lane == 0 && err) atomicExch(err, 1);
+    return;
+  }
+  const float* src = feat + ((int64_t)b * N + i) * C;
+  float* dst = out + w * C;
+  for (int c = lane; c < C; c += 32) dst[c] = __ldg(src + c);
+}
+
+int gather_feat_launch(const float* feat, const void* ind, int ind_is_int64, const int32_t* count, int B, int64_t N, int C,
+                       int K, float* out, int32_t* err_flag, cudaStream_t stream) {
+  if (!feat || !ind || !out || B < 0 || N < 1 || C < 1 || K < 0) {
+    set_error("gather_feat: NULL pointer or bad sizes (B=%d N=%lld C=%d K=%d)", B, (long long)N, C, K);
+    return CVPP_ERR_INVALID_ARG;
+  }
+  if (err_flag) CVPP_CUDA_TRY(cudaMemsetAsync(err_flag, 0, sizeof(int32_t), stream));
+  const int64_t warps = (int64_t)B * K;
+  if (warps == 0) return CVPP_OK;
+  const unsigned grid = (unsigned)((warps * 32 + 255) / 256);
+  if (ind_is_int64)
+    gather_feat_kernel<long long><<<grid, 256, 0, stream>>>(feat, reinterpret_cast<const long long*>(ind), count, B, N, C, K,
+                                                            out, err_flag);
+  else
+    gather_feat_kernel<int32_t><<<grid, 256, 0, stream>>>(feat, reinterpret_cast<const int32_t*>(ind), count, B, N, C, K, out,
+                                                          err_flag);
+  CVPP_CUDA_TRY(cudaGetLastError());
+  return CVPP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// detection_epilogue: one thread per output row
+// ---------------------------------------------------------------------------------------------------
+struct EpilogueParams {
+  const float4* det_box;
+  const float* det_score;
+  const int32_t* det_cls;
+  const int32_t* det_anchor;
+  const int32_t* det_count;
+  const float2* aux_dense;
+  const float* letterbox;  // (B, 5): in_w, in_h, left, top, scale
+  float* rows;
+  int B, max_out, layout, box_mode, width;
+  int64_t A;
+};
+
+__global__ void __launch_bounds__(256) detection_epilogue_kernel(const EpilogueParams p) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (int64_t)p.B * p.max_out) return;
+  const int b = (int)(t / p.max_out), k = (int)(t - (int64_t)b * p.max_out);
+  float* row = p.rows + t * p.width;
+  const int n = min(p.det_count[b], p.max_out);
+  if (k >= n) {
+    for (int c = 0; c < p.width; ++c) row[c] = 0.0f;
+    return;
+  }
+  float4 bx = p.det_box[t];
+  if (p.box_mode != CVPP_BOX_KEEP) {
+    const float* L = p.letterbox + 5 * b;
+    const float in_w = L[0], in_h = L[1], left = L[2], top = L[3], scale = L[4];
+    if (p.box_mode == CVPP_BOX_NORMALISE_CORRECT) {  // yolo_v8.py:233-234
+      bx.x = fdiv(bx.x, in_w);
+      bx.z = fdiv(bx.z, in_w);
+      bx.y = fdiv(bx.y, in_h);
+      bx.w = fdiv(bx.w, in_h);
+    }
+    // (x1y1 + x2y2) / 2, x2y2 - x1y1 (yolo_v7.py:416-417), then c -/+ wh / 2 (image_process.py:80-83)
+    const float cx = fmul(fadd(bx.x, bx.z), 0.5f), cy = fmul(fadd(bx.y, bx.w), 0.5f);
+    const float hw = fmul(fsub(bx.z, bx.x), 0.5f), hh = fmul(fsub(bx.w, bx.y), 0.5f);
+    // * input size, - padding, * scale (image_process.py:85-96); without letterbox the table holds
+    // (image_w, image_h, 0, 0, 1) and the same sequence is image_process.py:178-181 bit for bit
+    bx.x = fmul(fsub(fmul(fsub(cx, hw), in_w), left), scale);
+    bx.z = fmul(fsub(fmul(fadd(cx, hw), in_w), left), scale);
+    bx.y = fmul(fsub(fmul(fsub(cy, hh), in_h), top), scale);
+    bx.w = fmul(fsub(fmul(fadd(cy, hh), in_h), top), scale);
+  }
+  row[0] = bx.x;
+  row[1] = bx.y;
+  row[2] = bx.z;
+  row[3] = bx.w;
+  const float cls = (float)p.det_cls[t];
+  if (p.layout == CVPP_ROWS_YOLOV8) {  // x1,y1,x2,y2,conf,cls
+    row[4] = p.det_score[t];
+    row[5] = cls;
+  } else if (p.layout == CVPP_ROWS_SSD) {  // x1,y1,x2,y2,label,conf
+    row[4] = cls;
+    row[5] = p.det_score[t];
+  } else if (p.layout == CVPP_ROWS_YOLOV7) {  // x1,y1,x2,y2,obj,class_conf,class_pred
+    const float2 a = p.aux_dense[(int64_t)b * p.A + p.det_anchor[t]];
+    row[4] = a.x;
+    row[5] = a.y;
+    row[6] = cls;
+  } else {  // CVPP_ROWS_FULL: x1,y1,x2,y2,score,cls,anchor
+    row[4] = p.det_score[t];
+    row[5] = cls;
+    row[6] = (float)p.det_anchor[t];
+  }
+}
+
+int detection_epilogue_launch(const float* det_box, const float* det_score, const int32_t* det_cls,
+                              const int32_t* det_anchor, const int32_t* det_count, const float* aux_dense, int B,
+                              int max_out, int64_t A, int layout, int box_mode, const float* letterbox, float* rows,
+                              cudaStream_t stream) {
+  if (!det_box || !det_score || !det_cls || !det_anchor || !det_count || !rows) {
+    set_error("detection_epilogue: NULL pointer argument");
+    return CVPP_ERR_INVALID_ARG;
+  }
+  if (B < 0 || max_out < 1 || layout < CVPP_ROWS_YOLOV8 || layout > CVPP_ROWS_FULL || box_mode < CVPP_BOX_KEEP ||
+      box_mode > CVPP_BOX_NORMALISE_CORRECT) {
+    set_error("detection_epilogue: bad sizes / layout %d / box_mode %d", layout, box_mode);
+    return CVPP_ERR_INVALID_ARG;
+  }
+  if (layout == CVPP_ROWS_YOLOV7 && (!aux_dense || A < 1)) {
+    set_error("detection_epilogue: the YOLOv7 layout needs aux_dense (B, A, 2)");
+    return CVPP_ERR_INVALID_ARG;
+  }
+  if (box_mode != CVPP_BOX_KEEP && !letterbox) {
+    set_error("detection_epilogue: box_mode %d needs the (B, 5) letterbox table", box_mode);
+    return CVPP_ERR_INVALID_ARG;
+  }
+  if (reinterpret_cast<uintptr_t>(det_box) & 15u) {
+    set_error("detection_epilogue: det_box must be 16-byte aligned");
+    return CVPP_ERR_ALIGNMENT;
+  }
+  if (B == 0) return CVPP_OK;
+  EpilogueParams p;
+  p.det_box = reinterpret_cast<const float4*>(det_box);
+  p.det_score = det_score;
+  p.det_cls = det_cls;
+  p.det_anchor = det_anchor;
+  p.det_count = det_count;
+  p.aux_dense = reinterpret_cast<const float2*>(aux_dense);
+  p.letterbox = letterbox;
+  p.rows = rows;
+  p.B = B;
+  p.max_out = max_out;
+  p.layout = layout;
+  p.box_mode = box_mode;
+  p.width = (layout == CVPP_ROWS_YOLOV8 || layout == CVPP_ROWS_SSD) ? 6 : 7;
+  p.A = A;
+  const int64_t total = (int64_t)B * max_out;
+  detection_epilogue_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(p);
+  CVPP_CUDA_TRY(cudaGetLastError());
+  return CVPP_OK;
+}
+
+}  // namespace cvpp

@@ -1,0 +1,647 @@
+// yolo_anchor_decode.cu — anchor-based YOLO head decode + confidence filter, fused (sm_100a).
+// One streaming kernel, two arithmetic modes:
+//
+// MODE_V7 replaces (reference file:line): YOLOv7.decode_box core/algorithms/yolo_v7.py:245-344 (per-level
+// reshape/permute, six sigmoids, grid + anchor box math, normalisation, concatenation) and the
+// candidate stage of YOLOv7._nms :361 (xywh_to_xyxy_torch, core/utils/bboxes.py:29-49), :370 (class max,
+// first index), :377 (obj * class_conf >= conf).  One key per surviving anchor.
+//
+// MODE_V3 replaces: predict_bounding_bbox core/predict/yolov3_decode.py:12-29, Decoder._yolo_post_process
+// :40-51 (xyxy, conf * prob), Decoder.__call__ :53-63 (concatenate scales) and the mask of yolo3_nms
+// core/utils/nms.py:60 (score >= conf per (anchor, class)).  One key per surviving (anchor, class).
+//
+// The per-class NMS that follows (yolo_v7.py:396-413, nms.py:66-71) is cvpp_segmented_sort + cvpp_nms with
+// CVPP_NMS_RULE_PER_CLASS / CVPP_ORDER_CLASS_MAJOR.
+//
+// Memory-bound: (5 + nc) fp32 per anchor, read once: 25 200 x 85 x 4 = 8 568 000 B per YOLOv7 image,
+// 10 647 x 25 x 4 = 1 064 700 B per YOLOv3-VOC image.  Same machinery as the YOLOv8 kernel: persistent
+// CTAs, independent warps, a tile = 128 cells of one (image, level, anchor), streamed as 16-channel x
+// 128-cell chunks by ONE 3-D tensor-map TMA load each into a private 2-stage ring.  V7: class argmax on
+// logits with the exact first-index tie repair.  V3: every class logit is compared with a per-cell
+// conservative logit cut derived from the objectness (sigma(o) * sigma(c) >= thr  =>  c >= logit(thr /
+// sigma(o)) - slack), and only the rare survivors evaluate the exact fp32 product.  Levels whose rows
+// are not 16-byte aligned (13 x 13 = 169 cells) go through the thread-per-anchor kernel instead.
+#include <cuda.h>
+
+#include "cvpp_common.cuh"
+
+namespace cvpp {
+
+constexpr int kYaTileA = 128;
+constexpr int kYaChunkRows = 16;
+constexpr int kYaStages = 2;
+constexpr int kYaWarps = 14;
+constexpr int kYaChunkFloats = kYaChunkRows * kYaTileA;
+constexpr int kYaMaxLevels = 4;
+constexpr int MODE_V7 = 0;
+constexpr int MODE_V3 = 1;
+
+struct YaLevel {
+  const float* ptr;
+  int64_t batch_stride;
+  int64_t chan_stride;
+  int hw, w, h;
+  float aw[3], ah[3];   // V7: anchors in grid units (anchor / stride); V3: anchors / input size (fp32, like the reference)
+  int anchor_off;       // first output anchor index of this level (times B when the batch is merged)
+  int image_stride;     // merged batch: 3 * hw (anchor index advance per image), else 0
+  int tile_off;         // first tile (within an image) of this level
+  int tiles_per_anchor;
+};
+
+struct YaParams {
+  CUtensorMap tmap[kYaMaxLevels];
+  YaLevel lv[kYaMaxLevels];
+  int num_levels, B, nc, tiles_per_image, total_tiles;
+  int merged;           // V3: Decoder flattens the batch (yolov3_decode.py:47-50): one output "image"
+  int64_t A;            // anchors per OUTPUT image
+  float conf_thres;
+  uint64_t* cand_key;
+  int32_t* cand_count;
+  float4* box_dense;
+  float2* aux_dense;    // V7: (obj, class_conf) per anchor
+  int max_cand;
+};
+
+__device__ __forceinline__ void ya_tma_load_3d(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+// ---- YOLOv7 arithmetic ----------------------------------------------------------------------------
+__device__ __forceinline__ void v7_class_step(float x, int c, float& best, int& arg, float& prev) {
+  const bool gt = x > best;
+  prev = gt ? best : prev;
+  arg = gt ? c : arg;
+  best = fmaxf(best, x);
+}
+
+// exact `class_conf, class_pred = max(sigmoid(cls), 1)`: first index of the maximum sigmoid
+__device__ __noinline__ void v7_class_argmax_sigmoid(const float* col, int64_t cs, int nc, float& s, int& arg) {
+  float bs = -1.0f;
+  int ba = 0;
+  for (int c = 0; c < nc; ++c) {
+    const float v = sigmoid_precise(col[(int64_t)c * cs]);
+    if (v > bs) {
+      bs = v;
+      ba = c;
+    }
+  }
+  s = bs;
+  arg = ba;
+}
+
+struct V7Cell {
+  float4 box;  // normalised xyxy
+  float obj, cconf, score;
+  int cls;
+  bool cand;
+};
+
+// yolo_v7.py:329-342 + :361: t = (tx, ty, tw, th) logits of one cell of a W x H grid
+__device__ __forceinline__ float4 v7_box(float tx, float ty, float tw, float th, int cell, int W, int H, float aw, float ah) {
+  const int iy = cell / W, ix = cell - iy * W;
+  const float sx = sigmoid_precise(tx), sy = sigmoid_precise(ty);
+  const float sw = sigmoid_precise(tw), sh = sigmoid_precise(th);
+  const float bx = fadd(fsub(fmul(sx, 2.0f), 0.5f), (float)ix);
+  const float by = fadd(fsub(fmul(sy, 2.0f), 0.5f), (float)iy);
+  const float w2 = fmul(sw, 2.0f), h2 = fmul(sh, 2.0f);
+  const float bw = fmul(fmul(w2, w2), aw), bh = fmul(fmul(h2, h2), ah);
+  const float cx = fdiv(bx, (float)W), cy = fdiv(by, (float)H);
+  const float w = fdiv(bw, (float)W), h = fdiv(bh, (float)H);
+  const float hw = fmul(w, 0.5f), hh = fmul(h, 0.5f);
+  return make_float4(fsub(cx, hw), fsub(cy, hh), fadd(cx, hw), fadd(cy, hh));
+}
+
+__device__ __forceinline__ void v7_finalize(float tobj, float best, int arg_in, float prev, const float* cls_col, int64_t cs,
+                                            int nc, float conf_thres, V7Cell& o) {
+  o.obj = sigmoid_precise(tobj);
+  o.cconf = sigmoid_precise(best);
+  o.cls = arg_in;
+  o.score = fmul(o.obj, o.cconf);
+  o.cand = o.score >= conf_thres;
+  if (o.cand && sigmoid_precise(prev) >= o.cconf) {  // an earlier class with the same rounded sigmoid
+    v7_class_argmax_sigmoid(cls_col, cs, nc, o.cconf, o.cls);
+    o.score = fmul(o.obj, o.cconf);
+    o.cand = o.score >= conf_thres;
+  }
+}
+
+// ---- YOLOv3 arithmetic ----------------------------------------------------------------------------
+// yolov3_decode.py:22-23,47: xy = (sigmoid(t) + grid) / H for BOTH coordinates, wh = exp(t) * anchor_norm
+__device__ __forceinline__ float4 v3_box(float tx, float ty, float tw, float th, int cell, int W, int H, float aw, float ah) {
+  const int iy = cell / W, ix = cell - iy * W;
+  const float bx = fdiv(fadd(sigmoid_precise(tx), (float)ix), (float)H);
+  const float by = fdiv(fadd(sigmoid_precise(ty), (float)iy), (float)H);
+  const float bw = fmul(expf(tw), aw), bh = fmul(expf(th), ah);
+  const float hw = fmul(bw, 0.5f), hh = fmul(bh, 0.5f);
+  return make_float4(fsub(bx, hw), fsub(by, hh), fadd(bx, hw), fadd(by, hh));
+}
+
+// per-cell logit cut: a class can only reach sigmoid(o) * sigmoid(c) >= thr when c >= cut.  Conservative
+// (relative margin 1e-5 on the probability, 0.05 on the logit): survivors are re-tested exactly.
+__device__ __forceinline__ float v3_logit_cut(float so, float thr) {
+  if (so < thr) return INFINITY;  // sigmoid(c) <= 1 and fmul rounds monotonically: no class can pass
+  if (thr <= 0.0f) return -INFINITY;
+  const float r = fminf(__fdividef(thr, so), 1.0f) * (1.0f - 1e-5f);
+  return __logf(__fdividef(r, 1.0f - r)) - 0.05f;
+}
+
+template <int MODE>
+__device__ __forceinline__ int ya_local_index(int a, int cell, int hw) {
+  return MODE == MODE_V7 ? a * hw + cell : cell * 3 + a;
+}
+
+__device__ __forceinline__ void ya_tile_info(const YaParams& p, int g, int& b, int& l, int& a, int& cell0, int& nA) {
+  b = g / p.tiles_per_image;
+  const int j = g - b * p.tiles_per_image;
+  l = 0;
+#pragma unroll
+  for (int q = 1; q < kYaMaxLevels; ++q)
+    if (q < p.num_levels && j >= p.lv[q].tile_off) l = q;
+  const int t = j - p.lv[l].tile_off;
+  a = t / p.lv[l].tiles_per_anchor;
+  cell0 = (t - a * p.lv[l].tiles_per_anchor) * kYaTileA;
+  nA = min(kYaTileA, p.lv[l].hw - cell0);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kYaWarps * 32, 1) yolo_anchor_stream_kernel(const __grid_constant__ YaParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* ring = reinterpret_cast<float*>(smem_raw) + (size_t)warp * (kYaStages * kYaChunkFloats);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kYaWarps * kYaStages * kYaChunkFloats * sizeof(float)) +
+                  warp * kYaStages;
+  const int nc = p.nc;
+  const int attrs = 5 + nc;
+  const int nchunks = (attrs + kYaChunkRows - 1) / kYaChunkRows;
+
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < kYaStages; ++s) mbar_init(&bar[s], 1);
+    mbar_fence_init();
+  }
+  __syncwarp();
+
+  const int stride_tiles = gridDim.x * kYaWarps;
+  const int first = blockIdx.x + gridDim.x * warp;
+  const int n_tiles = first < p.total_tiles ? (p.total_tiles - first + stride_tiles - 1) / stride_tiles : 0;
+  const int total_q = n_tiles * nchunks;
+
+  int pq = 0, pj = 0, pg = first, pb = 0, pl = 0, pa = 0, pcell0 = 0;
+  auto issue = [&]() {
+    if (pj == 0) {
+      int nA_unused;
+      ya_tile_info(p, pg, pb, pl, pa, pcell0, nA_unused);
+    }
+    if (lane == 0) {
+      uint64_t* fb = &bar[pq & (kYaStages - 1)];
+      mbar_arrive_expect_tx(fb, (uint32_t)(kYaChunkFloats * sizeof(float)));
+      ya_tma_load_3d(ring + (pq & (kYaStages - 1)) * kYaChunkFloats, &p.tmap[pl], pcell0, pa * attrs + kYaChunkRows * pj,
+                     pb, fb);
+    }
+    ++pq;
+    if (++pj == nchunks) {
+      pj = 0;
+      pg += stride_tiles;
+    }
+  };
+  for (int q = 0; q < kYaStages && q < total_q; ++q) issue();
+
+  float t5[5][4];  // tx, ty, tw, th, tobj logits of the lane's 4 cells
+  float best[4], prev[4];  // V7: running class scan
+  int arg[4];
+  float so[4], cut[4];     // V3: sigmoid(obj), per-cell class logit cut
+  unsigned boxed = 0;      // V3: cells whose box has been written
+  int b = 0, l = 0, a = 0, cell0 = 0, nA = 0;
+  int j = 0, g = first;
+  for (int q = 0; q < total_q; ++q) {
+    if (j == 0) {
+      ya_tile_info(p, g, b, l, a, cell0, nA);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        best[k] = -INFINITY;
+        prev[k] = -INFINITY;
+        arg[k] = 0;
+      }
+      boxed = 0;
+    }
+    const YaLevel& L = p.lv[l];
+    const int s = q & (kYaStages - 1);
+    mbar_wait(&bar[s], (uint32_t)(q / kYaStages) & 1u);
+    float4 v[kYaChunkRows];
+    {
+      const float4* src = reinterpret_cast<const float4*>(ring + s * kYaChunkFloats) + lane;
+#pragma unroll
+      for (int r = 0; r < kYaChunkRows; ++r) v[r] = src[r * (kYaTileA / 4)];
+    }
+    __syncwarp();
+    if (pq < total_q) issue();
+
+    // rows of this chunk are attributes [16 j, 16 j + 16) of the anchor: 0..4 box/obj, 5.. classes
+    const int a0 = kYaChunkRows * j;
+    const int rows = min(kYaChunkRows, attrs - a0);
+    const bool active = 4 * lane < nA;
+    const int ob = p.merged ? 0 : b;
+    const int anchor_base = L.anchor_off + b * L.image_stride;
+    if (j == 0) {
+#pragma unroll
+      for (int r = 0; r < 5; ++r) {
+        t5[r][0] = v[r].x;
+        t5[r][1] = v[r].y;
+        t5[r][2] = v[r].z;
+        t5[r][3] = v[r].w;
+      }
+      if (MODE == MODE_V3) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          so[k] = sigmoid_precise(t5[4][k]);
+          cut[k] = active ? v3_logit_cut(so[k], p.conf_thres) : INFINITY;
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < kYaChunkRows; ++r) {
+      if (r < rows && !(j == 0 && r < 5)) {
+        const int c = a0 + r - 5;
+        const float x[4] = {v[r].x, v[r].y, v[r].z, v[r].w};
+        if (MODE == MODE_V7) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) v7_class_step(x[k], c, best[k], arg[k], prev[k]);
+        } else {
+          const bool maybe = (x[0] >= cut[0]) | (x[1] >= cut[1]) | (x[2] >= cut[2]) | (x[3] >= cut[3]);
+          if (__any_sync(0xffffffffu, maybe)) {  // rare: exact fp32 score of the survivors of this class row
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              bool hit = false;
+              float score = 0.0f;
+              if (x[k] >= cut[k]) {
+                score = fmul(so[k], sigmoid_precise(x[k]));  // confidence * class_prob (yolov3_decode.py:49)
+                hit = score >= p.conf_thres;                  // nms.py:60
+              }
+              const unsigned mk = __ballot_sync(0xffffffffu, hit);
+              if (mk == 0) continue;
+              int base = 0;
+              if (lane == 0) base = atomicAdd(p.cand_count + ob, __popc(mk));
+              base = __shfl_sync(0xffffffffu, base, 0);
+              if (hit) {
+                const int cell = cell0 + 4 * lane + k;
+                const int anchor = anchor_base + ya_local_index<MODE_V3>(a, cell, L.hw);
+                const int slot = base + __popc(mk & ((1u << lane) - 1u));
+                if (slot < p.max_cand)
+                  p.cand_key[(int64_t)ob * p.max_cand + slot] = key_pack((uint32_t)c, __float_as_uint(score), (uint32_t)anchor);
+                if (!(boxed & (1u << k))) {
+                  boxed |= 1u << k;
+                  p.box_dense[(int64_t)ob * p.A + anchor] =
+                      v3_box(t5[0][k], t5[1][k], t5[2][k], t5[3][k], cell, L.w, L.h, L.aw[a], L.ah[a]);
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+
+    if (++j == nchunks) {  // tile complete
+      j = 0;
+      g += stride_tiles;
+      if (MODE == MODE_V7) {
+        const float* col = L.ptr + (int64_t)b * L.batch_stride + (int64_t)(a * attrs + 5) * L.chan_stride + cell0 + 4 * lane;
+        V7Cell cell[4];
+        unsigned m[4];
+        int total = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          cell[k].cand = false;
+          if (active) {
+            v7_finalize(t5[4][k], best[k], arg[k], prev[k], col + k, L.chan_stride, nc, p.conf_thres, cell[k]);
+            if (cell[k].cand)
+              cell[k].box = v7_box(t5[0][k], t5[1][k], t5[2][k], t5[3][k], cell0 + 4 * lane + k, L.w, L.h, L.aw[a], L.ah[a]);
+          }
+          m[k] = __ballot_sync(0xffffffffu, cell[k].cand);
+          total += __popc(m[k]);
+        }
+        if (total) {
+          int base = 0;
+          if (lane == 0) base = atomicAdd(p.cand_count + ob, total);
+          base = __shfl_sync(0xffffffffu, base, 0);
+          const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (cell[k].cand) {
+              const int slot = base + __popc(m[k] & lt);
+              const int anchor = anchor_base + ya_local_index<MODE_V7>(a, cell0 + 4 * lane + k, L.hw);
+              if (slot < p.max_cand)
+                p.cand_key[(int64_t)ob * p.max_cand + slot] =
+                    key_pack((uint32_t)cell[k].cls, __float_as_uint(cell[k].score), (uint32_t)anchor);
+              p.box_dense[(int64_t)ob * p.A + anchor] = cell[k].box;
+              p.aux_dense[(int64_t)ob * p.A + anchor] = make_float2(cell[k].obj, cell[k].cconf);
+            }
+            base += __popc(m[k]);
+          }
+        }
+      }
+    }
+  }
+}
+
+// generic kernel: one thread per anchor, no alignment requirements
+template <int MODE>
+__global__ void __launch_bounds__(128) yolo_anchor_generic_kernel(const __grid_constant__ YaParams p, int anchors_in) {
+  const int nc = p.nc, attrs = 5 + nc;
+  const int b = blockIdx.y;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // position among the anchors of the listed levels
+  const int lane = threadIdx.x & 31;
+  const int ob = p.merged ? 0 : b;
+  V7Cell o;
+  o.cand = false;
+  int anchor = 0;
+  if (idx < anchors_in) {
+    int l = 0, start = 0, acc = 0;
+#pragma unroll
+    for (int q = 0; q < kYaMaxLevels; ++q) {
+      if (q < p.num_levels) {
+        if (idx >= acc) {
+          l = q;
+          start = acc;
+        }
+        acc += 3 * p.lv[q].hw;
+      }
+    }
+    const YaLevel& L = p.lv[l];
+    const int rel = idx - start;
+    const int a = rel / L.hw, cell = rel - a * L.hw;
+    anchor = L.anchor_off + b * L.image_stride + ya_local_index<MODE>(a, cell, L.hw);
+    const float* base = L.ptr + (int64_t)b * L.batch_stride + (int64_t)(a * attrs) * L.chan_stride + cell;
+    const int64_t cs = L.chan_stride;
+    if (MODE == MODE_V7) {
+      float best = -INFINITY, prev = -INFINITY;
+      int arg = 0;
+      for (int c = 0; c < nc; ++c) v7_class_step(base[(int64_t)(5 + c) * cs], c, best, arg, prev);
+      v7_finalize(base[4 * cs], best, arg, prev, base + 5 * cs, cs, nc, p.conf_thres, o);
+      if (o.cand) o.box = v7_box(base[0], base[cs], base[2 * cs], base[3 * cs], cell, L.w, L.h, L.aw[a], L.ah[a]);
+    } else {
+      const float so = sigmoid_precise(base[4 * cs]);
+      const float cut = v3_logit_cut(so, p.conf_thres);
+      bool boxed = false;
+      for (int c = 0; c < nc; ++c) {
+        const float x = base[(int64_t)(5 + c) * cs];
+        if (!(x >= cut)) continue;
+        const float score = fmul(so, sigmoid_precise(x));
+        if (!(score >= p.conf_thres)) continue;
+        const int slot = atomicAdd(p.cand_count + ob, 1);
+        if (slot < p.max_cand)
+          p.cand_key[(int64_t)ob * p.max_cand + slot] = key_pack((uint32_t)c, __float_as_uint(score), (uint32_t)anchor);
+        if (!boxed) {
+          boxed = true;
+          p.box_dense[(int64_t)ob * p.A + anchor] = v3_box(base[0], base[cs], base[2 * cs], base[3 * cs], cell, L.w, L.h, L.aw[a], L.ah[a]);
+        }
+      }
+    }
+  }
+  if (MODE == MODE_V7) {
+    const unsigned mk = __ballot_sync(0xffffffffu, o.cand);
+    if (mk == 0) return;
+    int slot0 = 0;
+    if (lane == 0) slot0 = atomicAdd(p.cand_count + ob, __popc(mk));
+    slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+    if (o.cand) {
+      const int slot = slot0 + __popc(mk & ((1u << lane) - 1u));
+      if (slot < p.max_cand)
+        p.cand_key[(int64_t)ob * p.max_cand + slot] = key_pack((uint32_t)o.cls, __float_as_uint(o.score), (uint32_t)anchor);
+      p.box_dense[(int64_t)ob * p.A + anchor] = o.box;
+      p.aux_dense[(int64_t)ob * p.A + anchor] = make_float2(o.obj, o.cconf);
+    }
+  }
+}
+
+typedef CUresult (*YaEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static YaEncodeTiledFn ya_encode_fn() {
+  static YaEncodeTiledFn fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      f = nullptr;
+    return reinterpret_cast<YaEncodeTiledFn>(f);
+  }();
+  return fn;
+}
+
+template <int MODE>
+static int ya_launch_mode(YaParams& stream_p, bool have_stream, YaParams& gen_p, int gen_anchors, int B, size_t smem,
+                          const DeviceInfo& di, cudaStream_t stream) {
+  if (have_stream) {
+    static unsigned long long attr_done = 0;
+    int rc = ensure_smem_attr(reinterpret_cast<const void*>(yolo_anchor_stream_kernel<MODE>), (int)smem, di.device, &attr_done);
+    if (rc != CVPP_OK) return rc;
+    const int grid = stream_p.total_tiles < di.sms ? stream_p.total_tiles : di.sms;
+    yolo_anchor_stream_kernel<MODE><<<grid, kYaWarps * 32, smem, stream>>>(stream_p);
+    CVPP_CUDA_TRY(cudaGetLastError());
+  }
+  if (gen_anchors > 0) {
+    dim3 grid((unsigned)((gen_anchors + 127) / 128), (unsigned)B);
+    yolo_anchor_generic_kernel<MODE><<<grid, 128, 0, stream>>>(gen_p, gen_anchors);
+    CVPP_CUDA_TRY(cudaGetLastError());
+  }
+  return CVPP_OK;
+}
+
+// mode 0: YOLOv7, mode 1: YOLOv3
+int yolo_anchor_decode_launch(int mode, const float* const* level_ptr, const int64_t* batch_stride,
+                              const int64_t* chan_stride, const int* level_h, const int* level_w,
+                              const float* level_anchors, int num_levels, int B, int nc, int input_h, int input_w,
+                              float conf_thres, int merge_batch, uint64_t* cand_key, int32_t* cand_count, float* box_dense,
+                              float* aux_dense, int max_cand, int force_generic, cudaStream_t stream) {
+  const char* name = mode == MODE_V7 ? "yolov7 decode" : "yolov3 decode";
+  if (!level_ptr || !batch_stride || !chan_stride || !level_h || !level_w || !level_anchors || !cand_key || !cand_count ||
+      !box_dense || (mode == MODE_V7 && !aux_dense)) {
+    set_error("%s: NULL pointer argument", name);
+    return CVPP_ERR_INVALID_ARG;
+  }
+  if (num_levels < 1 || num_levels > kYaMaxLevels || B < 0 || nc < 1 || nc > CVPP_MAX_CLASSES || max_cand < 1 ||
+      input_h < 1 || input_w < 1) {
+    set_error("%s: bad num_levels=%d / B=%d / nc=%d / max_cand=%d", name, num_levels, B, nc, max_cand);
+    return CVPP_ERR_INVALID_ARG;
+  }
+  if (!(conf_thres >= 0.0f && conf_thres <= 1.0f)) {
+    set_error("%s: confidence threshold %f outside [0, 1]", name, conf_thres);
+    return CVPP_ERR_INVALID_ARG;
+  }
+  if ((reinterpret_cast<uintptr_t>(box_dense) & 15u) || (reinterpret_cast<uintptr_t>(aux_dense) & 7u)) {
+    set_error("%s: box_dense / aux_dense misaligned", name);
+    return CVPP_ERR_ALIGNMENT;
+  }
+  const bool merged = mode == MODE_V3 && merge_batch;
+  YaLevel lv[kYaMaxLevels];
+  bool tma_level[kYaMaxLevels];
+  int64_t A = 0;
+  const int attrs = 5 + nc;
+  for (int l = 0; l < num_levels; ++l) {
+    if (!level_ptr[l] || level_h[l] < 1 || level_w[l] < 1) {
+      set_error("%s: level %d is empty", name, l);
+      return CVPP_ERR_INVALID_ARG;
+    }
+    YaLevel& L = lv[l];
+    L.ptr = level_ptr[l];
+    L.batch_stride = batch_stride[l];
+    L.chan_stride = chan_stride[l];
+    L.h = level_h[l];
+    L.w = level_w[l];
+    L.hw = level_h[l] * level_w[l];
+    for (int a = 0; a < 3; ++a) {
+      const float pw = level_anchors[(3 * l + a) * 2 + 0], ph = level_anchors[(3 * l + a) * 2 + 1];
+      if (mode == MODE_V7) {
+        // stride = input / feature size (Python doubles), anchors / stride evaluated in fp32 (yolo_v7.py:254-262)
+        const float stride_h = (float)((double)input_h / level_h[l]), stride_w = (float)((double)input_w / level_w[l]);
+        L.aw[a] = pw / stride_w;
+        L.ah[a] = ph / stride_h;
+      } else {
+        // generate_yolo3_anchor (core/utils/anchor.py:102-117): fp32 tensor divided in place by w, h
+        L.aw[a] = pw / (float)input_w;
+        L.ah[a] = ph / (float)input_h;
+      }
+    }
+    L.anchor_off = (int)(merged ? A * B : A);
+    L.image_stride = merged ? 3 * L.hw : 0;
+    L.tile_off = 0;
+    L.tiles_per_anchor = (L.hw + kYaTileA - 1) / kYaTileA;
+    A += 3 * (int64_t)L.hw;
+    tma_level[l] = !force_generic && !((reinterpret_cast<uintptr_t>(L.ptr) & 15u) || (L.batch_stride & 3) ||
+                                       (L.chan_stride & 3) || (L.hw & 3));
+  }
+  const int64_t A_out = merged ? A * B : A;
+  if (A_out > CVPP_MAX_ANCHORS) {
+    set_error("%s: %lld anchors exceed the %d-anchor key field", name, (long long)A_out, CVPP_MAX_ANCHORS);
+    return CVPP_ERR_UNSUPPORTED;
+  }
+  const int n_out = merged ? (B > 0 ? 1 : 0) : B;
+  CVPP_CUDA_TRY(cudaMemsetAsync(cand_count, 0, sizeof(int32_t) * (size_t)n_out, stream));
+  if (B == 0) return CVPP_OK;
+
+  DeviceInfo di;
+  int rc = device_info(&di);
+  if (rc != CVPP_OK) return rc;
+  const size_t smem = (size_t)kYaWarps * kYaStages * kYaChunkFloats * sizeof(float) + (size_t)kYaWarps * kYaStages * sizeof(uint64_t);
+  const bool tma_avail = smem <= (size_t)di.max_smem && ya_encode_fn();
+
+  alignas(64) YaParams sp{}, gp{};
+  for (YaParams* q : {&sp, &gp}) {
+    q->B = B;
+    q->nc = nc;
+    q->merged = merged ? 1 : 0;
+    q->A = A_out;
+    q->conf_thres = conf_thres;
+    q->cand_key = cand_key;
+    q->cand_count = cand_count;
+    q->box_dense = reinterpret_cast<float4*>(box_dense);
+    q->aux_dense = reinterpret_cast<float2*>(aux_dense);
+    q->max_cand = max_cand;
+  }
+  int gen_anchors = 0, tiles = 0;
+  for (int l = 0; l < num_levels; ++l) {
+    bool ok = tma_avail && tma_level[l];
+    if (ok) {
+      const YaLevel& L = lv[l];
+      cuuint64_t dims[3] = {(cuuint64_t)L.hw, (cuuint64_t)(3 * attrs), (cuuint64_t)B};
+      cuuint64_t strides[2] = {(cuuint64_t)L.chan_stride * 4u, (cuuint64_t)L.batch_stride * 4u};
+      if (B == 1) strides[1] = (cuuint64_t)L.chan_stride * 4u * (cuuint64_t)(3 * attrs);
+      cuuint32_t box[3] = {(cuuint32_t)kYaTileA, (cuuint32_t)kYaChunkRows, 1u};
+      cuuint32_t estr[3] = {1u, 1u, 1u};
+      ok = ya_encode_fn()(&sp.tmap[sp.num_levels], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(L.ptr), dims,
+                          strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    }
+    if (ok) {
+      YaLevel& D = sp.lv[sp.num_levels++];
+      D = lv[l];
+      D.tile_off = tiles;
+      tiles += 3 * D.tiles_per_anchor;
+    } else {
+      gp.lv[gp.num_levels++] = lv[l];
+      gen_anchors += 3 * lv[l].hw;
+    }
+  }
+  sp.tiles_per_image = tiles;
+  sp.total_tiles = tiles * B;
+  if (mode == MODE_V7) return ya_launch_mode<MODE_V7>(sp, sp.num_levels > 0, gp, gen_anchors, B, smem, di, stream);
+  return ya_launch_mode<MODE_V3>(sp, sp.num_levels > 0, gp, gen_anchors, B, smem, di, stream);
+}
+
+// ---- predict_bounding_bbox (dense), core/predict/yolov3_decode.py:12-29 -----------------------------
+// One CTA transposes a 32-cell x 3*(5+nc)-channel tile through shared memory: channel rows are read
+// coalesced along the cells, the four NHWC outputs are written coalesced along (anchor, attribute).
+__global__ void __launch_bounds__(256)
+yolov3_predict_bbox_kernel(const float* __restrict__ feature, int nc, int H, int W, float aw0, float ah0, float aw1,
+                           float ah1, float aw2, float ah2, float* __restrict__ box_xy, float* __restrict__ box_wh,
+                           float* __restrict__ confidence, float* __restrict__ class_prob) {
+  extern __shared__ float tile[];  // [3 * attrs][33]
+  const int attrs = 5 + nc, C = 3 * attrs, HW = H * W;
+  const int b = blockIdx.y, cell0 = blockIdx.x * 32;
+  const int ncell = min(32, HW - cell0);
+  const float* src = feature + (int64_t)b * C * HW + cell0;
+  for (int i = threadIdx.x; i < C * 32; i += blockDim.x) {
+    const int ch = i >> 5, x = i & 31;
+    if (x < ncell) tile[ch * 33 + x] = __ldg(src + (int64_t)ch * HW + x);
+  }
+  __syncthreads();
+  const float aw[3] = {aw0, aw1, aw2}, ah[3] = {ah0, ah1, ah2};
+  const int64_t base = (int64_t)b * HW + cell0;  // first output cell
+  // box_xy / box_wh: (cell, a, 2)
+  for (int i = threadIdx.x; i < ncell * 6; i += blockDim.x) {
+    const int x = i / 6, r = i - x * 6, a = r >> 1, d = r & 1;
+    const int cell = cell0 + x;
+    const float g = d == 0 ? (float)(cell % W) : (float)(cell / W);
+    box_xy[base * 6 + i] = fdiv(fadd(sigmoid_precise(tile[(a * attrs + d) * 33 + x]), g), (float)H);
+    box_wh[base * 6 + i] = fmul(expf(tile[(a * attrs + 2 + d) * 33 + x]), d == 0 ? aw[a] : ah[a]);
+  }
+  for (int i = threadIdx.x; i < ncell * 3; i += blockDim.x) {
+    const int x = i / 3, a = i - x * 3;
+    confidence[base * 3 + i] = sigmoid_precise(tile[(a * attrs + 4) * 33 + x]);
+  }
+  const int per_cell = 3 * nc;
+  for (int i = threadIdx.x; i < ncell * per_cell; i += blockDim.x) {
+    const int x = i / per_cell, r = i - x * per_cell, a = r / nc, c = r - a * nc;
+    class_prob[base * per_cell + i] = sigmoid_precise(tile[(a * attrs + 5 + c) * 33 + x]);
+  }
+}
+
+int yolov3_predict_bbox_launch(const float* feature, int B, int nc, int H, int W, const float* anchors, float* box_xy,
+                               float* box_wh, float* confidence, float* class_prob, cudaStream_t stream) {
+  if (!feature || !anchors || !box_xy || !box_wh || !confidence || !class_prob) {
+    set_error("yolov3_predict_bbox: NULL pointer argument");
+    return CVPP_ERR_INVALID_ARG;
+  }
+  if (B < 0 || nc < 1 || nc > CVPP_MAX_CLASSES || H < 1 || W < 1) {
+    set_error("yolov3_predict_bbox: bad sizes (B=%d nc=%d H=%d W=%d)", B, nc, H, W);
+    return CVPP_ERR_INVALID_ARG;
+  }
+  if (B == 0) return CVPP_OK;
+  const size_t smem = (size_t)3 * (5 + nc) * 33 * sizeof(float);
+  DeviceInfo di;
+  int rc = device_info(&di);
+  if (rc != CVPP_OK) return rc;
+  if (smem > (size_t)di.max_smem) {
+    set_error("yolov3_predict_bbox: nc=%d needs %zu bytes of shared memory", nc, smem);
+    return CVPP_ERR_UNSUPPORTED;
+  }
+  static unsigned long long attr_done = 0;
+  static int attr_bytes = 0;
+  if ((int)smem > attr_bytes) {
+    attr_done = 0;
+    attr_bytes = (int)smem;
+  }
+  rc = ensure_smem_attr(reinterpret_cast<const void*>(yolov3_predict_bbox_kernel), attr_bytes, di.device, &attr_done);
+  if (rc != CVPP_OK) return rc;
+  dim3 grid((unsigned)((H * W + 31) / 32), (unsigned)B);
+  yolov3_predict_bbox_kernel<<<grid, 256, smem, stream>>>(feature, nc, H, W, anchors[0], anchors[1], anchors[2], anchors[3],
+                                                        anchors[4], anchors[5], box_xy, box_wh, confidence, class_prob);
+  CVPP_CUDA_TRY(cudaGetLastError());
+  return CVPP_OK;
+}
+
+}  // namespace cvpp

@@ -9,7 +9,8 @@ from typing import List, Optional, Sequence, Tuple
 import torch
 
 from . import _lib
-from ._lib import (ORDER_CLASS_MAJOR, ORDER_SCORE_DESC, RULE_COORD_TRICK, RULE_PER_CLASS,  # noqa: F401
+from ._lib import (BOX_CORRECT, BOX_KEEP, BOX_NORMALISE_CORRECT, ORDER_CLASS_MAJOR, ORDER_SCORE_DESC,  # noqa: F401
+                   ROWS_FULL, ROWS_SSD, ROWS_YOLOV7, ROWS_YOLOV8, RULE_COORD_TRICK, RULE_PER_CLASS,
                    RULE_TORCHVISION_CPU, check)
 
 c_vp = ctypes.c_void_p
@@ -47,11 +48,14 @@ class LevelSet:
     keep: tuple  # tensors kept alive
 
 
-def make_levels(levels: Sequence[torch.Tensor], strides: Sequence[float],
+def make_levels(levels: Sequence[torch.Tensor], strides: Optional[Sequence[float]] = None,
                 sizes: Optional[Sequence[Tuple[int, int]]] = None) -> LevelSet:
     """levels: list of (B, C, H, W) tensors (any batch/channel strides, cells contiguous), or - with
-    `sizes` - list of (B, C, H*W) views, e.g. slices of the concatenated x_cat."""
+    `sizes` - list of (B, C, H*W) views, e.g. slices of the concatenated x_cat.  `strides` is the YOLOv8
+    stride per level (None for the anchor-based heads, which take an anchor table instead)."""
     n = len(levels)
+    if strides is None:
+        strides = [0.0] * n
     if n < 1 or n > 4 or len(strides) != n:
         raise ValueError("between 1 and 4 head levels with one stride each are supported")
     keep = []
@@ -94,6 +98,7 @@ class Candidates:
     max_cand: int
     A: int
     nc: int
+    aux_dense: Optional[torch.Tensor] = None  # YOLOv7: (B, A, 2) float32 (obj, class_conf)
 
 
 @dataclass
@@ -343,6 +348,188 @@ def ssd_parse_loc(loc: torch.Tensor, priors: torch.Tensor) -> torch.Tensor:
         check(_lib.lib().cvpp_ssd_parse_loc(_ptr(loc), _ptr(priors), int(loc.shape[0]), int(loc.shape[1]), _ptr(out),
                                             _stream(loc.device)))
     return out.reshape(shape)
+
+
+def _anchor_table(anchors, n_levels: int) -> ctypes.Array:
+    flat = [float(v) for row in anchors for v in (row if hasattr(row, "__len__") else [row])]
+    if len(flat) != n_levels * 6:
+        raise ValueError(f"expected {n_levels * 3} (w, h) anchors, 3 per level, got {len(flat) // 2}")
+    return (ctypes.c_float * len(flat))(*flat)
+
+
+def yolov7_decode_filter(ls: LevelSet, nc: int, anchors, input_hw: Sequence[int], conf_thres: float,
+                         max_cand: Optional[int] = None) -> Candidates:
+    """ls: levels (B, 3*(5+nc), H, W) in the reference's order; anchors: (3*levels, 2) pixels, row 3*l + a =
+    anchors[anchors_mask[l]][a].  Candidate keys + normalised xyxy + (obj, class_conf) per anchor."""
+    if ls.C != 3 * (5 + nc):
+        raise ValueError(f"head has {ls.C} channels, expected 3*(5+{nc})")
+    A = 3 * ls.A
+    max_cand = int(max_cand or A)
+    dev = ls.device
+    key = torch.empty((ls.B, max_cand), dtype=torch.int64, device=dev)
+    count = torch.empty((ls.B,), dtype=torch.int32, device=dev)
+    box_dense = torch.empty((ls.B, A, 4), dtype=torch.float32, device=dev)
+    aux_dense = torch.empty((ls.B, A, 2), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(_lib.lib().cvpp_yolov7_decode_filter(ls.ptr, ls.batch_stride, ls.chan_stride, ls.h, ls.w,
+                                                   _anchor_table(anchors, ls.n), ls.n, ls.B, nc, int(input_hw[0]),
+                                                   int(input_hw[1]), float(conf_thres), _ptr(key), _ptr(count),
+                                                   _ptr(box_dense), _ptr(aux_dense), max_cand, _stream(dev)))
+    return Candidates(key, count, box_dense, max_cand, A, nc, aux_dense)
+
+
+def yolov7_pred_filter(pred: torch.Tensor, nc: int, conf_thres: float, max_cand: Optional[int] = None) -> Candidates:
+    """pred (B, A, 5+nc) decoded (cx, cy, w, h, obj, cls...) -> candidates (YOLOv7._nms / yolo7_nms front half)."""
+    _require_cuda(pred, "prediction")
+    if pred.dim() != 3 or pred.shape[2] < 5 + nc:
+        raise ValueError(f"prediction must be (B, A, 5+nc), got {tuple(pred.shape)}")
+    if pred.shape[2] != 5 + nc:
+        pred = pred[..., :5 + nc]
+    pred = pred.contiguous()
+    B, A = int(pred.shape[0]), int(pred.shape[1])
+    max_cand = int(max_cand or A)
+    dev = pred.device
+    key = torch.empty((B, max_cand), dtype=torch.int64, device=dev)
+    count = torch.empty((B,), dtype=torch.int32, device=dev)
+    box_dense = torch.empty((B, A, 4), dtype=torch.float32, device=dev)
+    aux_dense = torch.empty((B, A, 2), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(_lib.lib().cvpp_yolov7_pred_filter(_ptr(pred), B, A, nc, float(conf_thres), _ptr(key), _ptr(count),
+                                                 _ptr(box_dense), _ptr(aux_dense), max_cand, _stream(dev)))
+    return Candidates(key, count, box_dense, max_cand, A, nc, aux_dense)
+
+
+def yolov3_decode_filter(ls: LevelSet, nc: int, anchors, input_hw: Sequence[int], conf_thres: float,
+                         merge_batch: bool = False, max_cand: Optional[int] = None) -> Candidates:
+    """ls: levels (B, 3*(5+nc), H, W) (13, 26, 52 for 416^2); anchors (3*levels, 2) pixels in level order.
+    One key per (anchor, class) with sigmoid(obj)*sigmoid(cls) >= conf.  merge_batch flattens the batch
+    into one output image like the reference Decoder."""
+    if ls.C != 3 * (5 + nc):
+        raise ValueError(f"head has {ls.C} channels, expected 3*(5+{nc})")
+    A = 3 * ls.A * (ls.B if merge_batch else 1)
+    n_out = (1 if ls.B > 0 else 0) if merge_batch else ls.B
+    max_cand = int(max_cand or min(A * nc, 1 << 16))
+    dev = ls.device
+    key = torch.empty((n_out, max_cand), dtype=torch.int64, device=dev)
+    count = torch.empty((n_out,), dtype=torch.int32, device=dev)
+    box_dense = torch.empty((n_out, A, 4), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(_lib.lib().cvpp_yolov3_decode_filter(ls.ptr, ls.batch_stride, ls.chan_stride, ls.h, ls.w,
+                                                   _anchor_table(anchors, ls.n), ls.n, ls.B, nc, int(input_hw[0]),
+                                                   int(input_hw[1]), float(conf_thres), int(bool(merge_batch)),
+                                                   _ptr(key), _ptr(count), _ptr(box_dense), max_cand, _stream(dev)))
+    return Candidates(key, count, box_dense, max_cand, A, nc)
+
+
+def yolov3_predict_bbox(feature: torch.Tensor, nc: int, anchors_norm):
+    """predict_bounding_bbox: feature (N, 3*(5+nc), H, W), anchors (3, 2) normalised ->
+    (box_xy (N,H,W,3,2), box_wh (N,H,W,3,2), confidence (N,H,W,3,1), class_prob (N,H,W,3,nc))."""
+    _require_cuda(feature, "feature_map")
+    feature = feature.contiguous()
+    N, C, H, W = (int(v) for v in feature.shape)
+    if C != 3 * (5 + nc):
+        raise ValueError(f"feature map has {C} channels, expected 3*(5+{nc})")
+    dev = feature.device
+    xy = torch.empty((N, H, W, 3, 2), dtype=torch.float32, device=dev)
+    wh = torch.empty((N, H, W, 3, 2), dtype=torch.float32, device=dev)
+    conf = torch.empty((N, H, W, 3, 1), dtype=torch.float32, device=dev)
+    prob = torch.empty((N, H, W, 3, nc), dtype=torch.float32, device=dev)
+    flat = [float(v) for row in anchors_norm for v in row]
+    if len(flat) != 6:
+        raise ValueError("expected 3 (w, h) anchors")
+    with torch.cuda.device(dev):
+        check(_lib.lib().cvpp_yolov3_predict_bbox(_ptr(feature), N, nc, H, W, (ctypes.c_float * 6)(*flat), _ptr(xy),
+                                                  _ptr(wh), _ptr(conf), _ptr(prob), _stream(dev)))
+    return xy, wh, conf, prob
+
+
+def score_matrix_filter(boxes: torch.Tensor, scores: torch.Tensor, conf_thres: float,
+                        max_cand: Optional[int] = None) -> Candidates:
+    """boxes (M, 4) xyxy + scores (M, nc) -> single-image candidates, one key per score >= conf."""
+    _require_cuda(boxes, "boxes")
+    _require_cuda(scores, "scores")
+    boxes, scores = boxes.contiguous(), scores.contiguous()
+    M, nc = int(scores.shape[0]), int(scores.shape[1])
+    if tuple(boxes.shape) != (M, 4):
+        raise ValueError("expected boxes (M, 4) and scores (M, nc)")
+    max_cand = int(max_cand or max(min(M * nc, 1 << 16), 1))
+    if boxes.data_ptr() % 16:
+        boxes = boxes.clone()
+    dev = boxes.device
+    while True:
+        key = torch.empty((1, max_cand), dtype=torch.int64, device=dev)
+        count = torch.empty((1,), dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            check(_lib.lib().cvpp_score_matrix_filter(_ptr(scores), M, nc, float(conf_thres), _ptr(key), _ptr(count),
+                                                      max_cand, _stream(dev)))
+        n = int(count.item())
+        if n <= max_cand:
+            return Candidates(key, count, boxes.reshape(1, M, 4), max_cand, M, nc)
+        max_cand = n
+
+
+def gather_feat(feat: torch.Tensor, ind: torch.Tensor, count: Optional[torch.Tensor] = None,
+                check_bounds: bool = True) -> torch.Tensor:
+    """feat (B, N, C) float32, ind (B, K) int32/int64 -> (B, K, C) rows feat[b, ind[b, k]]."""
+    _require_cuda(feat, "feat")
+    if ind.dtype not in (torch.int32, torch.int64) or not ind.is_cuda:
+        raise ValueError("ind must be an int32 / int64 CUDA tensor")
+    feat, ind = feat.contiguous(), ind.contiguous()
+    B, N, C = (int(v) for v in feat.shape)
+    K = int(ind.shape[1])
+    dev = feat.device
+    out = torch.zeros((B, K, C), dtype=torch.float32, device=dev) if count is not None else \
+        torch.empty((B, K, C), dtype=torch.float32, device=dev)
+    err = torch.empty((1,), dtype=torch.int32, device=dev) if check_bounds else None
+    with torch.cuda.device(dev):
+        check(_lib.lib().cvpp_gather_feat(_ptr(feat), _ptr(ind), int(ind.dtype == torch.int64), _ptr(count), B, N, C, K,
+                                          _ptr(out), _ptr(err), _stream(dev)))
+    if check_bounds and int(err.item()):
+        raise IndexError("gather_feat: index out of range")
+    return out
+
+
+def detection_epilogue(det: Detections, layout: int, box_mode: int = BOX_KEEP, letterbox: Optional[torch.Tensor] = None,
+                       aux_dense: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """cvpp_detection_epilogue: (B, max_out, 6|7) caller-facing rows on the device."""
+    B, max_out = int(det.box.shape[0]), int(det.box.shape[1])
+    dev = det.box.device
+    width = 6 if layout in (ROWS_YOLOV8, ROWS_SSD) else 7
+    rows = torch.empty((B, max_out, width), dtype=torch.float32, device=dev)
+    A = int(aux_dense.shape[1]) if aux_dense is not None else 0
+    if letterbox is not None:
+        letterbox = letterbox.to(device=dev, dtype=torch.float32).contiguous()
+        if tuple(letterbox.shape) != (B, 5):
+            raise ValueError("letterbox must be (B, 5)")
+    with torch.cuda.device(dev):
+        check(_lib.lib().cvpp_detection_epilogue(_ptr(det.box), _ptr(det.score), _ptr(det.cls), _ptr(det.anchor),
+                                                 _ptr(det.count), _ptr(aux_dense), B, max_out, A, int(layout),
+                                                 int(box_mode), _ptr(letterbox), _ptr(rows), _stream(dev)))
+    return rows
+
+
+def correct_boxes_params(image_hw: Sequence[Tuple[int, int]], input_hw: Sequence[int], letterbox_image: bool,
+                         device) -> torch.Tensor:
+    """The (B, 5) table cvpp_detection_epilogue wants for yolo_correct_boxes (image_process.py:161-181)."""
+    if letterbox_image:
+        return letterbox_params(image_hw, input_hw, device)
+    rows = [[float(w), float(h), 0.0, 0.0, 1.0] for (h, w) in image_hw]
+    return torch.tensor(rows, dtype=torch.float32).to(device)
+
+
+def per_class_nms_device(c: Candidates, nms_thres: float, initial_out: int = 4096) -> Detections:
+    """sort + per-class NMS (class-major order, no cap), result left on the device; retries with a larger
+    output capacity when the first guess overflows (one scalar D2H read of the max count)."""
+    if int(c.count.max().item()) > c.max_cand:
+        raise OverflowError("candidate buffer overflow: re-run the filter with a larger max_cand")
+    segmented_sort(c, RULE_PER_CLASS)
+    max_out = max(min(c.max_cand, initial_out), 1)
+    while True:
+        det = nms(c, nms_thres, RULE_PER_CLASS, ORDER_CLASS_MAJOR, max_det=0, max_out=max_out)
+        need = int(det.count.max().item()) if det.count.numel() else 0
+        if need <= max_out:
+            return det
+        max_out = need
 
 
 def per_class_nms_rows(c: Candidates, nms_thres: float, initial_out: int = 4096):

@@ -64,6 +64,21 @@ enum {
   CVPP_ORDER_CLASS_MAJOR = 1 /* class ascending then score descending, no cap (YOLOv7/SSD/YOLOv3)  */
 };
 
+/* row layouts written by cvpp_detection_epilogue */
+enum {
+  CVPP_ROWS_YOLOV8 = 0, /* x1,y1,x2,y2,conf,cls            (non_max_suppression, ultralytics_ops.py:226) */
+  CVPP_ROWS_SSD = 1,    /* x1,y1,x2,y2,label,conf          (Ssd.decode_boxes, ssd.py:275-278)            */
+  CVPP_ROWS_YOLOV7 = 2, /* x1,y1,x2,y2,obj,class_conf,cls  (YOLOv7._nms, yolo_v7.py:391)                 */
+  CVPP_ROWS_FULL = 3    /* x1,y1,x2,y2,score,cls,anchor    (the all-gather payload)        */
+};
+
+/* box transform of cvpp_detection_epilogue */
+enum {
+  CVPP_BOX_KEEP = 0,             /* copy det_box                                                          */
+  CVPP_BOX_CORRECT = 1,          /* normalised xyxy -> centre/size -> yolo_correct_boxes (original pixels) */
+  CVPP_BOX_NORMALISE_CORRECT = 2 /* input-pixel xyxy: / (in_w, in_h) first (yolo_v8.py:233-234), then 1  */
+};
+
 CVPP_API int cvpp_version(void);
 CVPP_API const char* cvpp_last_error(void);
 CVPP_API const char* cvpp_error_name(int code);
@@ -210,6 +225,89 @@ CVPP_API int cvpp_ssd_decode_filter(const float* loc, const float* conf, const f
                                     int max_cand, cvpp_stream_t stream);
 CVPP_API int cvpp_ssd_parse_loc(const float* loc, const float* priors, int B, int P, float* out,
                                 cvpp_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * YOLOv7 3-scale anchor decode + confidence filter, fused.
+ * Replaces: YOLOv7.decode_box  core/algorithms/yolo_v7.py:245-344 (sigmoids, grid/anchor box math,
+ *           normalisation, concatenation of the levels) and the candidate stage of YOLOv7._nms
+ *           :361 (xywh_to_xyxy_torch core/utils/bboxes.py:29-49), :370 (class max, first index),
+ *           :377 (obj * class_conf >= conf).
+ * Level l is (B, 3*(5+nc), H_l, W_l) addressed like cvpp_yolov8_decode_filter; channel a*(5+nc)+k is
+ * attribute k (tx,ty,tw,th,obj,classes) of anchor a.  level_anchors: HOST (num_levels*3, 2) fp32 anchor
+ * (w, h) in input pixels, row 3*l + a (the reference's anchors[anchors_mask[l]]).  Anchor index within an
+ * image: level offset + a*H*W + y*W + x (levels in the order given: 20x20, 40x40, 80x80 for the reference).
+ * Outputs: one key per anchor with obj*class_conf >= conf_thres (score = that product, class = first
+ * argmax), box_dense (B, A, 4) normalised xyxy and aux_dense (B, A, 2) = (obj, class_conf) at candidate
+ * anchors.  Follow with cvpp_segmented_sort + cvpp_nms(PER_CLASS, CLASS_MAJOR) for yolo_v7.py:396-413.
+ * cvpp_yolov7_pred_filter is the same candidate stage on an already decoded (B, A, 5+nc) tensor, the
+ * argument of YOLOv7._nms (yolo_v7.py:348) and yolo7_nms (core/utils/nms.py:87).
+ * ------------------------------------------------------------------------------------------- */
+CVPP_API int cvpp_yolov7_decode_filter(const float* const* level_ptr, const int64_t* batch_stride,
+                                       const int64_t* chan_stride, const int* level_h, const int* level_w,
+                                       const float* level_anchors, int num_levels, int B, int nc, int input_h,
+                                       int input_w, float conf_thres, uint64_t* cand_key, int32_t* cand_count,
+                                       float* box_dense, float* aux_dense, int max_cand, cvpp_stream_t stream);
+CVPP_API int cvpp_yolov7_pred_filter(const float* pred, int B, int64_t A, int nc, float conf_thres,
+                                     uint64_t* cand_key, int32_t* cand_count, float* box_dense, float* aux_dense,
+                                     int max_cand, cvpp_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * YOLOv3 3-scale decode + per-(anchor, class) confidence filter, fused.
+ * Replaces: predict_bounding_bbox      core/predict/yolov3_decode.py:12-29
+ *           Decoder._yolo_post_process core/predict/yolov3_decode.py:40-51
+ *           Decoder.__call__           core/predict/yolov3_decode.py:53-63 (scale concatenation)
+ *           the mask of yolo3_nms      core/utils/nms.py:60
+ *           generate_yolo3_anchor      core/utils/anchor.py:102-117 (anchor / input size)
+ * Level l is (B, 3*(5+nc), H_l, W_l); level_anchors as above (the rows 3*l..3*l+2 of the reshaped
+ * cfg.arch.anchor).  Anchor index within a level: (y*W + x)*3 + a.  xy is divided by H for both axes like
+ * the reference (:22).  merge_batch != 0 reproduces Decoder's flattening of the batch (:47-50): ONE
+ * output image whose anchor index is B*level_offset + b*3*H*W + (y*W + x)*3 + a; cand_count has one entry
+ * and box_dense is (1, B*A, 4).  One key per (anchor, class) with sigmoid(obj)*sigmoid(cls) >= conf_thres.
+ * cvpp_yolov3_predict_bbox is predict_bounding_bbox alone (dense): box_xy (B,H,W,3,2), box_wh (B,H,W,3,2),
+ * confidence (B,H,W,3,1), class_prob (B,H,W,3,nc) for one level; anchors: HOST (3, 2) already normalised.
+ * ------------------------------------------------------------------------------------------- */
+CVPP_API int cvpp_yolov3_decode_filter(const float* const* level_ptr, const int64_t* batch_stride,
+                                       const int64_t* chan_stride, const int* level_h, const int* level_w,
+                                       const float* level_anchors, int num_levels, int B, int nc, int input_h,
+                                       int input_w, float conf_thres, int merge_batch, uint64_t* cand_key,
+                                       int32_t* cand_count, float* box_dense, int max_cand, cvpp_stream_t stream);
+CVPP_API int cvpp_yolov3_predict_bbox(const float* feature, int B, int nc, int H, int W, const float* anchors,
+                                      float* box_xy, float* box_wh, float* confidence, float* class_prob,
+                                      cvpp_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Candidate mask of the standalone yolo3_nms (core/utils/nms.py:54-60): scores (M, nc) fp32 row-major ->
+ * one key (class c, score, row m) per element >= conf_thres; single image (cand_count is one int32).
+ * The caller's (M, 4) xyxy boxes serve directly as box_dense for cvpp_nms (A = M).
+ * ------------------------------------------------------------------------------------------- */
+CVPP_API int cvpp_score_matrix_filter(const float* scores, int64_t M, int nc, float conf_thres, uint64_t* cand_key,
+                                      int32_t* cand_count, int max_cand, cvpp_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Row gather: out[b, k, :] = feat[b, ind[b, k], :] for k < (count ? count[b] : K).
+ * Replaces: RegL1Loss.gather_feat  core/loss/centernet_loss.py:37-43
+ *           gather_op              core/utils/nms.py:34-51 (B = 1)
+ * feat (B, N, C) fp32, ind (B, K) int32 or int64 (ind_is_int64), out (B, K, C).  err_flag (nullable,
+ * one int32) is set to 1 when an index falls outside [0, N) (torch.gather would raise).
+ * ------------------------------------------------------------------------------------------- */
+CVPP_API int cvpp_gather_feat(const float* feat, const void* ind, int ind_is_int64, const int32_t* count, int B,
+                              int64_t N, int C, int K, float* out, int32_t* err_flag, cvpp_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Detection epilogue: assemble the caller-facing rows from cvpp_nms outputs, with the box mapped back to
+ * the original image, batched (one (h, w) per image) and on the device.
+ * Replaces: row assembly            ultralytics_ops.py:226,257; yolo_v7.py:391,410; ssd.py:275-278
+ *           YOLOv8 normalisation    core/algorithms/yolo_v8.py:233-234
+ *           centre/size round trip  yolo_v8.py:237-238; yolo_v7.py:416-417; ssd.py:284-285
+ *           yolo_correct_boxes / reverse_letter_box_numpy  core/utils/image_process.py:69-97,161-181
+ * letterbox: (B, 5) fp32 rows in_w, in_h, left, top, scale (host-computed in double like the reference,
+ * then cast; for letterbox_image == False pass image_w, image_h, 0, 0, 1).  rows: (B, max_out, 6 or 7)
+ * by layout; rows >= det_count[b] are zero-filled.  aux_dense / A only for CVPP_ROWS_YOLOV7.
+ * ------------------------------------------------------------------------------------------- */
+CVPP_API int cvpp_detection_epilogue(const float* det_box, const float* det_score, const int32_t* det_cls,
+                                     const int32_t* det_anchor, const int32_t* det_count, const float* aux_dense,
+                                     int B, int max_out, int64_t A, int layout, int box_mode, const float* letterbox,
+                                     float* rows, cvpp_stream_t stream);
 
 #ifdef __cplusplus
 }

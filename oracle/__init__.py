@@ -294,3 +294,104 @@ def yolo_correct_rows(rows: np.ndarray, input_hw, image_hw, letterbox: bool = Tr
         nb[:, 1::2] *= image_hw[0]
     out[:, :4] = nb
     return out
+
+
+# --------------------------------------------------------------------------
+# YOLOv7
+# --------------------------------------------------------------------------
+YOLOV7_ANCHORS = (12, 16, 19, 36, 40, 28, 36, 75, 76, 55, 72, 146, 142, 110, 192, 243, 459, 401)
+YOLOV7_MASK = ((6, 7, 8), (3, 4, 5), (0, 1, 2))
+
+
+def yolov7_level_anchors(anchors=YOLOV7_ANCHORS, mask=YOLOV7_MASK) -> np.ndarray:
+    """(num_levels*3, 2) anchors in pixels, row 3*i + a = anchors[mask[i][a]] (yolo_v7.py:259-262)."""
+    a = np.array(anchors, dtype=np.float32).reshape(-1, 2)
+    return np.concatenate([a[list(m)] for m in mask], axis=0)
+
+
+def yolov7_decode(levels, nc: int, input_hw=(640, 640), anchors=YOLOV7_ANCHORS, mask=YOLOV7_MASK) -> np.ndarray:
+    """YOLOv7.decode_box up to `decoded_outputs` (yolo_v7.py:245-344): (B, A, 5+nc)."""
+    levels = [_f32(l) for l in levels]
+    nl = len(levels)
+    B = levels[0].shape[0]
+    hs = (ctypes.c_int * nl)(*[l.shape[2] for l in levels])
+    ws = (ctypes.c_int * nl)(*[l.shape[3] for l in levels])
+    ptrs = (_f32p * nl)(*[_ptr(l, _f32p) for l in levels])
+    la = yolov7_level_anchors(anchors, mask)
+    A = sum(3 * l.shape[2] * l.shape[3] for l in levels)
+    out = np.empty((B, A, 5 + nc), np.float32)
+    lib().orc_yolov7_decode(ptrs, ctypes.c_int(nl), hs, ws, _ptr(la, _f32p), ctypes.c_int(input_hw[0]),
+                            ctypes.c_int(input_hw[1]), ctypes.c_int(B), ctypes.c_int(nc), _ptr(out, _f32p))
+    return out
+
+
+def yolov7_nms(decoded, conf_thres: float, nms_thres: float, cap: int = 0):
+    """YOLOv7._nms (yolo_v7.py:348-413) before the letterbox epilogue: per image (rows (n,7), anchors (n,))
+    plus the candidate counts."""
+    decoded = _f32(decoded)
+    B, A, attrs = decoded.shape
+    nc = attrs - 5
+    cap = cap or A
+    rows = np.zeros((B, cap, 7), np.float32)
+    anc = np.zeros((B, cap), np.int32)
+    cnt = np.zeros((B,), np.int32)
+    cand = np.zeros((B,), np.int32)
+    lib().orc_yolov7_nms(_ptr(decoded, _f32p), ctypes.c_int(B), ctypes.c_int64(A), ctypes.c_int(nc),
+                         ctypes.c_float(conf_thres), ctypes.c_double(float(nms_thres)), ctypes.c_int(cap),
+                         _ptr(rows, _f32p), _ptr(anc, _i32p), _ptr(cnt, _i32p), _ptr(cand, _i32p))
+    return [(rows[b, :min(cnt[b], cap)].copy(), anc[b, :min(cnt[b], cap)].copy()) for b in range(B)], cand
+
+
+# --------------------------------------------------------------------------
+# YOLOv3
+# --------------------------------------------------------------------------
+YOLOV3_ANCHORS = (116, 90, 156, 198, 373, 326, 30, 61, 62, 45, 59, 119, 10, 13, 16, 30, 33, 23)
+
+
+def yolov3_anchors_norm(anchors=YOLOV3_ANCHORS, input_hw=(416, 416)) -> np.ndarray:
+    """generate_yolo3_anchor (core/utils/anchor.py:102-117): fp32 anchors divided in place by w, h."""
+    a = np.array(anchors, dtype=np.float32).reshape(-1, 2)
+    a[:, 0] /= np.float32(input_hw[1])
+    a[:, 1] /= np.float32(input_hw[0])
+    return a
+
+
+def yolov3_dense(levels, nc: int, anchors=YOLOV3_ANCHORS, input_hw=(416, 416)):
+    """Decoder.__call__ up to the NMS (yolov3_decode.py:40-63): boxes (M, 4), scores (M, nc) with the batch
+    flattened per scale and the scales concatenated."""
+    an = yolov3_anchors_norm(anchors, input_hw)
+    boxes, scores = [], []
+    for i, l in enumerate(levels):
+        l = _f32(l)
+        N, _, H, W = l.shape
+        b = np.empty((N * H * W * 3, 4), np.float32)
+        s = np.empty((N * H * W * 3, nc), np.float32)
+        a = np.ascontiguousarray(an[3 * i:3 * i + 3])
+        lib().orc_yolov3_scale(_ptr(l, _f32p), ctypes.c_int(N), ctypes.c_int(nc), ctypes.c_int(H), ctypes.c_int(W),
+                               _ptr(a, _f32p), _ptr(b, _f32p), _ptr(s, _f32p))
+        boxes.append(b)
+        scores.append(s)
+    return np.concatenate(boxes, 0), np.concatenate(scores, 0)
+
+
+def yolo3_nms(boxes, scores, conf_thres: float, iou_thres: float):
+    """yolo3_nms (core/utils/nms.py:54-84): -> (boxes (K,4), scores (K,), classes (K,) int32, rows (K,) int64,
+    candidate count)."""
+    boxes, scores = _f32(boxes), _f32(scores)
+    M, nc = scores.shape
+    l = lib()
+    l.orc_yolo3_nms.restype = ctypes.c_int64
+    cap = max(M, 1)
+    while True:
+        ob = np.zeros((cap, 4), np.float32)
+        os_ = np.zeros((cap,), np.float32)
+        oc = np.zeros((cap,), np.int32)
+        orow = np.zeros((cap,), np.int64)
+        cands = ctypes.c_int64(0)
+        k = int(l.orc_yolo3_nms(_ptr(boxes, _f32p), _ptr(scores, _f32p), ctypes.c_int64(M), ctypes.c_int(nc),
+                                ctypes.c_float(conf_thres), ctypes.c_double(float(iou_thres)), ctypes.c_int64(cap),
+                                _ptr(ob, _f32p), _ptr(os_, _f32p), _ptr(oc, _i32p), _ptr(orow, _i64p),
+                                ctypes.byref(cands)))
+        if k <= cap:
+            return ob[:k], os_[:k], oc[:k], orow[:k], int(cands.value)
+        cap = k

@@ -810,3 +810,210 @@ ORC_API void orc_ssd_decode(const float* loc, const float* conf, const float* pr
   orc_ssd_ctx c = {loc, conf, priors, P, nc, conf_thres, nms_thres, cap, rows, row_prior, count};
   orc_parallel_for(B, orc_ssd_body, &c);
 }
+
+/* ========================================================================= */
+/* YOLOv7 — core/algorithms/yolo_v7.py:234-346 (decode_box), :348-422 (_nms)  */
+/* ========================================================================= */
+typedef struct {
+  const float* const* levels; /* level i: (B, 3*(5+nc), H_i, W_i) NCHW */
+  int num_levels;
+  const int* level_h;
+  const int* level_w;
+  const float* anchors;  /* (num_levels*3, 2) pixels, already ordered by anchors_mask: row 3*i + a */
+  int input_h, input_w;
+  int nc;
+  int64_t A;
+  float* out; /* (B, A, 5 + nc): cx, cy, w, h (normalised), obj, cls... */
+} orc_v7dec_ctx;
+
+static void orc_v7dec_body(int b, void* vctx) {
+  const orc_v7dec_ctx* c = (const orc_v7dec_ctx*)vctx;
+  const int nc = c->nc, attrs = 5 + nc;
+  float* ob = c->out + (int64_t)b * c->A * attrs;
+  int64_t off = 0;
+  for (int l = 0; l < c->num_levels; ++l) {
+    const int H = c->level_h[l], W = c->level_w[l];
+    const int64_t HW = (int64_t)H * W;
+    /* stride = input / feature size; anchors scaled to grid units (:254-262) in fp32 */
+    const float stride_h = (float)((double)c->input_h / H), stride_w = (float)((double)c->input_w / W);
+    const float* base = c->levels[l] + (int64_t)b * 3 * attrs * HW;
+    for (int a = 0; a < 3; ++a) {
+      const float aw = c->anchors[(3 * l + a) * 2 + 0] / stride_w;
+      const float ah = c->anchors[(3 * l + a) * 2 + 1] / stride_h;
+      for (int64_t cell = 0; cell < HW; ++cell) {
+        const float* p = base + (int64_t)a * attrs * HW + cell;
+        const float gx = (float)(cell % W), gy = (float)(cell / W);
+        float x = sigmoidf_ref(p[0 * HW]), y = sigmoidf_ref(p[1 * HW]);
+        float w = sigmoidf_ref(p[2 * HW]), h = sigmoidf_ref(p[3 * HW]);
+        float bx = x * 2.0f - 0.5f + gx;
+        float by = y * 2.0f - 0.5f + gy;
+        float tw = w * 2.0f, th = h * 2.0f;
+        float bw = tw * tw * aw;
+        float bh = th * th * ah;
+        float* o = ob + (off + (int64_t)a * HW + cell) * attrs;
+        o[0] = bx / (float)W;
+        o[1] = by / (float)H;
+        o[2] = bw / (float)W;
+        o[3] = bh / (float)H;
+        o[4] = sigmoidf_ref(p[4 * HW]);
+        for (int k = 0; k < nc; ++k) o[5 + k] = sigmoidf_ref(p[(int64_t)(5 + k) * HW]);
+      }
+    }
+    off += 3 * HW;
+  }
+}
+
+ORC_API void orc_yolov7_decode(const float* const* levels, int num_levels, const int* level_h, const int* level_w,
+                               const float* anchors, int input_h, int input_w, int B, int nc, float* out) {
+  orc_v7dec_ctx c = {levels, num_levels, level_h, level_w, anchors, input_h, input_w, nc, 0, out};
+  for (int l = 0; l < num_levels; ++l) c.A += 3 * (int64_t)level_h[l] * level_w[l];
+  orc_parallel_for(B, orc_v7dec_body, &c);
+}
+
+typedef struct {
+  const float* pred; /* (B, A, 5 + nc) decoded */
+  int64_t A;
+  int nc;
+  float conf_thres;
+  double nms_thres;
+  int cap;
+  float* rows;         /* (B, cap, 7): x1,y1,x2,y2,obj,class_conf,class_pred (normalised) */
+  int32_t* row_anchor; /* (B, cap) */
+  int32_t* count;
+  int32_t* cand_count;
+} orc_v7nms_ctx;
+
+static void orc_v7nms_body(int b, void* vctx) {
+  const orc_v7nms_ctx* c = (const orc_v7nms_ctx*)vctx;
+  const int64_t A = c->A;
+  const int attrs = 5 + c->nc;
+  const float* p = c->pred + (int64_t)b * A * attrs;
+  float* box = (float*)malloc(sizeof(float) * 4 * (size_t)A);
+  float* sc = (float*)malloc(sizeof(float) * (size_t)A);
+  float* obj = (float*)malloc(sizeof(float) * (size_t)A);
+  float* cc = (float*)malloc(sizeof(float) * (size_t)A);
+  int32_t* cls = (int32_t*)malloc(sizeof(int32_t) * (size_t)A);
+  int32_t* anc = (int32_t*)malloc(sizeof(int32_t) * (size_t)A);
+  int64_t n = 0;
+  for (int64_t a = 0; a < A; ++a) {
+    const float* q = p + a * attrs;
+    float best = q[5];
+    int bj = 0;
+    for (int k = 1; k < c->nc; ++k)
+      if (q[5 + k] > best) {
+        best = q[5 + k];
+        bj = k;
+      }
+    if (!(q[4] * best >= c->conf_thres)) continue; /* (:377) non-strict */
+    box[4 * n + 0] = q[0] - q[2] / 2.0f;             /* xywh_to_xyxy_torch (:361) */
+    box[4 * n + 1] = q[1] - q[3] / 2.0f;
+    box[4 * n + 2] = q[0] + q[2] / 2.0f;
+    box[4 * n + 3] = q[1] + q[3] / 2.0f;
+    obj[n] = q[4];
+    cc[n] = best;
+    sc[n] = q[4] * best;
+    cls[n] = bj;
+    anc[n] = (int32_t)a;
+    ++n;
+  }
+  if (c->cand_count) c->cand_count[b] = (int32_t)n;
+  int64_t* keep = (int64_t*)malloc(sizeof(int64_t) * (size_t)(n > 0 ? n : 1));
+  int64_t k = orc_nms_per_class(box, sc, cls, n, c->nc, c->nms_thres, keep);
+  for (int64_t t = 0; t < k && t < c->cap; ++t) {
+    float* row = c->rows + ((int64_t)b * c->cap + t) * 7;
+    memcpy(row, box + 4 * keep[t], sizeof(float) * 4);
+    row[4] = obj[keep[t]];
+    row[5] = cc[keep[t]];
+    row[6] = (float)cls[keep[t]];
+    c->row_anchor[(int64_t)b * c->cap + t] = anc[keep[t]];
+  }
+  c->count[b] = (int32_t)k;
+  free(box);
+  free(sc);
+  free(obj);
+  free(cc);
+  free(cls);
+  free(anc);
+  free(keep);
+}
+
+ORC_API void orc_yolov7_nms(const float* pred, int B, int64_t A, int nc, float conf_thres, double nms_thres, int cap,
+                            float* rows, int32_t* row_anchor, int32_t* count, int32_t* cand_count) {
+  orc_v7nms_ctx c = {pred, A, nc, conf_thres, nms_thres, cap, rows, row_anchor, count, cand_count};
+  orc_parallel_for(B, orc_v7nms_body, &c);
+}
+
+/* ========================================================================= */
+/* YOLOv3 — core/predict/yolov3_decode.py:12-66 (predict_bounding_bbox,       */
+/* Decoder), core/utils/nms.py:54-84 (yolo3_nms), core/utils/anchor.py:102-117 */
+/* ========================================================================= */
+/* One scale, dense: feature (N, 3*(5+nc), H, W) NCHW -> boxes (N*H*W*3, 4) xyxy and      */
+/* scores (N*H*W*3, nc) in the reference's flattened order ((n*H + y)*W + x)*3 + a.        */
+/* anchors_norm (3, 2): anchor / input size, already divided in fp32 by the caller exactly */
+/* like generate_yolo3_anchor.                                                             */
+ORC_API void orc_yolov3_scale(const float* feature, int N, int nc, int H, int W, const float* anchors_norm,
+                              float* boxes, float* scores) {
+  const int attrs = 5 + nc;
+  const int64_t HW = (int64_t)H * W;
+  for (int n = 0; n < N; ++n)
+    for (int64_t cell = 0; cell < HW; ++cell)
+      for (int a = 0; a < 3; ++a) {
+        const float* p = feature + ((int64_t)n * 3 * attrs + (int64_t)a * attrs) * HW + cell;
+        const int64_t row = ((int64_t)n * HW + cell) * 3 + a;
+        const float gx = (float)(cell % W), gy = (float)(cell / W);
+        /* (:22) box_xy = (sigmoid(t) + grid) / H  — H for both coordinates */
+        const float bx = (sigmoidf_ref(p[0]) + gx) / (float)H;
+        const float by = (sigmoidf_ref(p[HW]) + gy) / (float)H;
+        /* (:23) box_wh = exp(t) * anchors */
+        const float bw = expf(p[2 * HW]) * anchors_norm[2 * a + 0];
+        const float bh = expf(p[3 * HW]) * anchors_norm[2 * a + 1];
+        const float conf = sigmoidf_ref(p[4 * HW]);
+        float* o = boxes + 4 * row; /* (:47) xy -/+ wh / 2 */
+        o[0] = bx - bw / 2.0f;
+        o[1] = by - bh / 2.0f;
+        o[2] = bx + bw / 2.0f;
+        o[3] = by + bh / 2.0f;
+        for (int k = 0; k < nc; ++k) scores[row * nc + k] = conf * sigmoidf_ref(p[(int64_t)(5 + k) * HW]); /* (:49) */
+      }
+}
+
+/* yolo3_nms (core/utils/nms.py:54-84) on boxes (M, 4), scores (M, nc): for each class ascending, the rows with
+ * score >= conf (float32 compare) go through nms; out rows (K): box, score, class, source row.  Returns K
+ * (rows beyond cap are counted but not written). */
+ORC_API int64_t orc_yolo3_nms(const float* boxes, const float* scores, int64_t M, int nc, float conf_thres,
+                              double iou_thres, int64_t cap, float* out_boxes, float* out_scores, int32_t* out_cls,
+                              int64_t* out_row, int64_t* cand_count) {
+  float* cb = (float*)malloc(sizeof(float) * 4 * (size_t)(M > 0 ? M : 1));
+  float* cs = (float*)malloc(sizeof(float) * (size_t)(M > 0 ? M : 1));
+  int64_t* ci = (int64_t*)malloc(sizeof(int64_t) * (size_t)(M > 0 ? M : 1));
+  int64_t* ck = (int64_t*)malloc(sizeof(int64_t) * (size_t)(M > 0 ? M : 1));
+  int64_t total = 0, cands = 0;
+  for (int c = 0; c < nc; ++c) {
+    int64_t m = 0;
+    for (int64_t i = 0; i < M; ++i)
+      if (scores[i * nc + c] >= conf_thres) {
+        memcpy(cb + 4 * m, boxes + 4 * i, sizeof(float) * 4);
+        cs[m] = scores[i * nc + c];
+        ci[m] = i;
+        ++m;
+      }
+    cands += m;
+    if (m == 0) continue;
+    int64_t k = orc_nms(cb, cs, m, iou_thres, ck);
+    for (int64_t t = 0; t < k; ++t) {
+      if (total < cap) {
+        memcpy(out_boxes + 4 * total, cb + 4 * ck[t], sizeof(float) * 4);
+        out_scores[total] = cs[ck[t]];
+        out_cls[total] = c;
+        out_row[total] = ci[ck[t]];
+      }
+      ++total;
+    }
+  }
+  if (cand_count) *cand_count = cands;
+  free(cb);
+  free(cs);
+  free(ci);
+  free(ck);
+  return total;
+}

@@ -287,3 +287,104 @@ def ssd_head(seed: int, B: int, P: int = 8732, nc: int = 20, conf_list: Sequence
         else:
             raise RuntimeError("ssd_head: separation did not converge; change the seed")
     return loc, conf
+
+
+# ------------------------------------------------------------------------------------------------
+# YOLOv7 (C5): 3 levels (B, 3*(5+nc), s, s), s in {20, 40, 80}
+# ------------------------------------------------------------------------------------------------
+YOLOV7_SIZES = ((20, 20), (40, 40), (80, 80))
+
+
+def yolov7_head(seed: int, B: int, nc: int = 80, sizes: Sequence[Tuple[int, int]] = YOLOV7_SIZES,
+                conf_list: Sequence[float] = (0.001, 0.5), obj_mu: float = -9.0, obj_sigma: float = 3.0,
+                cls_mu: float = -1.0, cls_sigma: float = 2.0) -> List[np.ndarray]:
+    """xywh logits N(0,1), objectness N(obj_mu, obj_sigma^2), class logits N(cls_mu, cls_sigma^2)
+    (~6 k candidates/img >= .001 and ~36 >= .5).  Candidate scores obj*max_cls are separated
+    per image by nudging the objectness logit."""
+    rng = rng_for(seed)
+    attrs = 5 + nc
+    levels = []
+    for (h, w) in sizes:
+        x = rng.standard_normal((B, 3, attrs, h, w), dtype=np.float32)
+        x[:, :, 4] = x[:, :, 4] * np.float32(obj_sigma) + np.float32(obj_mu)
+        x[:, :, 5:] = x[:, :, 5:] * np.float32(cls_sigma) + np.float32(cls_mu)
+        levels.append(x.reshape(B, 3 * attrs, h, w))
+    lo = 0.5 * min(conf_list)
+    for b in range(B):
+        views = [l[b].reshape(3, attrs, -1) for l in levels]      # views into the level arrays
+        for _ in range(100):
+            obj = np.concatenate([_sigmoid64(v[:, 4]).reshape(-1) for v in views])
+            cls = np.concatenate([_sigmoid64(v[:, 5:].max(axis=1)).reshape(-1) for v in views])
+            s = obj * cls
+            s2 = separate_scores(s, conf_list, lo)
+            moved = np.nonzero(s2 != s)[0]
+            if moved.size == 0:
+                break
+            off = 0
+            for v in views:
+                n = v.shape[0] * v.shape[2]
+                for i in moved[(moved >= off) & (moved < off + n)]:
+                    a, cell = divmod(int(i - off), v.shape[2])
+                    target_obj = min(s2[i] / cls[i], 1.0 - 1e-6)
+                    v[a, 4, cell] = np.float32(_logit64(target_obj))
+                off += n
+        else:
+            raise RuntimeError("yolov7_head: separation did not converge; change the seed")
+    return levels
+
+
+# ------------------------------------------------------------------------------------------------
+# YOLOv3 (VOC): 3 levels (B, 3*(5+nc), s, s), s in {13, 26, 52} for a 416^2 input
+# ------------------------------------------------------------------------------------------------
+YOLOV3_SIZES = ((13, 13), (26, 26), (52, 52))
+
+
+def yolov3_head(seed: int, B: int, nc: int = 20, sizes: Sequence[Tuple[int, int]] = YOLOV3_SIZES,
+                conf_list: Sequence[float] = (0.001, 0.6), obj_mu: float = -10.0, obj_sigma: float = 2.5,
+                cls_mu: float = -3.0, cls_sigma: float = 2.0, boost_frac: float = 0.004,
+                merged: bool = False) -> List[np.ndarray]:
+    """xy logits N(0,1), wh logits N(0,0.5^2), objectness N(obj_mu, obj_sigma^2), class logits
+    N(cls_mu, cls_sigma^2); `boost_frac` of the anchors become objects (objectness N(3,1.5^2), one class
+    N(2,2^2)), neighbouring cells of a level included so that NMS has overlaps to suppress.  Scores sigmoid(obj)*sigmoid(cls_c) of all (anchor, class) pairs are separated
+    per image - or over the whole batch with merged=True (the reference Decoder flattens the batch) - by
+    nudging the class logit of the pair."""
+    rng = rng_for(seed)
+    attrs = 5 + nc
+    levels = []
+    for (h, w) in sizes:
+        x = rng.standard_normal((B, 3, attrs, h, w), dtype=np.float32)
+        x[:, :, 2:4] *= np.float32(0.5)
+        x[:, :, 4] = x[:, :, 4] * np.float32(obj_sigma) + np.float32(obj_mu)
+        x[:, :, 5:] = x[:, :, 5:] * np.float32(cls_sigma) + np.float32(cls_mu)
+        n_boost = max(1, int(B * 3 * h * w * boost_frac))
+        bb, aa = rng.integers(0, B, n_boost), rng.integers(0, 3, n_boost)
+        yy, xx, cc = rng.integers(0, h, n_boost), rng.integers(0, w, n_boost), rng.integers(0, nc, n_boost)
+        for dx in (0, 1):                                               # the cell and its right neighbour
+            xs = np.minimum(xx + dx, w - 1)
+            x[bb, aa, 4, yy, xs] = rng.normal(3.0, 1.5, n_boost).astype(np.float32)
+            x[bb, aa, 5 + cc, yy, xs] = rng.normal(2.0, 2.0, n_boost).astype(np.float32)
+        levels.append(x.reshape(B, 3 * attrs, h, w))
+    lo = 0.5 * min(conf_list)
+    groups = [list(range(B))] if merged else [[b] for b in range(B)]
+    for grp in groups:
+        views = [l[b].reshape(3, attrs, -1) for b in grp for l in levels]   # views into the level arrays
+        for _ in range(100):
+            obj = [_sigmoid64(v[:, 4]) for v in views]                        # (3, cells)
+            sc = [o[:, None, :] * _sigmoid64(v[:, 5:]) for o, v in zip(obj, views)]   # (3, nc, cells)
+            flat = np.concatenate([s.reshape(-1) for s in sc])
+            idx = np.nonzero(flat >= lo)[0]
+            s = flat[idx]
+            s2 = separate_scores(s, conf_list, lo)
+            moved = np.nonzero(s2 != s)[0]
+            if moved.size == 0:
+                break
+            bounds = np.cumsum([0] + [x.size for x in sc])
+            for j in moved:
+                i = int(idx[j])
+                vi = int(np.searchsorted(bounds, i, side="right") - 1)
+                a, c, cell = np.unravel_index(i - bounds[vi], sc[vi].shape)
+                target = min(s2[j] / obj[vi][a, cell], 1.0 - 1e-6)
+                views[vi][a, 5 + c, cell] = np.float32(_logit64(target))
+        else:
+            raise RuntimeError("yolov3_head: separation did not converge; change the seed")
+    return levels

@@ -146,3 +146,63 @@ def test_ssd_decode(golden_dir):
             assert got.shape == ref.shape and np.array_equal(got[:, 4], ref[:, 4])
             assert np.all(np.abs(got[:, 5] - ref[:, 5]) <= SCORE_RTOL * ref[:, 5])
             assert np.all(np.abs(got[:, :4] - ref[:, :4]) <= BOX_RTOL * np.abs(ref[:, :4]) + BOX_ATOL * 2.2)
+
+
+def _close(got, ref, rtol, atol=0.0):
+    return got.shape == ref.shape and bool(np.all(np.abs(got - ref) <= rtol * np.abs(ref) + atol))
+
+
+def test_yolov7_decode_and_nms(golden_dir):
+    g = load(golden_dir, "yolov7")
+    for tag in g["cases"]:
+        seed, B, nc = [int(v) for v in g[f"{tag}_cfg"]]
+        levels = synth.yolov7_head(seed, B, nc=nc)
+        assert synth.checksum(levels) == int(g[f"{tag}_crc"])
+        dec = oracle.yolov7_decode(levels, nc)
+        for ctag, thr in (("eval", 0.001), ("pred", 0.5)):
+            out, cand = oracle.yolov7_nms(dec, thr, 0.3)
+            for b, (rows, anchors) in enumerate(out):
+                ref = g[f"{tag}_{b}_{ctag}"]
+                got = oracle.yolo_correct_rows(rows, (640, 640), (480, 640), True)
+                assert got.shape == ref.shape and np.array_equal(got[:, 6], ref[:, 6])      # class ids, order
+                assert _close(got[:, 4:6], ref[:, 4:6], SCORE_RTOL)
+                assert _close(got[:, :4], ref[:, :4], BOX_RTOL, BOX_ATOL)
+                assert (len(rows) == 0) == bool(g[f"{tag}_{b}_{ctag}_none"])
+                if ctag == "eval":
+                    assert 0 < len(rows) < cand[b]                                          # NMS suppressed something
+        if tag == "voc":
+            assert synth.checksum([dec]) == int(g["voc_decoded_crc"])
+            out, _ = oracle.yolov7_nms(dec, 0.01, 0.4)
+            for b, (rows, anchors) in enumerate(out):
+                ref = g[f"voc_{b}_free"]
+                got = oracle.yolo_correct_rows(rows, (640, 640), (333, 500), False)
+                assert got.shape == ref.shape and np.array_equal(got[:, 4:], ref[:, 4:])   # same decoded input: exact
+                assert _close(got[:, :4], ref[:, :4], 1e-6, 1e-5)
+
+
+def test_yolov3_decoder_and_nms(golden_dir):
+    g = load(golden_dir, "yolov3")
+    for tag in ("one", "two"):
+        seed, B, merged = [int(v) for v in g[f"{tag}_cfg"]]
+        levels = synth.yolov3_head(seed, B, merged=bool(merged))
+        assert synth.checksum(levels) == int(g[f"{tag}_crc"])
+        boxes, scores = oracle.yolov3_dense(levels, 20)
+        for ctag, thr in (("eval", 0.001), ("pred", 0.6)):
+            ob, os_, oc, orow, cands = oracle.yolo3_nms(boxes, scores, thr, 0.5)
+            assert np.array_equal(oc, g[f"{tag}_{ctag}_classes"]) and oc.dtype == np.int32
+            assert _close(os_, g[f"{tag}_{ctag}_scores"], SCORE_RTOL)
+            assert _close(ob, g[f"{tag}_{ctag}_boxes"], BOX_RTOL, 1e-6)
+            assert 0 < len(oc) < cands
+    # dense predict_bounding_bbox on the 13 x 13 scale
+    levels = synth.yolov3_head(51, 1)
+    b13, s13 = oracle.yolov3_dense(levels[:1], 20)
+    xy, wh = g["pbb_xy"].reshape(-1, 2), g["pbb_wh"].reshape(-1, 2)
+    ref_boxes = np.concatenate([xy - wh / 2, xy + wh / 2], 1)
+    assert _close(b13, ref_boxes, BOX_RTOL, 1e-6)
+    ref_scores = (g["pbb_conf"].reshape(-1, 1) * np.ones((1, 20), np.float32)).reshape(-1)[::7]
+    # scores = conf * prob: compare through the sub-sampled prob digest
+    assert _close(s13.reshape(-1)[::7], ref_scores * g["pbb_prob_sub"], SCORE_RTOL)
+    # standalone yolo3_nms on identical inputs: exact
+    ob, os_, oc, orow, cands = oracle.yolo3_nms(g["nms3_boxes_in"], g["nms3_scores_in"], 0.5, 0.45)
+    assert np.array_equal(ob, g["nms3_boxes"]) and np.array_equal(os_[:, None], g["nms3_scores"])
+    assert np.array_equal(oc, g["nms3_classes"]) and len(oc) < cands
