@@ -30,7 +30,9 @@ namespace cvpp {
 constexpr int kYaTileA = 128;
 constexpr int kYaChunkRows = 16;
 constexpr int kYaStages = 2;
-constexpr int kYaWarps = 14;
+constexpr int kYaWarpsV7 = 14;    // 14 x 16 KB rings = 224 KB
+constexpr int kYaWarpsV3 = 12;    // 12 x 16 KB rings + 12 x 2 KB hit buffers
+constexpr int kYaHitCap = 224;    // V3: per-warp staging of candidate records (12 B each, see V3Stage)
 constexpr int kYaChunkFloats = kYaChunkRows * kYaTileA;
 constexpr int kYaMaxLevels = 4;
 constexpr int MODE_V7 = 0;
@@ -49,7 +51,10 @@ struct YaLevel {
 };
 
 struct YaParams {
-  CUtensorMap tmap[kYaMaxLevels];
+  CUtensorMap tmap[kYaMaxLevels];       // box 128 cells x 16 rows x 1 image
+  CUtensorMap tmap_tail[kYaMaxLevels];  // box 128 cells x tail_rows x 1 image: the last chunk of an anchor reads
+                                        // exactly the rows that are left ((5 + nc) mod 16), not 16
+  int tail_rows;
   YaLevel lv[kYaMaxLevels];
   int num_levels, B, nc, tiles_per_image, total_tiles;
   int merged;           // V3: Decoder flattens the batch (yolov3_decode.py:47-50): one output "image"
@@ -166,13 +171,104 @@ __device__ __forceinline__ void ya_tile_info(const YaParams& p, int g, int& b, i
   nA = min(kYaTileA, p.lv[l].hw - cell0);
 }
 
+// ---- V3 candidate staging ---------------------------------------------------------------------------
+// A class logit that passes the per-cell cut is pushed as a RECORD (logit, sigmoid(obj), class | cell) into
+// a per-warp shared-memory list with one shared-memory atomic; records are evaluated exactly, 32 at a
+// time at full warp efficiency, when the list fills up or the tile ends, and the surviving keys leave with
+// ONE global atomic per flush.  (First version: exact evaluation + a global atomic per class row; at eval
+// thresholds nearly every 128-cell row has a survivor, so the "rare" path ran for every row: 2.6 ms for
+// 256 images.)
+struct V3Stage {
+  float2* rec_x;   // (logit, sigmoid(obj)); reused for the packed keys during a flush
+  uint32_t* rec_m; // class << 8 | cell within the tile
+  int* count;
+};
+
+__device__ __forceinline__ void v3_flush(const V3Stage& st, const YaParams& p, int ob, int anchor_base, int a, int cell0,
+                                         int hw) {
+  const int lane = threadIdx.x & 31;
+  __syncwarp();
+  const int n = *st.count;
+  if (n == 0) return;
+  uint64_t* keys = reinterpret_cast<uint64_t*>(st.rec_x);
+  int out_n = 0;
+  for (int base = 0; base < n; base += 32) {
+    const int i = base + lane;
+    bool hit = false;
+    uint64_t key = 0;
+    if (i < n) {
+      const float2 r = st.rec_x[i];
+      const uint32_t m = st.rec_m[i];
+      const float score = fmul(r.y, sigmoid_precise(r.x));  // confidence * class_prob (yolov3_decode.py:49)
+      hit = score >= p.conf_thres;                           // nms.py:60
+      const int anchor = anchor_base + ya_local_index<MODE_V3>(a, cell0 + (int)(m & 0xffu), hw);
+      key = key_pack(m >> 8, __float_as_uint(score), (uint32_t)anchor);
+    }
+    const unsigned mk = __ballot_sync(0xffffffffu, hit);
+    // every record of this batch is in registers; keys are written at or below the batch's own slots
+    if (hit) keys[out_n + __popc(mk & ((1u << lane) - 1u))] = key;
+    out_n += __popc(mk);
+    __syncwarp();
+  }
+  int gbase = 0;
+  if (lane == 0 && out_n) gbase = atomicAdd(p.cand_count + ob, out_n);
+  gbase = __shfl_sync(0xffffffffu, gbase, 0);
+  uint64_t* dst = p.cand_key + (int64_t)ob * p.max_cand;
+  for (int i = lane; i < out_n; i += 32)
+    if (gbase + i < p.max_cand) dst[gbase + i] = keys[i];
+  __syncwarp();
+  if (lane == 0) *st.count = 0;
+  __syncwarp();
+}
+
+// class rows [RBEGIN, rows) of one 16-row chunk; FULL: rows == 16 at compile time
+template <int MODE, int RBEGIN, bool FULL>
+__device__ __forceinline__ void ya_class_rows(const float4 (&v)[kYaChunkRows], int rows, int c_first, float (&best)[4],
+                                              int (&arg)[4], float (&prev)[4], const float (&so)[4], const float (&cut)[4],
+                                              unsigned& boxed, const V3Stage& st, const YaParams& p, int ob,
+                                              int anchor_base, int a, int cell0, int hw) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int r = RBEGIN; r < kYaChunkRows; ++r) {
+    if (FULL || r < rows) {
+      const int c = c_first + (r - RBEGIN);
+      const float x[4] = {v[r].x, v[r].y, v[r].z, v[r].w};
+      if (MODE == MODE_V7) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v7_class_step(x[k], c, best[k], arg[k], prev[k]);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (x[k] >= cut[k]) {
+            const int pos = atomicAdd(st.count, 1);
+            st.rec_x[pos] = make_float2(x[k], so[k]);
+            st.rec_m[pos] = ((uint32_t)c << 8) | (uint32_t)(4 * lane + k);
+            boxed |= 1u << k;
+          }
+        }
+        __syncwarp();
+        if (*st.count > kYaHitCap - 4 * 32) v3_flush(st, p, ob, anchor_base, a, cell0, hw);  // room for one more row
+      }
+    }
+  }
+}
+
 template <int MODE>
-__global__ void __launch_bounds__(kYaWarps * 32, 1) yolo_anchor_stream_kernel(const __grid_constant__ YaParams p) {
+__global__ void __launch_bounds__((MODE == MODE_V7 ? kYaWarpsV7 : kYaWarpsV3) * 32, 1)
+yolo_anchor_stream_kernel(const __grid_constant__ YaParams p) {
+  constexpr int kYaWarps = MODE == MODE_V7 ? kYaWarpsV7 : kYaWarpsV3;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float* ring = reinterpret_cast<float*>(smem_raw) + (size_t)warp * (kYaStages * kYaChunkFloats);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kYaWarps * kYaStages * kYaChunkFloats * sizeof(float)) +
-                  warp * kYaStages;
+  unsigned char* after_rings = smem_raw + (size_t)kYaWarps * kYaStages * kYaChunkFloats * sizeof(float);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(after_rings) + warp * kYaStages;
+  V3Stage st;  // V3 only: [rec_x float2 x cap][rec_m u32 x cap] per warp, then the counters
+  {
+    unsigned char* q = after_rings + (size_t)kYaWarps * kYaStages * sizeof(uint64_t);
+    st.rec_x = reinterpret_cast<float2*>(q) + (size_t)warp * kYaHitCap;
+    st.rec_m = reinterpret_cast<uint32_t*>(q + (size_t)kYaWarps * kYaHitCap * sizeof(float2)) + (size_t)warp * kYaHitCap;
+    st.count = reinterpret_cast<int*>(q + (size_t)kYaWarps * kYaHitCap * (sizeof(float2) + sizeof(uint32_t))) + warp;
+  }
   const int nc = p.nc;
   const int attrs = 5 + nc;
   const int nchunks = (attrs + kYaChunkRows - 1) / kYaChunkRows;
@@ -181,6 +277,7 @@ __global__ void __launch_bounds__(kYaWarps * 32, 1) yolo_anchor_stream_kernel(co
 #pragma unroll
     for (int s = 0; s < kYaStages; ++s) mbar_init(&bar[s], 1);
     mbar_fence_init();
+    if (MODE == MODE_V3) *st.count = 0;
   }
   __syncwarp();
 
@@ -197,9 +294,10 @@ __global__ void __launch_bounds__(kYaWarps * 32, 1) yolo_anchor_stream_kernel(co
     }
     if (lane == 0) {
       uint64_t* fb = &bar[pq & (kYaStages - 1)];
-      mbar_arrive_expect_tx(fb, (uint32_t)(kYaChunkFloats * sizeof(float)));
-      ya_tma_load_3d(ring + (pq & (kYaStages - 1)) * kYaChunkFloats, &p.tmap[pl], pcell0, pa * attrs + kYaChunkRows * pj,
-                     pb, fb);
+      const bool tail = pj == nchunks - 1;
+      mbar_arrive_expect_tx(fb, (uint32_t)((tail ? p.tail_rows : kYaChunkRows) * kYaTileA * sizeof(float)));
+      ya_tma_load_3d(ring + (pq & (kYaStages - 1)) * kYaChunkFloats, tail ? &p.tmap_tail[pl] : &p.tmap[pl], pcell0,
+                     pa * attrs + kYaChunkRows * pj, pb, fb);
     }
     ++pq;
     if (++pj == nchunks) {
@@ -209,24 +307,22 @@ __global__ void __launch_bounds__(kYaWarps * 32, 1) yolo_anchor_stream_kernel(co
   };
   for (int q = 0; q < kYaStages && q < total_q; ++q) issue();
 
-  float t5[5][4];  // tx, ty, tw, th, tobj logits of the lane's 4 cells
+  float t5[5][4];          // tx, ty, tw, th, tobj logits of the lane's 4 cells
   float best[4], prev[4];  // V7: running class scan
   int arg[4];
   float so[4], cut[4];     // V3: sigmoid(obj), per-cell class logit cut
-  unsigned boxed = 0;      // V3: cells whose box has been written
+  unsigned boxed = 0;      // V3: cells that pushed a record (their box is written at the end of the tile)
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    best[k] = prev[k] = -INFINITY;
+    arg[k] = 0;
+    so[k] = 0.0f;
+    cut[k] = INFINITY;
+  }
   int b = 0, l = 0, a = 0, cell0 = 0, nA = 0;
   int j = 0, g = first;
   for (int q = 0; q < total_q; ++q) {
-    if (j == 0) {
-      ya_tile_info(p, g, b, l, a, cell0, nA);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        best[k] = -INFINITY;
-        prev[k] = -INFINITY;
-        arg[k] = 0;
-      }
-      boxed = 0;
-    }
+    if (j == 0) ya_tile_info(p, g, b, l, a, cell0, nA);
     const YaLevel& L = p.lv[l];
     const int s = q & (kYaStages - 1);
     mbar_wait(&bar[s], (uint32_t)(q / kYaStages) & 1u);
@@ -240,8 +336,6 @@ __global__ void __launch_bounds__(kYaWarps * 32, 1) yolo_anchor_stream_kernel(co
     if (pq < total_q) issue();
 
     // rows of this chunk are attributes [16 j, 16 j + 16) of the anchor: 0..4 box/obj, 5.. classes
-    const int a0 = kYaChunkRows * j;
-    const int rows = min(kYaChunkRows, attrs - a0);
     const bool active = 4 * lane < nA;
     const int ob = p.merged ? 0 : b;
     const int anchor_base = L.anchor_off + b * L.image_stride;
@@ -253,6 +347,12 @@ __global__ void __launch_bounds__(kYaWarps * 32, 1) yolo_anchor_stream_kernel(co
         t5[r][2] = v[r].z;
         t5[r][3] = v[r].w;
       }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        best[k] = prev[k] = -INFINITY;
+        arg[k] = 0;
+      }
+      boxed = 0;
       if (MODE == MODE_V3) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -260,53 +360,32 @@ __global__ void __launch_bounds__(kYaWarps * 32, 1) yolo_anchor_stream_kernel(co
           cut[k] = active ? v3_logit_cut(so[k], p.conf_thres) : INFINITY;
         }
       }
-    }
-#pragma unroll
-    for (int r = 0; r < kYaChunkRows; ++r) {
-      if (r < rows && !(j == 0 && r < 5)) {
-        const int c = a0 + r - 5;
-        const float x[4] = {v[r].x, v[r].y, v[r].z, v[r].w};
-        if (MODE == MODE_V7) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) v7_class_step(x[k], c, best[k], arg[k], prev[k]);
-        } else {
-          const bool maybe = (x[0] >= cut[0]) | (x[1] >= cut[1]) | (x[2] >= cut[2]) | (x[3] >= cut[3]);
-          if (__any_sync(0xffffffffu, maybe)) {  // rare: exact fp32 score of the survivors of this class row
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              bool hit = false;
-              float score = 0.0f;
-              if (x[k] >= cut[k]) {
-                score = fmul(so[k], sigmoid_precise(x[k]));  // confidence * class_prob (yolov3_decode.py:49)
-                hit = score >= p.conf_thres;                  // nms.py:60
-              }
-              const unsigned mk = __ballot_sync(0xffffffffu, hit);
-              if (mk == 0) continue;
-              int base = 0;
-              if (lane == 0) base = atomicAdd(p.cand_count + ob, __popc(mk));
-              base = __shfl_sync(0xffffffffu, base, 0);
-              if (hit) {
-                const int cell = cell0 + 4 * lane + k;
-                const int anchor = anchor_base + ya_local_index<MODE_V3>(a, cell, L.hw);
-                const int slot = base + __popc(mk & ((1u << lane) - 1u));
-                if (slot < p.max_cand)
-                  p.cand_key[(int64_t)ob * p.max_cand + slot] = key_pack((uint32_t)c, __float_as_uint(score), (uint32_t)anchor);
-                if (!(boxed & (1u << k))) {
-                  boxed |= 1u << k;
-                  p.box_dense[(int64_t)ob * p.A + anchor] =
-                      v3_box(t5[0][k], t5[1][k], t5[2][k], t5[3][k], cell, L.w, L.h, L.aw[a], L.ah[a]);
-                }
-              }
-            }
-          }
-        }
-      }
+      if (attrs >= kYaChunkRows)
+        ya_class_rows<MODE, 5, true>(v, kYaChunkRows, 0, best, arg, prev, so, cut, boxed, st, p, ob, anchor_base, a, cell0, L.hw);
+      else
+        ya_class_rows<MODE, 5, false>(v, attrs, 0, best, arg, prev, so, cut, boxed, st, p, ob, anchor_base, a, cell0, L.hw);
+    } else if (j < nchunks - 1) {
+      ya_class_rows<MODE, 0, true>(v, kYaChunkRows, kYaChunkRows * j - 5, best, arg, prev, so, cut, boxed, st, p, ob,
+                                   anchor_base, a, cell0, L.hw);
+    } else {
+      ya_class_rows<MODE, 0, false>(v, attrs - kYaChunkRows * j, kYaChunkRows * j - 5, best, arg, prev, so, cut, boxed, st, p,
+                                    ob, anchor_base, a, cell0, L.hw);
     }
 
     if (++j == nchunks) {  // tile complete
       j = 0;
       g += stride_tiles;
-      if (MODE == MODE_V7) {
+      if (MODE == MODE_V3) {
+        v3_flush(st, p, ob, anchor_base, a, cell0, L.hw);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (boxed & (1u << k)) {
+            const int cell = cell0 + 4 * lane + k;
+            p.box_dense[(int64_t)ob * p.A + anchor_base + ya_local_index<MODE_V3>(a, cell, L.hw)] =
+                v3_box(t5[0][k], t5[1][k], t5[2][k], t5[3][k], cell, L.w, L.h, L.aw[a], L.ah[a]);
+          }
+        }
+      } else {
         const float* col = L.ptr + (int64_t)b * L.batch_stride + (int64_t)(a * attrs + 5) * L.chan_stride + cell0 + 4 * lane;
         V7Cell cell[4];
         unsigned m[4];
@@ -432,9 +511,17 @@ static YaEncodeTiledFn ya_encode_fn() {
   return fn;
 }
 
+static size_t ya_smem_bytes(int mode) {
+  const int warps = mode == MODE_V7 ? kYaWarpsV7 : kYaWarpsV3;
+  size_t s = (size_t)warps * kYaStages * kYaChunkFloats * sizeof(float) + (size_t)warps * kYaStages * sizeof(uint64_t);
+  if (mode == MODE_V3) s += (size_t)warps * (kYaHitCap * (sizeof(float2) + sizeof(uint32_t)) + sizeof(int));
+  return s;
+}
+
 template <int MODE>
 static int ya_launch_mode(YaParams& stream_p, bool have_stream, YaParams& gen_p, int gen_anchors, int B, size_t smem,
                           const DeviceInfo& di, cudaStream_t stream) {
+  constexpr int kYaWarps = MODE == MODE_V7 ? kYaWarpsV7 : kYaWarpsV3;
   if (have_stream) {
     static unsigned long long attr_done = 0;
     int rc = ensure_smem_attr(reinterpret_cast<const void*>(yolo_anchor_stream_kernel<MODE>), (int)smem, di.device, &attr_done);
@@ -526,7 +613,7 @@ int yolo_anchor_decode_launch(int mode, const float* const* level_ptr, const int
   DeviceInfo di;
   int rc = device_info(&di);
   if (rc != CVPP_OK) return rc;
-  const size_t smem = (size_t)kYaWarps * kYaStages * kYaChunkFloats * sizeof(float) + (size_t)kYaWarps * kYaStages * sizeof(uint64_t);
+  const size_t smem = ya_smem_bytes(mode);
   const bool tma_avail = smem <= (size_t)di.max_smem && ya_encode_fn();
 
   alignas(64) YaParams sp{}, gp{};
@@ -541,6 +628,7 @@ int yolo_anchor_decode_launch(int mode, const float* const* level_ptr, const int
     q->box_dense = reinterpret_cast<float4*>(box_dense);
     q->aux_dense = reinterpret_cast<float2*>(aux_dense);
     q->max_cand = max_cand;
+    q->tail_rows = attrs % kYaChunkRows ? attrs % kYaChunkRows : kYaChunkRows;
   }
   int gen_anchors = 0, tiles = 0;
   for (int l = 0; l < num_levels; ++l) {
@@ -555,6 +643,12 @@ int yolo_anchor_decode_launch(int mode, const float* const* level_ptr, const int
       ok = ya_encode_fn()(&sp.tmap[sp.num_levels], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(L.ptr), dims,
                           strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+      if (ok) {
+        box[1] = (cuuint32_t)sp.tail_rows;
+        ok = ya_encode_fn()(&sp.tmap_tail[sp.num_levels], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(L.ptr), dims,
+                            strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+      }
     }
     if (ok) {
       YaLevel& D = sp.lv[sp.num_levels++];

@@ -1,0 +1,163 @@
+"""Per-configuration device timings of every decode path (BASELINE.json configs[1..4] + YOLOv3), with the
+algorithmic-bytes bandwidth of each decode/filter kernel.  One JSON line per configuration.
+
+    python tools/bench_paths.py [--iters 50] [--only yolov8,centernet,ssd,yolov7,yolov3]
+
+Inputs are generated on the device with the SURVEY.md §8d distributions (no score separation: this is a
+timing tool, parity lives in tests/)."""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+from computervision.pytorch_b200 import ops  # noqa: E402
+
+DEV = torch.device("cuda:0")
+PEAK = 6504.1
+try:
+    PEAK = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+except Exception:
+    pass
+
+
+def timed(fn, iters, warm=5):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def report(name, B, bytes_per_image, ms_decode, ms_total, extra=None):
+    gbs = B * bytes_per_image / (ms_decode * 1e-3) / 1e9
+    line = {"path": name, "batch": B, "decode_ms": round(ms_decode, 4), "total_ms": round(ms_total, 4),
+            "decode_GBps": round(gbs, 1), "decode_frac_of_hbm_peak": round(gbs / PEAK, 4),
+            "images_per_s": round(B / (ms_total * 1e-3), 1), "bytes_per_image": bytes_per_image}
+    line.update(extra or {})
+    print(json.dumps(line), flush=True)
+
+
+def gen():
+    g = torch.Generator(device=DEV)
+    g.manual_seed(99)
+    return g
+
+
+def bench_yolov8(iters, B=64):
+    g = gen()
+    levels = []
+    for h, w in ((80, 80), (40, 40), (20, 20)):
+        x = torch.randn((B, 144, h, w), generator=g, device=DEV)
+        x[:, :64] *= 3.0
+        x[:, 64:] *= 4.3155
+        x[:, 64:] += -18.19
+        levels.append(x)
+    ls = ops.make_levels(levels, (8.0, 16.0, 32.0))
+    post = ops.Yolov8Postprocessor(B, 8400, 80, DEV)
+    c = ops.yolov8_decode_filter(ls, 80, 0.001)
+    ms_dec = timed(lambda: ops.yolov8_decode_filter(ls, 80, 0.001), iters)
+    ms_tot = timed(lambda: post(ls, 0.001, 0.7), iters)
+    cand = float(c.count.float().mean())
+    report("yolov8_C2", B, 144 * 8400 * 4 + 24 * cand, ms_dec, ms_tot, {"cand_per_image": cand})
+
+
+def bench_centernet(iters, B=64):
+    g = gen()
+    pred = torch.empty((B, 128, 128, 84), device=DEV)
+    pred[..., :80] = torch.randn((B, 128, 128, 80), generator=g, device=DEV) * 1.5 - 5.0
+    pred[..., 80:82] = torch.rand((B, 128, 128, 2), generator=g, device=DEV)
+    pred[..., 82:] = torch.rand((B, 128, 128, 2), generator=g, device=DEV) * 20
+    ms = timed(lambda: ops.centernet_decode(pred, 100, 0.001), iters)
+    ms_nms = timed(lambda: ops.centernet_decode(pred, 100, 0.001, use_nms=True), iters)
+    report("centernet_C3", B, 128 * 128 * 84 * 4, ms, ms, {"total_ms_with_diou_nms": round(ms_nms, 4)})
+
+
+def bench_ssd(iters, B=128):
+    import oracle
+    g = gen()
+    P = 8732
+    loc = torch.randn((B, P, 4), generator=g, device=DEV)
+    conf = torch.randn((B, P, 21), generator=g, device=DEV) * 2.0
+    conf[..., 0] = torch.randn((B, P), generator=g, device=DEV) + 12.0
+    boost = torch.rand((B, P), generator=g, device=DEV) < 0.003
+    cls = torch.randint(1, 21, (B, P), generator=g, device=DEV)
+    val = conf[..., 0] + torch.randn((B, P), generator=g, device=DEV) * 2.0 + 2.0
+    conf.scatter_(2, cls.unsqueeze(2), torch.where(boost, val, conf.gather(2, cls.unsqueeze(2)).squeeze(2)).unsqueeze(2))
+    pri = torch.from_numpy(oracle.ssd_priors()).to(DEV)
+    c = ops.ssd_decode_filter(loc, conf, pri, 0.001, max_cand=32768)
+    ms_dec = timed(lambda: ops.ssd_decode_filter(loc, conf, pri, 0.001, max_cand=32768), iters)
+
+    def full():
+        cc = ops.ssd_decode_filter(loc, conf, pri, 0.001, max_cand=32768)
+        ops.segmented_sort(cc, ops.RULE_PER_CLASS)
+        ops.nms(cc, 0.5, ops.RULE_PER_CLASS, ops.ORDER_CLASS_MAJOR, max_det=0, max_out=4096)
+    ms_tot = timed(full, iters)
+    report("ssd_C4", B, 873200, ms_dec, ms_tot, {"cand_per_image": float(c.count.float().mean())})
+
+
+def bench_yolov7(iters, B=128):
+    import oracle
+    g = gen()
+    levels = []
+    for s in (20, 40, 80):
+        x = torch.randn((B, 3, 85, s, s), generator=g, device=DEV)
+        x[:, :, 4] = x[:, :, 4] * 3.0 - 9.0
+        x[:, :, 5:] = x[:, :, 5:] * 2.0 - 1.0
+        levels.append(x.reshape(B, 255, s, s))
+    ls = ops.make_levels(levels)
+    anchors = oracle.yolov7_level_anchors()
+    c = ops.yolov7_decode_filter(ls, 80, anchors, (640, 640), 0.001)
+    ms_dec = timed(lambda: ops.yolov7_decode_filter(ls, 80, anchors, (640, 640), 0.001), iters)
+
+    def full():
+        cc = ops.yolov7_decode_filter(ls, 80, anchors, (640, 640), 0.001)
+        ops.segmented_sort(cc, ops.RULE_PER_CLASS)
+        ops.nms(cc, 0.3, ops.RULE_PER_CLASS, ops.ORDER_CLASS_MAJOR, max_det=0, max_out=8192)
+    ms_tot = timed(full, iters)
+    report("yolov7_C5_shard", B, 25200 * 85 * 4, ms_dec, ms_tot, {"cand_per_image": float(c.count.float().mean())})
+
+
+def bench_yolov3(iters, B=256):
+    import oracle
+    g = gen()
+    levels = []
+    for s in (13, 26, 52):
+        x = torch.randn((B, 3, 25, s, s), generator=g, device=DEV)
+        x[:, :, 2:4] *= 0.5
+        x[:, :, 4] = x[:, :, 4] * 2.5 - 10.0
+        x[:, :, 5:] = x[:, :, 5:] * 2.0 - 3.0
+        levels.append(x.reshape(B, 75, s, s))
+    ls = ops.make_levels(levels)
+    anchors = np.array(oracle.YOLOV3_ANCHORS, np.float32).reshape(-1, 2)
+    c = ops.yolov3_decode_filter(ls, 20, anchors, (416, 416), 0.001, max_cand=16384)
+    ms_dec = timed(lambda: ops.yolov3_decode_filter(ls, 20, anchors, (416, 416), 0.001, max_cand=16384), iters)
+
+    def full():
+        cc = ops.yolov3_decode_filter(ls, 20, anchors, (416, 416), 0.001, max_cand=16384)
+        ops.segmented_sort(cc, ops.RULE_PER_CLASS)
+        ops.nms(cc, 0.5, ops.RULE_PER_CLASS, ops.ORDER_CLASS_MAJOR, max_det=0, max_out=8192)
+    ms_tot = timed(full, iters)
+    report("yolov3_voc", B, 10647 * 25 * 4, ms_dec, ms_tot, {"cand_per_image": float(c.count.float().mean())})
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--iters", type=int, default=50)
+    ap.add_argument("--only", default="yolov8,centernet,ssd,yolov7,yolov3")
+    a = ap.parse_args()
+    table = {"yolov8": bench_yolov8, "centernet": bench_centernet, "ssd": bench_ssd, "yolov7": bench_yolov7,
+             "yolov3": bench_yolov3}
+    for name in a.only.split(","):
+        table[name](a.iters)
