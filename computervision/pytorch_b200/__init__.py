@@ -7,5 +7,6 @@ points under `computervision.pytorch_b200.core`.  There is no CPU fallback.
 """
 from . import _lib  # noqa: F401
 from . import ops  # noqa: F401
+from . import distributed  # noqa: F401
 
-__all__ = ["ops", "_lib"]
+__all__ = ["ops", "_lib", "distributed"]
