@@ -43,6 +43,9 @@ _PROTOS = {
     "cvpp_nms_workspace_bytes": (c_size, [c_int, c_int, c_int]),
     "cvpp_nms": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_i64, c_int, c_f64, c_int, c_int, c_int, c_int, c_vp, c_vp,
                          c_vp, c_vp, c_vp, c_vp, c_size, c_vp]),
+    "cvpp_sort_nms_workspace_bytes": (c_size, [c_int, c_int, c_int]),
+    "cvpp_sort_nms": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_i64, c_int, c_f64, c_int, c_int, c_int, c_int, c_int,
+                              c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_size, c_vp]),
     "cvpp_yolov8_workspace_bytes": (c_size, [c_int, c_i64, c_int, c_int]),
     "cvpp_yolov8_postprocess": (c_int, [P(c_vp), P(c_i64), P(c_i64), P(c_int), P(c_int), P(c_f32), c_int, c_int,
                                         c_int, c_int, c_f32, c_f64, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp,

@@ -7,7 +7,6 @@ import torch
 
 from ... import ops
 from ..utils.anchor import generate_ssd_anchor_v2
-from ..utils.image_process import yolo_correct_boxes
 
 
 class Ssd:
@@ -54,17 +53,12 @@ class Ssd:
         cand = ops.ssd_decode_filter(loc, conf, self._priors(loc.device), conf_threshold,
                                      max_cand=min(self.num_anchors * self.num_classes, 32768))
         try:
-            per_image = ops.per_class_nms_rows(cand, self.nms_threshold)
+            det = ops.per_class_nms_device(cand, self.nms_threshold)
         except OverflowError:
             cand = ops.ssd_decode_filter(loc, conf, self._priors(loc.device), conf_threshold)
-            per_image = ops.per_class_nms_rows(cand, self.nms_threshold)
-        results = []
-        for box, score, cls, _ in per_image:
-            if box.shape[0] == 0:
-                results.append([])
-                continue
-            rows = torch.cat((box, cls[:, None].float(), score[:, None]), 1).numpy()
-            centre, size = (rows[:, 0:2] + rows[:, 2:4]) / 2, rows[:, 2:4] - rows[:, 0:2]
-            rows[:, :4] = yolo_correct_boxes(centre, size, self.input_image_size, [h, w], self.letterbox_image)
-            results.append(rows)
-        return results
+            det = ops.per_class_nms_device(cand, self.nms_threshold)
+        B = int(loc.shape[0])
+        table = ops.correct_boxes_params([(h, w)] * B, self.input_image_size, self.letterbox_image, loc.device)
+        rows = ops.detection_epilogue(det, ops.ROWS_SSD, ops.BOX_CORRECT, table)   # ssd.py:275-287 on the device
+        rows_h, counts = rows.cpu().numpy(), det.count.cpu().tolist()               # one transfer for the batch
+        return [rows_h[b, :n].copy() if n > 0 else [] for b, n in enumerate(counts)]

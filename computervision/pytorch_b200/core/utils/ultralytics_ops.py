@@ -1,8 +1,8 @@
 """Mirror of reference core/utils/ultralytics_ops.py for the detection path:
 `non_max_suppression` (:131-264) and `xywh2xyxy` (:360-375).
 
-`non_max_suppression` keeps the reference signature.  It runs three CUDA kernels through the C ABI
-(confidence filter -> segmented sort -> class-aware NMS) and reads the per-image counts back once;
+`non_max_suppression` keeps the reference signature.  It runs two CUDA kernels through the C ABI
+(confidence filter -> fused per-class sort + class-aware NMS) and reads the per-image counts back once;
 there is no per-image Python loop and no torchvision call.  The dead branches of the reference that no
 caller reaches (multi_label, autolabelling `labels`, merge-NMS) raise NotImplementedError instead of
 silently doing something else; `agnostic` is accepted and ignored exactly like the reference, whose
@@ -88,8 +88,7 @@ def non_max_suppression(
     cand = ops.pred_filter(prediction, nc, conf_thres)
     if classes is not None:
         _keep_classes(cand, classes)
-    ops.segmented_sort(cand, rule, max_nms=max_nms)
-    det = ops.nms(cand, iou_thres, rule, ops.ORDER_SCORE_DESC, max_det=max_det, max_out=max_det)
+    det = ops.sort_nms(cand, iou_thres, rule, ops.ORDER_SCORE_DESC, max_det=max_det, max_nms=max_nms, max_out=max_det)
     rows = _rows_from_detections(prediction.contiguous(), det, nc, nm)
     if return_anchors:
         counts = det.count.tolist()

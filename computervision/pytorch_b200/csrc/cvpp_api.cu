@@ -66,6 +66,12 @@ int nms_launch(const uint64_t* sorted_key, const int32_t* cand_count, const floa
                float* det_score, int32_t* det_cls, int32_t* det_anchor, int32_t* det_count, void* workspace,
                size_t workspace_bytes, cudaStream_t stream);
 
+size_t sort_nms_workspace_bytes(int B, int max_cand, int nc);
+int sort_nms_launch(const uint64_t* cand_key, const int32_t* cand_count, const float* box_dense, int B, int max_cand, int64_t A,
+                    int nc, double iou_thres, int rule, int order, int max_det, int max_nms, int max_out, float* det_box,
+                    float* det_score, int32_t* det_cls, int32_t* det_anchor, int32_t* det_count, void* workspace,
+                    size_t workspace_bytes, cudaStream_t stream);
+
 size_t centernet_workspace_bytes(int B, int H, int W, int nc, int K);
 int centernet_launch(const float* pred, int B, int H, int W, int nc, int K, float conf, int pool_mode, int use_nms,
                      float nms_thr, const float* letterbox, float* det_box, float* det_score, int32_t* det_cls,
@@ -185,14 +191,27 @@ int cvpp_nms(const uint64_t* sorted_key, const int32_t* cand_count, const float*
                     (cudaStream_t)stream);
 }
 
+size_t cvpp_sort_nms_workspace_bytes(int B, int max_cand, int nc) {
+  if (B < 0 || max_cand < 1 || nc < 1) return 0;
+  return sort_nms_workspace_bytes(B, max_cand, nc);
+}
+
+int cvpp_sort_nms(const uint64_t* cand_key, const int32_t* cand_count, const float* box_dense, int B, int max_cand, int64_t A, int nc,
+                  double iou_thres, int rule, int order, int max_det, int max_nms, int max_out, float* det_box,
+                  float* det_score, int32_t* det_cls, int32_t* det_anchor, int32_t* det_count, void* workspace,
+                  size_t workspace_bytes, cvpp_stream_t stream) {
+  return sort_nms_launch(cand_key, cand_count, box_dense, B, max_cand, A, nc, iou_thres, rule, order, max_det, max_nms,
+                         max_out, det_box, det_score, det_cls, det_anchor, det_count, workspace, workspace_bytes,
+                         (cudaStream_t)stream);
+}
+
 size_t cvpp_yolov8_workspace_bytes(int B, int64_t A, int max_cand, int nc) {
   if (B < 0 || A < 1 || max_cand < 1 || nc < 1) return 0;
   size_t s = 256;
   s += align256((size_t)B * max_cand * sizeof(uint64_t));  // cand_key
   s += align256((size_t)B * sizeof(int32_t));              // cand_count
   s += align256((size_t)B * (size_t)A * 16);               // box_dense
-  s += align256(segsort_workspace_bytes(B, max_cand));
-  s += align256(nms_workspace_bytes(B, max_cand, nc));
+  s += align256(sort_nms_workspace_bytes(B, max_cand, nc));
   return s;
 }
 
@@ -224,24 +243,19 @@ int cvpp_yolov8_postprocess(const float* const* level_ptr, const int64_t* batch_
   p += align256((size_t)B * sizeof(int32_t));
   float* box_dense = reinterpret_cast<float*>(p);
   p += align256((size_t)B * (size_t)A * 16);
-  void* sort_ws = reinterpret_cast<void*>(p);
-  size_t sort_bytes = segsort_workspace_bytes(B, max_cand);
-  p += align256(sort_bytes);
-  void* nms_ws = reinterpret_cast<void*>(p);
-  size_t nms_bytes = nms_workspace_bytes(B, max_cand, nc);
+  void* sn_ws = reinterpret_cast<void*>(p);
+  const size_t sn_bytes = sort_nms_workspace_bytes(B, max_cand, nc);
 
   int rc = cvpp_yolov8_decode_filter(level_ptr, batch_stride, chan_stride, level_h, level_w, level_stride, num_levels,
                                      B, nc, reg_max, conf_thres, cand_key, cand_count, box_dense, max_cand, stream);
   if (rc != CVPP_OK) return rc;
-  rc = segsort_launch(cand_key, cand_count, B, max_cand, rule, max_nms, sort_ws, sort_bytes, (cudaStream_t)stream);
-  if (rc != CVPP_OK) return rc;
-  rc = nms_launch(cand_key, cand_count, box_dense, B, max_cand, A, nc, iou_thres, rule, CVPP_ORDER_SCORE_DESC, max_det,
-                  max_det, det_box, det_score, det_cls, det_anchor, det_count, nms_ws, nms_bytes, (cudaStream_t)stream);
-  if (rc != CVPP_OK) return rc;
+  // the candidate counts are copied out before the fallback sort can truncate them to max_nms
   if (cand_count_out && B > 0)
     CVPP_CUDA_TRY(cudaMemcpyAsync(cand_count_out, cand_count, sizeof(int32_t) * (size_t)B, cudaMemcpyDeviceToDevice,
                                   (cudaStream_t)stream));
-  return CVPP_OK;
+  return sort_nms_launch(cand_key, cand_count, box_dense, B, max_cand, A, nc, iou_thres, rule, CVPP_ORDER_SCORE_DESC,
+                         max_det, max_nms, max_det, det_box, det_score, det_cls, det_anchor, det_count, sn_ws, sn_bytes,
+                         (cudaStream_t)stream);
 }
 
 size_t cvpp_centernet_workspace_bytes(int B, int H, int W, int nc, int K) {

@@ -62,6 +62,7 @@ struct NmsParams {
   int smem_boxes;    // positions that fit in shared memory
   int mask_words;    // words reserved for each of the two bitmasks
   int count_warps;   // warps taking part in the counting split (per-warp class counters)
+  const int32_t* skip;  // optional [B]: images the fused sort+NMS kernel already finished
 };
 
 struct SupTest {
@@ -97,20 +98,46 @@ struct BoxView<false> {
 
 // Is box j suppressed by kept box i (symmetric in i, j)?  torchvision: ovr = inter / (iarea + jarea -
 // inter) in fp32, suppressed iff (double)ovr > thr.  RN(inter/uni) > thr_eff  <=>  inter/uni > thr_mid
-// (>= when the tie rounds up), and inter vs thr_mid*uni is exact in fp64.  Branch-free on the common
-// path; degenerate unions (<= 0, inf, NaN) fall back to the division.
-__device__ __forceinline__ bool suppresses(const float4& bi, float ai, const float4& bj, float aj, const SupTest& t) {
-  const float xx1 = fmaxf(bi.x, bj.x), yy1 = fmaxf(bi.y, bj.y);
-  const float xx2 = fminf(bi.z, bj.z), yy2 = fminf(bi.w, bj.w);
-  const float w = fmaxf(0.0f, fsub(xx2, xx1));
-  const float h = fmaxf(0.0f, fsub(yy2, yy1));
-  const float inter = fmul(w, h);
-  const float uni = fsub(fadd(ai, aj), inter);
+// (>= when the tie rounds up), and inter vs thr_mid*uni is exact in fp64.  Degenerate unions (<= 0, inf,
+// NaN) fall back to the division.  This is the exact (slow) form.
+__device__ __noinline__ bool suppresses_exact(float inter, float uni, const SupTest& t) {
   const double lhs = (double)inter, rhs = t.thr_mid * (double)uni;
   const bool cmp = t.tie_up ? lhs >= rhs : lhs > rhs;
   const bool regular = uni > 0.0f && uni < INFINITY && inter < INFINITY;
   bool sup = inter > 0.0f && regular && cmp;  // inter == 0 / NaN: ovr is 0 or NaN, never above thr
   if (inter > 0.0f && !regular) sup = fdiv(inter, uni) > t.thr_eff;
+  return sup;
+}
+
+__device__ __forceinline__ void inter_union(const float4& bi, float ai, const float4& bj, float aj, float& inter, float& uni) {
+  const float xx1 = fmaxf(bi.x, bj.x), yy1 = fmaxf(bi.y, bj.y);
+  const float xx2 = fminf(bi.z, bj.z), yy2 = fminf(bi.w, bj.w);
+  const float w = fmaxf(0.0f, fsub(xx2, xx1));
+  const float h = fmaxf(0.0f, fsub(yy2, yy1));
+  inter = fmul(w, h);
+  uni = fsub(fadd(ai, aj), inter);
+}
+
+// Fast classification of the same test in fp32: d = inter - thr_eff * uni (one rounding, fma).  The decision
+// boundary inter = thr_mid * uni lies within thr_eff * 2^-24 * uni of d = 0, and the fma is off by at most
+// 2^-24 |d|, so |d| > 2^-21 * uni decides the exact test with a wide margin: d above -> suppressed, below ->
+// kept.  Anything else (near-threshold pairs, non-positive / non-finite unions, NaN) is `ambiguous` and must
+// go through suppresses_exact.  A pair with inter == 0 is never suppressed (d = -thr_eff * uni <= 0).
+__device__ __forceinline__ bool suppresses_fast(float inter, float uni, const SupTest& t, bool& ambiguous) {
+  const float d = fmaf(-t.thr_eff, uni, inter);
+  const float m = uni * 4.76837158203125e-07f;  // 2^-21
+  const bool clear = fabsf(d) > m && m > 0.0f && fabsf(d) < INFINITY;  // false for NaN, uni <= 0, infinities
+  ambiguous = !clear && inter > 0.0f;  // inter == 0 (or NaN): never suppressed
+  return clear && d > 0.0f && inter > 0.0f;
+}
+
+// fast classification, exact test only for the (rare) ambiguous pairs
+__device__ __forceinline__ bool suppresses(const float4& bi, float ai, const float4& bj, float aj, const SupTest& t) {
+  float inter, uni;
+  inter_union(bi, ai, bj, aj, inter, uni);
+  bool amb;
+  bool sup = suppresses_fast(inter, uni, t, amb);
+  if (amb) sup = suppresses_exact(inter, uni, t);
   return sup;
 }
 
@@ -152,25 +179,26 @@ __device__ __forceinline__ uint32_t resolve_word(int w, int s, int e, const BoxV
   // pairs are at most `span` lanes apart; rotations beyond min(span, 16) have nothing to test
   const int span = (31 - __clz(am)) - (__ffs(am) - 1);
   const int rounds = span < 16 ? span : 16;
-  uint32_t col = 0;  // which LATER live boxes of this word box `lane` suppresses
+  // lane i owns two bit rows: col = LATER live boxes of the word that box i suppresses (pairs it tested as
+  // the earlier box), row = EARLIER boxes that suppress box i (pairs it tested as the later box, i.e. the
+  // wrapped rotations).  The greedy replay below combines them, so no per-round routing of verdicts.
+  uint32_t col = 0, row = 0;
   for (int r = 1; r <= rounds; ++r) {
     const int j = (lane + r) & 31;
     const bool pair = me && ((am >> j) & 1u) && (r < 16 || lane < 16);
     bool sup = false;
     if (pair) sup = suppresses(bi, ai, bv.load_box(base + j), bv.load_area(base + j), t);
-    const uint32_t v = __ballot_sync(0xffffffffu, sup);
-    // verdicts owned by this lane as the earlier box: (lane, lane + r) tested here if lane + r < 32,
-    // (lane, lane - r + 32) tested by lane' = lane - r + 32 if that is a later lane
-    if (lane + r < 32) col |= ((v >> lane) & 1u) << (lane + r);
-    const int k = lane - r + 32;
-    if (k < 32 && (r < 16 || k < 16)) col |= ((v >> k) & 1u) << k;
+    const uint32_t bit = sup ? (1u << j) : 0u;
+    if (j > lane) col |= bit;
+    else row |= bit;
   }
-  // replay the greedy order on bitmasks: a live box kills the later boxes in its column mask
+  // replay the greedy order on bitmasks: a live box kills the later boxes in its column mask and every
+  // later box whose row mask names it
   uint32_t rem = am;
   while (rem) {
     const int i = __ffs(rem) - 1;
     rem &= rem - 1;
-    const uint32_t c = __shfl_sync(0xffffffffu, col, i);
+    const uint32_t c = __shfl_sync(0xffffffffu, col, i) | __ballot_sync(0xffffffffu, (row >> i) & 1u);
     am &= ~c;
     rem &= ~c;
   }
@@ -272,7 +300,7 @@ __device__ void nms_segment_cta(int s, int e, int cap, const BoxView<SMEM>& bv, 
     if (done) {
       for (int w2 = w + 1 + threadIdx.x; w2 <= w1; w2 += blockDim.x) atomicAnd(&alive[w2], ~seg_mask_of_word(w2, s, e));
     } else if (am) {
-      for (int w2 = w + 1 + warp; w2 <= w1; w2 += kNmsWarps) apply_word(am, w, w2, e, bv, alive, t);
+      for (int w2 = w + 1 + warp; w2 <= w1; w2 += (int)(blockDim.x >> 5)) apply_word(am, w, w2, e, bv, alive, t);
     }
     __syncthreads();
     if (done) break;
@@ -283,7 +311,7 @@ __device__ void nms_segment_cta(int s, int e, int cap, const BoxView<SMEM>& bv, 
 template <bool SMEM>
 __device__ void suppress_all(const BoxView<SMEM>& bv, bool trick, int n, int nwords, int nc, int cap, uint32_t* alive,
                              const int* seg_begin, const int* seg_end, const SupTest& st, int* sh_next,
-                             uint32_t* sh_mask, int* sh_kept) {
+                             uint32_t* sh_mask, int* sh_kept, bool any_large = true) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (trick) {
     if (nwords > kCoopMinWords) {
@@ -306,6 +334,7 @@ __device__ void suppress_all(const BoxView<SMEM>& bv, bool trick, int n, int nwo
     nms_segment_warp(s, e, cap, bv, alive, st);
   }
   __syncthreads();
+  if (!any_large) return;  // (a scan over all classes by every thread costs ~5 us at nc = 80)
   for (int c = 0; c < nc; ++c) {
     const int s = seg_begin[c], e = seg_end[c];
     if (e <= s) continue;
@@ -336,6 +365,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.x;
+  if (p.skip && p.skip[b]) return;  // already done by the fused kernel
   int n = p.cand_count[b];
   if (n > p.max_cand) n = p.max_cand;
   if (n <= 0) {
@@ -576,10 +606,23 @@ size_t nms_workspace_bytes(int B, int max_cand, int nc) {
   return per * (size_t)B + 256;
 }
 
+int nms_launch_skip(const uint64_t* sorted_key, const int32_t* cand_count, const float* box_dense, int B, int max_cand,
+                    int64_t A, int nc, double iou_thres, int rule, int order, int max_det, int max_out, float* det_box,
+                    float* det_score, int32_t* det_cls, int32_t* det_anchor, int32_t* det_count, void* workspace,
+                    size_t workspace_bytes, const int32_t* skip, cudaStream_t stream);
+
 int nms_launch(const uint64_t* sorted_key, const int32_t* cand_count, const float* box_dense, int B, int max_cand,
                int64_t A, int nc, double iou_thres, int rule, int order, int max_det, int max_out, float* det_box,
                float* det_score, int32_t* det_cls, int32_t* det_anchor, int32_t* det_count, void* workspace,
                size_t workspace_bytes, cudaStream_t stream) {
+  return nms_launch_skip(sorted_key, cand_count, box_dense, B, max_cand, A, nc, iou_thres, rule, order, max_det, max_out,
+                         det_box, det_score, det_cls, det_anchor, det_count, workspace, workspace_bytes, nullptr, stream);
+}
+
+int nms_launch_skip(const uint64_t* sorted_key, const int32_t* cand_count, const float* box_dense, int B, int max_cand,
+                    int64_t A, int nc, double iou_thres, int rule, int order, int max_det, int max_out, float* det_box,
+                    float* det_score, int32_t* det_cls, int32_t* det_anchor, int32_t* det_count, void* workspace,
+                    size_t workspace_bytes, const int32_t* skip, cudaStream_t stream) {
   if (!sorted_key || !cand_count || !box_dense || !det_box || !det_score || !det_cls || !det_anchor || !det_count) {
     set_error("nms: NULL pointer argument");
     return CVPP_ERR_INVALID_ARG;
@@ -635,6 +678,7 @@ int nms_launch(const uint64_t* sorted_key, const int32_t* cand_count, const floa
   p.det_cls = det_cls;
   p.det_anchor = det_anchor;
   p.det_count = det_count;
+  p.skip = skip;
   // workspace carve-up
   const size_t cap = pos_capacity(max_cand, nc);
   p.pos_cap = (int)cap;
@@ -671,6 +715,540 @@ int nms_launch(const uint64_t* sorted_key, const int32_t* cand_count, const floa
   nms_kernel<<<B, kNmsThreads, smem, stream>>>(p);
   CVPP_CUDA_TRY(cudaGetLastError());
   return CVPP_OK;
+}
+
+// =====================================================================================================
+// Fused sort + NMS (v2): one kernel per image, no global sort.
+//
+// The separate segmented sort (a full bitonic sort of ~2 500 keys padded to 4 096, 28 us for 64 images)
+// plus nms_kernel (66 us) made the latency-bound stages longer than the HBM-bound decode (70 us).  Only two
+// orders are actually needed: score order WITHIN a class (torchvision's processing order) and the global
+// score order of the max_det SURVIVORS.  So:
+//   1. histogram of the (unsorted) candidate keys by class, 32-aligned class segments (shared-memory atomics);
+//   2. scatter into the segments, then every class segment is sorted on its own - a typical ~30-box class is
+//      ONE warp-register bitonic sort of 32 keys (15 shuffle steps), classes run in parallel over 32 warps;
+//      the warp that sorted a class also gathers its boxes/areas into shared memory;
+//   3. greedy suppression exactly as in nms_kernel (same device functions, same bit-exact IoU test);
+//   4. class-major output: ordered compaction of the alive bitmask; score-ordered output: histogram of the
+//      survivors' score bits (4 096 bins), the bin where the cumulative count reaches max_det, and a sort of
+//      only the selected <= max_det + boundary-bin keys.
+// The coordinate-trick branch (<= 1000 candidates) needs the global score order for its class-agnostic pass
+// and sorts its <= 1 024 keys in shared memory.  Images that do not fit shared memory (or exceed max_nms) are
+// left to the two-kernel path: this kernel writes done[b] = 0 and segsort_kernel / nms_kernel, launched
+// behind it with done as their skip list, pick them up.
+// =====================================================================================================
+constexpr int kN2Threads = 1024;
+constexpr int kN2Warps = kN2Threads / 32;
+constexpr int kN2Bins = 4096;
+constexpr int kN2WarpSortMax = 256;  // keys per class a single warp sorts in registers (E <= 8)
+
+struct Nms2Params {
+  const uint64_t* cand_key;  // UNSORTED class-major keys
+  const int32_t* cand_count;
+  const float4* box_dense;
+  int max_cand;
+  int64_t A;
+  int nc;
+  float thr_eff;
+  double thr_mid;
+  int tie_up;
+  int rule, order, max_det, max_nms, max_out;
+  float4* det_box;
+  float* det_score;
+  int32_t* det_cls;
+  int32_t* det_anchor;
+  int32_t* det_count;
+  int32_t* done;   // [B]
+  int cap_pos;     // class-major positions that fit shared memory (multiple of 32)
+  int mask_words;  // cap_pos / 32
+};
+
+template <int E>
+__device__ __forceinline__ void warp_sort_segment(uint64_t* seg, int t) {
+  const int lane = threadIdx.x & 31;
+  uint64_t x[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) x[e] = (e * 32 + lane) < t ? seg[e * 32 + lane] : ~0ull;
+#pragma unroll
+  for (int k = 2; k <= 32 * E; k <<= 1) warp_bitonic_steps<E>(x, 0, k, k >> 1);
+#pragma unroll
+  for (int e = 0; e < E; ++e)
+    if ((e * 32 + lane) < t) seg[e * 32 + lane] = x[e];
+  __syncwarp();
+}
+
+__device__ __forceinline__ void block_sort_smem_max8(uint64_t* a, int P) {
+  const int T = blockDim.x;
+  const int E = P > T ? P / T : 1;
+  switch (E) {
+    case 1: block_sort_smem_e<1>(a, P); break;
+    case 2: block_sort_smem_e<2>(a, P); break;
+    case 4: block_sort_smem_e<4>(a, P); break;
+    case 8: block_sort_smem_e<8>(a, P); break;
+    default: bitonic_sort_u64_generic(a, P); break;
+  }
+}
+
+// exclusive block scan helper over one int per thread (blockDim = kN2Threads); returns the exclusive prefix,
+// *total receives the block total.  Two __syncthreads.
+__device__ __forceinline__ int block_excl_scan(int v, int* sh_warp /*[kN2Warps]*/, int* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int incl = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int u = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += u;
+  }
+  if (lane == 31) sh_warp[warp] = incl;
+  __syncthreads();
+  int woff = 0, tot = 0;
+  for (int q = 0; q < kN2Warps; ++q) {
+    const int u = sh_warp[q];
+    if (q < warp) woff += u;
+    tot += u;
+  }
+  __syncthreads();
+  *total = tot;
+  return woff + incl - v;
+}
+
+#ifdef CVPP_NMS_TIMING
+__device__ long long g_n2_t[16 * 64];
+#define N2_MARK(i) do { __syncthreads(); if (threadIdx.x == 0 && blockIdx.x < 64) g_n2_t[blockIdx.x * 16 + (i)] = clock64(); } while (0)
+#else
+#define N2_MARK(i) do {} while (0)
+#endif
+
+__global__ void __launch_bounds__(kN2Threads, 1) nms2_kernel(const __grid_constant__ Nms2Params p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  // layout: [box float4 x cap][key u64 x cap][area f32 x cap][alive u32 x words][seg_begin, seg_end, fill int x nc]
+  float4* sh_box = reinterpret_cast<float4*>(smem_raw);
+  uint64_t* ckey = reinterpret_cast<uint64_t*>(sh_box + p.cap_pos);
+  float* sh_area = reinterpret_cast<float*>(ckey + p.cap_pos);
+  uint32_t* alive = reinterpret_cast<uint32_t*>(sh_area + p.cap_pos);
+  int* seg_begin = reinterpret_cast<int*>(alive + p.mask_words);
+  int* seg_end = seg_begin + p.nc;
+  int* fill = seg_end + p.nc;
+  __shared__ float sh_red[kN2Warps];
+  __shared__ int sh_scan[kN2Warps];
+  __shared__ uint32_t sh_mask;
+  __shared__ int sh_kept, sh_next, sh_npos, sh_i0, sh_maxt;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.x;
+  int n = p.cand_count[b];
+  if (n > p.max_cand) n = p.max_cand;
+  if (n <= 0) {
+    if (tid == 0) {
+      p.det_count[b] = 0;
+      p.done[b] = 1;
+    }
+    return;
+  }
+  const uint64_t* keys = p.cand_key + (int64_t)b * p.max_cand;
+  const float4* dense = p.box_dense + (int64_t)b * p.A;
+  const bool trick = rule_uses_trick(p.rule, n);
+  const int nc = p.nc;
+  const SupTest st{p.thr_eff, p.thr_mid, p.tie_up != 0};
+  const int cap = (p.order == CVPP_ORDER_SCORE_DESC && p.max_det > 0) ? p.max_det : 0;
+  bool fits = !(p.max_nms > 0 && n > p.max_nms);
+  if (trick && pow2_ceil(n < 32 ? 32 : n) > p.cap_pos) fits = false;
+  if (!fits) {
+    if (tid == 0) p.done[b] = 0;
+    return;
+  }
+
+  N2_MARK(0);
+  for (int w = tid; w < p.mask_words; w += kN2Threads) alive[w] = 0u;
+  if (tid == 0) sh_next = 0;
+  int npos;
+
+  if (trick) {
+    // ---- coordinate trick: global score order, one class-agnostic segment on shifted boxes (boxes.py:95-97)
+    const int P = pow2_ceil(n < 32 ? 32 : n);
+    for (int i = tid; i < P; i += kN2Threads) ckey[i] = i < n ? key_to_score_major(keys[i]) : ~0ull;
+    __syncthreads();
+    block_sort_smem_max8(ckey, P);
+    npos = n;
+    float m = -INFINITY;
+    for (int r = tid; r < n; r += kN2Threads) {
+      const float4 bx = dense[(uint32_t)(ckey[r] >> 12) & 0x1fffffu];
+      sh_box[r] = bx;
+      m = fmaxf(m, fmaxf(fmaxf(bx.x, bx.y), fmaxf(bx.z, bx.w)));
+    }
+    for (int d = 16; d > 0; d >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
+    if (lane == 0) sh_red[warp] = m;
+    __syncthreads();
+    m = sh_red[0];
+    for (int q = 1; q < kN2Warps; ++q) m = fmaxf(m, sh_red[q]);
+    const float mult = fadd(m, 1.0f);
+    for (int r = tid; r < n; r += kN2Threads) {
+      const float off = fmul((float)(uint32_t)(ckey[r] & 0xfffu), mult);
+      float4 bx = sh_box[r];
+      bx.x = fadd(bx.x, off);
+      bx.y = fadd(bx.y, off);
+      bx.z = fadd(bx.z, off);
+      bx.w = fadd(bx.w, off);
+      sh_box[r] = bx;
+      sh_area[r] = box_area(bx);
+    }
+    for (int w = tid; w < ((n + 31) >> 5); w += kN2Threads) {
+      const int rem = n - (w << 5);
+      alive[w] = rem >= 32 ? 0xffffffffu : ((1u << rem) - 1u);
+    }
+    __syncthreads();
+  } else {
+    // ---- class histogram -> 32-aligned segments -> scatter -> per-class sort
+    for (int c = tid; c < nc; c += kN2Threads) {
+      seg_end[c] = 0;
+      fill[c] = 0;
+    }
+    __syncthreads();
+    for (int r = tid; r < n; r += kN2Threads) {
+      const int c = (int)(keys[r] >> 52);
+      if (c < nc) atomicAdd(&seg_end[c], 1);
+    }
+    __syncthreads();
+    if (warp == 0) {
+      int running = 0, tmax = 0;
+      for (int c0 = 0; c0 < nc; c0 += 32) {
+        const int c = c0 + lane;
+        const int t = c < nc ? seg_end[c] : 0;
+        tmax = max(tmax, t);
+        const int ta = (t + 31) & ~31;
+        int incl = ta;
+        for (int d = 1; d < 32; d <<= 1) {
+          const int v = __shfl_up_sync(0xffffffffu, incl, d);
+          if (lane >= d) incl += v;
+        }
+        if (c < nc) {
+          const int s0 = running + incl - ta;
+          seg_begin[c] = s0;
+          seg_end[c] = s0 + t;
+        }
+        running += __shfl_sync(0xffffffffu, incl, 31);
+      }
+      for (int d = 16; d > 0; d >>= 1) tmax = max(tmax, __shfl_xor_sync(0xffffffffu, tmax, d));
+      if (lane == 0) {
+        sh_npos = running;
+        sh_maxt = tmax;
+      }
+    }
+    __syncthreads();
+    N2_MARK(1);
+    npos = sh_npos;
+    if (npos > p.cap_pos) {  // does not fit: leave the image to the two-kernel path
+      if (tid == 0) p.done[b] = 0;
+      return;
+    }
+    for (int r = tid; r < n; r += kN2Threads) {
+      const uint64_t k = keys[r];
+      const int c = (int)(k >> 52);
+      if (c < nc) ckey[seg_begin[c] + atomicAdd(&fill[c], 1)] = k;
+    }
+    __syncthreads();
+    N2_MARK(2);
+    // warps claim classes; the warp that sorts a class also gathers its boxes and sets its live bits
+    for (;;) {
+      int c = 0;
+      if (lane == 0) c = atomicAdd(&sh_next, 1);
+      c = __shfl_sync(0xffffffffu, c, 0);
+      if (c >= nc) break;
+      const int s = seg_begin[c], t = seg_end[c] - s;
+      if (t <= 0) continue;
+      if (t <= kN2WarpSortMax) {
+        uint64_t* seg = ckey + s;
+        if (t <= 32) warp_sort_segment<1>(seg, t);
+        else if (t <= 64) warp_sort_segment<2>(seg, t);
+        else if (t <= 128) warp_sort_segment<4>(seg, t);
+        else warp_sort_segment<8>(seg, t);
+        for (int w = lane; w < ((t + 31) >> 5); w += 32) {
+          const int rem = t - (w << 5);
+          alive[(s >> 5) + w] = rem >= 32 ? 0xffffffffu : ((1u << rem) - 1u);
+        }
+      }
+    }
+    __syncthreads();
+    N2_MARK(8);
+    // classes too large for one warp: CTA-wide sort in a scratch area (the box array of the positions
+    // behind npos is free only if it fits; otherwise sort in place through the generic network)
+    for (int c = 0; c < nc && sh_maxt > kN2WarpSortMax; ++c) {
+      const int s = seg_begin[c], t = seg_end[c] - s;
+      if (t <= kN2WarpSortMax) continue;
+      const int P = pow2_ceil(t);
+      uint64_t* scratch = reinterpret_cast<uint64_t*>(sh_box + s);  // 16 B per position >= 8 B * 2 t
+      for (int i = tid; i < P; i += kN2Threads) scratch[i] = i < t ? ckey[s + i] : ~0ull;
+      __syncthreads();
+      block_sort_smem_max8(scratch, P);
+      for (int i = tid; i < t; i += kN2Threads) ckey[s + i] = scratch[i];
+      __syncthreads();
+      for (int w = tid; w < ((t + 31) >> 5); w += kN2Threads) {
+        const int rem = t - (w << 5);
+        alive[(s >> 5) + w] = rem >= 32 ? 0xffffffffu : ((1u << rem) - 1u);
+      }
+      __syncthreads();
+    }
+    N2_MARK(9);
+    if (tid == 0) sh_next = 0;
+    // gather the boxes of every live position, all threads, all loads in flight at once
+    for (int i = tid; i < npos; i += kN2Threads) {
+      if ((alive[i >> 5] >> (i & 31)) & 1u) {
+        const float4 bx = dense[(uint32_t)(ckey[i] & 0x1fffffu)];
+        sh_box[i] = bx;
+        sh_area[i] = box_area(bx);
+      }
+    }
+    __syncthreads();
+  }
+  const int nwords = (npos + 31) >> 5;
+  N2_MARK(3);
+
+  // ---- greedy suppression (shared with nms_kernel) -------------------------------------------------
+  {
+    const BoxView<true> bv{smem_u32(sh_box), smem_u32(sh_area)};
+    suppress_all(bv, trick, n, nwords, nc, cap, alive, seg_begin, seg_end, st, &sh_next, &sh_mask, &sh_kept,
+                 trick || sh_maxt > 32 * kCoopMinWords);
+  }
+  __syncthreads();
+  N2_MARK(4);
+
+  float4* ob = p.det_box + (int64_t)b * p.max_out;
+  float* os = p.det_score + (int64_t)b * p.max_out;
+  int32_t* oc = p.det_cls + (int64_t)b * p.max_out;
+  int32_t* oa = p.det_anchor + (int64_t)b * p.max_out;
+
+  if (p.order == CVPP_ORDER_SCORE_DESC && !trick) {
+    // ---- top-max_det survivors in score order: bin selection + a small sort ------------------------
+    // (boxes and areas are dead: the histogram and the selected keys reuse their memory)
+    int* hist = reinterpret_cast<int*>(sh_box);                               // kN2Bins ints
+    uint64_t* sel = reinterpret_cast<uint64_t*>(hist + kN2Bins);              // up to cap_pos keys (16 B/pos - 16 KB)
+    for (int i = tid; i < kN2Bins; i += kN2Threads) hist[i] = 0;
+    if (tid == 0) {
+      sh_i0 = kN2Bins - 1;
+      sh_kept = 0;
+    }
+    __syncthreads();
+    for (int i = tid; i < npos; i += kN2Threads)
+      if ((alive[i >> 5] >> (i & 31)) & 1u) atomicAdd(&hist[(int)(key_to_score_major(ckey[i]) >> 52)], 1);
+    __syncthreads();
+    // first bin whose inclusive cumulative count reaches max_det (all bins when fewer survivors)
+    constexpr int kPer = kN2Bins / kN2Threads;
+    int local[kPer], lsum = 0;
+#pragma unroll
+    for (int q = 0; q < kPer; ++q) {
+      local[q] = hist[tid * kPer + q];
+      lsum += local[q];
+    }
+    int total = 0;
+    int run = block_excl_scan(lsum, sh_scan, &total);
+    const int want = (p.max_det > 0 && p.max_det < total) ? p.max_det : total;
+#pragma unroll
+    for (int q = 0; q < kPer; ++q) {
+      if (run < want && run + local[q] >= want) sh_i0 = tid * kPer + q;  // exactly one thread/bin matches
+      run += local[q];
+    }
+    __syncthreads();
+    const int tbin = sh_i0;
+    for (int i = tid; i < npos; i += kN2Threads) {
+      if ((alive[i >> 5] >> (i & 31)) & 1u) {
+        const uint64_t k = key_to_score_major(ckey[i]);
+        if ((int)(k >> 52) <= tbin) sel[atomicAdd(&sh_kept, 1)] = k;
+      }
+    }
+    __syncthreads();
+    const int nsel = sh_kept;
+    const int P = pow2_ceil(nsel < 32 ? 32 : nsel);
+    for (int i = nsel + tid; i < P; i += kN2Threads) sel[i] = ~0ull;
+    __syncthreads();
+    N2_MARK(5);
+    block_sort_smem_max8(sel, P);
+    N2_MARK(6);
+    const int n_kept = want;
+    const int n_rows = min(n_kept, p.max_out);
+    for (int o = tid; o < n_rows; o += kN2Threads) {
+      const uint64_t k = sel[o];
+      const uint32_t anchor = (uint32_t)(k >> 12) & 0x1fffffu;
+      ob[o] = dense[anchor];
+      os[o] = __uint_as_float(0x7fffffffu - (uint32_t)(k >> 33));
+      oc[o] = (int32_t)(k & 0xfffu);
+      oa[o] = (int32_t)anchor;
+    }
+    N2_MARK(7);
+    if (tid == 0) {
+      p.det_count[b] = n_kept;
+      p.done[b] = 1;
+    }
+    return;
+  }
+
+  // ---- positions already in output order (class-major, or global score order for the trick) ---------
+  int* out_idx = reinterpret_cast<int*>(sh_area);
+  const int out_cap = (cap > 0 && cap < p.max_out) ? cap : p.max_out;
+  int running = 0;
+  for (int base = 0; base < nwords; base += kN2Threads) {
+    const int wi = base + tid;
+    uint32_t m = wi < nwords ? alive[wi] : 0u;
+    const int c = __popc(m);
+    int total = 0;
+    int pos = running + block_excl_scan(c, sh_scan, &total);
+    while (m && pos < out_cap) {
+      const int bit = __ffs(m) - 1;
+      m &= m - 1;
+      out_idx[pos++] = (wi << 5) + bit;
+    }
+    running += total;
+  }
+  __syncthreads();
+  int n_kept = running;
+  if (cap > 0 && n_kept > cap) n_kept = cap;
+  const int n_rows = min(n_kept, out_cap);
+  for (int o = tid; o < n_rows; o += kN2Threads) {
+    const uint64_t k = trick ? ckey[out_idx[o]] : key_to_score_major(ckey[out_idx[o]]);
+    const uint32_t anchor = (uint32_t)(k >> 12) & 0x1fffffu;
+    ob[o] = dense[anchor];
+    os[o] = __uint_as_float(0x7fffffffu - (uint32_t)(k >> 33));
+    oc[o] = (int32_t)(k & 0xfffu);
+    oa[o] = (int32_t)anchor;
+  }
+  if (tid == 0) {
+    p.det_count[b] = n_kept;
+    p.done[b] = 1;
+  }
+}
+
+#ifdef CVPP_NMS_TIMING
+extern "C" __attribute__((visibility("default"))) int cvpp_debug_n2_timing(long long* out) {
+  return (int)cudaMemcpyFromSymbol(out, g_n2_t, sizeof(long long) * 16 * 64);
+}
+#endif
+
+size_t segsort_workspace_bytes(int B, int max_cand);
+int segsort_launch_skip(uint64_t* keys, int32_t* cand_count, int B, int max_cand, int rule, int max_nms, void* workspace,
+                        size_t workspace_bytes, const int32_t* skip, uint64_t* out_keys, int32_t* out_count,
+                        cudaStream_t stream);
+
+static size_t align256_(size_t x) { return (x + 255) & ~(size_t)255; }
+
+size_t sort_nms_workspace_bytes(int B, int max_cand, int nc) {
+  return 256 + 2 * align256_((size_t)B * sizeof(int32_t)) + align256_((size_t)B * (size_t)max_cand * sizeof(uint64_t)) +
+         align256_(segsort_workspace_bytes(B, max_cand)) + align256_(nms_workspace_bytes(B, max_cand, nc));
+}
+
+// cand_key: UNSORTED class-major keys (as the filter kernels emit them); never modified (the fallback sorts
+// into the workspace), so the call can be repeated on the same candidates.
+int sort_nms_launch(const uint64_t* cand_key, const int32_t* cand_count, const float* box_dense, int B, int max_cand, int64_t A,
+                    int nc, double iou_thres, int rule, int order, int max_det, int max_nms, int max_out, float* det_box,
+                    float* det_score, int32_t* det_cls, int32_t* det_anchor, int32_t* det_count, void* workspace,
+                    size_t workspace_bytes, cudaStream_t stream) {
+  if (!cand_key || !cand_count || !box_dense || !det_box || !det_score || !det_cls || !det_anchor || !det_count) {
+    set_error("sort_nms: NULL pointer argument");
+    return CVPP_ERR_INVALID_ARG;
+  }
+  if (B < 0 || max_cand < 1 || A < 1 || nc < 1 || nc > CVPP_MAX_CLASSES || max_out < 1) {
+    set_error("sort_nms: bad sizes (B=%d max_cand=%d A=%lld nc=%d max_out=%d)", B, max_cand, (long long)A, nc, max_out);
+    return CVPP_ERR_INVALID_ARG;
+  }
+  if (!(iou_thres >= 0.0 && iou_thres <= 1.0)) {
+    set_error("sort_nms: Invalid IoU %f, valid values are between 0.0 and 1.0", iou_thres);
+    return CVPP_ERR_INVALID_ARG;
+  }
+  if (rule < 0 || rule > 2 || order < 0 || order > 1) {
+    set_error("sort_nms: unknown rule %d / order %d", rule, order);
+    return CVPP_ERR_INVALID_ARG;
+  }
+  if ((reinterpret_cast<uintptr_t>(box_dense) & 15u) || (reinterpret_cast<uintptr_t>(det_box) & 15u)) {
+    set_error("sort_nms: box arrays must be 16-byte aligned");
+    return CVPP_ERR_ALIGNMENT;
+  }
+  if (B == 0) return CVPP_OK;
+  if (!workspace || workspace_bytes < sort_nms_workspace_bytes(B, max_cand, nc)) {
+    set_error("sort_nms: workspace of %zu bytes needed, got %zu", sort_nms_workspace_bytes(B, max_cand, nc), workspace_bytes);
+    return CVPP_ERR_WORKSPACE;
+  }
+  DeviceInfo di;
+  int rc = device_info(&di);
+  if (rc != CVPP_OK) return rc;
+  uintptr_t base = (reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255;
+  int32_t* done = reinterpret_cast<int32_t*>(base);
+  base += align256_((size_t)B * sizeof(int32_t));
+  int32_t* fb_count = reinterpret_cast<int32_t*>(base);  // fallback: counts after the max_nms cut
+  base += align256_((size_t)B * sizeof(int32_t));
+  uint64_t* fb_keys = reinterpret_cast<uint64_t*>(base);  // fallback: sorted keys
+  base += align256_((size_t)B * (size_t)max_cand * sizeof(uint64_t));
+  void* sort_ws = reinterpret_cast<void*>(base);
+  const size_t sort_bytes = segsort_workspace_bytes(B, max_cand);
+  base += align256_(sort_bytes);
+  void* nms_ws = reinterpret_cast<void*>(base);
+  const size_t nms_bytes = nms_workspace_bytes(B, max_cand, nc);
+
+  Nms2Params p{};
+  float thr_eff = (float)iou_thres;
+  if ((double)thr_eff > iou_thres) thr_eff = nextafterf(thr_eff, -INFINITY);
+  const float thr_next = nextafterf(thr_eff, INFINITY);
+  p.thr_eff = thr_eff;
+  p.thr_mid = ((double)thr_eff + (double)thr_next) * 0.5;
+  uint32_t next_bits;
+  memcpy(&next_bits, &thr_next, sizeof(next_bits));
+  p.tie_up = (next_bits & 1u) == 0;
+  p.cand_key = cand_key;
+  p.cand_count = cand_count;
+  p.box_dense = reinterpret_cast<const float4*>(box_dense);
+  p.max_cand = max_cand;
+  p.A = A;
+  p.nc = nc;
+  p.rule = rule;
+  p.order = order;
+  p.max_det = max_det;
+  p.max_nms = max_nms;
+  p.max_out = max_out;
+  p.det_box = reinterpret_cast<float4*>(det_box);
+  p.det_score = det_score;
+  p.det_cls = det_cls;
+  p.det_anchor = det_anchor;
+  p.det_count = det_count;
+  p.done = done;
+  // shared memory: 28 B per position + 1 bit, 3 ints per class; the selection stage needs 16 KB of histogram
+  // inside the 16 B/position box array and 8 B/position of selected keys behind it
+  const size_t fixed = (size_t)nc * 12 + 256;
+  bool fused_possible = fixed + 64 * 1024 <= (size_t)di.max_smem;
+  size_t cap_pos = 0;
+  if (fused_possible) {
+    cap_pos = ((size_t)di.max_smem - fixed - 1024) * 8 / (28 * 8 + 1);
+    const size_t worst = (size_t)max_cand + 32u * (size_t)nc;  // never need more positions than this
+    if (cap_pos > worst) cap_pos = worst;
+    cap_pos &= ~(size_t)31;
+    if (cap_pos < 2048) {  // 16 B * cap_pos must hold the 16 KB histogram + 8 B * cap_pos of selected keys
+      cap_pos = 2048;
+      if (fixed + cap_pos * 28 + cap_pos / 8 + 1024 > (size_t)di.max_smem) fused_possible = false;
+    }
+  }
+  if (fused_possible) {
+    p.cap_pos = (int)cap_pos;
+    p.mask_words = (int)(cap_pos / 32);
+    const size_t smem = cap_pos * 28 + (size_t)p.mask_words * 4 + (size_t)nc * 12;
+    static unsigned long long attr_done = 0;
+    static int attr_bytes = 0;
+    if ((int)smem > attr_bytes) {
+      attr_done = 0;
+      attr_bytes = (int)smem;
+    }
+    rc = ensure_smem_attr(reinterpret_cast<const void*>(nms2_kernel), attr_bytes, di.device, &attr_done);
+    if (rc != CVPP_OK) return rc;
+    nms2_kernel<<<B, kN2Threads, smem, stream>>>(p);
+    CVPP_CUDA_TRY(cudaGetLastError());
+    // every image fits when even the worst-case padded layout does and max_nms cannot bind
+    const bool all_fit = (size_t)max_cand + 32u * (size_t)nc <= cap_pos && !(max_nms > 0 && max_cand > max_nms) &&
+                         pow2_ceil(max_cand < CVPP_TRICK_MAX_BOXES ? max_cand : CVPP_TRICK_MAX_BOXES) <= (int)cap_pos &&
+                         rule != CVPP_NMS_RULE_COORD_TRICK;
+    if (all_fit) return CVPP_OK;
+  } else {
+    CVPP_CUDA_TRY(cudaMemsetAsync(done, 0, sizeof(int32_t) * (size_t)B, stream));
+  }
+  rc = segsort_launch_skip(const_cast<uint64_t*>(cand_key), const_cast<int32_t*>(cand_count), B, max_cand, rule, max_nms,
+                           sort_ws, sort_bytes, done, fb_keys, fb_count, stream);
+  if (rc != CVPP_OK) return rc;
+  return nms_launch_skip(fb_keys, fb_count, box_dense, B, max_cand, A, nc, iou_thres, rule, order, max_det, max_out,
+                         det_box, det_score, det_cls, det_anchor, det_count, nms_ws, nms_bytes, done, stream);
 }
 
 }  // namespace cvpp

@@ -20,14 +20,20 @@ constexpr int kSortThreads = 1024;
 
 __global__ void __launch_bounds__(kSortThreads, 1)
 segsort_kernel(uint64_t* __restrict__ keys, int32_t* __restrict__ count, int max_cand, int max_nms,
-               uint64_t* __restrict__ ws, int64_t ws_stride, int smem_elems) {
+               uint64_t* __restrict__ ws, int64_t ws_stride, int smem_elems, const int32_t* __restrict__ skip,
+               uint64_t* __restrict__ out_keys, int32_t* __restrict__ out_count) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint64_t* sbuf = reinterpret_cast<uint64_t*>(smem_raw);
   const int b = blockIdx.x;
+  if (skip && skip[b]) return;  // already done by the fused sort+NMS kernel
   int n = count[b];
   if (n > max_cand) n = max_cand;
-  if (n <= 0) return;
+  if (n <= 0) {
+    if (out_count && threadIdx.x == 0) out_count[b] = n;
+    return;
+  }
   uint64_t* kb = keys + (int64_t)b * max_cand;
+  uint64_t* ko = out_keys ? out_keys + (int64_t)b * max_cand : kb;  // out of place keeps the caller's keys intact
   const int P = pow2_ceil(n < 32 ? 32 : n);
   const bool in_smem = P <= smem_elems;
   uint64_t* a = in_smem ? sbuf : (ws + (int64_t)b * ws_stride);
@@ -39,8 +45,11 @@ segsort_kernel(uint64_t* __restrict__ keys, int32_t* __restrict__ count, int max
     bitonic_sort_u64_generic(a, P);
   // ultralytics :240 keeps only the max_nms best scores (over all classes) before batched_nms
   const int n_final = (max_nms > 0 && n > max_nms) ? max_nms : n;
-  for (int i = threadIdx.x; i < n_final; i += blockDim.x) kb[i] = a[i];
-  if (n_final != n && threadIdx.x == 0) count[b] = n_final;
+  for (int i = threadIdx.x; i < n_final; i += blockDim.x) ko[i] = a[i];
+  if (threadIdx.x == 0) {
+    if (out_count) out_count[b] = n_final;
+    else if (n_final != n) count[b] = n_final;
+  }
 }
 
 size_t segsort_workspace_bytes(int B, int max_cand) {
@@ -49,8 +58,19 @@ size_t segsort_workspace_bytes(int B, int max_cand) {
   return (size_t)B * (size_t)P * sizeof(uint64_t);
 }
 
+int segsort_launch_skip(uint64_t* keys, int32_t* cand_count, int B, int max_cand, int rule, int max_nms, void* workspace,
+                        size_t workspace_bytes, const int32_t* skip, uint64_t* out_keys, int32_t* out_count,
+                        cudaStream_t stream);
+
 int segsort_launch(uint64_t* keys, int32_t* cand_count, int B, int max_cand, int rule, int max_nms,
                    void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  return segsort_launch_skip(keys, cand_count, B, max_cand, rule, max_nms, workspace, workspace_bytes, nullptr, nullptr,
+                             nullptr, stream);
+}
+
+int segsort_launch_skip(uint64_t* keys, int32_t* cand_count, int B, int max_cand, int rule, int max_nms, void* workspace,
+                        size_t workspace_bytes, const int32_t* skip, uint64_t* out_keys, int32_t* out_count,
+                        cudaStream_t stream) {
   if (!keys || !cand_count || B < 0 || max_cand < 1) {
     set_error("segmented_sort: NULL pointer or bad sizes (B=%d, max_cand=%d)", B, max_cand);
     return CVPP_ERR_INVALID_ARG;
@@ -83,7 +103,7 @@ int segsort_launch(uint64_t* keys, int32_t* cand_count, int B, int max_cand, int
   rc = ensure_smem_attr(reinterpret_cast<const void*>(segsort_kernel), attr_bytes, di.device, &attr_done);
   if (rc != CVPP_OK) return rc;
   segsort_kernel<<<B, kSortThreads, smem, stream>>>(keys, cand_count, max_cand, max_nms,
-                                                    reinterpret_cast<uint64_t*>(workspace), (int64_t)P, smem_elems);
+                                                    reinterpret_cast<uint64_t*>(workspace), (int64_t)P, smem_elems, skip, out_keys, out_count);
   CVPP_CUDA_TRY(cudaGetLastError());
   return CVPP_OK;
 }

@@ -188,6 +188,29 @@ def nms(c: Candidates, iou_thres: float, rule: int = RULE_TORCHVISION_CPU, order
     return det
 
 
+def sort_nms(c: Candidates, iou_thres: float, rule: int = RULE_TORCHVISION_CPU, order: int = ORDER_SCORE_DESC,
+             max_det: int = 300, max_nms: int = 0, max_out: Optional[int] = None) -> Detections:
+    """cvpp_sort_nms: the fused equivalent of segmented_sort(c) + nms(c) on UNSORTED candidate keys."""
+    l = _lib.lib()
+    B = int(c.key.shape[0])
+    dev = c.key.device
+    if max_out is None:
+        max_out = max_det if (order == ORDER_SCORE_DESC and max_det > 0) else c.max_cand
+    max_out = max(int(max_out), 1)
+    nbytes = int(l.cvpp_sort_nms_workspace_bytes(B, c.max_cand, c.nc))
+    ws = torch.empty((max(nbytes, 1),), dtype=torch.uint8, device=dev)
+    det = Detections(box=torch.empty((B, max_out, 4), dtype=torch.float32, device=dev),
+                     score=torch.empty((B, max_out), dtype=torch.float32, device=dev),
+                     cls=torch.empty((B, max_out), dtype=torch.int32, device=dev),
+                     anchor=torch.empty((B, max_out), dtype=torch.int32, device=dev),
+                     count=torch.empty((B,), dtype=torch.int32, device=dev), cand_count=c.count)
+    with torch.cuda.device(dev):
+        check(l.cvpp_sort_nms(_ptr(c.key), _ptr(c.count), _ptr(c.box_dense), B, c.max_cand, c.A, c.nc, float(iou_thres),
+                              rule, order, int(max_det), int(max_nms), max_out, _ptr(det.box), _ptr(det.score),
+                              _ptr(det.cls), _ptr(det.anchor), _ptr(det.count), _ptr(ws), nbytes, _stream(dev)))
+    return det
+
+
 class Yolov8Postprocessor:
     """Pre-allocated buffers + one C call (cvpp_yolov8_postprocess) per batch: decode+filter, sort, NMS.
 
@@ -522,10 +545,9 @@ def per_class_nms_device(c: Candidates, nms_thres: float, initial_out: int = 409
     output capacity when the first guess overflows (one scalar D2H read of the max count)."""
     if int(c.count.max().item()) > c.max_cand:
         raise OverflowError("candidate buffer overflow: re-run the filter with a larger max_cand")
-    segmented_sort(c, RULE_PER_CLASS)
     max_out = max(min(c.max_cand, initial_out), 1)
     while True:
-        det = nms(c, nms_thres, RULE_PER_CLASS, ORDER_CLASS_MAJOR, max_det=0, max_out=max_out)
+        det = sort_nms(c, nms_thres, RULE_PER_CLASS, ORDER_CLASS_MAJOR, max_det=0, max_out=max_out)
         need = int(det.count.max().item()) if det.count.numel() else 0
         if need <= max_out:
             return det

@@ -163,7 +163,22 @@ CVPP_API int cvpp_nms(const uint64_t* sorted_key, const int32_t* cand_count, con
              void* workspace, size_t workspace_bytes, cvpp_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
- * The whole YOLOv8 path in one call: decode+filter -> sort -> NMS (3 kernels + 1 memset on `stream`).
+ * Fused sort + NMS: the same result as cvpp_segmented_sort followed by cvpp_nms, in ONE kernel per
+ * batch for every image whose candidates fit shared memory (no global sort: per-class warp sorts, greedy
+ * suppression, and - for CVPP_ORDER_SCORE_DESC - a histogram selection of the max_det best survivors).
+ * cand_key holds the UNSORTED keys as the filter kernels emit them.  Images that do not fit (or have more
+ * than max_nms candidates) are finished by the two-kernel path inside the same call (sorting into the
+ * workspace); cand_key / cand_count are never modified.
+ * workspace: cvpp_sort_nms_workspace_bytes(B, max_cand, nc).
+ * ------------------------------------------------------------------------------------------- */
+CVPP_API size_t cvpp_sort_nms_workspace_bytes(int B, int max_cand, int nc);
+CVPP_API int cvpp_sort_nms(const uint64_t* cand_key, const int32_t* cand_count, const float* box_dense, int B, int max_cand,
+                           int64_t A, int nc, double iou_thres, int rule, int order, int max_det, int max_nms,
+                           int max_out, float* det_box, float* det_score, int32_t* det_cls, int32_t* det_anchor,
+                           int32_t* det_count, void* workspace, size_t workspace_bytes, cvpp_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * The whole YOLOv8 path in one call: decode+filter -> fused sort+NMS (cvpp_sort_nms) on `stream`.
  * Replaces Detect.forward eval tail + non_max_suppression as chained by YOLOv8.decode_box
  * (core/algorithms/yolo_v8.py:222-227).  Scratch buffers are carved from `workspace`
  * (cvpp_yolov8_workspace_bytes).  max_cand = A is always sufficient.

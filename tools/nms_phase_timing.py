@@ -1,0 +1,30 @@
+"""Per-phase clock64 breakdown of the fused sort+NMS kernel (needs libcvpp_timing.so built with -DCVPP_NMS_TIMING)."""
+import ctypes, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+from computervision.pytorch_b200 import _lib
+_lib.SO_PATH = os.path.join(ROOT, "computervision", "pytorch_b200", "libcvpp_timing.so")
+import numpy as np, torch
+from computervision.pytorch_b200 import ops
+dev = torch.device("cuda:0")
+g = torch.Generator(device=dev); g.manual_seed(1234)
+levels = []
+for h, w in ((80, 80), (40, 40), (20, 20)):
+    x = torch.randn((64, 144, h, w), generator=g, device=dev)
+    x[:, :64] *= 3.0; x[:, 64:] *= 4.3155; x[:, 64:] += -18.19
+    levels.append(x)
+ls = ops.make_levels(levels, (8.0, 16.0, 32.0))
+c = ops.yolov8_decode_filter(ls, 80, 0.001)
+for _ in range(3):
+    det = ops.sort_nms(c, 0.7, max_det=300, max_nms=30000)
+torch.cuda.synchronize()
+buf = (ctypes.c_longlong * 1024)()
+_lib.lib().cvpp_debug_n2_timing(buf)
+t16 = np.array(buf[:]).reshape(64, 16)
+t = t16[:, :8]
+print('  class sorts', ((t16[:,8]-t16[:,2])/1.965e3).mean(), 'big classes', ((t16[:,9]-t16[:,8])/1.965e3).mean(), 'gather', ((t16[:,3]-t16[:,9])/1.965e3).mean())
+d = np.diff(t, axis=1) / 1.965e3   # us at 1965 MHz
+names = ["hist+scan", "scatter", "class sort+gather", "suppress", "select", "final sort", "output"]
+for i, nme in enumerate(names):
+    print(f"{nme:20s} mean {d[:, i].mean():7.2f} us   max {d[:, i].max():7.2f} us")
+print("total", (t[:, 7] - t[:, 0]).mean() / 1.965e3, "us; cands", c.count.float().mean().item())
