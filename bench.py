@@ -3,7 +3,7 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-One "step" = one pass of the hot path (decode+filter -> segmented sort -> class-aware NMS) over one
+One "step" = one pass of the hot path (decode+filter -> fused per-class sort + class-aware NMS) over one
 batch of synthetic head tensors per GPU: bs=64, 640x640 (8400 anchors), 80 classes, reg_max=16,
 conf .001, IoU .7, max_det 300.  N>1 is launched by torchrun (one rank per GPU, NCCL); every rank owns
 its own batch (weak scaling, images shard naturally) and each step ends with the single all-gather of
@@ -273,17 +273,15 @@ def run_ours(args):
 
     # ---- roofline of the dominant kernel (decode+filter): CUDA events around every stage of the
     #      three-call pipeline (same kernels as the fused call), accumulated over K in-situ iterations
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(K)]
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
 
     def staged(i):
         e = ev[i]
         e[0].record()
         c = ops.yolov8_decode_filter(ls, NC, CONF)
         e[1].record()
-        ops.segmented_sort(c, max_nms=30000)
+        ops.sort_nms(c, IOU, max_det=MAX_DET, max_nms=30000)
         e[2].record()
-        ops.nms(c, IOU, max_det=MAX_DET)
-        e[3].record()
 
     for i in range(min(3, K)):
         staged(i)
@@ -292,13 +290,37 @@ def run_ours(args):
         staged(i)
     barrier()
     ms_dec = sum(e[0].elapsed_time(e[1]) for e in ev) / K
-    ms_sort = sum(e[1].elapsed_time(e[2]) for e in ev) / K
-    ms_nms = sum(e[2].elapsed_time(e[3]) for e in ev) / K
+    ms_nms = sum(e[1].elapsed_time(e[2]) for e in ev) / K
     if world > 1:
-        t = torch.tensor([ms_dec, ms_sort, ms_nms], device=dev, dtype=torch.float64)
+        t = torch.tensor([ms_dec, ms_nms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_dec, ms_sort, ms_nms = (float(v) for v in t.tolist())
+        ms_dec, ms_nms = (float(v) for v in t.tolist())
     clocks = sampler.stop() if rank == 0 else None
+
+    # ---- bs=1 latency (BASELINE configs[0] shape: conf .25, IoU .7), CUDA-graph replay, L2 flushed
+    #      before every timed replay (the 4.8 MB head would otherwise sit in the 126 MB L2)
+    bs1 = None
+    if rank == 0:
+        lv1 = [l[:1].contiguous() for l in levels]
+        ls1 = ops.make_levels(lv1, STRIDES)
+        post1 = ops.Yolov8Postprocessor(1, A, NC, dev, max_det=MAX_DET)
+        g1 = post1.capture(ls1, 0.25, IOU)
+        flush = torch.empty((192 * 1024 * 1024,), dtype=torch.uint8, device=dev)
+        lat = []
+        for i in range(60):
+            flush.fill_(i & 0xFF)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            g1.replay()
+            b.record()
+            torch.cuda.synchronize()
+            if i >= 10:
+                lat.append(a.elapsed_time(b) * 1e3)
+        lat.sort()
+        bs1 = {"p50_us": lat[len(lat) // 2], "p95_us": lat[int(len(lat) * 0.95)], "reps": len(lat),
+               "config": "bs=1, conf=0.25, iou=0.7 (BASELINE.json configs[0] shape), graph replay, L2 flushed",
+               "kept": int(post1.det.count.item())}
+        del flush
 
     # ---- e2e: pinned host buffers -> device -> kernels -> host
     host_levels = [torch.empty(l.shape, dtype=l.dtype).pin_memory() for l in levels]
@@ -367,14 +389,17 @@ def run_ours(args):
                            launch="CUDA graph replay of cvpp_yolov8_postprocess" if graphed is not None else "eager C call",
                            timing=f"median of {len(ms_runs)} back-to-back {K}-step CUDA-event measurements"),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "yolov8_decode_tma_kernel<false> (decode+filter)",
+                         "traffic": traffic, "kernel": "yolov8_decode_stream_kernel<0> (decode+filter)",
                          "ms_per_launch": ms_dec, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src},
-            "stages_ms": {"decode_filter": ms_dec, "segmented_sort": ms_sort, "nms": ms_nms},
+            "stages_ms": {"decode_filter": ms_dec, "fused_sort_nms": ms_nms},
+            "bs1_latency": bs1,
             "cpu_baseline": cpu,
             "clocks": clocks,
             "e2e": {"value": world * BS * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s / K},
-            "gpu_launches": (3 if world == 1 else 4) * K,
+            # per step: decode+filter, fused sort+NMS, and the two fallback kernels that exit at once when
+            # every image fitted the fused kernel (+ the row-packing epilogue for the all-gather when N > 1)
+            "gpu_launches": (4 if world == 1 else 5) * K,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
