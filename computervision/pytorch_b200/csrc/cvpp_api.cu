@@ -102,7 +102,7 @@ int gather_feat_launch(const float* feat, const void* ind, int ind_is_int64, con
 int detection_epilogue_launch(const float* det_box, const float* det_score, const int32_t* det_cls,
                               const int32_t* det_anchor, const int32_t* det_count, const float* aux_dense, int B,
                               int max_out, int64_t A, int layout, int box_mode, const float* letterbox, float* rows,
-                              cudaStream_t stream);
+                              float* count_out, float* const* peer_dst, int n_peers, int slot, cudaStream_t stream);
 
 static int force_generic() {
   const char* e = getenv("CVPP_FORCE_GENERIC");
@@ -332,9 +332,21 @@ int cvpp_gather_feat(const float* feat, const void* ind, int ind_is_int64, const
 int cvpp_detection_epilogue(const float* det_box, const float* det_score, const int32_t* det_cls,
                             const int32_t* det_anchor, const int32_t* det_count, const float* aux_dense, int B,
                             int max_out, int64_t A, int layout, int box_mode, const float* letterbox, float* rows,
-                            cvpp_stream_t stream) {
+                            float* count_out, cvpp_stream_t stream) {
   return detection_epilogue_launch(det_box, det_score, det_cls, det_anchor, det_count, aux_dense, B, max_out, A, layout,
-                                   box_mode, letterbox, rows, (cudaStream_t)stream);
+                                   box_mode, letterbox, rows, count_out, nullptr, 0, 0, (cudaStream_t)stream);
+}
+
+int cvpp_detection_epilogue_allgather(const float* det_box, const float* det_score, const int32_t* det_cls,
+                                      const int32_t* det_anchor, const int32_t* det_count, const float* aux_dense, int B,
+                                      int max_out, int64_t A, int layout, int box_mode, const float* letterbox,
+                                      float* const* peer_dst, int n_peers, int rank, cvpp_stream_t stream) {
+  if (n_peers < 1) {
+    set_error("detection_epilogue_allgather: n_peers must be >= 1");
+    return CVPP_ERR_INVALID_ARG;
+  }
+  return detection_epilogue_launch(det_box, det_score, det_cls, det_anchor, det_count, aux_dense, B, max_out, A, layout,
+                                   box_mode, letterbox, nullptr, nullptr, peer_dst, n_peers, rank, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -12,6 +12,7 @@
 #define CVPP_MAX_ANCHORS (1 << CVPP_KEY_ANCHOR_BITS)
 #define CVPP_MAX_CLASSES (1 << CVPP_KEY_CLASS_BITS)
 #define CVPP_MAX_LEVELS 4
+#define CVPP_MAX_PEERS 16
 
 // torchvision.ops.batched_nms on CPU switches to the per-class branch when boxes.numel() > 4000
 // (torchvision/ops/boxes.py:80), i.e. more than 1000 boxes.

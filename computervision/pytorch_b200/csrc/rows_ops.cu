@@ -217,68 +217,89 @@ struct EpilogueParams {
   const float2* aux_dense;
   const float* letterbox;  // (B, 5): in_w, in_h, left, top, scale
   float* rows;
+  float* count_out;  // optional [B]: min(det_count, max_out) as fp32 (so rows + counts travel in one buffer)
+  // peer scatter (fused all-gather over NVLink peer memory): when n_dst > 0 the row and the count are stored
+  // into EVERY destination buffer dst[d] (peer-mapped device pointers, one per rank, own rank included) at
+  // this rank's slot: rows at dst[d] + (slot * B + b) * max_out * width, counts at dst[d] + count_off + slot * B.
+  float* dst[CVPP_MAX_PEERS];
+  int n_dst, slot;
+  int64_t count_off;
   int B, max_out, layout, box_mode, width;
   int64_t A;
 };
 
-__global__ void __launch_bounds__(256) detection_epilogue_kernel(const EpilogueParams p) {
+__global__ void __launch_bounds__(256) detection_epilogue_kernel(const __grid_constant__ EpilogueParams p) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (int64_t)p.B * p.max_out) return;
   const int b = (int)(t / p.max_out), k = (int)(t - (int64_t)b * p.max_out);
-  float* row = p.rows + t * p.width;
   const int n = min(p.det_count[b], p.max_out);
-  if (k >= n) {
-    for (int c = 0; c < p.width; ++c) row[c] = 0.0f;
+  float row[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (k < n) {
+    float4 bx = p.det_box[t];
+    if (p.box_mode != CVPP_BOX_KEEP) {
+      const float* L = p.letterbox + 5 * b;
+      const float in_w = L[0], in_h = L[1], left = L[2], top = L[3], scale = L[4];
+      if (p.box_mode == CVPP_BOX_NORMALISE_CORRECT) {  // yolo_v8.py:233-234
+        bx.x = fdiv(bx.x, in_w);
+        bx.z = fdiv(bx.z, in_w);
+        bx.y = fdiv(bx.y, in_h);
+        bx.w = fdiv(bx.w, in_h);
+      }
+      // (x1y1 + x2y2) / 2, x2y2 - x1y1 (yolo_v7.py:416-417), then c -/+ wh / 2 (image_process.py:80-83)
+      const float cx = fmul(fadd(bx.x, bx.z), 0.5f), cy = fmul(fadd(bx.y, bx.w), 0.5f);
+      const float hw = fmul(fsub(bx.z, bx.x), 0.5f), hh = fmul(fsub(bx.w, bx.y), 0.5f);
+      // * input size, - padding, * scale (image_process.py:85-96); without letterbox the table holds
+      // (image_w, image_h, 0, 0, 1) and the same sequence is image_process.py:178-181 bit for bit
+      bx.x = fmul(fsub(fmul(fsub(cx, hw), in_w), left), scale);
+      bx.z = fmul(fsub(fmul(fadd(cx, hw), in_w), left), scale);
+      bx.y = fmul(fsub(fmul(fsub(cy, hh), in_h), top), scale);
+      bx.w = fmul(fsub(fmul(fadd(cy, hh), in_h), top), scale);
+    }
+    row[0] = bx.x;
+    row[1] = bx.y;
+    row[2] = bx.z;
+    row[3] = bx.w;
+    const float cls = (float)p.det_cls[t];
+    if (p.layout == CVPP_ROWS_YOLOV8) {  // x1,y1,x2,y2,conf,cls
+      row[4] = p.det_score[t];
+      row[5] = cls;
+    } else if (p.layout == CVPP_ROWS_SSD) {  // x1,y1,x2,y2,label,conf
+      row[4] = cls;
+      row[5] = p.det_score[t];
+    } else if (p.layout == CVPP_ROWS_YOLOV7) {  // x1,y1,x2,y2,obj,class_conf,class_pred
+      const float2 a = p.aux_dense[(int64_t)b * p.A + p.det_anchor[t]];
+      row[4] = a.x;
+      row[5] = a.y;
+      row[6] = cls;
+    } else {  // CVPP_ROWS_FULL: x1,y1,x2,y2,score,cls,anchor
+      row[4] = p.det_score[t];
+      row[5] = cls;
+      row[6] = (float)p.det_anchor[t];
+    }
+  }
+  if (p.n_dst == 0) {
+    float* o = p.rows + t * p.width;
+    for (int c = 0; c < p.width; ++c) o[c] = row[c];
+    if (k == 0 && p.count_out) p.count_out[b] = (float)n;
     return;
   }
-  float4 bx = p.det_box[t];
-  if (p.box_mode != CVPP_BOX_KEEP) {
-    const float* L = p.letterbox + 5 * b;
-    const float in_w = L[0], in_h = L[1], left = L[2], top = L[3], scale = L[4];
-    if (p.box_mode == CVPP_BOX_NORMALISE_CORRECT) {  // yolo_v8.py:233-234
-      bx.x = fdiv(bx.x, in_w);
-      bx.z = fdiv(bx.z, in_w);
-      bx.y = fdiv(bx.y, in_h);
-      bx.w = fdiv(bx.w, in_h);
-    }
-    // (x1y1 + x2y2) / 2, x2y2 - x1y1 (yolo_v7.py:416-417), then c -/+ wh / 2 (image_process.py:80-83)
-    const float cx = fmul(fadd(bx.x, bx.z), 0.5f), cy = fmul(fadd(bx.y, bx.w), 0.5f);
-    const float hw = fmul(fsub(bx.z, bx.x), 0.5f), hh = fmul(fsub(bx.w, bx.y), 0.5f);
-    // * input size, - padding, * scale (image_process.py:85-96); without letterbox the table holds
-    // (image_w, image_h, 0, 0, 1) and the same sequence is image_process.py:178-181 bit for bit
-    bx.x = fmul(fsub(fmul(fsub(cx, hw), in_w), left), scale);
-    bx.z = fmul(fsub(fmul(fadd(cx, hw), in_w), left), scale);
-    bx.y = fmul(fsub(fmul(fsub(cy, hh), in_h), top), scale);
-    bx.w = fmul(fsub(fmul(fadd(cy, hh), in_h), top), scale);
-  }
-  row[0] = bx.x;
-  row[1] = bx.y;
-  row[2] = bx.z;
-  row[3] = bx.w;
-  const float cls = (float)p.det_cls[t];
-  if (p.layout == CVPP_ROWS_YOLOV8) {  // x1,y1,x2,y2,conf,cls
-    row[4] = p.det_score[t];
-    row[5] = cls;
-  } else if (p.layout == CVPP_ROWS_SSD) {  // x1,y1,x2,y2,label,conf
-    row[4] = cls;
-    row[5] = p.det_score[t];
-  } else if (p.layout == CVPP_ROWS_YOLOV7) {  // x1,y1,x2,y2,obj,class_conf,class_pred
-    const float2 a = p.aux_dense[(int64_t)b * p.A + p.det_anchor[t]];
-    row[4] = a.x;
-    row[5] = a.y;
-    row[6] = cls;
-  } else {  // CVPP_ROWS_FULL: x1,y1,x2,y2,score,cls,anchor
-    row[4] = p.det_score[t];
-    row[5] = cls;
-    row[6] = (float)p.det_anchor[t];
+  const int64_t at = ((int64_t)p.slot * p.B * p.max_out + t) * p.width;
+  for (int d = 0; d < p.n_dst; ++d) {  // plain stores into peer memory; visible to the peers at kernel end
+    float* o = p.dst[d] + at;
+    for (int c = 0; c < p.width; ++c) o[c] = row[c];
+    if (k == 0) p.dst[d][p.count_off + (int64_t)p.slot * p.B + b] = (float)n;
   }
 }
 
 int detection_epilogue_launch(const float* det_box, const float* det_score, const int32_t* det_cls,
                               const int32_t* det_anchor, const int32_t* det_count, const float* aux_dense, int B,
                               int max_out, int64_t A, int layout, int box_mode, const float* letterbox, float* rows,
-                              cudaStream_t stream) {
-  if (!det_box || !det_score || !det_cls || !det_anchor || !det_count || !rows) {
+                              float* count_out, float* const* peer_dst, int n_peers, int slot, cudaStream_t stream) {
+  if (n_peers < 0 || n_peers > CVPP_MAX_PEERS || (n_peers > 0 && (!peer_dst || slot < 0 || slot >= n_peers))) {
+    set_error("detection_epilogue: bad peer list (n_peers=%d slot=%d)", n_peers, slot);
+    return CVPP_ERR_INVALID_ARG;
+  }
+  if (!det_box || !det_score || !det_cls || !det_anchor || !det_count || (!rows && n_peers == 0)) {
     set_error("detection_epilogue: NULL pointer argument");
     return CVPP_ERR_INVALID_ARG;
   }
@@ -309,11 +330,22 @@ int detection_epilogue_launch(const float* det_box, const float* det_score, cons
   p.aux_dense = reinterpret_cast<const float2*>(aux_dense);
   p.letterbox = letterbox;
   p.rows = rows;
+  p.count_out = count_out;
+  p.n_dst = n_peers;
+  p.slot = slot;
+  for (int d = 0; d < n_peers; ++d) {
+    if (!peer_dst[d]) {
+      set_error("detection_epilogue: peer destination %d is NULL", d);
+      return CVPP_ERR_INVALID_ARG;
+    }
+    p.dst[d] = peer_dst[d];
+  }
   p.B = B;
   p.max_out = max_out;
   p.layout = layout;
   p.box_mode = box_mode;
   p.width = (layout == CVPP_ROWS_YOLOV8 || layout == CVPP_ROWS_SSD) ? 6 : 7;
+  p.count_off = (int64_t)n_peers * B * max_out * p.width;
   p.A = A;
   const int64_t total = (int64_t)B * max_out;
   detection_epilogue_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(p);

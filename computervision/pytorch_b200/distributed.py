@@ -69,6 +69,65 @@ def gather_detections(rows: torch.Tensor, counts: torch.Tensor, n_global: Option
     return rows_all.index_select(0, keep), counts_all.index_select(0, keep)
 
 
+def gather_packed(packed: torch.Tensor, group=None) -> torch.Tensor:
+    """ONE all-gather of the flat [rows | counts] buffer of ops.detection_epilogue(packed=True) (equal shards):
+    returns (world, len(packed))."""
+    if not dist.is_available() or not dist.is_initialized():
+        return packed.reshape(1, -1)
+    world = dist.get_world_size(group)
+    out = packed.new_empty((world, packed.numel()))
+    if packed.is_cuda:
+        dist.all_gather_into_tensor(out, packed.contiguous(), group=group)
+    else:
+        dist.all_gather(list(out.unbind(0)), packed.contiguous(), group=group)
+    return out
+
+
+def unpack_detections(gathered: torch.Tensor, b_local: int, max_det: int, width: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(world, B*max_det*W + B) -> (rows (world*B, max_det, W), counts (world*B,) int32) in global image order."""
+    world = gathered.shape[0]
+    n_rows = b_local * max_det * width
+    rows = gathered[:, :n_rows].reshape(world * b_local, max_det, width)
+    counts = gathered[:, n_rows:].reshape(world * b_local).to(torch.int32)
+    return rows, counts
+
+
+class PeerGather:
+    """Gather buffers for cvpp_detection_epilogue_allgather: one symmetric-memory allocation per rank, mapped
+    into every peer over NVLink (torch.distributed._symmetric_memory), `depth` alternating slots so that the
+    stores of step k+1 never land in the buffer a consumer of step k may still be reading.
+
+        pg = PeerGather(b_local, max_det, width, device)          # collective
+        ops.detection_epilogue_allgather(det, ops.ROWS_FULL, pg.peer_ptrs(i), pg.rank)
+        pg.barrier(i)                                             # stream-ordered cross-rank barrier
+        rows, counts = pg.view(i)                                 # (world*B, max_det, W), (world*B,) int32
+    """
+
+    def __init__(self, b_local: int, max_det: int, width: int, device, depth: int = 2, group=None):
+        import torch.distributed._symmetric_memory as symm
+        group = group or dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.b_local, self.max_det, self.width, self.depth = int(b_local), int(max_det), int(width), int(depth)
+        self.n_rows = self.world * self.b_local * self.max_det * self.width
+        self.slot_elems = (self.n_rows + self.world * self.b_local + 3) & ~3       # 16-byte aligned slots
+        self.buf = symm.empty((self.depth * self.slot_elems,), dtype=torch.float32, device=device)
+        self.buf.zero_()
+        self.handle = symm.rendezvous(self.buf, group)
+        self._ptrs = [int(p) for p in self.handle.buffer_ptrs]
+
+    def peer_ptrs(self, i: int) -> List[int]:
+        off = 4 * (i % self.depth) * self.slot_elems
+        return [p + off for p in self._ptrs]
+
+    def barrier(self, i: int = 0) -> None:
+        self.handle.barrier(channel=i % self.depth)
+
+    def view(self, i: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        s = self.buf[(i % self.depth) * self.slot_elems:][: self.n_rows + self.world * self.b_local]
+        rows = s[: self.n_rows].reshape(self.world * self.b_local, self.max_det, self.width)
+        return rows, s[self.n_rows:].to(torch.int32)
+
+
 def split_rows(rows_all: torch.Tensor, counts_all: torch.Tensor) -> List[torch.Tensor]:
     """Per-image (n_i, W) views of the gathered rows (one host read of the counts)."""
     cap = rows_all.shape[1]

@@ -513,12 +513,21 @@ def gather_feat(feat: torch.Tensor, ind: torch.Tensor, count: Optional[torch.Ten
 
 
 def detection_epilogue(det: Detections, layout: int, box_mode: int = BOX_KEEP, letterbox: Optional[torch.Tensor] = None,
-                       aux_dense: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """cvpp_detection_epilogue: (B, max_out, 6|7) caller-facing rows on the device."""
+                       aux_dense: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+                       packed: bool = False) -> torch.Tensor:
+    """cvpp_detection_epilogue: (B, max_out, 6|7) caller-facing rows on the device.
+    packed=True returns ONE flat fp32 buffer [B*max_out*W rows | B counts] (the all-gather payload; see
+    distributed.gather_packed / unpack_detections); `out` reuses a buffer of the right size."""
     B, max_out = int(det.box.shape[0]), int(det.box.shape[1])
     dev = det.box.device
     width = 6 if layout in (ROWS_YOLOV8, ROWS_SSD) else 7
-    rows = torch.empty((B, max_out, width), dtype=torch.float32, device=dev)
+    n_rows = B * max_out * width
+    if out is None:
+        out = torch.empty((n_rows + (B if packed else 0),), dtype=torch.float32, device=dev)
+    flat = out.reshape(-1)
+    if flat.numel() != n_rows + (B if packed else 0) or flat.dtype != torch.float32 or not flat.is_contiguous():
+        raise ValueError("`out` has the wrong size / dtype for this epilogue")
+    count_ptr = c_vp(flat.data_ptr() + 4 * n_rows) if packed else c_vp(0)
     A = int(aux_dense.shape[1]) if aux_dense is not None else 0
     if letterbox is not None:
         letterbox = letterbox.to(device=dev, dtype=torch.float32).contiguous()
@@ -527,8 +536,26 @@ def detection_epilogue(det: Detections, layout: int, box_mode: int = BOX_KEEP, l
     with torch.cuda.device(dev):
         check(_lib.lib().cvpp_detection_epilogue(_ptr(det.box), _ptr(det.score), _ptr(det.cls), _ptr(det.anchor),
                                                  _ptr(det.count), _ptr(aux_dense), B, max_out, A, int(layout),
-                                                 int(box_mode), _ptr(letterbox), _ptr(rows), _stream(dev)))
-    return rows
+                                                 int(box_mode), _ptr(letterbox), _ptr(flat), count_ptr, _stream(dev)))
+    return flat if packed else flat.reshape(B, max_out, width)
+
+
+def detection_epilogue_allgather(det: Detections, layout: int, peer_ptrs: Sequence[int], rank: int,
+                                 box_mode: int = BOX_KEEP, letterbox: Optional[torch.Tensor] = None,
+                                 aux_dense: Optional[torch.Tensor] = None) -> None:
+    """cvpp_detection_epilogue_allgather: rows + counts stored into every rank's gather buffer (peer-mapped
+    device pointers `peer_ptrs`, one per rank) at slot `rank`.  See distributed.PeerGather."""
+    B, max_out = int(det.box.shape[0]), int(det.box.shape[1])
+    dev = det.box.device
+    A = int(aux_dense.shape[1]) if aux_dense is not None else 0
+    n = len(peer_ptrs)
+    if letterbox is not None:
+        letterbox = letterbox.to(device=dev, dtype=torch.float32).contiguous()
+    arr = (c_vp * n)(*[int(p) for p in peer_ptrs])
+    with torch.cuda.device(dev):
+        check(_lib.lib().cvpp_detection_epilogue_allgather(_ptr(det.box), _ptr(det.score), _ptr(det.cls), _ptr(det.anchor),
+                                                           _ptr(det.count), _ptr(aux_dense), B, max_out, A, int(layout),
+                                                           int(box_mode), _ptr(letterbox), arr, n, int(rank), _stream(dev)))
 
 
 def correct_boxes_params(image_hw: Sequence[Tuple[int, int]], input_hw: Sequence[int], letterbox_image: bool,

@@ -317,12 +317,31 @@ CVPP_API int cvpp_gather_feat(const float* feat, const void* ind, int ind_is_int
  *           yolo_correct_boxes / reverse_letter_box_numpy  core/utils/image_process.py:69-97,161-181
  * letterbox: (B, 5) fp32 rows in_w, in_h, left, top, scale (host-computed in double like the reference,
  * then cast; for letterbox_image == False pass image_w, image_h, 0, 0, 1).  rows: (B, max_out, 6 or 7)
- * by layout; rows >= det_count[b] are zero-filled.  aux_dense / A only for CVPP_ROWS_YOLOV7.
+ * by layout; rows >= det_count[b] are zero-filled.  aux_dense / A only for CVPP_ROWS_YOLOV7.  count_out
+ * (nullable, [B] fp32) receives min(det_count[b], max_out), so that rows and counts can share one buffer
+ * (the single all-gather payload of SURVEY.md 8e).
  * ------------------------------------------------------------------------------------------- */
 CVPP_API int cvpp_detection_epilogue(const float* det_box, const float* det_score, const int32_t* det_cls,
                                      const int32_t* det_anchor, const int32_t* det_count, const float* aux_dense,
                                      int B, int max_out, int64_t A, int layout, int box_mode, const float* letterbox,
-                                     float* rows, cvpp_stream_t stream);
+                                     float* rows, float* count_out, cvpp_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Detection epilogue fused with the evaluation all-gather: the same rows as
+ * cvpp_detection_epilogue, but every row (and the per-image count) is stored straight into the gather
+ * buffer of EVERY rank through NVLink peer mappings - one kernel, no NCCL launch, no staging copy.
+ * peer_dst: HOST array of n_peers (<= 16) device pointers, peer_dst[d] = rank d's gather buffer mapped into
+ * this process (CUDA IPC / symmetric memory; own rank included), each laid out as
+ *     [n_peers][B][max_out][W] fp32 rows | [n_peers][B] fp32 counts,
+ * this rank writing slot `rank`.  The stores are ordinary global stores: they are visible to the peers once
+ * the kernel has completed, so consumers synchronise on a cross-rank barrier / signal issued after it in
+ * stream order (torch symmetric-memory `barrier`, or any later collective).
+ * ------------------------------------------------------------------------------------------- */
+CVPP_API int cvpp_detection_epilogue_allgather(const float* det_box, const float* det_score, const int32_t* det_cls,
+                                               const int32_t* det_anchor, const int32_t* det_count,
+                                               const float* aux_dense, int B, int max_out, int64_t A, int layout,
+                                               int box_mode, const float* letterbox, float* const* peer_dst,
+                                               int n_peers, int rank, cvpp_stream_t stream);
 
 #ifdef __cplusplus
 }

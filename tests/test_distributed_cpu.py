@@ -45,6 +45,11 @@ def _worker(rank, world, port, n_global, q):
         ok = torch.equal(all_rows, rows) and torch.equal(all_counts, counts)
         per_image = cvd.split_rows(all_rows, all_counts)
         ok = ok and all(p.shape[0] == int(c) for p, c in zip(per_image, counts))
+        if n_global % world == 0:   # the packed single-collective form (equal shards)
+            packed = torch.cat((my_rows.reshape(-1), my_counts.to(torch.float32)))
+            g = cvd.gather_packed(packed)
+            r2, c2 = cvd.unpack_detections(g, n_global // world, rows.shape[1], rows.shape[2])
+            ok = ok and torch.equal(r2, rows) and torch.equal(c2, counts)
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()

@@ -1,0 +1,43 @@
+"""-m gpu: the fused epilogue + all-gather kernel (cvpp_detection_epilogue_allgather) on ONE GPU, with the
+peer buffers emulated by ordinary device buffers: every destination must receive exactly the rows and counts
+that cvpp_detection_epilogue produces, at the writing rank's slot."""
+import numpy as np
+import pytest
+import torch
+
+import synth
+
+pytestmark = pytest.mark.gpu
+
+from computervision.pytorch_b200 import ops  # noqa: E402
+
+DEV = "cuda:0"
+
+
+@pytest.mark.parametrize("layout,width", [(ops.ROWS_FULL, 7), (ops.ROWS_YOLOV8, 6)])
+def test_allgather_epilogue_matches_plain_epilogue(layout, width):
+    pred = torch.from_numpy(synth.yolov8_pred(3, 4, 8400, nc=80)).to(DEV)
+    det = ops.sort_nms(ops.pred_filter(pred, 80, 0.05), 0.7, max_det=50, max_nms=30000)
+    table = ops.correct_boxes_params([(480, 640)] * 4, (640, 640), True, DEV)
+    ref = ops.detection_epilogue(det, layout, ops.BOX_NORMALISE_CORRECT, table, packed=True)
+    world, B, md = 3, 4, 50
+    n_rows = world * B * md * width
+    bufs = [torch.full((n_rows + world * B,), -1.0, device=DEV) for _ in range(world)]
+    for rank in range(world):
+        ops.detection_epilogue_allgather(det, layout, [b.data_ptr() for b in bufs], rank, ops.BOX_NORMALISE_CORRECT, table)
+    torch.cuda.synchronize()
+    per = B * md * width
+    for b in bufs:
+        for rank in range(world):
+            assert torch.equal(b[rank * per:(rank + 1) * per], ref[:per])
+            assert torch.equal(b[n_rows + rank * B: n_rows + (rank + 1) * B], ref[per:])
+    assert np.array_equal(ref[per:].cpu().numpy(), np.minimum(det.count.cpu().numpy(), md).astype(np.float32))
+
+
+def test_bad_peer_list_is_rejected():
+    pred = torch.from_numpy(synth.yolov8_pred(3, 1, 2100, nc=20)).to(DEV)
+    det = ops.sort_nms(ops.pred_filter(pred, 20, 0.05), 0.7, max_det=10)
+    with pytest.raises(RuntimeError):
+        ops.detection_epilogue_allgather(det, ops.ROWS_FULL, [0], 0)
+    with pytest.raises(RuntimeError):
+        ops.detection_epilogue_allgather(det, ops.ROWS_FULL, [1] * 17, 0)
