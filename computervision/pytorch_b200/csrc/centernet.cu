@@ -29,6 +29,8 @@ struct CnParams {
   const float* pred;
   int B, H, W, nc, K;
   unsigned long long* tau;  // [B] running upper bound of the K-th best key
+  float* tau_logit;         // [B] the same bound as a heat LOGIT (conservative), for the cheap in-loop test
+  uint32_t* hist;           // [B][kCnBins] scores of every emitted peak, best bin first
   uint64_t* list;           // [B][list_cap]
   int32_t* list_count;      // [B]
   int list_cap;             // H * K
@@ -54,18 +56,117 @@ __device__ __forceinline__ uint64_t cn_key(float score, uint32_t flat) {
 // ---------------------------------------------------------------------------------------------
 // pass A
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kCnThreads, 1) centernet_peaks_kernel(const __grid_constant__ CnParams p) {
+constexpr int kCnBins = 1024;       // per-image histogram of emitted peak scores (float-bit bins, best first)
+constexpr int kCnGroup = 30;        // classes per warp item (lanes 1..30; lanes 0 and 31 are halo classes)
+constexpr float kCnTieEps = 1e-3f;  // logits closer than this may round to the same sigmoid
+
+__device__ __forceinline__ int cn_score_bin(uint64_t key) {
+  // inv_score = 0x7fffffff - bits(score); scores in (0, 1] -> bits <= 0x3f800000
+  const uint32_t bits = 0x7fffffffu - (uint32_t)(key >> 32);
+  const int bin = (int)((0x3f800000u - min(bits, 0x3f800000u)) >> 17);
+  return bin < kCnBins - 1 ? bin : kCnBins - 1;
+}
+
+// conservative logit bound of "score < lower edge of bin e": a peak whose logit is below it is worse than
+// every peak counted in bins 0..e
+__device__ __forceinline__ float cn_bin_logit_bound(int e) {
+  if (e >= kCnBins - 1) return -INFINITY;
+  const float s = __uint_as_float(0x3f800000u - ((uint32_t)(e + 1) << 17));
+  if (!(s > 0.0f) || !(s < 1.0f)) return -INFINITY;
+  return logf(s / (1.0f - s)) - 4.0f * kCnTieEps;
+}
+
+__device__ __forceinline__ void atomic_max_float(float* addr, float v) {
+  int* a = reinterpret_cast<int*>(addr);
+  int old = *reinterpret_cast<volatile int*>(a);
+  while (__int_as_float(old) < v) {
+    const int seen = atomicCAS(a, old, __float_as_int(v));
+    if (seen == old) break;
+    old = seen;
+  }
+}
+
+constexpr int kCnAThreads = 512;  // pass A: 16 warps, two CTAs per SM (four 43 KB rows in flight per SM)
+constexpr int kCnAWarps = kCnAThreads / 32;
+constexpr int kCnStage = 2048;    // staged keys per row before they are cut to the best K
+
+// Row scan.  FAST PATH: a warp owns whole columns x; lane l holds the 4 consecutive classes 4l..4l+3 of the
+// column (one LDS.128) and only asks "is any of them >= thr" (thr = the image's running logit bound): 3 max,
+// 1 compare, 1 vote per 4*32 cells.  Once the bound is tight almost no column passes.  SLOW PATH (a lane
+// with a cell above the bound): the 3x3 (x, class) window maximum is read from the staged row, the
+// reference's `heatmap == maxpool(heatmap)` test is evaluated on the rounded sigmoids, and the peak is
+// staged as a key.  Returns nothing; sh_cnt counts every push (also the ones that did not fit).
+__device__ __forceinline__ void cn_scan_columns(const float* row, int x_begin, int x_end, int y, int W, int nc, int Cf,
+                                                float thr, unsigned long long tau, uint64_t* keys, int* sh_cnt) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool vec = (Cf & 3) == 0;
+  for (int x = x_begin + warp; x < x_end; x += kCnAWarps) {
+    const float* colx = row + x * Cf;
+    for (int c0 = 4 * lane; c0 < nc; c0 += 128) {  // one pass for nc <= 128 (uniform trip count + 1 for the vote)
+      float v[4];
+      if (vec && c0 + 3 < nc) {
+        const float4 q = *reinterpret_cast<const float4*>(colx + c0);
+        v[0] = q.x, v[1] = q.y, v[2] = q.z, v[3] = q.w;
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = c0 + k < nc ? colx[c0 + k] : -INFINITY;
+      }
+      const float mx = fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3]));
+      if (!(mx >= thr)) continue;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int c = c0 + k;
+        if (!(v[k] >= thr) || c >= nc) continue;
+        float m = v[k];  // 3x3 window maximum over (x-1..x+1, c-1..c+1), -inf outside the map
+        for (int dx = -1; dx <= 1; ++dx) {
+          const int xx = x + dx;
+          if (xx < 0 || xx >= W) continue;
+          const float* q = row + xx * Cf + c;
+          if (c > 0) m = fmaxf(m, q[-1]);
+          m = fmaxf(m, q[0]);
+          if (c + 1 < nc) m = fmaxf(m, q[1]);
+        }
+        // heatmap == maxpool(heatmap) on the ROUNDED sigmoids: v == m implies it; below the maximum the
+        // rounded sigmoids can still coincide (nearly equal logits, or saturation)
+        const float sc = sigmoid_precise(v[k]);
+        bool peak = v[k] >= m;
+        if (!peak && (m - v[k] < kCnTieEps || v[k] > 8.0f)) peak = sc == sigmoid_precise(m);
+        if (peak) {
+          const uint64_t key = cn_key(sc, (uint32_t)((y * W + x) * nc + c));
+          if (key <= tau) {
+            const int pos = atomicAdd(sh_cnt, 1);
+            if (pos < kCnStage) keys[pos] = key;
+          }
+        }
+      }
+    }
+  }
+}
+
+// keep the best K of the staged keys (all threads call); returns the new count
+__device__ __forceinline__ int cn_truncate(uint64_t* keys, int n, int K, int* sh_cnt) {
+  if (n <= K) return n;
+  const int P = pow2_ceil(n < 32 ? 32 : n);
+  for (int t = n + threadIdx.x; t < P; t += kCnAThreads) keys[t] = ~0ull;
+  __syncthreads();
+  block_sort_smem(keys, P);
+  if (threadIdx.x == 0) *sh_cnt = K;
+  __syncthreads();
+  return K;
+}
+
+__global__ void __launch_bounds__(kCnAThreads, 2) centernet_peaks_kernel(const __grid_constant__ CnParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int W = p.W, nc = p.nc, Cf = p.nc + 4;
   const int row_floats = W * Cf;
   const uint32_t row_bytes = (uint32_t)row_floats * 4u;
   float* ring = reinterpret_cast<float*>(smem_raw);                                 // [2][row_floats]
-  uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw + (((size_t)2 * row_bytes + 127) & ~(size_t)127));
-  uint64_t* bar = keys + p.key_cap;                                                 // [2]
-  __shared__ int sh_cnt;
+  uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw + (((size_t)2 * row_bytes + 127) & ~(size_t)127));  // [kCnStage]
+  uint64_t* bar = keys + kCnStage;                                                  // [2]
+  __shared__ int sh_cnt2[2];  // per ring stage: the counter of row i is never reset while row i is being read
   __shared__ int sh_base;
 
-  const int tid = threadIdx.x, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int rows_total = p.B * p.H;
   const int n_my = ((int)blockIdx.x < rows_total) ? (rows_total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
@@ -91,75 +192,89 @@ __global__ void __launch_bounds__(kCnThreads, 1) centernet_peaks_kernel(const __
     const int r = blockIdx.x + i * gridDim.x;
     const int b = r % p.B, y = r / p.B;
     const float* row = ring + (size_t)(i & 1) * row_floats;
+    int& sh_cnt = sh_cnt2[i & 1];
     if (tid == 0) sh_cnt = 0;
-    const unsigned long long tau = *reinterpret_cast<volatile unsigned long long*>(p.tau + b);
+    unsigned long long tau = *reinterpret_cast<volatile unsigned long long*>(p.tau + b);
+    const float thr = *reinterpret_cast<volatile float*>(p.tau_logit + b) - kCnTieEps;
     mbar_wait(&bar[i & 1], (uint32_t)(i >> 1) & 1u);
     __syncthreads();
 
-    const int cells = W * nc;
-    for (int e0 = 0; e0 < cells; e0 += kCnThreads) {
-      const int e = e0 + tid;
-      bool take = false;
-      uint64_t key = 0;
-      if (e < cells) {
-        const int x = e / nc, c = e - x * nc;
-        const float* q = row + x * Cf + c;
-        const float v = q[0];
-        float nmax = -INFINITY;
-        const bool xl = x > 0, xr = x + 1 < W, cl = c > 0, cr = c + 1 < nc;
-        if (cl) nmax = fmaxf(nmax, q[-1]);
-        if (cr) nmax = fmaxf(nmax, q[1]);
-        if (xl) {
-          nmax = fmaxf(nmax, q[-Cf]);
-          if (cl) nmax = fmaxf(nmax, q[-Cf - 1]);
-          if (cr) nmax = fmaxf(nmax, q[-Cf + 1]);
-        }
-        if (xr) {
-          nmax = fmaxf(nmax, q[Cf]);
-          if (cl) nmax = fmaxf(nmax, q[Cf - 1]);
-          if (cr) nmax = fmaxf(nmax, q[Cf + 1]);
-        }
-        // heatmap == maxpool(heatmap) on the rounded sigmoid values.  v >= nmax implies it; below a
-        // neighbour the rounded sigmoids can still coincide (nearly equal logits, or saturation).
-        bool peak = v >= nmax;
-        float sc = 0.f;
-        if (peak) {
-          sc = sigmoid_precise(v);
-        } else if (nmax - v < 1e-3f || v > 8.0f) {
-          sc = sigmoid_precise(v);
-          peak = sc == sigmoid_precise(nmax);
-        }
-        if (peak) {
-          key = cn_key(sc, (uint32_t)((y * W + x) * nc + c));
-          take = key <= tau;
-        }
-      }
-      const unsigned m = __ballot_sync(0xffffffffu, take);
-      if (m) {
-        int base = 0;
-        if (lane == 0) base = atomicAdd(&sh_cnt, __popc(m));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (take) keys[base + __popc(m & ((1u << lane) - 1u))] = key;
-      }
-    }
-    __syncthreads();  // the row has been consumed: refill this stage, and sh_cnt is final
-    if (tid == 0 && i + 2 < n_my) issue(i + 2);
-    const int n_r = sh_cnt;
-    int n_emit = n_r;
-    if (n_r > p.K) {
-      const int P = pow2_ceil(n_r < 32 ? 32 : n_r);
-      for (int t = n_r + tid; t < P; t += kCnThreads) keys[t] = ~0ull;
+    cn_scan_columns(row, 0, W, y, W, nc, Cf, thr, tau, keys, &sh_cnt);
+    __syncthreads();
+    int n_r = sh_cnt;
+    if (n_r > kCnStage) {
+      // more peaks above the bound than the stage holds (no bound yet on a dense map): redo the row in column
+      // chunks that cannot overflow, cutting to the best K after each
       __syncthreads();
-      block_sort_smem(keys, P);
-      n_emit = p.K;
-      if (tid == 0) atomicMin(p.tau + b, (unsigned long long)keys[p.K - 1]);
+      if (tid == 0) sh_cnt = 0;
+      __syncthreads();
+      int xc = (kCnStage - p.K) / nc;
+      if (xc < 1) xc = 1;  // (launch checks K + nc <= kCnStage)
+      n_r = 0;
+      for (int xb = 0; xb < W; xb += xc) {
+        cn_scan_columns(row, xb, min(W, xb + xc), y, W, nc, Cf, thr, tau, keys, &sh_cnt);
+        __syncthreads();
+        n_r = cn_truncate(keys, sh_cnt, p.K, &sh_cnt);
+        if (n_r == p.K) tau = min(tau, (unsigned long long)keys[p.K - 1]);
+      }
     }
-    if (tid == 0) sh_base = atomicAdd(p.list_count + b, n_emit);
+    if (tid == 0 && i + 2 < n_my) issue(i + 2);  // every read of the row is behind a barrier: refill the stage
+    const bool cut = n_r > p.K;
+    const int n_emit = cn_truncate(keys, n_r, p.K, &sh_cnt);
+    if (tid == 0) {
+      if (cut || n_emit == p.K) {
+        atomicMin(p.tau + b, (unsigned long long)keys[p.K - 1]);
+        // the same bound in the logit domain: score of the row's K-th best peak
+        const float s = __uint_as_float(0x7fffffffu - (uint32_t)(keys[p.K - 1] >> 32));
+        if (s > 0.0f && s < 1.0f) atomic_max_float(p.tau_logit + b, logf(s / (1.0f - s)) - 4.0f * kCnTieEps);
+      }
+      if (n_emit > 0) sh_base = atomicAdd(p.list_count + b, n_emit);
+    }
+    if (n_emit == 0) continue;  // (uniform) nothing above the bound in this row: the common case
     __syncthreads();
     const int base = sh_base;
     uint64_t* dst = p.list + (size_t)b * p.list_cap;
-    for (int t = tid; t < n_emit; t += kCnThreads)
-      if (base + t < p.list_cap) dst[base + t] = keys[t];
+    uint32_t* hist = p.hist + (size_t)b * kCnBins;
+    for (int t = tid; t < n_emit; t += kCnAThreads) {
+      const uint64_t k = keys[t];
+      if (base + t < p.list_cap) dst[base + t] = k;
+      atomicAdd(hist + cn_score_bin(k), 1u);
+    }
+    // tighten the image's bound from the histogram of everything emitted so far (any row, any CTA): the
+    // first bin (best scores first) at which the cumulative count reaches K
+    if (n_emit >= 4 && warp == 0) {
+      __threadfence();
+      int run = 0, edge = -1;
+      for (int b0 = 0; b0 < kCnBins && edge < 0; b0 += 32 * 4) {
+        const uint4 h = __ldcg(reinterpret_cast<const uint4*>(hist + b0 + 4 * lane));  // L2, never a stale L1 line
+        const int mine = (int)(h.x + h.y + h.z + h.w);
+        int incl = mine;
+        for (int d = 1; d < 32; d <<= 1) {
+          const int u = __shfl_up_sync(0xffffffffu, incl, d);
+          if (lane >= d) incl += u;
+        }
+        const int before = run + incl - mine;
+        int e = 0x7fffffff;
+        if (before < p.K && before + mine >= p.K) {  // the crossing is inside this lane's 4 bins
+          int acc = before;
+          const int hv[4] = {(int)h.x, (int)h.y, (int)h.z, (int)h.w};
+          for (int q = 0; q < 4; ++q) {
+            acc += hv[q];
+            if (acc >= p.K) {
+              e = b0 + 4 * lane + q;
+              break;
+            }
+          }
+        }
+        for (int d = 16; d > 0; d >>= 1) e = min(e, __shfl_xor_sync(0xffffffffu, e, d));
+        if (e != 0x7fffffff) edge = e;
+        run += __shfl_sync(0xffffffffu, incl, 31);
+      }
+      if (lane == 0 && edge >= 0) {
+        const float bound = cn_bin_logit_bound(edge);
+        if (bound > -INFINITY) atomic_max_float(p.tau_logit + b, bound);
+      }
+    }
     __syncthreads();
   }
 }
@@ -370,6 +485,15 @@ diou_nms_kernel(const float4* __restrict__ boxes, const float* __restrict__ scor
 // ---------------------------------------------------------------------------------------------
 // host
 // ---------------------------------------------------------------------------------------------
+__global__ void cn_fill_u32_kernel(uint32_t* p, uint32_t v, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+static cudaError_t cudaMemsetD32Async_compat(void* p, uint32_t v, size_t n, cudaStream_t stream) {
+  cn_fill_u32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(reinterpret_cast<uint32_t*>(p), v, n);
+  return cudaGetLastError();
+}
+
 static int cn_sort_cap(int H, int K) {
   int P = 32;
   while (P < H * K) P <<= 1;
@@ -382,6 +506,8 @@ size_t centernet_workspace_bytes(int B, int H, int W, int nc, int K) {
   size_t s = 256;
   s += ((size_t)B * 8 + 255) & ~(size_t)255;                          // tau
   s += ((size_t)B * 4 + 255) & ~(size_t)255;                          // list_count
+  s += ((size_t)B * 4 + 255) & ~(size_t)255;                          // tau_logit
+  s += ((size_t)B * 1024 * 4 + 255) & ~(size_t)255;                   // hist
   s += ((size_t)B * (size_t)H * K * 8 + 255) & ~(size_t)255;          // list
   s += ((size_t)B * (size_t)cn_sort_cap(H, K) * 8 + 255) & ~(size_t)255;  // sort scratch
   return s;
@@ -445,22 +571,26 @@ int centernet_launch(const float* pred, int B, int H, int W, int nc, int K, floa
   w += ((size_t)B * 8 + 255) & ~(size_t)255;
   p.list_count = reinterpret_cast<int32_t*>(w);
   w += ((size_t)B * 4 + 255) & ~(size_t)255;
+  p.tau_logit = reinterpret_cast<float*>(w);
+  w += ((size_t)B * 4 + 255) & ~(size_t)255;
+  p.hist = reinterpret_cast<uint32_t*>(w);
+  w += ((size_t)B * 1024 * 4 + 255) & ~(size_t)255;
   p.list = reinterpret_cast<uint64_t*>(w);
   w += ((size_t)B * (size_t)H * K * 8 + 255) & ~(size_t)255;
   p.ws_sort = reinterpret_cast<uint64_t*>(w);
 
   CVPP_CUDA_TRY(cudaMemsetAsync(p.tau, 0xff, sizeof(unsigned long long) * (size_t)B, stream));
-  CVPP_CUDA_TRY(cudaMemsetAsync(p.list_count, 0, sizeof(int32_t) * (size_t)B, stream));
+  // list_count, tau_logit (0xff800000 = -inf is written below), hist: one contiguous region
+  CVPP_CUDA_TRY(cudaMemsetAsync(p.list_count, 0, reinterpret_cast<uintptr_t>(p.list) - reinterpret_cast<uintptr_t>(p.list_count), stream));
+  CVPP_CUDA_TRY(cudaMemsetD32Async_compat(p.tau_logit, 0xff800000u, (size_t)B, stream));
 
-  // pass A shared memory: 2 row stages + key buffer (power of two >= W*nc) + 2 barriers
-  int key_cap = 32;
-  while (key_cap < W * nc) key_cap <<= 1;
-  const size_t smem_a = ((2 * row_bytes + 127) & ~(size_t)127) + (size_t)key_cap * 8 + 16;
-  if (smem_a > (size_t)di.max_smem || key_cap > 16384) {
-    set_error("centernet: a row of %d x %d cells does not fit the shared-memory pipeline", W, nc + 4);
+  // pass A shared memory: 2 row stages + the key stage + 2 barriers; two CTAs per SM when they fit
+  const size_t smem_a = ((2 * row_bytes + 127) & ~(size_t)127) + (size_t)kCnStage * 8 + 16;
+  if (smem_a > (size_t)di.max_smem || K + nc > kCnStage) {
+    set_error("centernet: a row of %d x %d cells (K=%d) does not fit the shared-memory pipeline", W, nc + 4, K);
     return CVPP_ERR_UNSUPPORTED;
   }
-  p.key_cap = key_cap;
+  p.key_cap = kCnStage;
   static unsigned long long done_a = 0;
   static int bytes_a = 0;
   if ((int)smem_a > bytes_a) {
@@ -470,8 +600,9 @@ int centernet_launch(const float* pred, int B, int H, int W, int nc, int K, floa
   rc = ensure_smem_attr(reinterpret_cast<const void*>(centernet_peaks_kernel), bytes_a, di.device, &done_a);
   if (rc != CVPP_OK) return rc;
   const int rows = B * H;
-  const int grid_a = rows < di.sms ? rows : di.sms;
-  centernet_peaks_kernel<<<grid_a, kCnThreads, smem_a, stream>>>(p);
+  const int ctas_per_sm = (2 * (smem_a + 1024) <= (size_t)di.max_smem + 1024) ? 2 : 1;
+  const int grid_a = rows < ctas_per_sm * di.sms ? rows : ctas_per_sm * di.sms;
+  centernet_peaks_kernel<<<grid_a, kCnAThreads, smem_a, stream>>>(p);
   CVPP_CUDA_TRY(cudaGetLastError());
 
   // pass B shared memory: sort buffer when it fits (<= 16384 keys), else the global scratch rows
