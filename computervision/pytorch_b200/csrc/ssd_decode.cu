@@ -15,6 +15,7 @@
 namespace cvpp {
 
 constexpr int kSsdThreads = 256;
+constexpr int kSsdKeyStage = 512;  // keys staged per block before the single global reservation
 
 // Ssd._parse_mbox_loc for one prior: ltrb prior + (dx, dy, dw, dh) -> clamped xyxy (ssd.py:293-324)
 __device__ __forceinline__ float4 ssd_decode_box(const float4& a, const float4& l) {
@@ -34,50 +35,123 @@ __device__ __forceinline__ float4 ssd_decode_box(const float4& a, const float4& 
   return o;
 }
 
+__device__ __forceinline__ float ssd_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// Two phases per 256-prior block (first version: 21 + 20 precise expf and 20 IEEE divisions for EVERY prior made
+// the kernel SFU/ALU-bound at 12 % of the HBM roofline, although only ~1 % of the (prior, class) pairs survive):
+//   1. thread per prior, approximate: softmax denominator with ex2.approx, then one logit cut per prior -
+//      prob_c > thr  <=>  x_c > m + ln(thr * sum) - and a compare per class; priors with any class above the
+//      (slightly lowered) cut are compacted into a shared list;
+//   2. thread per LISTED prior, exact: the reference's softmax arithmetic (max-subtract, expf, sequential sum,
+//      IEEE division) for the classes above the cut, the threshold test on the exact probability, the key, and
+//      the prior's decoded box.
 __global__ void __launch_bounds__(kSsdThreads)
 ssd_decode_filter_kernel(const float4* __restrict__ loc, const float* __restrict__ conf,
                          const float4* __restrict__ priors, int P, int nc, float conf_thres,
                          uint64_t* __restrict__ cand_key, int32_t* __restrict__ cand_count,
                          float4* __restrict__ box_dense, int max_cand) {
   extern __shared__ float sm[];  // [kSsdThreads][nc + 1]
+  __shared__ int sh_list[kSsdThreads];
+  __shared__ float sh_cut[kSsdThreads];
+  __shared__ int sh_n, sh_k, sh_gbase;
+  __shared__ uint64_t sh_key[kSsdKeyStage];
   const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
   const int p0 = blockIdx.x * kSsdThreads;
   const int rows = min(kSsdThreads, P - p0);
   const int nc1 = nc + 1;
   const float* src = conf + ((int64_t)b * P + p0) * nc1;
-  for (int i = tid; i < rows * nc1; i += kSsdThreads) sm[i] = __ldg(src + i);
+  if (tid == 0) {
+    sh_n = 0;
+    sh_k = 0;
+  }
+  {  // the block's conf rows are one contiguous run: 128-bit loads when its start is 16-byte aligned
+    const int total = rows * nc1;
+    if ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) {
+      const int n4 = total >> 2;
+      const float4* s4 = reinterpret_cast<const float4*>(src);
+      float4* d4 = reinterpret_cast<float4*>(sm);
+      for (int i = tid; i < n4; i += kSsdThreads) d4[i] = __ldg(s4 + i);
+      for (int i = (n4 << 2) + tid; i < total; i += kSsdThreads) sm[i] = __ldg(src + i);
+    } else {
+      for (int i = tid; i < total; i += kSsdThreads) sm[i] = __ldg(src + i);
+    }
+  }
   __syncthreads();
 
-  const int pr = p0 + tid;
-  const bool valid = tid < rows;
-  const float* x = sm + tid * nc1;
-  float m = -INFINITY, sum = 1.0f;
-  if (valid) {
-    for (int k = 0; k < nc1; ++k) m = fmaxf(m, x[k]);
-    sum = 0.0f;
-    for (int k = 0; k < nc1; ++k) sum = fadd(sum, expf(fsub(x[k], m)));  // torch.softmax: exp(x - max) / sum
-  }
-  bool any = false;
-  for (int c = 1; c <= nc; ++c) {
-    float prob = 0.0f;
-    bool hit = false;
-    if (valid) {
-      prob = fdiv(expf(fsub(x[c], m)), sum);
-      hit = prob > conf_thres;
+  // ---- phase 1: approximate per-prior cut
+  {
+    const float* x = sm + tid * nc1;
+    bool cand = false;
+    float cut = INFINITY;
+    if (tid < rows) {
+      float m = x[0];
+      for (int k = 1; k < nc1; ++k) m = fmaxf(m, x[k]);
+      const float kLog2e = 1.4426950408889634f;
+      float sum = 0.0f;
+      for (int k = 0; k < nc1; ++k) sum += ssd_ex2((x[k] - m) * kLog2e);
+      // exact: prob_c = exp(x_c - m) / sum > thr.  The approximations (ex2.approx, fast log, different
+      // summation order) are far below the 0.02 slack taken off the cut.
+      cut = conf_thres > 0.0f ? m + __logf(conf_thres * sum) - 0.02f : -INFINITY;
+      float top = -INFINITY;
+      for (int k = 1; k < nc1; ++k) top = fmaxf(top, x[k]);
+      cand = top >= cut;
     }
-    const unsigned mk = __ballot_sync(0xffffffffu, hit);
-    if (mk == 0) continue;
-    int base = 0;
-    if (lane == 0) base = atomicAdd(cand_count + b, __popc(mk));
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (hit) {
-      const int slot = base + __popc(mk & ((1u << lane) - 1u));
-      if (slot < max_cand)
-        cand_key[(int64_t)b * max_cand + slot] = key_pack((uint32_t)(c - 1), __float_as_uint(prob), (uint32_t)pr);
+    const unsigned mk = __ballot_sync(0xffffffffu, cand);
+    if (mk) {
+      int base = 0;
+      if (lane == 0) base = atomicAdd(&sh_n, __popc(mk));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (cand) {
+        const int slot = base + __popc(mk & ((1u << lane) - 1u));
+        sh_list[slot] = tid;
+        sh_cut[slot] = cut;
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 2: exact evaluation of the listed priors; keys are staged in shared memory and leave with ONE
+  //      global reservation per block (a per-hit atomicAdd with its L2 round trip serialised the threads)
+  const int n_list = sh_n;
+  if (n_list == 0) return;  // uniform
+  if (tid < n_list) {
+    const int row = sh_list[tid];
+    const float cut = sh_cut[tid];
+    const float* x = sm + row * nc1;
+    const int pr = p0 + row;
+    float m = -INFINITY;
+    for (int k = 0; k < nc1; ++k) m = fmaxf(m, x[k]);
+    float sum = 0.0f;
+    for (int k = 0; k < nc1; ++k) sum = fadd(sum, expf(fsub(x[k], m)));  // torch.softmax: exp(x - max) / sum
+    bool any = false;
+    for (int c = 1; c <= nc; ++c) {
+      if (!(x[c] >= cut)) continue;
+      const float prob = fdiv(expf(fsub(x[c], m)), sum);
+      if (!(prob > conf_thres)) continue;
+      const uint64_t key = key_pack((uint32_t)(c - 1), __float_as_uint(prob), (uint32_t)pr);
+      const int pos = atomicAdd(&sh_k, 1);
+      if (pos < kSsdKeyStage) {
+        sh_key[pos] = key;
+      } else {  // stage full (a dense block): reserve directly
+        const int slot = atomicAdd(cand_count + b, 1);
+        if (slot < max_cand) cand_key[(int64_t)b * max_cand + slot] = key;
+      }
       any = true;
     }
+    if (any) box_dense[(int64_t)b * P + pr] = ssd_decode_box(priors[pr], loc[(int64_t)b * P + pr]);
   }
-  if (any) box_dense[(int64_t)b * P + pr] = ssd_decode_box(priors[pr], loc[(int64_t)b * P + pr]);
+  __syncthreads();
+  const int n_stage = min(sh_k, kSsdKeyStage);
+  if (n_stage == 0) return;  // uniform
+  if (tid == 0) sh_gbase = atomicAdd(cand_count + b, n_stage);
+  __syncthreads();
+  const int gbase = sh_gbase;
+  for (int i = tid; i < n_stage; i += kSsdThreads)
+    if (gbase + i < max_cand) cand_key[(int64_t)b * max_cand + gbase + i] = sh_key[i];
 }
 
 __global__ void __launch_bounds__(256)

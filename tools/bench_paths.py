@@ -101,8 +101,7 @@ def bench_ssd(iters, B=128):
 
     def full():
         cc = ops.ssd_decode_filter(loc, conf, pri, 0.001, max_cand=32768)
-        ops.segmented_sort(cc, ops.RULE_PER_CLASS)
-        ops.nms(cc, 0.5, ops.RULE_PER_CLASS, ops.ORDER_CLASS_MAJOR, max_det=0, max_out=4096)
+        ops.sort_nms(cc, 0.5, ops.RULE_PER_CLASS, ops.ORDER_CLASS_MAJOR, max_det=0, max_out=4096)
     ms_tot = timed(full, iters)
     report("ssd_C4", B, 873200, ms_dec, ms_tot, {"cand_per_image": float(c.count.float().mean())})
 
@@ -123,8 +122,7 @@ def bench_yolov7(iters, B=128):
 
     def full():
         cc = ops.yolov7_decode_filter(ls, 80, anchors, (640, 640), 0.001)
-        ops.segmented_sort(cc, ops.RULE_PER_CLASS)
-        ops.nms(cc, 0.3, ops.RULE_PER_CLASS, ops.ORDER_CLASS_MAJOR, max_det=0, max_out=8192)
+        ops.sort_nms(cc, 0.3, ops.RULE_PER_CLASS, ops.ORDER_CLASS_MAJOR, max_det=0, max_out=8192)
     ms_tot = timed(full, iters)
     report("yolov7_C5_shard", B, 25200 * 85 * 4, ms_dec, ms_tot, {"cand_per_image": float(c.count.float().mean())})
 
@@ -146,8 +144,7 @@ def bench_yolov3(iters, B=256):
 
     def full():
         cc = ops.yolov3_decode_filter(ls, 20, anchors, (416, 416), 0.001, max_cand=16384)
-        ops.segmented_sort(cc, ops.RULE_PER_CLASS)
-        ops.nms(cc, 0.5, ops.RULE_PER_CLASS, ops.ORDER_CLASS_MAJOR, max_det=0, max_out=8192)
+        ops.sort_nms(cc, 0.5, ops.RULE_PER_CLASS, ops.ORDER_CLASS_MAJOR, max_det=0, max_out=8192)
     ms_tot = timed(full, iters)
     report("yolov3_voc", B, 10647 * 25 * 4, ms_dec, ms_tot, {"cand_per_image": float(c.count.float().mean())})
 
