@@ -859,9 +859,15 @@ __global__ void __launch_bounds__(kN2Threads, 1) nms2_kernel(const __grid_consta
   }
 
   N2_MARK(0);
+  int npos = 0, nwords = 0;
+  // attempt 0: score-prefix subset (only when the output is score-ordered, capped, and the image is large);
+  // attempt 1: every candidate
+  int attempt = (!trick && cap > 0 && n > 2 * cap + 256) ? 0 : 1;
+  int tb = kN2Bins - 1;  // candidates with score bin <= tb take part
+  for (;;) {
   for (int w = tid; w < p.mask_words; w += kN2Threads) alive[w] = 0u;
   if (tid == 0) sh_next = 0;
-  int npos;
+  __syncthreads();
 
   if (trick) {
     // ---- coordinate trick: global score order, one class-agnostic segment on shifted boxes (boxes.py:95-97)
@@ -898,6 +904,37 @@ __global__ void __launch_bounds__(kN2Threads, 1) nms2_kernel(const __grid_consta
     }
     __syncthreads();
   } else {
+    if (attempt == 0) {
+      // ---- score-prefix shortcut (score-ordered output capped at max_det): a candidate's fate depends only on
+      //      better-scored candidates of its class, so greedy NMS restricted to "every candidate with score bin
+      //      <= tb" yields exactly the true survivors of that score range.  If at least max_det of them
+      //      survive, they contain the global top max_det and the remaining ~80 % of the candidates never
+      //      need to be sorted, gathered or tested; otherwise the image is redone in full (attempt 1).
+      int* hist = reinterpret_cast<int*>(sh_box);  // boxes are not loaded yet
+      for (int i = tid; i < kN2Bins; i += kN2Threads) hist[i] = 0;
+      if (tid == 0) sh_i0 = kN2Bins - 1;
+      __syncthreads();
+      for (int r = tid; r < n; r += kN2Threads) atomicAdd(&hist[(int)((keys[r] >> 40) & 0xfffu)], 1);
+      __syncthreads();
+      constexpr int kPer = kN2Bins / kN2Threads;
+      int local[kPer], lsum = 0;
+#pragma unroll
+      for (int q = 0; q < kPer; ++q) {
+        local[q] = hist[tid * kPer + q];
+        lsum += local[q];
+      }
+      int total = 0;
+      int run = block_excl_scan(lsum, sh_scan, &total);
+      const int want = 2 * cap;
+#pragma unroll
+      for (int q = 0; q < kPer; ++q) {
+        if (run < want && run + local[q] >= want) sh_i0 = tid * kPer + q;
+        run += local[q];
+      }
+      __syncthreads();
+      tb = sh_i0;
+      __syncthreads();
+    }
     // ---- class histogram -> 32-aligned segments -> scatter -> per-class sort
     for (int c = tid; c < nc; c += kN2Threads) {
       seg_end[c] = 0;
@@ -905,8 +942,9 @@ __global__ void __launch_bounds__(kN2Threads, 1) nms2_kernel(const __grid_consta
     }
     __syncthreads();
     for (int r = tid; r < n; r += kN2Threads) {
-      const int c = (int)(keys[r] >> 52);
-      if (c < nc) atomicAdd(&seg_end[c], 1);
+      const uint64_t k = keys[r];
+      const int c = (int)(k >> 52);
+      if (c < nc && (int)((k >> 40) & 0xfffu) <= tb) atomicAdd(&seg_end[c], 1);
     }
     __syncthreads();
     if (warp == 0) {
@@ -944,7 +982,7 @@ __global__ void __launch_bounds__(kN2Threads, 1) nms2_kernel(const __grid_consta
     for (int r = tid; r < n; r += kN2Threads) {
       const uint64_t k = keys[r];
       const int c = (int)(k >> 52);
-      if (c < nc) ckey[seg_begin[c] + atomicAdd(&fill[c], 1)] = k;
+      if (c < nc && (int)((k >> 40) & 0xfffu) <= tb) ckey[seg_begin[c] + atomicAdd(&fill[c], 1)] = k;
     }
     __syncthreads();
     N2_MARK(2);
@@ -1000,16 +1038,31 @@ __global__ void __launch_bounds__(kN2Threads, 1) nms2_kernel(const __grid_consta
     }
     __syncthreads();
   }
-  const int nwords = (npos + 31) >> 5;
+  nwords = (npos + 31) >> 5;
   N2_MARK(3);
 
   // ---- greedy suppression (shared with nms_kernel) -------------------------------------------------
   {
     const BoxView<true> bv{smem_u32(sh_box), smem_u32(sh_area)};
-    suppress_all(bv, trick, n, nwords, nc, cap, alive, seg_begin, seg_end, st, &sh_next, &sh_mask, &sh_kept,
+    suppress_all(bv, trick, trick ? n : npos, nwords, nc, cap, alive, seg_begin, seg_end, st, &sh_next, &sh_mask, &sh_kept,
                  trick || sh_maxt > 32 * kCoopMinWords);
   }
   __syncthreads();
+  if (attempt == 0) {
+    int ns = 0;
+    for (int base = 0; base < nwords; base += kN2Threads) {
+      int total = 0;
+      block_excl_scan(base + tid < nwords ? __popc(alive[base + tid]) : 0, sh_scan, &total);
+      ns += total;
+    }
+    if (ns >= cap) break;  // the subset already holds the global top max_det survivors
+    attempt = 1;
+    tb = kN2Bins - 1;
+    __syncthreads();
+    continue;
+  }
+  break;
+  }
   N2_MARK(4);
 
   float4* ob = p.det_box + (int64_t)b * p.max_out;
