@@ -11,7 +11,7 @@ SO_PATH = os.path.join(_HERE, "libcvpp.so")
 CVPP_OK = 0
 RULE_TORCHVISION_CPU, RULE_COORD_TRICK, RULE_PER_CLASS = 0, 1, 2
 ORDER_SCORE_DESC, ORDER_CLASS_MAJOR = 0, 1
-ROWS_YOLOV8, ROWS_SSD, ROWS_YOLOV7, ROWS_FULL = 0, 1, 2, 3
+ROWS_YOLOV8, ROWS_SSD, ROWS_YOLOV7, ROWS_FULL, ROWS_COCO, ROWS_VOC = 0, 1, 2, 3, 4, 5
 BOX_KEEP, BOX_CORRECT, BOX_NORMALISE_CORRECT = 0, 1, 2
 
 c_int, c_i64, c_f32, c_f64 = ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_double

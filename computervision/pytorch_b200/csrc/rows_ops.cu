@@ -271,6 +271,18 @@ __global__ void __launch_bounds__(256) detection_epilogue_kernel(const __grid_co
       row[4] = a.x;
       row[5] = a.y;
       row[6] = cls;
+    } else if (p.layout == CVPP_ROWS_COCO) {  // x,y,w,h,score,cls (yolo_v8.py:364-372: right - left, bottom - top in fp32)
+      row[2] = fsub(bx.z, bx.x);
+      row[3] = fsub(bx.w, bx.y);
+      row[4] = p.det_score[t];
+      row[5] = cls;
+    } else if (p.layout == CVPP_ROWS_VOC) {  // cls,score,int(left),int(top),int(right),int(bottom) (yolo_v8.py:286-296)
+      row[0] = cls;
+      row[1] = p.det_score[t];
+      row[2] = truncf(bx.x);
+      row[3] = truncf(bx.y);
+      row[4] = truncf(bx.z);
+      row[5] = truncf(bx.w);
     } else {  // CVPP_ROWS_FULL: x1,y1,x2,y2,score,cls,anchor
       row[4] = p.det_score[t];
       row[5] = cls;
@@ -303,7 +315,7 @@ int detection_epilogue_launch(const float* det_box, const float* det_score, cons
     set_error("detection_epilogue: NULL pointer argument");
     return CVPP_ERR_INVALID_ARG;
   }
-  if (B < 0 || max_out < 1 || layout < CVPP_ROWS_YOLOV8 || layout > CVPP_ROWS_FULL || box_mode < CVPP_BOX_KEEP ||
+  if (B < 0 || max_out < 1 || layout < CVPP_ROWS_YOLOV8 || layout > CVPP_ROWS_VOC || box_mode < CVPP_BOX_KEEP ||
       box_mode > CVPP_BOX_NORMALISE_CORRECT) {
     set_error("detection_epilogue: bad sizes / layout %d / box_mode %d", layout, box_mode);
     return CVPP_ERR_INVALID_ARG;
@@ -344,7 +356,7 @@ int detection_epilogue_launch(const float* det_box, const float* det_score, cons
   p.max_out = max_out;
   p.layout = layout;
   p.box_mode = box_mode;
-  p.width = (layout == CVPP_ROWS_YOLOV8 || layout == CVPP_ROWS_SSD) ? 6 : 7;
+  p.width = (layout == CVPP_ROWS_YOLOV7 || layout == CVPP_ROWS_FULL) ? 7 : 6;
   p.count_off = (int64_t)n_peers * B * max_out * p.width;
   p.A = A;
   const int64_t total = (int64_t)B * max_out;

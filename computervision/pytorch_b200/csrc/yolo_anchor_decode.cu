@@ -282,7 +282,7 @@ yolo_anchor_stream_kernel(const __grid_constant__ YaParams p) {
   __syncwarp();
 
   const int stride_tiles = gridDim.x * kYaWarps;
-  const int first = blockIdx.x + gridDim.x * warp;
+  const int first = blockIdx.x * kYaWarps + warp;  // the warps of a CTA stream ADJACENT tiles: their 512 B row pieces share DRAM pages
   const int n_tiles = first < p.total_tiles ? (p.total_tiles - first + stride_tiles - 1) / stride_tiles : 0;
   const int total_q = n_tiles * nchunks;
 

@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) yolov8_decode_stream_kernel(co
 
   // tiles of this warp: first, first + stride, ...  (CTA-major so small batches spread over all SMs)
   const int stride_tiles = gridDim.x * kWarps;
-  const int first = blockIdx.x + gridDim.x * warp;
+  const int first = blockIdx.x * kWarps + warp;  // the warps of a CTA stream ADJACENT tiles: their 512 B row pieces share DRAM pages
   const int n_tiles = first < p.total_tiles ? (p.total_tiles - first + stride_tiles - 1) / stride_tiles : 0;
   const int total_q = n_tiles * nchunks;
 

@@ -10,7 +10,7 @@ import torch
 
 from . import _lib
 from ._lib import (BOX_CORRECT, BOX_KEEP, BOX_NORMALISE_CORRECT, ORDER_CLASS_MAJOR, ORDER_SCORE_DESC,  # noqa: F401
-                   ROWS_FULL, ROWS_SSD, ROWS_YOLOV7, ROWS_YOLOV8, RULE_COORD_TRICK, RULE_PER_CLASS,
+                   ROWS_COCO, ROWS_FULL, ROWS_SSD, ROWS_VOC, ROWS_YOLOV7, ROWS_YOLOV8, RULE_COORD_TRICK, RULE_PER_CLASS,
                    RULE_TORCHVISION_CPU, check)
 
 c_vp = ctypes.c_void_p
@@ -520,7 +520,7 @@ def detection_epilogue(det: Detections, layout: int, box_mode: int = BOX_KEEP, l
     distributed.gather_packed / unpack_detections); `out` reuses a buffer of the right size."""
     B, max_out = int(det.box.shape[0]), int(det.box.shape[1])
     dev = det.box.device
-    width = 6 if layout in (ROWS_YOLOV8, ROWS_SSD) else 7
+    width = 7 if layout in (ROWS_YOLOV7, ROWS_FULL) else 6
     n_rows = B * max_out * width
     if out is None:
         out = torch.empty((n_rows + (B if packed else 0),), dtype=torch.float32, device=dev)

@@ -69,7 +69,9 @@ enum {
   CVPP_ROWS_YOLOV8 = 0, /* x1,y1,x2,y2,conf,cls            (non_max_suppression, ultralytics_ops.py:226) */
   CVPP_ROWS_SSD = 1,    /* x1,y1,x2,y2,label,conf          (Ssd.decode_boxes, ssd.py:275-278)            */
   CVPP_ROWS_YOLOV7 = 2, /* x1,y1,x2,y2,obj,class_conf,cls  (YOLOv7._nms, yolo_v7.py:391)                 */
-  CVPP_ROWS_FULL = 3    /* x1,y1,x2,y2,score,cls,anchor    (the all-gather payload)        */
+  CVPP_ROWS_FULL = 3,   /* x1,y1,x2,y2,score,cls,anchor    (the all-gather payload)        */
+  CVPP_ROWS_COCO = 4,   /* x,y,w,h,score,cls               (COCO json rows, yolo_v8.py:364-372)          */
+  CVPP_ROWS_VOC = 5     /* cls,score,int(l),int(t),int(r),int(b) (VOC txt lines, yolo_v8.py:286-296)     */
 };
 
 /* box transform of cvpp_detection_epilogue */
