@@ -456,9 +456,8 @@ def run_ours(args):
             "clocks": clocks,
             "e2e": {"value": world * BS * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s / K},
-            # per step: decode+filter, fused sort+NMS, and the two fallback kernels that exit at once when
-            # every image fitted the fused kernel (+ the row-packing epilogue for the all-gather when N > 1)
-            "gpu_launches": (4 if world == 1 else 5) * K,
+            # per step: decode+filter and fused sort+NMS (+ the epilogue / peer-store gather kernel when N > 1)
+            "gpu_launches": (2 if world == 1 else 3) * K,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -343,8 +343,10 @@ __device__ void suppress_all(const BoxView<SMEM>& bv, bool trick, int n, int nwo
   }
 }
 
-__global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_constant__ NmsParams p) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+// The body of nms_kernel for a CTA of T threads working on image b (also the in-kernel fallback of nms2_kernel).
+template <int T>
+__device__ __forceinline__ void nms_body(const NmsParams& p, const int b, unsigned char* smem_raw) {
+  constexpr int kThreads = T, kWarps = T / 32;
   // layout: [boxes float4 x N][areas float x N][rank int x N][alive u32 x W][galive u32 x W]
   //         [seg_begin int x nc][seg_end int x nc][cnt int x count_warps x nc]
   float4* sh_box = reinterpret_cast<float4*>(smem_raw);
@@ -355,8 +357,8 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
   int* seg_begin = reinterpret_cast<int*>(galive + p.mask_words);
   int* seg_end = seg_begin + p.nc;
   int* cnt = seg_end + p.nc;
-  __shared__ float sh_red[kNmsWarps];
-  __shared__ int sh_scan[kNmsWarps];
+  __shared__ float sh_red[kWarps];
+  __shared__ int sh_scan[kWarps];
   __shared__ int sh_running;
   __shared__ uint32_t sh_mask;
   __shared__ int sh_kept;
@@ -364,7 +366,6 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
   __shared__ int sh_npos;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int b = blockIdx.x;
   if (p.skip && p.skip[b]) return;  // already done by the fused kernel
   int n = p.cand_count[b];
   if (n > p.max_cand) n = p.max_cand;
@@ -384,7 +385,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
   int32_t* wrank;
   int npos;  // size of the position space (== n for the trick branch, 32-aligned class segments otherwise)
 
-  for (int w = tid; w < p.mask_words; w += kNmsThreads) {
+  for (int w = tid; w < p.mask_words; w += kThreads) {
     alive[w] = 0u;
     galive[w] = 0u;
   }
@@ -400,7 +401,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
     warea = in_smem ? sh_area : p.ws_area + (int64_t)b * p.pos_cap;
     wrank = in_smem ? sh_rank : p.ws_rank + (int64_t)b * p.pos_cap;
     float m = -INFINITY;
-    for (int r = tid; r < n; r += kNmsThreads) {
+    for (int r = tid; r < n; r += kThreads) {
       const float4 bx = dense[(uint32_t)(keys[r] >> 12) & 0x1fffffu];
       m = fmaxf(m, fmaxf(fmaxf(bx.x, bx.y), fmaxf(bx.z, bx.w)));
     }
@@ -408,9 +409,9 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
     if (lane == 0) sh_red[warp] = m;
     __syncthreads();
     m = sh_red[0];
-    for (int q = 1; q < kNmsWarps; ++q) m = fmaxf(m, sh_red[q]);
+    for (int q = 1; q < kWarps; ++q) m = fmaxf(m, sh_red[q]);
     const float mult = fadd(m, 1.0f);
-    for (int r = tid; r < n; r += kNmsThreads) {
+    for (int r = tid; r < n; r += kThreads) {
       const uint64_t k = keys[r];
       const float off = fmul((float)(uint32_t)(k & 0xfffu), mult);
       float4 bx = dense[(uint32_t)(k >> 12) & 0x1fffffu];
@@ -421,7 +422,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
       wbox[r] = bx;
       warea[r] = box_area(bx);
     }
-    for (int w = tid; w < rank_words; w += kNmsThreads) {
+    for (int w = tid; w < rank_words; w += kThreads) {
       const int rem = n - (w << 5);
       alive[w] = rem >= 32 ? 0xffffffffu : ((1u << rem) - 1u);
     }
@@ -429,7 +430,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
   } else {
     // ---- stable counting split by class: position = class start + #earlier ranks of that class
     const int cw = p.count_warps;
-    for (int i = tid; i < cw * nc; i += kNmsThreads) cnt[i] = 0;
+    for (int i = tid; i < cw * nc; i += kThreads) cnt[i] = 0;
     __syncthreads();
     const int per_warp = (((n + cw - 1) / cw) + 31) & ~31;  // contiguous rank range per counting warp
     const int r_begin = warp * per_warp, r_end = min(n, r_begin + per_warp);
@@ -446,7 +447,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
     }
     __syncthreads();
     // per class: exclusive offsets over the counting warps, class totals into seg_end (temporarily)
-    for (int c = tid; c < nc; c += kNmsThreads) {
+    for (int c = tid; c < nc; c += kThreads) {
       int run = 0;
       for (int w = 0; w < cw; ++w) {
         const int t = cnt[w * nc + c];
@@ -531,7 +532,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
   // into `galive`, indexed by global score rank.
   const bool by_rank = (p.order == CVPP_ORDER_SCORE_DESC) && !trick;
   if (by_rank) {
-    for (int w = tid; w < nwords; w += kNmsThreads) {
+    for (int w = tid; w < nwords; w += kThreads) {
       uint32_t m = alive[w];
       while (m) {
         const int bit = __ffs(m) - 1;
@@ -555,7 +556,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
   int* out_idx = reinterpret_cast<int*>(warea);
   if (tid == 0) sh_running = 0;
   __syncthreads();
-  for (int base = 0; base < mwords; base += kNmsThreads) {
+  for (int base = 0; base < mwords; base += kThreads) {
     const int wi = base + tid;
     uint32_t m = wi < mwords ? mask[wi] : 0u;
     const int c = __popc(m);
@@ -567,7 +568,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
     if (lane == 31) sh_scan[warp] = incl;
     __syncthreads();
     int woff = 0, total = 0;
-    for (int q = 0; q < kNmsWarps; ++q) {
+    for (int q = 0; q < kWarps; ++q) {
       const int v = sh_scan[q];
       if (q < warp) woff += v;
       total += v;
@@ -586,7 +587,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
   if (p.order == CVPP_ORDER_SCORE_DESC && p.max_det > 0 && n_kept > p.max_det) n_kept = p.max_det;
   // pass 2: one output row per thread, all gathers in flight at once
   const int n_rows = min(n_kept, out_cap);
-  for (int o = tid; o < n_rows; o += kNmsThreads) {
+  for (int o = tid; o < n_rows; o += kThreads) {
     const int at = out_idx[o];
     const uint64_t k = keys[pos_is_rank ? at : wrank[at]];
     const uint32_t anchor = (uint32_t)(k >> 12) & 0x1fffffu;
@@ -596,6 +597,11 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_consta
     oa[o] = (int32_t)anchor;
   }
   if (tid == 0) p.det_count[b] = n_kept;
+}
+
+__global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const __grid_constant__ NmsParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  nms_body<kNmsThreads>(p, (int)blockIdx.x, smem_raw);
 }
 
 static size_t pos_capacity(int max_cand, int nc) { return (size_t)max_cand + 32u * (size_t)nc; }
@@ -619,10 +625,11 @@ int nms_launch(const uint64_t* sorted_key, const int32_t* cand_count, const floa
                          det_box, det_score, det_cls, det_anchor, det_count, workspace, workspace_bytes, nullptr, stream);
 }
 
-int nms_launch_skip(const uint64_t* sorted_key, const int32_t* cand_count, const float* box_dense, int B, int max_cand,
-                    int64_t A, int nc, double iou_thres, int rule, int order, int max_det, int max_out, float* det_box,
-                    float* det_score, int32_t* det_cls, int32_t* det_anchor, int32_t* det_count, void* workspace,
-                    size_t workspace_bytes, const int32_t* skip, cudaStream_t stream) {
+// Validates the arguments, fills the kernel parameters and reports the dynamic shared memory nms_body needs.
+static int nms_prepare(NmsParams& p, size_t& smem, const uint64_t* sorted_key, const int32_t* cand_count,
+                       const float* box_dense, int B, int max_cand, int64_t A, int nc, double iou_thres, int rule, int order,
+                       int max_det, int max_out, float* det_box, float* det_score, int32_t* det_cls, int32_t* det_anchor,
+                       int32_t* det_count, void* workspace, size_t workspace_bytes, const int32_t* skip, int max_smem) {
   if (!sorted_key || !cand_count || !box_dense || !det_box || !det_score || !det_cls || !det_anchor || !det_count) {
     set_error("nms: NULL pointer argument");
     return CVPP_ERR_INVALID_ARG;
@@ -643,17 +650,11 @@ int nms_launch_skip(const uint64_t* sorted_key, const int32_t* cand_count, const
     set_error("nms: box arrays must be 16-byte aligned");
     return CVPP_ERR_ALIGNMENT;
   }
-  if (B == 0) return CVPP_OK;
   if (!workspace || workspace_bytes < nms_workspace_bytes(B, max_cand, nc)) {
     set_error("nms: workspace of %zu bytes needed, got %zu", nms_workspace_bytes(B, max_cand, nc), workspace_bytes);
     return CVPP_ERR_WORKSPACE;
   }
-  DeviceInfo di;
-  int rc = device_info(&di);
-  if (rc != CVPP_OK) return rc;
-  const int max_smem = di.max_smem;
-
-  NmsParams p{};
+  p = NmsParams{};
   // (double)ovr > thr  <=>  ovr > thr_eff := largest float <= thr   (ovr is a float)
   float thr_eff = (float)iou_thres;
   if ((double)thr_eff > iou_thres) thr_eff = nextafterf(thr_eff, -INFINITY);
@@ -703,7 +704,23 @@ int nms_launch_skip(const uint64_t* sorted_key, const int32_t* cand_count, const
   if (smem_boxes > cap) smem_boxes = cap;
   smem_boxes &= ~(size_t)3;
   p.smem_boxes = (int)smem_boxes;
-  size_t smem = fixed + smem_boxes * 24;
+  smem = fixed + smem_boxes * 24;
+  return CVPP_OK;
+}
+
+int nms_launch_skip(const uint64_t* sorted_key, const int32_t* cand_count, const float* box_dense, int B, int max_cand,
+                    int64_t A, int nc, double iou_thres, int rule, int order, int max_det, int max_out, float* det_box,
+                    float* det_score, int32_t* det_cls, int32_t* det_anchor, int32_t* det_count, void* workspace,
+                    size_t workspace_bytes, const int32_t* skip, cudaStream_t stream) {
+  if (B == 0) return CVPP_OK;
+  DeviceInfo di;
+  int rc = device_info(&di);
+  if (rc != CVPP_OK) return rc;
+  NmsParams p;
+  size_t smem = 0;
+  rc = nms_prepare(p, smem, sorted_key, cand_count, box_dense, B, max_cand, A, nc, iou_thres, rule, order, max_det, max_out,
+                   det_box, det_score, det_cls, det_anchor, det_count, workspace, workspace_bytes, skip, di.max_smem);
+  if (rc != CVPP_OK) return rc;
   static unsigned long long attr_done = 0;
   static int attr_bytes = 0;  // the attribute must cover the largest request seen so far
   if ((int)smem > attr_bytes) {
@@ -716,6 +733,10 @@ int nms_launch_skip(const uint64_t* sorted_key, const int32_t* cand_count, const
   CVPP_CUDA_TRY(cudaGetLastError());
   return CVPP_OK;
 }
+
+}  // namespace cvpp
+
+namespace cvpp {
 
 // =====================================================================================================
 // Fused sort + NMS (v2): one kernel per image, no global sort.
@@ -733,9 +754,9 @@ int nms_launch_skip(const uint64_t* sorted_key, const int32_t* cand_count, const
 //      survivors' score bits (4 096 bins), the bin where the cumulative count reaches max_det, and a sort of
 //      only the selected <= max_det + boundary-bin keys.
 // The coordinate-trick branch (<= 1000 candidates) needs the global score order for its class-agnostic pass
-// and sorts its <= 1 024 keys in shared memory.  Images that do not fit shared memory (or exceed max_nms) are
-// left to the two-kernel path: this kernel writes done[b] = 0 and segsort_kernel / nms_kernel, launched
-// behind it with done as their skip list, pick them up.
+// and sorts its <= 1 024 keys in shared memory.  Images that do not fit shared memory (or exceed max_nms) take
+// the slow path inside the same CTA (nms2_fallback: global score-order sort + the body of nms_kernel), so the
+// whole stage is always ONE launch.
 // =====================================================================================================
 constexpr int kN2Threads = 1024;
 constexpr int kN2Warps = kN2Threads / 32;
@@ -758,9 +779,16 @@ struct Nms2Params {
   int32_t* det_cls;
   int32_t* det_anchor;
   int32_t* det_count;
-  int32_t* done;   // [B]
   int cap_pos;     // class-major positions that fit shared memory (multiple of 32)
   int mask_words;  // cap_pos / 32
+  // in-kernel fallback (images that do not fit shared memory, or with more than max_nms candidates): global
+  // score-order sort into fb_keys, then the body of nms_kernel on them
+  NmsParams fb;
+  uint64_t* fb_keys;    // [B][max_cand]
+  int32_t* fb_count;    // [B]
+  uint64_t* fb_sort_ws; // [B][fb_sort_stride] scratch for sorts larger than shared memory
+  int64_t fb_sort_stride;
+  int fb_smem_keys;     // keys that fit the dynamic shared memory for the fallback sort (power of two)
 };
 
 template <int E>
@@ -812,6 +840,29 @@ __device__ __forceinline__ int block_excl_scan(int v, int* sh_warp /*[kN2Warps]*
   return woff + incl - v;
 }
 
+// The slow path of nms2_kernel, all threads of the CTA: what cvpp_segmented_sort + cvpp_nms do for one image.
+__device__ __noinline__ void nms2_fallback(const Nms2Params& p, int b, unsigned char* smem_raw) {
+  int n = p.cand_count[b];
+  if (n > p.max_cand) n = p.max_cand;
+  const uint64_t* kb = p.cand_key + (int64_t)b * p.max_cand;
+  uint64_t* ko = p.fb_keys + (int64_t)b * p.max_cand;
+  const int P = pow2_ceil(n < 32 ? 32 : n);
+  const bool in_smem = P <= p.fb_smem_keys;
+  uint64_t* a = in_smem ? reinterpret_cast<uint64_t*>(smem_raw) : p.fb_sort_ws + (int64_t)b * p.fb_sort_stride;
+  for (int i = threadIdx.x; i < P; i += blockDim.x) a[i] = i < n ? key_to_score_major(kb[i]) : ~0ull;
+  __syncthreads();
+  if (in_smem)
+    block_sort_smem_max8(a, P);
+  else
+    bitonic_sort_u64_generic(a, P);
+  const int n_final = (p.max_nms > 0 && n > p.max_nms) ? p.max_nms : n;  // ultralytics_ops.py:240
+  for (int i = threadIdx.x; i < n_final; i += blockDim.x) ko[i] = a[i];
+  if (threadIdx.x == 0) p.fb_count[b] = n_final;
+  __threadfence_block();
+  __syncthreads();
+  nms_body<kN2Threads>(p.fb, b, smem_raw);
+}
+
 #ifdef CVPP_NMS_TIMING
 __device__ long long g_n2_t[16 * 64];
 #define N2_MARK(i) do { __syncthreads(); if (threadIdx.x == 0 && blockIdx.x < 64) g_n2_t[blockIdx.x * 16 + (i)] = clock64(); } while (0)
@@ -839,10 +890,7 @@ __global__ void __launch_bounds__(kN2Threads, 1) nms2_kernel(const __grid_consta
   int n = p.cand_count[b];
   if (n > p.max_cand) n = p.max_cand;
   if (n <= 0) {
-    if (tid == 0) {
-      p.det_count[b] = 0;
-      p.done[b] = 1;
-    }
+    if (tid == 0) p.det_count[b] = 0;
     return;
   }
   const uint64_t* keys = p.cand_key + (int64_t)b * p.max_cand;
@@ -851,10 +899,10 @@ __global__ void __launch_bounds__(kN2Threads, 1) nms2_kernel(const __grid_consta
   const int nc = p.nc;
   const SupTest st{p.thr_eff, p.thr_mid, p.tie_up != 0};
   const int cap = (p.order == CVPP_ORDER_SCORE_DESC && p.max_det > 0) ? p.max_det : 0;
-  bool fits = !(p.max_nms > 0 && n > p.max_nms);
+  bool fits = p.cap_pos > 0 && !(p.max_nms > 0 && n > p.max_nms);
   if (trick && pow2_ceil(n < 32 ? 32 : n) > p.cap_pos) fits = false;
-  if (!fits) {
-    if (tid == 0) p.done[b] = 0;
+  if (!fits) {  // uniform
+    nms2_fallback(p, b, smem_raw);
     return;
   }
 
@@ -975,8 +1023,9 @@ __global__ void __launch_bounds__(kN2Threads, 1) nms2_kernel(const __grid_consta
     __syncthreads();
     N2_MARK(1);
     npos = sh_npos;
-    if (npos > p.cap_pos) {  // does not fit: leave the image to the two-kernel path
-      if (tid == 0) p.done[b] = 0;
+    if (npos > p.cap_pos) {  // does not fit shared memory (uniform): global-memory path
+      __syncthreads();
+      nms2_fallback(p, b, smem_raw);
       return;
     }
     for (int r = tid; r < n; r += kN2Threads) {
@@ -1127,10 +1176,7 @@ __global__ void __launch_bounds__(kN2Threads, 1) nms2_kernel(const __grid_consta
       oa[o] = (int32_t)anchor;
     }
     N2_MARK(7);
-    if (tid == 0) {
-      p.det_count[b] = n_kept;
-      p.done[b] = 1;
-    }
+    if (tid == 0) p.det_count[b] = n_kept;
     return;
   }
 
@@ -1163,10 +1209,7 @@ __global__ void __launch_bounds__(kN2Threads, 1) nms2_kernel(const __grid_consta
     oc[o] = (int32_t)(k & 0xfffu);
     oa[o] = (int32_t)anchor;
   }
-  if (tid == 0) {
-    p.det_count[b] = n_kept;
-    p.done[b] = 1;
-  }
+  if (tid == 0) p.det_count[b] = n_kept;
 }
 
 #ifdef CVPP_NMS_TIMING
@@ -1222,8 +1265,7 @@ int sort_nms_launch(const uint64_t* cand_key, const int32_t* cand_count, const f
   int rc = device_info(&di);
   if (rc != CVPP_OK) return rc;
   uintptr_t base = (reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255;
-  int32_t* done = reinterpret_cast<int32_t*>(base);
-  base += align256_((size_t)B * sizeof(int32_t));
+  base += align256_((size_t)B * sizeof(int32_t));  // (formerly the per-image done flags)
   int32_t* fb_count = reinterpret_cast<int32_t*>(base);  // fallback: counts after the max_nms cut
   base += align256_((size_t)B * sizeof(int32_t));
   uint64_t* fb_keys = reinterpret_cast<uint64_t*>(base);  // fallback: sorted keys
@@ -1235,14 +1277,22 @@ int sort_nms_launch(const uint64_t* cand_key, const int32_t* cand_count, const f
   const size_t nms_bytes = nms_workspace_bytes(B, max_cand, nc);
 
   Nms2Params p{};
-  float thr_eff = (float)iou_thres;
-  if ((double)thr_eff > iou_thres) thr_eff = nextafterf(thr_eff, -INFINITY);
-  const float thr_next = nextafterf(thr_eff, INFINITY);
-  p.thr_eff = thr_eff;
-  p.thr_mid = ((double)thr_eff + (double)thr_next) * 0.5;
-  uint32_t next_bits;
-  memcpy(&next_bits, &thr_next, sizeof(next_bits));
-  p.tie_up = (next_bits & 1u) == 0;
+  // the in-kernel fallback runs the body of nms_kernel on the keys it has sorted into fb_keys
+  size_t smem_fb = 0;
+  rc = nms_prepare(p.fb, smem_fb, fb_keys, fb_count, box_dense, B, max_cand, A, nc, iou_thres, rule, order, max_det, max_out,
+                   det_box, det_score, det_cls, det_anchor, det_count, nms_ws, nms_bytes, nullptr, di.max_smem);
+  if (rc != CVPP_OK) return rc;
+  p.fb_keys = fb_keys;
+  p.fb_count = fb_count;
+  p.fb_sort_ws = reinterpret_cast<uint64_t*>(sort_ws);
+  {
+    int P = 32;
+    while (P < max_cand) P <<= 1;
+    p.fb_sort_stride = P;
+  }
+  p.thr_eff = p.fb.thr_eff;
+  p.thr_mid = p.fb.thr_mid;
+  p.tie_up = p.fb.tie_up;
   p.cand_key = cand_key;
   p.cand_count = cand_count;
   p.box_dense = reinterpret_cast<const float4*>(box_dense);
@@ -1259,49 +1309,37 @@ int sort_nms_launch(const uint64_t* cand_key, const int32_t* cand_count, const f
   p.det_cls = det_cls;
   p.det_anchor = det_anchor;
   p.det_count = det_count;
-  p.done = done;
-  // shared memory: 28 B per position + 1 bit, 3 ints per class; the selection stage needs 16 KB of histogram
-  // inside the 16 B/position box array and 8 B/position of selected keys behind it
+  // shared memory of the fused path: 28 B per position + 1 bit, 3 ints per class; the selection stage needs
+  // 16 KB of histogram inside the 16 B/position box array and 8 B/position of selected keys behind it
   const size_t fixed = (size_t)nc * 12 + 256;
-  bool fused_possible = fixed + 64 * 1024 <= (size_t)di.max_smem;
   size_t cap_pos = 0;
-  if (fused_possible) {
+  if (fixed + 64 * 1024 <= (size_t)di.max_smem) {
     cap_pos = ((size_t)di.max_smem - fixed - 1024) * 8 / (28 * 8 + 1);
     const size_t worst = (size_t)max_cand + 32u * (size_t)nc;  // never need more positions than this
     if (cap_pos > worst) cap_pos = worst;
     cap_pos &= ~(size_t)31;
-    if (cap_pos < 2048) {  // 16 B * cap_pos must hold the 16 KB histogram + 8 B * cap_pos of selected keys
-      cap_pos = 2048;
-      if (fixed + cap_pos * 28 + cap_pos / 8 + 1024 > (size_t)di.max_smem) fused_possible = false;
-    }
+    if (cap_pos < 2048) cap_pos = 2048;  // 16 B * cap_pos must hold the 16 KB histogram + 8 B * cap_pos of keys
+    if (fixed + cap_pos * 28 + cap_pos / 8 + 1024 > (size_t)di.max_smem) cap_pos = 0;
   }
-  if (fused_possible) {
-    p.cap_pos = (int)cap_pos;
-    p.mask_words = (int)(cap_pos / 32);
-    const size_t smem = cap_pos * 28 + (size_t)p.mask_words * 4 + (size_t)nc * 12;
-    static unsigned long long attr_done = 0;
-    static int attr_bytes = 0;
-    if ((int)smem > attr_bytes) {
-      attr_done = 0;
-      attr_bytes = (int)smem;
-    }
-    rc = ensure_smem_attr(reinterpret_cast<const void*>(nms2_kernel), attr_bytes, di.device, &attr_done);
-    if (rc != CVPP_OK) return rc;
-    nms2_kernel<<<B, kN2Threads, smem, stream>>>(p);
-    CVPP_CUDA_TRY(cudaGetLastError());
-    // every image fits when even the worst-case padded layout does and max_nms cannot bind
-    const bool all_fit = (size_t)max_cand + 32u * (size_t)nc <= cap_pos && !(max_nms > 0 && max_cand > max_nms) &&
-                         pow2_ceil(max_cand < CVPP_TRICK_MAX_BOXES ? max_cand : CVPP_TRICK_MAX_BOXES) <= (int)cap_pos &&
-                         rule != CVPP_NMS_RULE_COORD_TRICK;
-    if (all_fit) return CVPP_OK;
-  } else {
-    CVPP_CUDA_TRY(cudaMemsetAsync(done, 0, sizeof(int32_t) * (size_t)B, stream));
+  p.cap_pos = (int)cap_pos;   // 0: nothing fits the fused layout, every image takes the fallback
+  p.mask_words = (int)(cap_pos / 32);
+  size_t smem = cap_pos * 28 + (size_t)p.mask_words * 4 + (size_t)nc * 12;
+  if (smem_fb > smem) smem = smem_fb;
+  // the fallback sort uses whatever dynamic shared memory the launch has (power-of-two key count)
+  int fb_keys_smem = 32;
+  while ((size_t)fb_keys_smem * 2 * sizeof(uint64_t) <= smem && fb_keys_smem < 8192) fb_keys_smem <<= 1;
+  p.fb_smem_keys = fb_keys_smem;
+  static unsigned long long attr_done = 0;
+  static int attr_bytes = 0;
+  if ((int)smem > attr_bytes) {
+    attr_done = 0;
+    attr_bytes = (int)smem;
   }
-  rc = segsort_launch_skip(const_cast<uint64_t*>(cand_key), const_cast<int32_t*>(cand_count), B, max_cand, rule, max_nms,
-                           sort_ws, sort_bytes, done, fb_keys, fb_count, stream);
+  rc = ensure_smem_attr(reinterpret_cast<const void*>(nms2_kernel), attr_bytes, di.device, &attr_done);
   if (rc != CVPP_OK) return rc;
-  return nms_launch_skip(fb_keys, fb_count, box_dense, B, max_cand, A, nc, iou_thres, rule, order, max_det, max_out,
-                         det_box, det_score, det_cls, det_anchor, det_count, nms_ws, nms_bytes, done, stream);
+  nms2_kernel<<<B, kN2Threads, smem, stream>>>(p);
+  CVPP_CUDA_TRY(cudaGetLastError());
+  return CVPP_OK;
 }
 
 }  // namespace cvpp
