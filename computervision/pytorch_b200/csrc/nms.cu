@@ -761,6 +761,7 @@ namespace cvpp {
 constexpr int kN2Threads = 1024;
 constexpr int kN2Warps = kN2Threads / 32;
 constexpr int kN2Bins = 4096;
+constexpr int kN2SmallMax = 256;     // coordinate-trick images up to this size are handled by one warp
 constexpr int kN2WarpSortMax = 256;  // keys per class a single warp sorts in registers (E <= 8)
 
 struct Nms2Params {
@@ -903,6 +904,69 @@ __global__ void __launch_bounds__(kN2Threads, 1) nms2_kernel(const __grid_consta
   if (trick && pow2_ceil(n < 32 ? 32 : n) > p.cap_pos) fits = false;
   if (!fits) {  // uniform
     nms2_fallback(p, b, smem_raw);
+    return;
+  }
+  if (trick && n <= kN2SmallMax) {
+    // ---- few candidates on the coordinate-trick branch (the bs = 1, conf .25 case): ONE warp does the whole
+    //      image - sort, shifted boxes, greedy pass, ordered output - without a single CTA barrier
+    if (warp != 0) return;
+    for (int i = lane; i < n; i += 32) ckey[i] = key_to_score_major(keys[i]);
+    __syncwarp();
+    if (n <= 32) warp_sort_segment<1>(ckey, n);
+    else if (n <= 64) warp_sort_segment<2>(ckey, n);
+    else if (n <= 128) warp_sort_segment<4>(ckey, n);
+    else warp_sort_segment<8>(ckey, n);
+    float m = -INFINITY;
+    for (int i = lane; i < n; i += 32) {
+      const float4 bx = dense[(uint32_t)(ckey[i] >> 12) & 0x1fffffu];
+      sh_box[i] = bx;
+      m = fmaxf(m, fmaxf(fmaxf(bx.x, bx.y), fmaxf(bx.z, bx.w)));
+    }
+    for (int d = 16; d > 0; d >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
+    const float mult = fadd(m, 1.0f);  // boxes.py:95-97: offsets = idxs * (max_coordinate + 1)
+    __syncwarp();
+    for (int i = lane; i < n; i += 32) {
+      const float off = fmul((float)(uint32_t)(ckey[i] & 0xfffu), mult);
+      float4 bx = sh_box[i];
+      bx.x = fadd(bx.x, off);
+      bx.y = fadd(bx.y, off);
+      bx.z = fadd(bx.z, off);
+      bx.w = fadd(bx.w, off);
+      sh_box[i] = bx;
+      sh_area[i] = box_area(bx);
+    }
+    const int words = (n + 31) >> 5;
+    for (int w = lane; w < words; w += 32) {
+      const int rem = n - (w << 5);
+      alive[w] = rem >= 32 ? 0xffffffffu : ((1u << rem) - 1u);
+    }
+    __syncwarp();
+    {
+      const BoxView<true> bv{smem_u32(sh_box), smem_u32(sh_area)};
+      nms_segment_warp(0, n, cap, bv, alive, st);
+    }
+    __syncwarp();
+    float4* ob = p.det_box + (int64_t)b * p.max_out;
+    float* os = p.det_score + (int64_t)b * p.max_out;
+    int32_t* oc = p.det_cls + (int64_t)b * p.max_out;
+    int32_t* oa = p.det_anchor + (int64_t)b * p.max_out;
+    int running = 0;
+    for (int w = 0; w < words; ++w) {
+      const uint32_t mw = alive[w];
+      if ((mw >> lane) & 1u) {
+        const int o = running + __popc(mw & ((1u << lane) - 1u));
+        if (o < p.max_out) {
+          const uint64_t k = ckey[(w << 5) + lane];
+          const uint32_t anchor = (uint32_t)(k >> 12) & 0x1fffffu;
+          ob[o] = dense[anchor];
+          os[o] = __uint_as_float(0x7fffffffu - (uint32_t)(k >> 33));
+          oc[o] = (int32_t)(k & 0xfffu);
+          oa[o] = (int32_t)anchor;
+        }
+      }
+      running += __popc(mw);
+    }
+    if (lane == 0) p.det_count[b] = (cap > 0 && running > cap) ? cap : running;
     return;
   }
 
