@@ -336,24 +336,23 @@ def run_ours(args):
 
     # ---- roofline of the dominant kernel (decode+filter): CUDA events around every stage of the
     #      three-call pipeline (same kernels as the fused call), accumulated over K in-situ iterations
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
+    # Each stage is launched K times back to back between two events on the launching stream (the
+    # current torch stream): the average launch duration without the dependency gap of a mixed sequence.
+    def burst(fn):
+        for _ in range(3):
+            fn()
+        barrier()
+        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(K):
+            fn()
+        b_.record()
+        barrier()
+        return a.elapsed_time(b_) / K
 
-    def staged(i):
-        e = ev[i]
-        e[0].record()
-        c = ops.yolov8_decode_filter(ls, NC, CONF)
-        e[1].record()
-        ops.sort_nms(c, IOU, max_det=MAX_DET, max_nms=30000)
-        e[2].record()
-
-    for i in range(min(3, K)):
-        staged(i)
-    barrier()
-    for i in range(K):
-        staged(i)
-    barrier()
-    ms_dec = sum(e[0].elapsed_time(e[1]) for e in ev) / K
-    ms_nms = sum(e[1].elapsed_time(e[2]) for e in ev) / K
+    ms_dec = burst(lambda: ops.yolov8_decode_filter(ls, NC, CONF))
+    cand_fixed = ops.yolov8_decode_filter(ls, NC, CONF)
+    ms_nms = burst(lambda: ops.sort_nms(cand_fixed, IOU, max_det=MAX_DET, max_nms=30000))
     if world > 1:
         t = torch.tensor([ms_dec, ms_nms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
