@@ -47,6 +47,12 @@ struct CnParams {
   int32_t* det_count;
   uint64_t* ws_sort;  // [B][sort_cap] for lists too large for shared memory
   int sort_cap;
+  // tile kernel (primary pass A) + exact redo of the images whose list overflowed
+  int tile_cols, tiles_per_row, total_tiles, tile_stage_floats;
+  int tile_lo;        // the launch covers units [tile_lo, total_tiles)
+  int row_lo, row_hi; // the row kernel covers image rows [row_lo, row_hi)
+  int32_t* redo;      // [B] 1 = the image is redone by the row kernel
+  int32_t* redo_any;  // [1]
 };
 
 __device__ __forceinline__ uint64_t cn_key(float score, uint32_t flat) {
@@ -155,6 +161,206 @@ __device__ __forceinline__ int cn_truncate(uint64_t* keys, int n, int K, int* sh
   return K;
 }
 
+// ---------------------------------------------------------------------------------------------
+// pass A, primary: independent warps streaming column tiles (the design of the YOLO decode kernels)
+// ---------------------------------------------------------------------------------------------
+// The row kernel below synchronises a whole CTA twice per image row and pays several L2 round trips per row
+// (bounds, list reservation, histogram): ~4 us per 43 KB row, 27 % of the HBM roofline.  Here a WARP owns a
+// tile = tile_cols columns of one image row plus one halo column each side (contiguous in the NHWC tensor ->
+// one bulk async copy into the warp's private 2-stage ring), never meets a CTA barrier, and touches global
+// memory only when the tile holds a cell above the image's running bound (13 % of the tiles once the bound
+// is tight).  Tiles are handed out image-fastest, so every image's bound tightens after its first few tiles.
+// There is no per-row cap here: an image that overflows its K*H list (dense maps before a bound exists,
+// massive score ties) is flagged and redone exactly by the row kernel.
+constexpr int kCtKeyStage = 256;  // staged keys per warp
+
+__device__ __forceinline__ void ct_tile_info(const CnParams& p, int g, int& b, int& y, int& x0, int& x1, int& xlo, int& xhi) {
+  // units are handed out image-fastest (every image's bound tightens early), but each image walks its units
+  // from a different starting point: the same (row, column) of different images lies a multiple of the image
+  // size apart (5 505 024 B = 21 * 2^18 at 128x128x84), and thousands of concurrent requests at such strides
+  // pile up on the same HBM channels / banks
+  const int g0 = g - p.tile_lo;
+  b = g0 % p.B;
+  const int per_image = (p.total_tiles - p.tile_lo) / p.B;
+  const int k = g0 / p.B;
+  const int t = p.tile_lo / p.B + (int)(((long long)k + (long long)b * 37) % per_image);
+  y = t / p.tiles_per_row;
+  x0 = (t - y * p.tiles_per_row) * p.tile_cols;
+  x1 = min(p.W, x0 + p.tile_cols);
+  xlo = max(x0 - 1, 0);
+  xhi = min(x1 + 1, p.W);
+}
+
+// all lanes of the warp; n = staged keys (warp-uniform)
+__device__ __forceinline__ void ct_flush(const CnParams& p, int b, uint64_t* keys, int* wcnt) {
+  const int lane = threadIdx.x & 31;
+  __syncwarp();
+  const int n = min(*wcnt, kCtKeyStage);
+  if (n == 0) return;
+  int base = 0;
+  if (lane == 0) base = atomicAdd(p.list_count + b, n);
+  base = __shfl_sync(0xffffffffu, base, 0);
+  uint64_t* dst = p.list + (size_t)b * p.list_cap;
+  uint32_t* hist = p.hist + (size_t)b * kCnBins;
+  for (int t = lane; t < n; t += 32) {
+    const uint64_t k = keys[t];
+    if (base + t < p.list_cap) dst[base + t] = k;
+    atomicAdd(hist + cn_score_bin(k), 1u);
+  }
+  if (lane == 0 && base + n > p.list_cap) atomicExch(p.redo_any, 1);  // list overflow: the image is redone exactly
+  // tighten the image's bound: first score bin (best first) at which the cumulative count of emitted peaks
+  // reaches K (counts only grow, so a stale read is conservative)
+  int run = 0, edge = -1;
+  for (int b0 = 0; b0 < kCnBins && edge < 0; b0 += 32 * 4) {
+    const uint4 h = __ldcg(reinterpret_cast<const uint4*>(hist + b0 + 4 * lane));
+    const int mine = (int)(h.x + h.y + h.z + h.w);
+    int incl = mine;
+    for (int d = 1; d < 32; d <<= 1) {
+      const int u = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += u;
+    }
+    const int before = run + incl - mine;
+    int e = 0x7fffffff;
+    if (before < p.K && before + mine >= p.K) {
+      int acc = before;
+      const int hv[4] = {(int)h.x, (int)h.y, (int)h.z, (int)h.w};
+      for (int q = 0; q < 4; ++q) {
+        acc += hv[q];
+        if (acc >= p.K) {
+          e = b0 + 4 * lane + q;
+          break;
+        }
+      }
+    }
+    for (int d = 16; d > 0; d >>= 1) e = min(e, __shfl_xor_sync(0xffffffffu, e, d));
+    if (e != 0x7fffffff) edge = e;
+    run += __shfl_sync(0xffffffffu, incl, 31);
+    if (b0 == 0 && run < p.K / 4) break;  // far from K peaks so far: do not walk the whole histogram
+  }
+  if (lane == 0 && edge >= 0) {
+    const float bound = cn_bin_logit_bound(edge);
+    if (bound > -INFINITY) atomic_max_float(p.tau_logit + b, bound);
+  }
+  __syncwarp();
+  if (lane == 0) *wcnt = 0;
+  __syncwarp();
+}
+
+// exact test of one cell above the bound (same arithmetic as the row kernel's slow path), key -> warp stage
+__device__ __noinline__ void ct_test_cell(const float* row, int x, int c, float v, int y, int W, int nc, int Cf,
+                                          uint64_t* keys, int* wcnt) {
+  float m = v;  // 3x3 window maximum over (x-1..x+1, c-1..c+1), -inf outside the map (max-pool padding)
+  for (int dx = -1; dx <= 1; ++dx) {
+    const int xx = x + dx;
+    if (xx < 0 || xx >= W) continue;
+    const float* q = row + xx * Cf + c;
+    if (c > 0) m = fmaxf(m, q[-1]);
+    m = fmaxf(m, q[0]);
+    if (c + 1 < nc) m = fmaxf(m, q[1]);
+  }
+  bool peak = v >= m;
+  if (!peak && !(m - v < kCnTieEps || v > 8.0f)) return;  // clearly below a neighbour: the common rejection
+  const float sc = sigmoid_precise(v);
+  if (!peak) peak = sc == sigmoid_precise(m);
+  if (!peak) return;
+  const int pos = atomicAdd(wcnt, 1);
+  if (pos < kCtKeyStage) keys[pos] = cn_key(sc, (uint32_t)((y * W + x) * nc + c));
+}
+
+// Streaming scan: no shared-memory staging at all.  A warp owns a unit = tile_cols consecutive columns of one
+// image row = a contiguous run of float4 groups in the NHWC tensor, and reads it with plain coalesced 128-bit
+// loads, kCtUnroll x 512 B in flight per warp (the bulk-copy pipelines, 1-D UBLKCP on 16-byte aligned 336-byte
+// columns, never exceeded 2 TB/s).  A float4 holds 4 consecutive classes of one column (or its reg/wh group,
+// which is skipped); the FAST PATH only asks "any of the 4 >= the image's running logit bound".  A cell above
+// the bound takes the SLOW PATH: its 3x3 (x, class) window is read back through L1/L2 (the neighbouring
+// columns are +-336 B away) and tested exactly.
+constexpr int kCtThreads = 256;
+constexpr int kCtUnroll = 4;
+
+__global__ void __launch_bounds__(kCtThreads, 4) centernet_tiles_kernel(const __grid_constant__ CnParams p) {
+  __shared__ uint64_t sh_keys[kCtThreads / 32][kCtKeyStage];
+  __shared__ int sh_wcnt[kCtThreads / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int kWarps = kCtThreads / 32;
+  const int W = p.W, nc = p.nc, Cf = p.nc + 4;
+  const int cf4 = Cf >> 2, nc4 = nc >> 2;  // float4 groups per column; group nc4 is reg/wh
+  const int r32 = 32 % cf4;
+  uint64_t* keys = sh_keys[warp];
+  int* wcnt = &sh_wcnt[warp];
+  if (lane == 0) *wcnt = 0;
+  __syncwarp();
+
+  const int stride = gridDim.x * kWarps;
+  const int first = p.tile_lo + blockIdx.x * kWarps + warp;
+  const int n_my = first < p.total_tiles ? (p.total_tiles - first + stride - 1) / stride : 0;
+
+  // the image's bound is fetched one unit ahead (its L2 round trip hides behind the current unit); the first
+  // units read it directly so that only ONE wave runs without a bound
+  float thr_pf = -INFINITY;
+  for (int i = 0; i < n_my; ++i) {
+    int b, y, x0, x1, xlo, xhi;
+    ct_tile_info(p, first + i * stride, b, y, x0, x1, xlo, xhi);
+    if (i < 3) thr_pf = *reinterpret_cast<volatile float*>(p.tau_logit + b);
+    const float thr = thr_pf - kCnTieEps;
+    if (i + 1 < n_my) thr_pf = *reinterpret_cast<volatile float*>(p.tau_logit + (first + (i + 1) * stride) % p.B);
+    const float* row = p.pred + ((size_t)b * p.H + y) * (size_t)W * Cf;  // column x of the row: row + x * Cf
+    const float4* src = reinterpret_cast<const float4*>(row + (size_t)x0 * Cf);
+    const int n4 = (x1 - x0) * cf4;
+    int mod = lane % cf4;  // (group index within its column) of this lane's next float4
+    const float4 kNone = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    float4 cur[kCtUnroll], nxt[kCtUnroll];
+#pragma unroll
+    for (int u = 0; u < kCtUnroll; ++u) {
+      const int idx = u * 32 + lane;
+      cur[u] = idx < n4 ? __ldg(src + idx) : kNone;
+    }
+    for (int it = 0; it < n4; it += 32 * kCtUnroll) {
+      // software pipeline: the next batch is in flight while this one is tested
+#pragma unroll
+      for (int u = 0; u < kCtUnroll; ++u) {
+        const int idx = it + 32 * kCtUnroll + u * 32 + lane;
+        nxt[u] = idx < n4 ? __ldg(src + idx) : kNone;
+      }
+#pragma unroll
+      for (int u = 0; u < kCtUnroll; ++u) {
+        const float4 t = cur[u];
+        const bool hit = mod != nc4 && fmaxf(fmaxf(t.x, t.y), fmaxf(t.z, t.w)) >= thr;
+        if (__any_sync(0xffffffffu, hit)) {  // rare once the bound is tight
+          if (hit) {
+            const int idx = it + u * 32 + lane;
+            const int x = x0 + idx / cf4, c0 = 4 * mod;
+            if (t.x >= thr) ct_test_cell(row, x, c0, t.x, y, W, nc, Cf, keys, wcnt);
+            if (t.y >= thr) ct_test_cell(row, x, c0 + 1, t.y, y, W, nc, Cf, keys, wcnt);
+            if (t.z >= thr) ct_test_cell(row, x, c0 + 2, t.z, y, W, nc, Cf, keys, wcnt);
+            if (t.w >= thr) ct_test_cell(row, x, c0 + 3, t.w, y, W, nc, Cf, keys, wcnt);
+          }
+          __syncwarp();
+          if (*wcnt > kCtKeyStage - 128) ct_flush(p, b, keys, wcnt);  // room for one more load of <= 128 cells
+        }
+        mod += r32;
+        if (mod >= cf4) mod -= cf4;
+      }
+#pragma unroll
+      for (int u = 0; u < kCtUnroll; ++u) cur[u] = nxt[u];
+    }
+    ct_flush(p, b, keys, wcnt);
+  }
+}
+
+// images whose list overflowed in the tile kernel are reset and flagged for the exact row kernel
+__global__ void centernet_redo_mark_kernel(const CnParams p) {
+  const int b = blockIdx.x;
+  const bool flag = *p.redo_any != 0 && p.list_count[b] > p.list_cap;
+  if (threadIdx.x == 0) p.redo[b] = flag ? 1 : 0;
+  if (!flag) return;
+  for (int i = threadIdx.x; i < kCnBins; i += blockDim.x) p.hist[(size_t)b * kCnBins + i] = 0u;
+  if (threadIdx.x == 0) {
+    p.list_count[b] = 0;
+    p.tau[b] = ~0ull;
+    p.tau_logit[b] = -INFINITY;
+  }
+}
+
 __global__ void __launch_bounds__(kCnAThreads, 2) centernet_peaks_kernel(const __grid_constant__ CnParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int W = p.W, nc = p.nc, Cf = p.nc + 4;
@@ -167,7 +373,8 @@ __global__ void __launch_bounds__(kCnAThreads, 2) centernet_peaks_kernel(const _
   __shared__ int sh_base;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int rows_total = p.B * p.H;
+  if (p.redo_any && *p.redo_any == 0) return;  // exact redo pass: nothing overflowed (the common case)
+  const int rows_total = p.B * (p.row_hi - p.row_lo);
   const int n_my = ((int)blockIdx.x < rows_total) ? (rows_total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
   if (tid == 0) {
@@ -179,7 +386,7 @@ __global__ void __launch_bounds__(kCnAThreads, 2) centernet_peaks_kernel(const _
 
   auto issue = [&](int i) {  // thread 0 only; rows are handed out image-fastest so that concurrently
     const int r = blockIdx.x + i * gridDim.x;  // running CTAs work on different images
-    const int b = r % p.B, y = r / p.B;
+    const int b = r % p.B, y = p.row_lo + r / p.B;
     mbar_arrive_expect_tx(&bar[i & 1], row_bytes);
     bulk_g2s(ring + (size_t)(i & 1) * row_floats, p.pred + ((size_t)b * p.H + y) * row_floats, row_bytes, &bar[i & 1]);
   };
@@ -190,7 +397,7 @@ __global__ void __launch_bounds__(kCnAThreads, 2) centernet_peaks_kernel(const _
 
   for (int i = 0; i < n_my; ++i) {
     const int r = blockIdx.x + i * gridDim.x;
-    const int b = r % p.B, y = r / p.B;
+    const int b = r % p.B, y = p.row_lo + r / p.B;
     const float* row = ring + (size_t)(i & 1) * row_floats;
     int& sh_cnt = sh_cnt2[i & 1];
     if (tid == 0) sh_cnt = 0;
@@ -199,7 +406,7 @@ __global__ void __launch_bounds__(kCnAThreads, 2) centernet_peaks_kernel(const _
     mbar_wait(&bar[i & 1], (uint32_t)(i >> 1) & 1u);
     __syncthreads();
 
-    cn_scan_columns(row, 0, W, y, W, nc, Cf, thr, tau, keys, &sh_cnt);
+    if (!p.redo || p.redo[b]) cn_scan_columns(row, 0, W, y, W, nc, Cf, thr, tau, keys, &sh_cnt);  // uniform
     __syncthreads();
     int n_r = sh_cnt;
     if (n_r > kCnStage) {
@@ -506,6 +713,7 @@ size_t centernet_workspace_bytes(int B, int H, int W, int nc, int K) {
   size_t s = 256;
   s += ((size_t)B * 8 + 255) & ~(size_t)255;                          // tau
   s += ((size_t)B * 4 + 255) & ~(size_t)255;                          // list_count
+  s += ((size_t)(B + 1) * 4 + 255) & ~(size_t)255;                    // redo flags + redo_any
   s += ((size_t)B * 4 + 255) & ~(size_t)255;                          // tau_logit
   s += ((size_t)B * 1024 * 4 + 255) & ~(size_t)255;                   // hist
   s += ((size_t)B * (size_t)H * K * 8 + 255) & ~(size_t)255;          // list
@@ -571,6 +779,9 @@ int centernet_launch(const float* pred, int B, int H, int W, int nc, int K, floa
   w += ((size_t)B * 8 + 255) & ~(size_t)255;
   p.list_count = reinterpret_cast<int32_t*>(w);
   w += ((size_t)B * 4 + 255) & ~(size_t)255;
+  p.redo = reinterpret_cast<int32_t*>(w);
+  p.redo_any = p.redo + B;
+  w += ((size_t)(B + 1) * 4 + 255) & ~(size_t)255;
   p.tau_logit = reinterpret_cast<float*>(w);
   w += ((size_t)B * 4 + 255) & ~(size_t)255;
   p.hist = reinterpret_cast<uint32_t*>(w);
@@ -584,13 +795,86 @@ int centernet_launch(const float* pred, int B, int H, int W, int nc, int K, floa
   CVPP_CUDA_TRY(cudaMemsetAsync(p.list_count, 0, reinterpret_cast<uintptr_t>(p.list) - reinterpret_cast<uintptr_t>(p.list_count), stream));
   CVPP_CUDA_TRY(cudaMemsetD32Async_compat(p.tau_logit, 0xff800000u, (size_t)B, stream));
 
-  // pass A shared memory: 2 row stages + the key stage + 2 barriers; two CTAs per SM when they fit
+  // ---- pass A, primary: independent warps over column tiles (needs 16-byte aligned columns: (nc + 4) % 4 == 0)
+  bool tiles_done = false;
+  if (((nc + 4) & 3) == 0) {
+    const int cf = nc + 4;
+    // unit = a quarter row or ~10 KB, whichever is smaller (enough units for the image-fastest hand-out)
+    int tc = (W + 3) / 4;
+    const int tc_cap = (int)(12288 / ((size_t)cf * 4));
+    if (tc > tc_cap) tc = tc_cap;
+    if (tc < 1) tc = 1;
+    p.tile_cols = tc;
+    p.tiles_per_row = (W + tc - 1) / tc;
+    p.total_tiles = B * H * p.tiles_per_row;
+    p.tile_stage_floats = 0;
+    int ctas_per_sm = 1;
+    CVPP_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, centernet_tiles_kernel, kCtThreads, 0));
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
+    constexpr int kW = kCtThreads / 32;
+    // Cold start: without a bound every cell takes the slow path and every peak is emitted, and a full-width
+    // first wave (thousands of warps) would do that for ~15 % of the tensor and overflow the lists.  A first
+    // SMALL launch covers the first two rows of every image (units are image-fastest) and leaves a bound
+    // (K-th best of ~2 rows of peaks) behind; the second launch streams the rest.
+    int boot_rows = 4;
+    if (boot_rows > H) boot_rows = H;
+    {
+      // the exact row kernel on the first rows: every CTA takes ~one row, sorts its peaks and leaves the image's
+      // bound (tau / tau_logit / histogram) and <= K keys per row behind
+      const size_t smem_boot = ((2 * row_bytes + 127) & ~(size_t)127) + (size_t)kCnStage * 8 + 16;
+      if (smem_boot > (size_t)di.max_smem || K + nc > kCnStage) {
+        set_error("centernet: a row of %d x %d cells (K=%d) does not fit the shared-memory pipeline", W, nc + 4, K);
+        return CVPP_ERR_UNSUPPORTED;
+      }
+      static unsigned long long done_bt = 0;
+      static int bytes_bt = 0;
+      if ((int)smem_boot > bytes_bt) {
+        done_bt = 0;
+        bytes_bt = (int)smem_boot;
+      }
+      rc = ensure_smem_attr(reinterpret_cast<const void*>(centernet_peaks_kernel), bytes_bt, di.device, &done_bt);
+      if (rc != CVPP_OK) return rc;
+      CnParams pa = p;
+      pa.redo = nullptr;
+      pa.redo_any = nullptr;
+      pa.row_lo = 0;
+      pa.row_hi = boot_rows;
+      pa.key_cap = kCnStage;
+      const int rows_b = B * boot_rows;
+      const int cps = (2 * (smem_boot + 1024) <= (size_t)di.max_smem + 1024) ? 2 : 1;
+      centernet_peaks_kernel<<<rows_b < cps * di.sms ? rows_b : cps * di.sms, kCnAThreads, smem_boot, stream>>>(pa);
+      CVPP_CUDA_TRY(cudaGetLastError());
+    }
+    const int boot_units = boot_rows * p.tiles_per_row * B;
+    if (boot_units < p.total_tiles) {
+      CnParams pb2 = p;
+      pb2.tile_lo = boot_units;
+      const int rest = p.total_tiles - boot_units;
+      const int warps_needed = (rest + kW - 1) / kW;
+      const int grid_t = warps_needed < ctas_per_sm * di.sms ? warps_needed : ctas_per_sm * di.sms;
+      centernet_tiles_kernel<<<grid_t, kCtThreads, 0, stream>>>(pb2);
+      CVPP_CUDA_TRY(cudaGetLastError());
+    }
+    centernet_redo_mark_kernel<<<B, 256, 0, stream>>>(p);  // flags (and resets) the images whose list overflowed
+    CVPP_CUDA_TRY(cudaGetLastError());
+    tiles_done = true;
+  }
+  CnParams pr = p;  // the exact row kernel: everything when the tile kernel could not run, else only flagged images
+  pr.row_lo = 0;
+  pr.row_hi = H;
+  if (!tiles_done) {
+    pr.redo = nullptr;
+    pr.redo_any = nullptr;
+  }
+
+  // pass A, exact (per-row cap K): 2 row stages + the key stage + 2 barriers; two CTAs per SM when they fit
   const size_t smem_a = ((2 * row_bytes + 127) & ~(size_t)127) + (size_t)kCnStage * 8 + 16;
   if (smem_a > (size_t)di.max_smem || K + nc > kCnStage) {
     set_error("centernet: a row of %d x %d cells (K=%d) does not fit the shared-memory pipeline", W, nc + 4, K);
     return CVPP_ERR_UNSUPPORTED;
   }
   p.key_cap = kCnStage;
+  pr.key_cap = kCnStage;
   static unsigned long long done_a = 0;
   static int bytes_a = 0;
   if ((int)smem_a > bytes_a) {
@@ -602,7 +886,7 @@ int centernet_launch(const float* pred, int B, int H, int W, int nc, int K, floa
   const int rows = B * H;
   const int ctas_per_sm = (2 * (smem_a + 1024) <= (size_t)di.max_smem + 1024) ? 2 : 1;
   const int grid_a = rows < ctas_per_sm * di.sms ? rows : ctas_per_sm * di.sms;
-  centernet_peaks_kernel<<<grid_a, kCnAThreads, smem_a, stream>>>(p);
+  centernet_peaks_kernel<<<grid_a, kCnAThreads, smem_a, stream>>>(pr);
   CVPP_CUDA_TRY(cudaGetLastError());
 
   // pass B shared memory: sort buffer when it fits (<= 16384 keys), else the global scratch rows

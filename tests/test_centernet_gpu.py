@@ -108,3 +108,27 @@ def test_stage_b_exact_and_edge_cases():
     keep = oracle.diou_nms(mb, ms, 0.5)
     assert np.array_equal(classes, mc[keep].astype(np.int64))
     assert np.all(np.abs(scores - ms[keep]) <= SCORE_RTOL * ms[keep])
+
+
+def test_list_overflow_is_redone_exactly():
+    """Dense maps overflow the tile kernel's candidate list (no per-tile cap): the flagged images are redone by
+    the exact row kernel.  A perfectly flat heatmap makes every cell a peak with the same score, so the top K are
+    the K lowest flat indices (tie rule: lower index first); a small K on a random map overflows H*K as well."""
+    H = W = 32
+    nc = 8
+    pred = torch.zeros((2, H, W, nc + 4), device=DEV)
+    pred[..., :nc] = 0.3
+    pred[..., nc:nc + 2] = 0.5
+    pred[..., nc + 2:] = 2.0
+    det = ops.centernet_decode(pred, 50, 0.001)
+    assert det.count.tolist() == [50, 50]
+    flat = (det.pixel.long() * nc + det.cls.long()).cpu()
+    assert torch.equal(flat[0], torch.arange(50)) and torch.equal(flat[1], torch.arange(50))
+    # random map, tiny K: H*K = 64 list slots, hundreds of peaks before a bound exists
+    p2 = synth.centernet_pred(77, 2, 32, 32, 8)
+    ref = oracle.centernet_decode(p2, 2, 0.001, 0, False, 0.5, None)
+    got = ops.centernet_decode(torch.from_numpy(p2).to(DEV), 2, 0.001)
+    for b, (box, score, cls, pix) in enumerate(ref):
+        n = int(got.count[b])
+        assert n == len(cls) and np.array_equal(got.cls[b, :n].cpu().numpy(), cls)
+        assert np.array_equal(got.pixel[b, :n].cpu().numpy(), pix)
