@@ -64,6 +64,8 @@ _PROTOS = {
     "cvpp_yolov3_predict_bbox": (c_int, [c_vp, c_int, c_int, c_int, c_int, P(c_f32), c_vp, c_vp, c_vp, c_vp, c_vp]),
     "cvpp_score_matrix_filter": (c_int, [c_vp, c_i64, c_int, c_f32, c_vp, c_vp, c_int, c_vp]),
     "cvpp_gather_feat": (c_int, [c_vp, c_vp, c_int, c_vp, c_int, c_i64, c_int, c_int, c_vp, c_vp, c_vp]),
+    "cvpp_letterbox_reverse": (c_int, [c_vp, c_i64, c_int, c_f32, c_f32, c_f32, c_f32, c_f32, c_vp, c_vp]),
+    "cvpp_centernet_suppress": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp]),
     "cvpp_detection_epilogue_allgather": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_i64, c_int, c_int,
                                                   c_vp, P(c_vp), c_int, c_int, c_vp]),
     "cvpp_detection_epilogue": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_i64, c_int, c_int, c_vp,

@@ -77,8 +77,10 @@ class CenterNetA:
     @staticmethod
     def _suppress_redundant_centers(heatmap, pool_size=3):
         """heatmap * (heatmap == maxpool(heatmap)).  Applied, like the reference, to the NHWC tensor as is,
-        so the window spans (x, class).  Dense helper kept for API parity; the fused
-        kernel never materialises it."""
+        so the window spans (x, class).  Dense helper kept for API parity (the fused
+        kernel never materialises it): pool_size 3 on a CUDA tensor runs cvpp_centernet_suppress."""
+        if pool_size == 3 and heatmap.is_cuda and heatmap.dim() == 4 and heatmap.dtype == torch.float32:
+            return ops.centernet_suppress(heatmap)
         pad = (pool_size - 1) // 2
         hmax = torch.nn.functional.max_pool2d(heatmap, kernel_size=pool_size, stride=1, padding=pad)
         return heatmap * (heatmap == hmax).to(torch.float32)

@@ -34,7 +34,11 @@ def reverse_letter_box_numpy(image_shape, input_shape, boxes, xywh=True):
 
 
 def reverse_letter_box(h, w, input_size, boxes, xywh=True):
-    """torch twin of reverse_letter_box_numpy."""
+    """torch twin of reverse_letter_box_numpy.  CUDA tensors go through cvpp_letterbox_reverse (one kernel);
+    CPU tensors (the reference also calls this on host tensors) keep the reference's eager arithmetic."""
+    if boxes.is_cuda and boxes.dtype == torch.float32 and boxes.shape[-1] == 4 and boxes.numel() > 0:
+        from ... import ops
+        return ops.letterbox_reverse(boxes, h, w, input_size, xywh)
     if xywh:
         out = torch.cat((boxes[..., 0:2] - boxes[..., 2:4] / 2, boxes[..., 0:2] + boxes[..., 2:4] / 2), dim=-1)
     else:

@@ -104,6 +104,10 @@ int detection_epilogue_launch(const float* det_box, const float* det_score, cons
                               int max_out, int64_t A, int layout, int box_mode, const float* letterbox, float* rows,
                               float* count_out, float* const* peer_dst, int n_peers, int slot, cudaStream_t stream);
 
+int letterbox_reverse_launch(const float* boxes, int64_t n, int xywh, float in_w, float in_h, float left, float top,
+                             float scale, float* out, cudaStream_t stream);
+int centernet_suppress_launch(const float* heat, int B, int H, int W, int C, float* out, cudaStream_t stream);
+
 static int force_generic() {
   const char* e = getenv("CVPP_FORCE_GENERIC");
   return e && e[0] == '1';
@@ -347,6 +351,15 @@ int cvpp_detection_epilogue_allgather(const float* det_box, const float* det_sco
   }
   return detection_epilogue_launch(det_box, det_score, det_cls, det_anchor, det_count, aux_dense, B, max_out, A, layout,
                                    box_mode, letterbox, nullptr, nullptr, peer_dst, n_peers, rank, (cudaStream_t)stream);
+}
+
+int cvpp_letterbox_reverse(const float* boxes, int64_t n, int xywh, float in_w, float in_h, float left, float top,
+                           float scale, float* out, cvpp_stream_t stream) {
+  return letterbox_reverse_launch(boxes, n, xywh, in_w, in_h, left, top, scale, out, (cudaStream_t)stream);
+}
+
+int cvpp_centernet_suppress(const float* heat, int B, int H, int W, int C, float* out, cvpp_stream_t stream) {
+  return centernet_suppress_launch(heat, B, H, W, C, out, (cudaStream_t)stream);
 }
 
 }  // extern "C"

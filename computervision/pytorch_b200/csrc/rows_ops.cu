@@ -365,4 +365,83 @@ int detection_epilogue_launch(const float* det_box, const float* det_score, cons
   return CVPP_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// letterbox_reverse: reverse_letter_box (core/utils/image_process.py:100-129) on n boxes, one thread each.
+// The scalars (in_w, in_h, left, top, scale) are computed by the caller in double like the reference and
+// passed as fp32 (the reference multiplies fp32 tensors by Python floats, i.e. fp32 scalars).
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+letterbox_reverse_kernel(const float4* __restrict__ boxes, int64_t n, int xywh, float in_w, float in_h, float left, float top,
+                         float scale, float4* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 b = boxes[i];
+  if (xywh) {  // (cx, cy, w, h) -> c -/+ wh / 2 (:112-113)
+    const float hw = fmul(b.z, 0.5f), hh = fmul(b.w, 0.5f);
+    b = make_float4(fsub(b.x, hw), fsub(b.y, hh), fadd(b.x, hw), fadd(b.y, hh));
+  }
+  b.x = fmul(fsub(fmul(b.x, in_w), left), scale);  // * input size, - padding, * scale (:116-128)
+  b.z = fmul(fsub(fmul(b.z, in_w), left), scale);
+  b.y = fmul(fsub(fmul(b.y, in_h), top), scale);
+  b.w = fmul(fsub(fmul(b.w, in_h), top), scale);
+  out[i] = b;
+}
+
+int letterbox_reverse_launch(const float* boxes, int64_t n, int xywh, float in_w, float in_h, float left, float top,
+                             float scale, float* out, cudaStream_t stream) {
+  if (n < 0 || (n > 0 && (!boxes || !out))) {
+    set_error("letterbox_reverse: NULL pointer or negative n");
+    return CVPP_ERR_INVALID_ARG;
+  }
+  if ((reinterpret_cast<uintptr_t>(boxes) | reinterpret_cast<uintptr_t>(out)) & 15u) {
+    set_error("letterbox_reverse: boxes / out must be 16-byte aligned");
+    return CVPP_ERR_ALIGNMENT;
+  }
+  if (n == 0) return CVPP_OK;
+  letterbox_reverse_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const float4*>(boxes), n, xywh, in_w,
+                                                                          in_h, left, top, scale, reinterpret_cast<float4*>(out));
+  CVPP_CUDA_TRY(cudaGetLastError());
+  return CVPP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// centernet_suppress: CenterNetA._suppress_redundant_centers (core/algorithms/centernet.py:316-326), dense:
+// out = heat * (heat == maxpool3x3(heat)) with the pool applied to the NHWC tensor as the reference does, i.e.
+// over (x, channel) of every image row, -inf padding.  One thread per element.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+centernet_suppress_kernel(const float* __restrict__ heat, int64_t rows, int W, int C, float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t per_row = (int64_t)W * C;
+  if (i >= rows * per_row) return;
+  const int64_t r = i / per_row;
+  const int e = (int)(i - r * per_row);
+  const int x = e / C, c = e - x * C;
+  const float* q = heat + r * per_row;
+  const float v = q[e];
+  float m = v;
+  for (int dx = -1; dx <= 1; ++dx) {
+    const int xx = x + dx;
+    if (xx < 0 || xx >= W) continue;
+    for (int dc = -1; dc <= 1; ++dc) {
+      const int cc = c + dc;
+      if (cc < 0 || cc >= C) continue;
+      m = fmaxf(m, __ldg(q + xx * C + cc));
+    }
+  }
+  out[i] = v == m ? v : fmul(v, 0.0f);  // heatmap * keep.float(): v * 1 or v * 0 (keeps the sign of zero / NaN rules)
+}
+
+int centernet_suppress_launch(const float* heat, int B, int H, int W, int C, float* out, cudaStream_t stream) {
+  if (B < 0 || H < 1 || W < 1 || C < 1 || !heat || !out) {
+    set_error("centernet_suppress: NULL pointer or bad sizes");
+    return CVPP_ERR_INVALID_ARG;
+  }
+  const int64_t total = (int64_t)B * H * W * C;
+  if (total == 0) return CVPP_OK;
+  centernet_suppress_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(heat, (int64_t)B * H, W, C, out);
+  CVPP_CUDA_TRY(cudaGetLastError());
+  return CVPP_OK;
+}
+
 }  // namespace cvpp

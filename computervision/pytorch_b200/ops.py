@@ -558,6 +558,37 @@ def detection_epilogue_allgather(det: Detections, layout: int, peer_ptrs: Sequen
                                                            int(box_mode), _ptr(letterbox), arr, n, int(rank), _stream(dev)))
 
 
+def letterbox_reverse(boxes: torch.Tensor, h: float, w: float, input_size: Sequence[int], xywh: bool = True) -> torch.Tensor:
+    """cvpp_letterbox_reverse: reverse_letter_box on CUDA boxes (..., 4) -> (..., 4) corners in original pixels."""
+    _require_cuda(boxes, "boxes")
+    shape = boxes.shape
+    flat = boxes.reshape(-1, 4).contiguous()
+    if flat.data_ptr() % 16:
+        flat = flat.clone()
+    out = torch.empty_like(flat)
+    scale = max(h / input_size[0], w / input_size[1])        # Python doubles, like the reference (:115-119)
+    top = (input_size[0] - h / scale) // 2
+    left = (input_size[1] - w / scale) // 2
+    with torch.cuda.device(flat.device):
+        check(_lib.lib().cvpp_letterbox_reverse(_ptr(flat), int(flat.shape[0]), int(bool(xywh)), float(input_size[1]),
+                                                float(input_size[0]), float(left), float(top), float(scale), _ptr(out),
+                                                _stream(flat.device)))
+    return out.reshape(shape)
+
+
+def centernet_suppress(heat: torch.Tensor) -> torch.Tensor:
+    """cvpp_centernet_suppress: heat (B, H, W, C) -> heat * (heat == maxpool3x3 over (x, channel))."""
+    _require_cuda(heat, "heatmap")
+    if heat.dim() != 4:
+        raise ValueError(f"heatmap must be (B, H, W, C), got {tuple(heat.shape)}")
+    heat = heat.contiguous()
+    B, H, W, C = (int(v) for v in heat.shape)
+    out = torch.empty_like(heat)
+    with torch.cuda.device(heat.device):
+        check(_lib.lib().cvpp_centernet_suppress(_ptr(heat), B, H, W, C, _ptr(out), _stream(heat.device)))
+    return out
+
+
 def correct_boxes_params(image_hw: Sequence[Tuple[int, int]], input_hw: Sequence[int], letterbox_image: bool,
                          device) -> torch.Tensor:
     """The (B, 5) table cvpp_detection_epilogue wants for yolo_correct_boxes (image_process.py:161-181)."""

@@ -345,6 +345,23 @@ CVPP_API int cvpp_detection_epilogue_allgather(const float* det_box, const float
                                                int box_mode, const float* letterbox, float* const* peer_dst,
                                                int n_peers, int rank, cvpp_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * reverse_letter_box (core/utils/image_process.py:100-129) on n boxes (n, 4): xywh != 0 converts (cx,cy,w,h)
+ * to corners first; then * (in_w, in_h), - (left, top), * scale, one fp32 rounding per step.  The five scalars
+ * are the reference's Python doubles cast to fp32 by the caller.  out may alias boxes.
+ * ------------------------------------------------------------------------------------------- */
+CVPP_API int cvpp_letterbox_reverse(const float* boxes, int64_t n, int xywh, float in_w, float in_h, float left,
+                                    float top, float scale, float* out, cvpp_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * CenterNetA._suppress_redundant_centers (core/algorithms/centernet.py:316-326), dense form:
+ * out = heat * (heat == maxpool3x3(heat)) with the pool over (x, channel) of each image row of the
+ * (B, H, W, C) NHWC tensor, exactly as the reference's MaxPool2d sees it.  (The fused
+ * cvpp_centernet_decode never materialises this tensor.)
+ * ------------------------------------------------------------------------------------------- */
+CVPP_API int cvpp_centernet_suppress(const float* heat, int B, int H, int W, int C, float* out,
+                                     cvpp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

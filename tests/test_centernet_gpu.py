@@ -132,3 +132,20 @@ def test_list_overflow_is_redone_exactly():
         n = int(got.count[b])
         assert n == len(cls) and np.array_equal(got.cls[b, :n].cpu().numpy(), cls)
         assert np.array_equal(got.pixel[b, :n].cpu().numpy(), pix)
+
+
+def test_dense_helpers_match_torch():
+    """_suppress_redundant_centers (cvpp_centernet_suppress) and reverse_letter_box (cvpp_letterbox_reverse)
+    against the reference's own eager arithmetic, bit for bit."""
+    from computervision.pytorch_b200.core.utils.image_process import reverse_letter_box
+    g = torch.Generator(device=DEV).manual_seed(3)
+    heat = torch.rand((2, 9, 17, 7), generator=g, device=DEV)
+    heat[0, 3, 5, 2] = heat[0, 3, 6, 3]                                   # a tie between neighbours: both are kept
+    got = CenterNetA._suppress_redundant_centers(heat)
+    hmax = torch.nn.functional.max_pool2d(heat, kernel_size=3, stride=1, padding=1)
+    assert torch.equal(got, heat * (heat == hmax).float())
+    boxes = torch.rand((37, 4), generator=g, device=DEV)
+    for xywh in (True, False):
+        for (h, w), inp in (((480, 640), (384, 384)), ((1080, 1920), (640, 640)), ((333, 500), (416, 416))):
+            want = reverse_letter_box(h, w, list(inp), boxes.cpu(), xywh=xywh)   # the reference's eager CPU arithmetic
+            assert torch.equal(reverse_letter_box(h, w, list(inp), boxes, xywh=xywh).cpu(), want)
