@@ -1,6 +1,9 @@
 set -x
-python bench.py --steps 50 --warmup 5 > gpurun_out/bench_r1_s3.json 2> gpurun_out/bench_r1_s3.err
-python bench.py --steps 3 --warmup 3 --no-cpu --no-graph > gpurun_out/plain_s3.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r1_s3.csv python bench.py --steps 3 --warmup 3 --no-cpu --no-graph > gpurun_out/ncu_s3a.log 2>&1
-python bench.py --steps 3 --warmup 3 --no-cpu --no-graph > gpurun_out/plain_s3b.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:'yolov8_decode_stream|nms2_kernel' -s 6 -c 2 -o gpurun_out/prof_r1_s3 -f python bench.py --steps 3 --warmup 3 --no-cpu --no-graph > gpurun_out/ncu_s3b.log 2>&1
-tail -3 gpurun_out/ncu_s3b.log
-cat gpurun_out/bench_r1_s3.json; cat gpurun_out/bench_r1_s3.err | tail -5
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke_r1_s4.log 2>&1; tail -1 gpurun_out/smoke_r1_s4.log
+python bench.py --steps 50 --warmup 5 > gpurun_out/bench_r1_s4.json 2> gpurun_out/bench_r1_s4.err
+python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_ref_r1_s4.json 2>&1
+python tools/bench_paths.py --iters 30 > gpurun_out/paths_r1_s4.jsonl 2> gpurun_out/paths_r1_s4.err
+python bench.py --steps 3 --warmup 3 --no-cpu --no-graph > gpurun_out/plain_s4.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r1_s4.csv python bench.py --steps 3 --warmup 3 --no-cpu --no-graph > gpurun_out/ncu_s4a.log 2>&1
+python bench.py --steps 3 --warmup 3 --no-cpu --no-graph > gpurun_out/plain_s4b.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:'yolov8_decode_stream|nms2_kernel' -s 6 -c 2 -o gpurun_out/prof_r1_s4 -f python bench.py --steps 3 --warmup 3 --no-cpu --no-graph > gpurun_out/ncu_s4b.log 2>&1
+tail -2 gpurun_out/ncu_s4b.log
+cat gpurun_out/bench_r1_s4.json | cut -c1-300; cat gpurun_out/bench_ref_r1_s4.json | cut -c1-200
