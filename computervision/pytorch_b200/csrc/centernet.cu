@@ -19,6 +19,8 @@
 // they sort with the hybrid bitonic network).  Each row appends at most K keys to the image's list.
 // Pass B (one CTA per image): sort the list, take K, gather reg/wh, assemble + clamp boxes, score
 // mask, optional class-agnostic DIoU-NMS (greedy, one barrier per candidate), letterbox inverse.
+#include <cstdlib>
+
 #include "cvpp_common.cuh"
 
 namespace cvpp {
@@ -29,7 +31,7 @@ struct CnParams {
   const float* pred;
   int B, H, W, nc, K;
   unsigned long long* tau;  // [B] running upper bound of the K-th best key
-  float* tau_logit;         // [B] the same bound as a heat LOGIT (conservative), for the cheap in-loop test
+  int* tau_logit;           // [B] the same bound as a heat LOGIT (conservative, cn_enc-encoded), for the cheap in-loop test
   uint32_t* hist;           // [B][kCnBins] scores of every emitted peak, best bin first
   uint64_t* list;           // [B][list_cap]
   int32_t* list_count;      // [B]
@@ -62,6 +64,9 @@ __device__ __forceinline__ uint64_t cn_key(float score, uint32_t flat) {
 // ---------------------------------------------------------------------------------------------
 // pass A
 // ---------------------------------------------------------------------------------------------
+constexpr int kCnPad = 32;          // per-image scalars (tau, tau_logit, list_count) sit 128 B apart: they are
+                                    // hammered by atomics and bound reads from every CTA, and 64 of them packed into
+                                    // two cache lines serialise on one L2 slice
 constexpr int kCnBins = 1024;       // per-image histogram of emitted peak scores (float-bit bins, best first)
 constexpr int kCnGroup = 30;        // classes per warp item (lanes 1..30; lanes 0 and 31 are halo classes)
 constexpr float kCnTieEps = 1e-3f;  // logits closer than this may round to the same sigmoid
@@ -82,14 +87,20 @@ __device__ __forceinline__ float cn_bin_logit_bound(int e) {
   return logf(s / (1.0f - s)) - 4.0f * kCnTieEps;
 }
 
-__device__ __forceinline__ void atomic_max_float(float* addr, float v) {
-  int* a = reinterpret_cast<int*>(addr);
-  int old = *reinterpret_cast<volatile int*>(a);
-  while (__int_as_float(old) < v) {
-    const int seen = atomicCAS(a, old, __float_as_int(v));
-    if (seen == old) break;
-    old = seen;
-  }
+// The logit bound is stored as a signed int whose order is the floats' order, so it can be raised with a
+// fire-and-forget atomicMax instead of a compare-and-swap loop (two L2 round trips on the critical path).
+__device__ __forceinline__ int cn_enc(float f) {
+  const int i = __float_as_int(f);
+  return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__device__ __forceinline__ float cn_dec(int e) { return __int_as_float(e >= 0 ? e : e ^ 0x7fffffff); }
+__device__ __forceinline__ void atomic_max_float(int* addr, float v) { atomicMax(addr, cn_enc(v)); }
+// L2 read of a value other CTAs keep raising: never cached in L1, never merged with an earlier read, and - unlike
+// a `volatile` access - free to be scheduled among the streaming loads (ld.volatile serialised them: 2x slower)
+__device__ __forceinline__ int ld_cg_s32(const int* p) {
+  int v;
+  asm volatile("ld.global.cg.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
 }
 
 constexpr int kCnAThreads = 512;  // pass A: 16 warps, two CTAs per SM (four 43 KB rows in flight per SM)
@@ -197,11 +208,14 @@ __device__ __forceinline__ void ct_flush(const CnParams& p, int b, uint64_t* key
   __syncwarp();
   const int n = min(*wcnt, kCtKeyStage);
   if (n == 0) return;
-  int base = 0;
-  if (lane == 0) base = atomicAdd(p.list_count + b, n);
-  base = __shfl_sync(0xffffffffu, base, 0);
   uint64_t* dst = p.list + (size_t)b * p.list_cap;
   uint32_t* hist = p.hist + (size_t)b * kCnBins;
+  // the list reservation and the read of the histogram's best 128 bins are issued together: ONE L2 round trip
+  // for the whole flush (the bound below is raised with a fire-and-forget atomicMax)
+  int base = 0;
+  if (lane == 0) base = atomicAdd(p.list_count + b * kCnPad, n);
+  uint4 h0 = __ldcg(reinterpret_cast<const uint4*>(hist + 4 * lane));
+  base = __shfl_sync(0xffffffffu, base, 0);
   for (int t = lane; t < n; t += 32) {
     const uint64_t k = keys[t];
     if (base + t < p.list_cap) dst[base + t] = k;
@@ -209,10 +223,10 @@ __device__ __forceinline__ void ct_flush(const CnParams& p, int b, uint64_t* key
   }
   if (lane == 0 && base + n > p.list_cap) atomicExch(p.redo_any, 1);  // list overflow: the image is redone exactly
   // tighten the image's bound: first score bin (best first) at which the cumulative count of emitted peaks
-  // reaches K (counts only grow, so a stale read is conservative)
+  // reaches K (counts only grow, so a stale read - it misses this flush's own keys - is conservative)
   int run = 0, edge = -1;
   for (int b0 = 0; b0 < kCnBins && edge < 0; b0 += 32 * 4) {
-    const uint4 h = __ldcg(reinterpret_cast<const uint4*>(hist + b0 + 4 * lane));
+    const uint4 h = b0 == 0 ? h0 : __ldcg(reinterpret_cast<const uint4*>(hist + b0 + 4 * lane));
     const int mine = (int)(h.x + h.y + h.z + h.w);
     int incl = mine;
     for (int d = 1; d < 32; d <<= 1) {
@@ -239,7 +253,7 @@ __device__ __forceinline__ void ct_flush(const CnParams& p, int b, uint64_t* key
   }
   if (lane == 0 && edge >= 0) {
     const float bound = cn_bin_logit_bound(edge);
-    if (bound > -INFINITY) atomic_max_float(p.tau_logit + b, bound);
+    if (bound > -INFINITY) atomic_max_float(p.tau_logit + b * kCnPad, bound);
   }
   __syncwarp();
   if (lane == 0) *wcnt = 0;
@@ -249,15 +263,15 @@ __device__ __forceinline__ void ct_flush(const CnParams& p, int b, uint64_t* key
 // exact test of one cell above the bound (same arithmetic as the row kernel's slow path), key -> warp stage
 __device__ __noinline__ void ct_test_cell(const float* row, int x, int c, float v, int y, int W, int nc, int Cf,
                                           uint64_t* keys, int* wcnt) {
-  float m = v;  // 3x3 window maximum over (x-1..x+1, c-1..c+1), -inf outside the map (max-pool padding)
-  for (int dx = -1; dx <= 1; ++dx) {
-    const int xx = x + dx;
-    if (xx < 0 || xx >= W) continue;
-    const float* q = row + xx * Cf + c;
-    if (c > 0) m = fmaxf(m, q[-1]);
-    m = fmaxf(m, q[0]);
-    if (c + 1 < nc) m = fmaxf(m, q[1]);
-  }
+  // 3x3 window maximum over (x-1..x+1, c-1..c+1) with -inf padding == the maximum over the window clamped to
+  // the map (a clamped index only repeats a cell that is in the window anyway).  Eight independent loads: one
+  // L1/L2 latency instead of eight.
+  const int xm = max(x - 1, 0), xp = min(x + 1, W - 1), cm = max(c - 1, 0), cp = min(c + 1, nc - 1);
+  const float* r0 = row + xm * Cf;
+  const float* r1 = row + x * Cf;
+  const float* r2 = row + xp * Cf;
+  const float a0 = r0[cm], a1 = r0[c], a2 = r0[cp], b0 = r1[cm], b2 = r1[cp], d0 = r2[cm], d1 = r2[c], d2 = r2[cp];
+  const float m = fmaxf(fmaxf(fmaxf(fmaxf(a0, a1), fmaxf(a2, b0)), fmaxf(fmaxf(b2, d0), fmaxf(d1, d2))), v);
   bool peak = v >= m;
   if (!peak && !(m - v < kCnTieEps || v > 8.0f)) return;  // clearly below a neighbour: the common rejection
   const float sc = sigmoid_precise(v);
@@ -277,7 +291,7 @@ __device__ __noinline__ void ct_test_cell(const float* row, int x, int c, float 
 constexpr int kCtThreads = 256;
 constexpr int kCtUnroll = 4;
 
-__global__ void __launch_bounds__(kCtThreads, 4) centernet_tiles_kernel(const __grid_constant__ CnParams p) {
+__global__ void __launch_bounds__(kCtThreads, 3) centernet_tiles_kernel(const __grid_constant__ CnParams p) {
   __shared__ uint64_t sh_keys[kCtThreads / 32][kCtKeyStage];
   __shared__ int sh_wcnt[kCtThreads / 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -296,13 +310,13 @@ __global__ void __launch_bounds__(kCtThreads, 4) centernet_tiles_kernel(const __
 
   // the image's bound is fetched one unit ahead (its L2 round trip hides behind the current unit); the first
   // units read it directly so that only ONE wave runs without a bound
-  float thr_pf = -INFINITY;
+  int thr_pf = cn_enc(-INFINITY);
   for (int i = 0; i < n_my; ++i) {
     int b, y, x0, x1, xlo, xhi;
     ct_tile_info(p, first + i * stride, b, y, x0, x1, xlo, xhi);
-    if (i < 3) thr_pf = *reinterpret_cast<volatile float*>(p.tau_logit + b);
-    const float thr = thr_pf - kCnTieEps;
-    if (i + 1 < n_my) thr_pf = *reinterpret_cast<volatile float*>(p.tau_logit + (first + (i + 1) * stride) % p.B);
+    if (i < 3) thr_pf = ld_cg_s32(p.tau_logit + b * kCnPad);
+    const float thr = cn_dec(thr_pf) - kCnTieEps;
+    if (i + 1 < n_my) thr_pf = ld_cg_s32(p.tau_logit + ((first + (i + 1) * stride) % p.B) * kCnPad);
     const float* row = p.pred + ((size_t)b * p.H + y) * (size_t)W * Cf;  // column x of the row: row + x * Cf
     const float4* src = reinterpret_cast<const float4*>(row + (size_t)x0 * Cf);
     const int n4 = (x1 - x0) * cf4;
@@ -314,8 +328,14 @@ __global__ void __launch_bounds__(kCtThreads, 4) centernet_tiles_kernel(const __
       const int idx = u * 32 + lane;
       cur[u] = idx < n4 ? __ldg(src + idx) : kNone;
     }
+    float thr_b = thr;
+    int thr_bpf = cn_enc(-INFINITY);
     for (int it = 0; it < n4; it += 32 * kCtUnroll) {
-      // software pipeline: the next batch is in flight while this one is tested
+      // software pipeline: the next batch is in flight while this one is tested; the bound is refreshed the same
+      // way every batch (a fresher bound means fewer cells on the slow path and fewer keys to flush)
+      const float thr = fmaxf(thr_b, cn_dec(thr_bpf) - kCnTieEps);
+      thr_b = thr;
+      thr_bpf = ld_cg_s32(p.tau_logit + b * kCnPad);
 #pragma unroll
       for (int u = 0; u < kCtUnroll; ++u) {
         const int idx = it + 32 * kCtUnroll + u * 32 + lane;
@@ -347,17 +367,76 @@ __global__ void __launch_bounds__(kCtThreads, 4) centernet_tiles_kernel(const __
   }
 }
 
+// Cold start of the streaming scan: a GUESS of the image's bound from a 4096-cell sample of the heat logits - the
+// logit that about 6 of the samples exceed, i.e. ~0.15 % of the map (~2 000 cells at 128x128x80), far more than K
+// peaks.  The guess is only a filter: every peak at or above it is emitted, so the K best emitted peaks are the
+// image's K best whenever at least K were emitted, and centernet_redo_mark_kernel sends the image to the exact
+// row kernel otherwise.  (An exact bootstrap on the first rows cost 40 us; this costs ~3 us.)
+constexpr int kCsSamples = 4096;
+constexpr int kCsTop = 6;
+
+__global__ void __launch_bounds__(256) centernet_sample_bound_kernel(const CnParams p) {
+  __shared__ int sh_hist[1024];  // logit bins of 1/16 over [-32, 32)
+  __shared__ int sh_coarse[16];  // sums of 64 bins
+  const int b = blockIdx.x;
+  const int Cf = p.nc + 4;
+  const unsigned cells = (unsigned)p.H * p.W * p.nc;  // < 2^32 (checked at launch)
+  for (int i = threadIdx.x; i < 1024; i += blockDim.x) sh_hist[i] = 0;
+  __syncthreads();
+  unsigned step = cells / kCsSamples;
+  if (step < 1) step = 1;
+  step |= 1;  // odd stride: walks through all classes
+  const float* base = p.pred + (size_t)b * p.H * p.W * Cf;
+  float v[kCsSamples / 256];
+#pragma unroll
+  for (int s = 0; s < kCsSamples / 256; ++s) {  // all loads of a thread in flight at once
+    const unsigned idx = (unsigned)(threadIdx.x + 256 * s) * step;
+    const unsigned pixel = idx / (unsigned)p.nc;
+    v[s] = idx < cells ? __ldg(base + (size_t)pixel * Cf + (idx - pixel * p.nc)) : -INFINITY;
+  }
+#pragma unroll
+  for (int s = 0; s < kCsSamples / 256; ++s) {
+    if (v[s] > -INFINITY) {
+      int bin = (int)((fminf(fmaxf(v[s], -32.0f), 31.9f) + 32.0f) * 16.0f);
+      bin = bin < 0 ? 0 : (bin > 1023 ? 1023 : bin);
+      atomicAdd(&sh_hist[bin], 1);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 16) {
+    int t = 0;
+    for (int i = 0; i < 64; ++i) t += sh_hist[threadIdx.x * 64 + i];
+    sh_coarse[threadIdx.x] = t;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int acc = 0, blk = 15;
+    for (; blk > 0 && acc + sh_coarse[blk] < kCsTop; --blk) acc += sh_coarse[blk];
+    int bin = blk * 64 + 63;
+    for (; bin > blk * 64; --bin) {
+      acc += sh_hist[bin];
+      if (acc >= kCsTop) break;
+    }
+    // lower edge of that bin; when even all samples are fewer than kCsTop this ends at bin 0 = -32: no bound
+    p.tau_logit[b * kCnPad] = cn_enc(bin > 0 ? (float)bin * 0.0625f - 32.0f : -INFINITY);
+  }
+}
+
 // images whose list overflowed in the tile kernel are reset and flagged for the exact row kernel
 __global__ void centernet_redo_mark_kernel(const CnParams p) {
   const int b = blockIdx.x;
-  const bool flag = *p.redo_any != 0 && p.list_count[b] > p.list_cap;
+  // overflowed list, or fewer than K keys above the guessed bound (and the map has at least K cells at all)
+  const int n_keys = p.list_count[b * kCnPad];
+  const long long cells = (long long)p.H * p.W * p.nc;
+  const bool flag = n_keys > p.list_cap || (n_keys < p.K && cells >= p.K);
+  if (flag && threadIdx.x == 0) atomicExch(p.redo_any, 1);
   if (threadIdx.x == 0) p.redo[b] = flag ? 1 : 0;
   if (!flag) return;
   for (int i = threadIdx.x; i < kCnBins; i += blockDim.x) p.hist[(size_t)b * kCnBins + i] = 0u;
   if (threadIdx.x == 0) {
-    p.list_count[b] = 0;
-    p.tau[b] = ~0ull;
-    p.tau_logit[b] = -INFINITY;
+    p.list_count[b * kCnPad] = 0;
+    p.tau[b * kCnPad] = ~0ull;
+    p.tau_logit[b * kCnPad] = cn_enc(-INFINITY);
   }
 }
 
@@ -401,8 +480,8 @@ __global__ void __launch_bounds__(kCnAThreads, 2) centernet_peaks_kernel(const _
     const float* row = ring + (size_t)(i & 1) * row_floats;
     int& sh_cnt = sh_cnt2[i & 1];
     if (tid == 0) sh_cnt = 0;
-    unsigned long long tau = *reinterpret_cast<volatile unsigned long long*>(p.tau + b);
-    const float thr = *reinterpret_cast<volatile float*>(p.tau_logit + b) - kCnTieEps;
+    unsigned long long tau = *reinterpret_cast<volatile unsigned long long*>(p.tau + b * kCnPad);
+    const float thr = cn_dec(*reinterpret_cast<volatile int*>(p.tau_logit + b * kCnPad)) - kCnTieEps;
     mbar_wait(&bar[i & 1], (uint32_t)(i >> 1) & 1u);
     __syncthreads();
 
@@ -430,12 +509,12 @@ __global__ void __launch_bounds__(kCnAThreads, 2) centernet_peaks_kernel(const _
     const int n_emit = cn_truncate(keys, n_r, p.K, &sh_cnt);
     if (tid == 0) {
       if (cut || n_emit == p.K) {
-        atomicMin(p.tau + b, (unsigned long long)keys[p.K - 1]);
+        atomicMin(p.tau + b * kCnPad, (unsigned long long)keys[p.K - 1]);
         // the same bound in the logit domain: score of the row's K-th best peak
         const float s = __uint_as_float(0x7fffffffu - (uint32_t)(keys[p.K - 1] >> 32));
-        if (s > 0.0f && s < 1.0f) atomic_max_float(p.tau_logit + b, logf(s / (1.0f - s)) - 4.0f * kCnTieEps);
+        if (s > 0.0f && s < 1.0f) atomic_max_float(p.tau_logit + b * kCnPad, logf(s / (1.0f - s)) - 4.0f * kCnTieEps);
       }
-      if (n_emit > 0) sh_base = atomicAdd(p.list_count + b, n_emit);
+      if (n_emit > 0) sh_base = atomicAdd(p.list_count + b * kCnPad, n_emit);
     }
     if (n_emit == 0) continue;  // (uniform) nothing above the bound in this row: the common case
     __syncthreads();
@@ -479,7 +558,7 @@ __global__ void __launch_bounds__(kCnAThreads, 2) centernet_peaks_kernel(const _
       }
       if (lane == 0 && edge >= 0) {
         const float bound = cn_bin_logit_bound(edge);
-        if (bound > -INFINITY) atomic_max_float(p.tau_logit + b, bound);
+        if (bound > -INFINITY) atomic_max_float(p.tau_logit + b * kCnPad, bound);
       }
     }
     __syncthreads();
@@ -539,9 +618,9 @@ __global__ void __launch_bounds__(kCnThreads, 1) centernet_finalize_kernel(const
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.x;
   const int W = p.W, H = p.H, nc = p.nc, Cf = p.nc + 4;
-  int m = p.list_count[b];
+  int m = p.list_count[b * kCnPad];
   if (m > p.list_cap) m = p.list_cap;
-  const unsigned long long tau = p.tau[b];
+  const unsigned long long tau = p.tau[b * kCnPad];
   const uint64_t* src = p.list + (size_t)b * p.list_cap;
 
   // keep the keys that can still be among the K best, compacted into the sort buffer
@@ -711,10 +790,10 @@ size_t centernet_workspace_bytes(int B, int H, int W, int nc, int K) {
   (void)W;
   (void)nc;
   size_t s = 256;
-  s += ((size_t)B * 8 + 255) & ~(size_t)255;                          // tau
-  s += ((size_t)B * 4 + 255) & ~(size_t)255;                          // list_count
+  s += ((size_t)B * 32 * 8 + 255) & ~(size_t)255;                     // tau (padded, kCnPad)
+  s += ((size_t)B * 32 * 4 + 255) & ~(size_t)255;                     // list_count (padded)
   s += ((size_t)(B + 1) * 4 + 255) & ~(size_t)255;                    // redo flags + redo_any
-  s += ((size_t)B * 4 + 255) & ~(size_t)255;                          // tau_logit
+  s += ((size_t)B * 32 * 4 + 255) & ~(size_t)255;                     // tau_logit (padded)
   s += ((size_t)B * 1024 * 4 + 255) & ~(size_t)255;                   // hist
   s += ((size_t)B * (size_t)H * K * 8 + 255) & ~(size_t)255;          // list
   s += ((size_t)B * (size_t)cn_sort_cap(H, K) * 8 + 255) & ~(size_t)255;  // sort scratch
@@ -776,24 +855,24 @@ int centernet_launch(const float* pred, int B, int H, int W, int nc, int K, floa
   p.sort_cap = cn_sort_cap(H, K);
   uintptr_t w = (reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255;
   p.tau = reinterpret_cast<unsigned long long*>(w);
-  w += ((size_t)B * 8 + 255) & ~(size_t)255;
+  w += ((size_t)B * kCnPad * 8 + 255) & ~(size_t)255;
   p.list_count = reinterpret_cast<int32_t*>(w);
-  w += ((size_t)B * 4 + 255) & ~(size_t)255;
+  w += ((size_t)B * kCnPad * 4 + 255) & ~(size_t)255;
   p.redo = reinterpret_cast<int32_t*>(w);
   p.redo_any = p.redo + B;
   w += ((size_t)(B + 1) * 4 + 255) & ~(size_t)255;
-  p.tau_logit = reinterpret_cast<float*>(w);
-  w += ((size_t)B * 4 + 255) & ~(size_t)255;
+  p.tau_logit = reinterpret_cast<int*>(w);
+  w += ((size_t)B * kCnPad * 4 + 255) & ~(size_t)255;
   p.hist = reinterpret_cast<uint32_t*>(w);
   w += ((size_t)B * 1024 * 4 + 255) & ~(size_t)255;
   p.list = reinterpret_cast<uint64_t*>(w);
   w += ((size_t)B * (size_t)H * K * 8 + 255) & ~(size_t)255;
   p.ws_sort = reinterpret_cast<uint64_t*>(w);
 
-  CVPP_CUDA_TRY(cudaMemsetAsync(p.tau, 0xff, sizeof(unsigned long long) * (size_t)B, stream));
-  // list_count, tau_logit (0xff800000 = -inf is written below), hist: one contiguous region
+  CVPP_CUDA_TRY(cudaMemsetAsync(p.tau, 0xff, sizeof(unsigned long long) * (size_t)B * kCnPad, stream));
+  // list_count, tau_logit (-inf in the ordered-int encoding is written below), hist: one contiguous region
   CVPP_CUDA_TRY(cudaMemsetAsync(p.list_count, 0, reinterpret_cast<uintptr_t>(p.list) - reinterpret_cast<uintptr_t>(p.list_count), stream));
-  CVPP_CUDA_TRY(cudaMemsetD32Async_compat(p.tau_logit, 0xff800000u, (size_t)B, stream));
+  CVPP_CUDA_TRY(cudaMemsetD32Async_compat(p.tau_logit, 0xff800000u ^ 0x7fffffffu, (size_t)B * kCnPad, stream));
 
   // ---- pass A, primary: independent warps over column tiles (needs 16-byte aligned columns: (nc + 4) % 4 == 0)
   bool tiles_done = false;
@@ -812,45 +891,14 @@ int centernet_launch(const float* pred, int B, int H, int W, int nc, int K, floa
     CVPP_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, centernet_tiles_kernel, kCtThreads, 0));
     if (ctas_per_sm < 1) ctas_per_sm = 1;
     constexpr int kW = kCtThreads / 32;
-    // Cold start: without a bound every cell takes the slow path and every peak is emitted, and a full-width
-    // first wave (thousands of warps) would do that for ~15 % of the tensor and overflow the lists.  A first
-    // SMALL launch covers the first two rows of every image (units are image-fastest) and leaves a bound
-    // (K-th best of ~2 rows of peaks) behind; the second launch streams the rest.
-    int boot_rows = 4;
-    if (boot_rows > H) boot_rows = H;
+    // Cold start: without a bound every cell takes the slow path and every peak is emitted; the sampled guess
+    // (centernet_sample_bound_kernel) gives every image a filter before the first unit is read.
+    centernet_sample_bound_kernel<<<B, 256, 0, stream>>>(p);
+    CVPP_CUDA_TRY(cudaGetLastError());
     {
-      // the exact row kernel on the first rows: every CTA takes ~one row, sorts its peaks and leaves the image's
-      // bound (tau / tau_logit / histogram) and <= K keys per row behind
-      const size_t smem_boot = ((2 * row_bytes + 127) & ~(size_t)127) + (size_t)kCnStage * 8 + 16;
-      if (smem_boot > (size_t)di.max_smem || K + nc > kCnStage) {
-        set_error("centernet: a row of %d x %d cells (K=%d) does not fit the shared-memory pipeline", W, nc + 4, K);
-        return CVPP_ERR_UNSUPPORTED;
-      }
-      static unsigned long long done_bt = 0;
-      static int bytes_bt = 0;
-      if ((int)smem_boot > bytes_bt) {
-        done_bt = 0;
-        bytes_bt = (int)smem_boot;
-      }
-      rc = ensure_smem_attr(reinterpret_cast<const void*>(centernet_peaks_kernel), bytes_bt, di.device, &done_bt);
-      if (rc != CVPP_OK) return rc;
-      CnParams pa = p;
-      pa.redo = nullptr;
-      pa.redo_any = nullptr;
-      pa.row_lo = 0;
-      pa.row_hi = boot_rows;
-      pa.key_cap = kCnStage;
-      const int rows_b = B * boot_rows;
-      const int cps = (2 * (smem_boot + 1024) <= (size_t)di.max_smem + 1024) ? 2 : 1;
-      centernet_peaks_kernel<<<rows_b < cps * di.sms ? rows_b : cps * di.sms, kCnAThreads, smem_boot, stream>>>(pa);
-      CVPP_CUDA_TRY(cudaGetLastError());
-    }
-    const int boot_units = boot_rows * p.tiles_per_row * B;
-    if (boot_units < p.total_tiles) {
       CnParams pb2 = p;
-      pb2.tile_lo = boot_units;
-      const int rest = p.total_tiles - boot_units;
-      const int warps_needed = (rest + kW - 1) / kW;
+      pb2.tile_lo = 0;
+      const int warps_needed = (p.total_tiles + kW - 1) / kW;
       const int grid_t = warps_needed < ctas_per_sm * di.sms ? warps_needed : ctas_per_sm * di.sms;
       centernet_tiles_kernel<<<grid_t, kCtThreads, 0, stream>>>(pb2);
       CVPP_CUDA_TRY(cudaGetLastError());
