@@ -382,6 +382,14 @@ __global__ void __launch_bounds__(256) centernet_sample_bound_kernel(const CnPar
   const int Cf = p.nc + 4;
   const unsigned cells = (unsigned)p.H * p.W * p.nc;  // < 2^32 (checked at launch)
   for (int i = threadIdx.x; i < 1024; i += blockDim.x) sh_hist[i] = 0;
+  // per-image state of the whole decode (replaces three memset / fill launches)
+  for (int i = threadIdx.x; i < kCnBins; i += blockDim.x) p.hist[(size_t)b * kCnBins + i] = 0u;
+  if (threadIdx.x == 0) {
+    p.tau[b * kCnPad] = ~0ull;
+    p.list_count[b * kCnPad] = 0;
+    p.redo[b] = 0;
+    if (b == 0) *p.redo_any = 0;
+  }
   __syncthreads();
   unsigned step = cells / kCsSamples;
   if (step < 1) step = 1;
@@ -869,14 +877,17 @@ int centernet_launch(const float* pred, int B, int H, int W, int nc, int K, floa
   w += ((size_t)B * (size_t)H * K * 8 + 255) & ~(size_t)255;
   p.ws_sort = reinterpret_cast<uint64_t*>(w);
 
-  CVPP_CUDA_TRY(cudaMemsetAsync(p.tau, 0xff, sizeof(unsigned long long) * (size_t)B * kCnPad, stream));
-  // list_count, tau_logit (-inf in the ordered-int encoding is written below), hist: one contiguous region
-  CVPP_CUDA_TRY(cudaMemsetAsync(p.list_count, 0, reinterpret_cast<uintptr_t>(p.list) - reinterpret_cast<uintptr_t>(p.list_count), stream));
-  CVPP_CUDA_TRY(cudaMemsetD32Async_compat(p.tau_logit, 0xff800000u ^ 0x7fffffffu, (size_t)B * kCnPad, stream));
+  const bool tile_path = ((nc + 4) & 3) == 0;
+  if (!tile_path) {  // (the tile path initialises everything in centernet_sample_bound_kernel)
+    CVPP_CUDA_TRY(cudaMemsetAsync(p.tau, 0xff, sizeof(unsigned long long) * (size_t)B * kCnPad, stream));
+    // list_count, tau_logit (-inf in the ordered-int encoding is written below), hist: one contiguous region
+    CVPP_CUDA_TRY(cudaMemsetAsync(p.list_count, 0, reinterpret_cast<uintptr_t>(p.list) - reinterpret_cast<uintptr_t>(p.list_count), stream));
+    CVPP_CUDA_TRY(cudaMemsetD32Async_compat(p.tau_logit, 0xff800000u ^ 0x7fffffffu, (size_t)B * kCnPad, stream));
+  }
 
   // ---- pass A, primary: independent warps over column tiles (needs 16-byte aligned columns: (nc + 4) % 4 == 0)
   bool tiles_done = false;
-  if (((nc + 4) & 3) == 0) {
+  if (tile_path) {
     const int cf = nc + 4;
     // unit = a quarter row or ~10 KB, whichever is smaller (enough units for the image-fastest hand-out)
     int tc = (W + 3) / 4;

@@ -149,3 +149,16 @@ def test_dense_helpers_match_torch():
         for (h, w), inp in (((480, 640), (384, 384)), ((1080, 1920), (640, 640)), ((333, 500), (416, 416))):
             want = reverse_letter_box(h, w, list(inp), boxes.cpu(), xywh=xywh)   # the reference's eager CPU arithmetic
             assert torch.equal(reverse_letter_box(h, w, list(inp), boxes, xywh=xywh).cpu(), want)
+
+
+@pytest.mark.parametrize("nc,H,W", [(6, 16, 24), (3, 8, 8), (12, 20, 36)])
+def test_odd_class_counts_take_the_row_kernel(nc, H, W):
+    """(nc + 4) % 4 != 0 (or tiny maps): columns are not 16-byte aligned, the exact row kernel does the whole map."""
+    p = synth.centernet_pred(31 + nc, 2, H, W, nc)
+    K = min(20, H * W * nc)
+    ref = oracle.centernet_decode(p, K, 0.001, 0, False, 0.5, None)
+    got = ops.centernet_decode(torch.from_numpy(p).to(DEV), K, 0.001)
+    for b, (box, score, cls, pix) in enumerate(ref):
+        n = int(got.count[b])
+        assert n == len(cls) and np.array_equal(got.cls[b, :n].cpu().numpy(), cls)
+        assert np.array_equal(got.pixel[b, :n].cpu().numpy(), pix)
