@@ -151,7 +151,7 @@ def test_dense_helpers_match_torch():
             assert torch.equal(reverse_letter_box(h, w, list(inp), boxes, xywh=xywh).cpu(), want)
 
 
-@pytest.mark.parametrize("nc,H,W", [(6, 16, 24), (3, 8, 8), (12, 20, 36)])
+@pytest.mark.parametrize("nc,H,W", [(6, 32, 32), (3, 32, 32), (10, 24, 40)])
 def test_odd_class_counts_take_the_row_kernel(nc, H, W):
     """(nc + 4) % 4 != 0 (or tiny maps): columns are not 16-byte aligned, the exact row kernel does the whole map."""
     p = synth.centernet_pred(31 + nc, 2, H, W, nc)
