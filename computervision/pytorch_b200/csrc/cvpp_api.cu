@@ -70,7 +70,7 @@ size_t sort_nms_workspace_bytes(int B, int max_cand, int nc);
 int sort_nms_launch(const uint64_t* cand_key, const int32_t* cand_count, const float* box_dense, int B, int max_cand, int64_t A,
                     int nc, double iou_thres, int rule, int order, int max_det, int max_nms, int max_out, float* det_box,
                     float* det_score, int32_t* det_cls, int32_t* det_anchor, int32_t* det_count, void* workspace,
-                    size_t workspace_bytes, cudaStream_t stream);
+                    size_t workspace_bytes, cudaStream_t stream, int32_t* cand_count_out = nullptr);
 
 size_t centernet_workspace_bytes(int B, int H, int W, int nc, int K);
 int centernet_launch(const float* pred, int B, int H, int W, int nc, int K, float conf, int pool_mode, int use_nms,
@@ -253,13 +253,10 @@ int cvpp_yolov8_postprocess(const float* const* level_ptr, const int64_t* batch_
   int rc = cvpp_yolov8_decode_filter(level_ptr, batch_stride, chan_stride, level_h, level_w, level_stride, num_levels,
                                      B, nc, reg_max, conf_thres, cand_key, cand_count, box_dense, max_cand, stream);
   if (rc != CVPP_OK) return rc;
-  // the candidate counts are copied out before the fallback sort can truncate them to max_nms
-  if (cand_count_out && B > 0)
-    CVPP_CUDA_TRY(cudaMemcpyAsync(cand_count_out, cand_count, sizeof(int32_t) * (size_t)B, cudaMemcpyDeviceToDevice,
-                                  (cudaStream_t)stream));
+  // (the fused kernel also copies the candidate counts out: no separate device-to-device copy node)
   return sort_nms_launch(cand_key, cand_count, box_dense, B, max_cand, A, nc, iou_thres, rule, CVPP_ORDER_SCORE_DESC,
                          max_det, max_nms, max_det, det_box, det_score, det_cls, det_anchor, det_count, sn_ws, sn_bytes,
-                         (cudaStream_t)stream);
+                         (cudaStream_t)stream, cand_count_out);
 }
 
 size_t cvpp_centernet_workspace_bytes(int B, int H, int W, int nc, int K) {

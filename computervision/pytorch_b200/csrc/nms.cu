@@ -780,6 +780,7 @@ struct Nms2Params {
   int32_t* det_cls;
   int32_t* det_anchor;
   int32_t* det_count;
+  int32_t* cand_count_out;  // optional [B]: copy of cand_count (saves the caller a device-to-device copy node)
   int cap_pos;     // class-major positions that fit shared memory (multiple of 32)
   int mask_words;  // cap_pos / 32
   // in-kernel fallback (images that do not fit shared memory, or with more than max_nms candidates): global
@@ -889,6 +890,7 @@ __global__ void __launch_bounds__(kN2Threads, 1) nms2_kernel(const __grid_consta
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.x;
   int n = p.cand_count[b];
+  if (tid == 0 && p.cand_count_out) p.cand_count_out[b] = n;
   if (n > p.max_cand) n = p.max_cand;
   if (n <= 0) {
     if (tid == 0) p.det_count[b] = 0;
@@ -1299,7 +1301,7 @@ size_t sort_nms_workspace_bytes(int B, int max_cand, int nc) {
 int sort_nms_launch(const uint64_t* cand_key, const int32_t* cand_count, const float* box_dense, int B, int max_cand, int64_t A,
                     int nc, double iou_thres, int rule, int order, int max_det, int max_nms, int max_out, float* det_box,
                     float* det_score, int32_t* det_cls, int32_t* det_anchor, int32_t* det_count, void* workspace,
-                    size_t workspace_bytes, cudaStream_t stream) {
+                    size_t workspace_bytes, cudaStream_t stream, int32_t* cand_count_out) {
   if (!cand_key || !cand_count || !box_dense || !det_box || !det_score || !det_cls || !det_anchor || !det_count) {
     set_error("sort_nms: NULL pointer argument");
     return CVPP_ERR_INVALID_ARG;
@@ -1373,6 +1375,7 @@ int sort_nms_launch(const uint64_t* cand_key, const int32_t* cand_count, const f
   p.det_cls = det_cls;
   p.det_anchor = det_anchor;
   p.det_count = det_count;
+  p.cand_count_out = cand_count_out;
   // shared memory of the fused path: 28 B per position + 1 bit, 3 ints per class; the selection stage needs
   // 16 KB of histogram inside the 16 B/position box array and 8 B/position of selected keys behind it
   const size_t fixed = (size_t)nc * 12 + 256;
