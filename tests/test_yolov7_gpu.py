@@ -141,3 +141,64 @@ def test_epilogue_matches_reference_box_correction():
         for b, (ref, _) in enumerate(out):
             want = oracle.yolo_correct_rows(ref, (640, 640), hw[b], letterbox)
             assert np.array_equal(rows[b, :n[b]], want)
+
+
+def test_c5_shard_full_size_greedy_nms_invariants():
+    """BASELINE config 5 per-GPU shard (128 images x 25 200 anchors x 85, eval threshold) through size-independent
+    properties.  With distinct scores the greedy per-class NMS result is the UNIQUE set such that (a) no two kept
+    boxes of a class overlap above the threshold and (b) every dropped candidate is suppressed by a kept box of its
+    class with a higher score - both are checked with numpy in torchvision's fp32 arithmetic on sampled images;
+    ordering / membership properties are checked on all 128."""
+    B, nc, thr = 128, 80, 0.3
+    g = torch.Generator(device=DEV).manual_seed(5)
+    levels = []
+    for s in (20, 40, 80):
+        x = torch.randn((B, 3, 5 + nc, s, s), generator=g, device=DEV)
+        x[:, :, 4] = x[:, :, 4] * 3.0 - 9.0
+        x[:, :, 5:] = x[:, :, 5:] * 2.0 - 1.0
+        levels.append(x.reshape(B, 3 * (5 + nc), s, s))
+    ls = ops.make_levels(levels)
+    cand = ops.yolov7_decode_filter(ls, nc, oracle.yolov7_level_anchors(), (640, 640), 0.001)
+    det = ops.per_class_nms_device(cand, thr)
+    cnt, n = cand.count.cpu().numpy(), det.count.cpu().numpy()
+    assert cnt.min() > 3000 and np.all(n <= cnt) and np.all(n > 0)
+    key = cand.key.cpu().numpy().view(np.uint64)
+    dense = cand.box_dense.cpu().numpy()
+    d_anchor, d_cls, d_score = det.anchor.cpu().numpy(), det.cls.cpu().numpy(), det.score.cpu().numpy()
+
+    def iou_gt(b1, b2):  # torchvision nms_kernel.cpp arithmetic: float32 ops, compare as double
+        xx1, yy1 = np.maximum(b1[:, None, 0], b2[None, :, 0]), np.maximum(b1[:, None, 1], b2[None, :, 1])
+        xx2, yy2 = np.minimum(b1[:, None, 2], b2[None, :, 2]), np.minimum(b1[:, None, 3], b2[None, :, 3])
+        w, h = np.maximum(np.float32(0), xx2 - xx1), np.maximum(np.float32(0), yy2 - yy1)
+        inter = w * h
+        a1 = (b1[:, 2] - b1[:, 0]) * (b1[:, 3] - b1[:, 1])
+        a2 = (b2[:, 2] - b2[:, 0]) * (b2[:, 3] - b2[:, 1])
+        with np.errstate(divide="ignore", invalid="ignore"):
+            ovr = inter / (a1[:, None] + a2[None, :] - inter)
+        return ovr.astype(np.float64) > thr
+
+    for b in range(B):
+        k = n[b]
+        # class-major order, scores descending inside a class, every kept anchor is a candidate of that class
+        order_key = d_cls[b, :k].astype(np.int64) * (1 << 32) - d_score[b, :k].view(np.int32).astype(np.int64)
+        assert np.all(np.diff(order_key) >= 0), b      # (random data: exact score ties are possible)
+    for b in (0, 17, 63, 127):
+        c_cls, c_score, c_anchor = decode_keys(key[b, :cnt[b]])
+        kept = set(zip(d_cls[b, :n[b]].tolist(), d_anchor[b, :n[b]].tolist()))
+        assert kept <= set(zip(c_cls.tolist(), c_anchor.tolist()))
+        suppressed_total = 0
+        for c in np.unique(c_cls):
+            m = c_cls == c
+            a, s = c_anchor[m], c_score[m]
+            is_kept = np.array([(int(c), int(x)) in kept for x in a])
+            kb, ks = dense[b, a[is_kept]], s[is_kept]
+            if is_kept.sum() > 1:                                   # (a) kept boxes are mutually compatible
+                ov = iou_gt(kb, kb)
+                np.fill_diagonal(ov, False)
+                assert not ov.any(), (b, int(c))
+            if (~is_kept).any():                                    # (b) every dropped box has a better kept suppressor
+                db, ds = dense[b, a[~is_kept]], s[~is_kept]
+                ov = iou_gt(db, kb) & (ks[None, :] >= ds[:, None])
+                assert ov.any(axis=1).all(), (b, int(c))
+                suppressed_total += int((~is_kept).sum())
+        assert suppressed_total == cnt[b] - n[b] and suppressed_total > 0
