@@ -256,7 +256,7 @@ __device__ __forceinline__ void ya_class_rows(const float4 (&v)[kYaChunkRows], i
 template <int MODE>
 __global__ void __launch_bounds__((MODE == MODE_V7 ? kYaWarpsV7 : kYaWarpsV3) * 32, 1)
 yolo_anchor_stream_kernel(const __grid_constant__ YaParams p) {
-  constexpr int kYaWarps = MODE == MODE_V7 ? kYaWarpsV7 : kYaWarpsV3;
+  const int kYaWarps = blockDim.x >> 5;  // picked by the host (ya_pick_warps)
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float* ring = reinterpret_cast<float*>(smem_raw) + (size_t)warp * (kYaStages * kYaChunkFloats);
@@ -511,8 +511,14 @@ static YaEncodeTiledFn ya_encode_fn() {
   return fn;
 }
 
-static size_t ya_smem_bytes(int mode) {
-  const int warps = mode == MODE_V7 ? kYaWarpsV7 : kYaWarpsV3;
+static int ya_pick_warps(int mode) {
+  const char* e = getenv("CVPP_YA_WARPS");
+  const int cap = mode == MODE_V7 ? kYaWarpsV7 : kYaWarpsV3;
+  if (e && atoi(e) >= 1 && atoi(e) <= cap) return atoi(e);
+  return cap;
+}
+
+static size_t ya_smem_bytes(int mode, int warps) {
   size_t s = (size_t)warps * kYaStages * kYaChunkFloats * sizeof(float) + (size_t)warps * kYaStages * sizeof(uint64_t);
   if (mode == MODE_V3) s += (size_t)warps * (kYaHitCap * (sizeof(float2) + sizeof(uint32_t)) + sizeof(int));
   return s;
@@ -521,12 +527,13 @@ static size_t ya_smem_bytes(int mode) {
 template <int MODE>
 static int ya_launch_mode(YaParams& stream_p, bool have_stream, YaParams& gen_p, int gen_anchors, int B, size_t smem,
                           const DeviceInfo& di, cudaStream_t stream) {
-  constexpr int kYaWarps = MODE == MODE_V7 ? kYaWarpsV7 : kYaWarpsV3;
+  const int kYaWarps = ya_pick_warps(MODE);
   if (have_stream) {
     static unsigned long long attr_done = 0;
-    int rc = ensure_smem_attr(reinterpret_cast<const void*>(yolo_anchor_stream_kernel<MODE>), (int)smem, di.device, &attr_done);
+    int rc = ensure_smem_attr(reinterpret_cast<const void*>(yolo_anchor_stream_kernel<MODE>), di.max_smem, di.device, &attr_done);
     if (rc != CVPP_OK) return rc;
-    const int grid = stream_p.total_tiles < di.sms ? stream_p.total_tiles : di.sms;
+    const int want = (stream_p.total_tiles + kYaWarps - 1) / kYaWarps;
+    const int grid = want < di.sms ? want : di.sms;
     yolo_anchor_stream_kernel<MODE><<<grid, kYaWarps * 32, smem, stream>>>(stream_p);
     CVPP_CUDA_TRY(cudaGetLastError());
   }
@@ -613,7 +620,7 @@ int yolo_anchor_decode_launch(int mode, const float* const* level_ptr, const int
   DeviceInfo di;
   int rc = device_info(&di);
   if (rc != CVPP_OK) return rc;
-  const size_t smem = ya_smem_bytes(mode);
+  const size_t smem = ya_smem_bytes(mode, ya_pick_warps(mode));
   const bool tma_avail = smem <= (size_t)di.max_smem && ya_encode_fn();
 
   alignas(64) YaParams sp{}, gp{};

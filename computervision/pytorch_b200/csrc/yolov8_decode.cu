@@ -8,31 +8,33 @@
 // Memory-bound: every image reads (4*reg_max + nc) x A fp32 once (4 838 400 B for the 8400-anchor,
 // 80-class head) and writes 8 B + 16 B per surviving candidate.  Design (v2, after the first ncu
 // capture showed the CTA-wide-barrier version stalled on barriers at 25 % of HBM peak):
-//   * one persistent CTA per SM, 14 fully independent warps; a warp owns whole tiles of 128
-//     consecutive cells of one level of one image (4 cells per lane) and never meets a CTA barrier;
-//   * a tile is streamed as chunks of 16 channel rows (one DFL side, or 16 classes) x 128 cells:
+//   * one persistent CTA per SM, ~12 fully independent warps; a warp owns whole tiles of 64
+//     consecutive cells of one level of one image (2 cells per lane) and never meets a CTA barrier;
+//   * a tile is streamed as chunks of 16 channel rows (one DFL side, or 16 classes) x 64 cells:
 //     one elected lane issues ONE 3-D tensor-map TMA load (cp.async.bulk.tensor -> UTMALDG, box
-//     128 cells x 16 channels x 1 image; out-of-range cells are zero-filled by the engine) into the
+//     64 cells x 16 channels x 1 image; out-of-range cells are zero-filled by the engine) into the
 //     warp's private 2-stage shared-memory ring, each stage guarded by an mbarrier armed with the
 //     box's byte count (v3: 16 per-row UBLKCPs cost ~160 issue slots per chunk in the v2 capture);
-//   * a landed chunk is pulled into registers with conflict-free LDS.128, the stage is re-armed at
+//   * a landed chunk is pulled into registers with conflict-free LDS.64, the stage is re-armed at
 //     once for the chunk after next, and the arithmetic (softmax-integral over the 16 DFL bins,
 //     running class argmax on logits) runs out of registers while two chunks are in flight;
+//   * v4 (launch-shape sweep on B200): the delivered bandwidth PEAKS at about 96 KB of
+//     requests in flight per SM (2 stages x 12 warps x 4 KB: 5.7 TB/s) and falls when more is kept in flight
+//     (224 KB: 4.9 TB/s - the requests only queue in the memory system), and the last partial round of
+//     tiles costs a whole round, so the host picks the warp count that fills the rounds (pick_shape);
 //   * sigmoid is evaluated once per cell (it is monotone); exact first-index tie semantics of
 //     `cls.max(1)` on sigmoid values are restored on a (rare) slow path;
 //   * survivors are compacted with one warp-aggregated atomic per tile into the per-image key list.
 #include <cuda.h>
+#include <cstdlib>
 
 #include "cvpp_common.cuh"
 
 namespace cvpp {
 
-constexpr int kTileA = 128;      // cells per tile (4 per lane)
 constexpr int kRegMax = 16;      // DFL bins (reference hard-codes 16, modules.py:413)
 constexpr int kChunkRows = 16;   // channel rows per chunk
-constexpr int kStages = 2;       // per-warp ring depth
-constexpr int kWarps = 14;       // independent warps per CTA (14 x 16 KB rings = 224 KB)
-constexpr int kChunkFloats = kChunkRows * kTileA;
+constexpr int kMaxWarps = 16;    // independent warps per CTA (the host picks 9..14, see pick_warps)
 
 struct LevelDesc {
   const float* ptr;
@@ -150,15 +152,15 @@ __device__ __forceinline__ void emit_candidate(bool flag, int b, uint64_t key, i
   }
 }
 
-__device__ __forceinline__ void tile_info(const DecodeParams& p, int g, int& b, int& l, int& cell0, int& nA) {
+__device__ __forceinline__ void tile_info(const DecodeParams& p, int tile_a, int g, int& b, int& l, int& cell0, int& nA) {
   b = g / p.tiles_per_image;
   int j = g - b * p.tiles_per_image;
   l = 0;
 #pragma unroll
   for (int q = 1; q < CVPP_MAX_LEVELS; ++q)
     if (q < p.num_levels && j >= p.lv[q].tile_off) l = q;
-  cell0 = (j - p.lv[l].tile_off) * kTileA;
-  nA = min(kTileA, p.lv[l].hw - cell0);
+  cell0 = (j - p.lv[l].tile_off) * tile_a;
+  nA = min(tile_a, p.lv[l].hw - cell0);
 }
 
 // score / class / candidate decision for one cell, shared by both kernels.
@@ -184,12 +186,50 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, in
       : "memory");
 }
 
-template <bool FULL>
-__global__ void __launch_bounds__(kWarps * 32, 1) yolov8_decode_stream_kernel(const __grid_constant__ DecodeParams p) {
+// CPL = cells per lane.  CPL = 2 (default): 64-cell tiles, 4 KB chunks, LDS.64, ~90 registers.  CPL = 4
+// (CVPP_DECODE_CPL=4, kept for comparison): 128-cell tiles, 8 KB chunks, LDS.128, ~125 registers.
+template <int CPL>
+struct VecOf;
+template <>
+struct VecOf<4> {
+  typedef float4 type;
+};
+template <>
+struct VecOf<2> {
+  typedef float2 type;
+};
+template <int CPL>
+__device__ __forceinline__ void vec_unpack(const typename VecOf<CPL>::type& q, float (&o)[CPL]);
+template <>
+__device__ __forceinline__ void vec_unpack<4>(const float4& q, float (&o)[4]) {
+  o[0] = q.x, o[1] = q.y, o[2] = q.z, o[3] = q.w;
+}
+template <>
+__device__ __forceinline__ void vec_unpack<2>(const float2& q, float (&o)[2]) {
+  o[0] = q.x, o[1] = q.y;
+}
+template <int CPL>
+__device__ __forceinline__ typename VecOf<CPL>::type vec_pack(const float (&o)[CPL]);
+template <>
+__device__ __forceinline__ float4 vec_pack<4>(const float (&o)[4]) {
+  return make_float4(o[0], o[1], o[2], o[3]);
+}
+template <>
+__device__ __forceinline__ float2 vec_pack<2>(const float (&o)[2]) {
+  return make_float2(o[0], o[1]);
+}
+
+template <bool FULL, int CPL, int STAGES>
+__global__ void __launch_bounds__(kMaxWarps * 32, 1) yolov8_decode_stream_kernel(const __grid_constant__ DecodeParams p) {
+  constexpr int kStages = STAGES;
+  const int Warps = blockDim.x >> 5;  // chosen by the host so that the tiles of an SM fill whole rounds
+  constexpr int TileA = 32 * CPL;            // cells per tile
+  constexpr int ChunkFloats = kChunkRows * TileA;
+  typedef typename VecOf<CPL>::type vec_t;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float* ring = reinterpret_cast<float*>(smem_raw) + (size_t)warp * (kStages * kChunkFloats);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kWarps * kStages * kChunkFloats * sizeof(float)) +
+  float* ring = reinterpret_cast<float*>(smem_raw) + (size_t)warp * (kStages * ChunkFloats);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)Warps * kStages * ChunkFloats * sizeof(float)) +
                   warp * kStages;
   const int nc = p.nc;
   const int C = 4 * kRegMax + nc;
@@ -203,83 +243,76 @@ __global__ void __launch_bounds__(kWarps * 32, 1) yolov8_decode_stream_kernel(co
   __syncwarp();
 
   // tiles of this warp: first, first + stride, ...  (CTA-major so small batches spread over all SMs)
-  const int stride_tiles = gridDim.x * kWarps;
-  const int first = blockIdx.x * kWarps + warp;  // the warps of a CTA stream ADJACENT tiles: their 512 B row pieces share DRAM pages
-  const int n_tiles = first < p.total_tiles ? (p.total_tiles - first + stride_tiles - 1) / stride_tiles : 0;
+  const int stride_tiles = gridDim.x * Warps;
+  const int first = blockIdx.x * Warps + warp;  // the warps of a CTA stream ADJACENT tiles: their row pieces share DRAM pages
+  // ... except in the last, partial round, whose tiles are dealt SM-minor so that every SM keeps streaming
+  const int full_rounds = p.total_tiles / stride_tiles;
+  const int last_slot = warp * gridDim.x + blockIdx.x;
+  const int n_tiles = full_rounds + (full_rounds * stride_tiles + last_slot < p.total_tiles ? 1 : 0);
+  auto tile_of = [&](int r) { return r * stride_tiles + (r < full_rounds ? first : last_slot); };
   const int total_q = n_tiles * nchunks;
 
   // producer cursor (runs kStages chunks ahead of the consumer cursor)
-  int pq = 0, pj = 0, pg = first, pb = 0, pl = 0, pcell0 = 0;
+  int pq = 0, pj = 0, pr = 0, pb = 0, pl = 0, pcell0 = 0;
   auto issue = [&]() {
     if (pj == 0) {
       int nA_unused;
-      tile_info(p, pg, pb, pl, pcell0, nA_unused);
+      tile_info(p, TileA, tile_of(pr), pb, pl, pcell0, nA_unused);
     }
     if (lane == 0) {
-      uint64_t* fb = &bar[pq & (kStages - 1)];
-      mbar_arrive_expect_tx(fb, (uint32_t)(kChunkFloats * sizeof(float)));
-      tma_load_3d(ring + (pq & (kStages - 1)) * kChunkFloats, &p.tmap[pl], pcell0, kChunkRows * pj, pb, fb);
+      uint64_t* fb = &bar[pq % kStages];
+      mbar_arrive_expect_tx(fb, (uint32_t)(ChunkFloats * sizeof(float)));
+      tma_load_3d(ring + (pq % kStages) * ChunkFloats, &p.tmap[pl], pcell0, kChunkRows * pj, pb, fb);
     }
     ++pq;
     if (++pj == nchunks) {
       pj = 0;
-      pg += stride_tiles;
+      ++pr;
     }
   };
   for (int q = 0; q < kStages && q < total_q; ++q) issue();
 
-  // per-lane state of the current tile: 4 cells
-  float d[4][4];  // [side][cell]
-  float best[4], prev[4];
-  int arg[4];
+  // per-lane state of the current tile: CPL cells
+  float d[4][CPL];  // [side][cell]
+  float best[CPL], prev[CPL];
+  int arg[CPL];
   int b = 0, l = 0, cell0 = 0, nA = 0;
-  int j = 0, g = first;
+  int j = 0, r = 0;
   for (int q = 0; q < total_q; ++q) {
     if (j == 0) {
-      tile_info(p, g, b, l, cell0, nA);
+      tile_info(p, TileA, tile_of(r), b, l, cell0, nA);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
+      for (int k = 0; k < CPL; ++k) {
         best[k] = -INFINITY;
         prev[k] = -INFINITY;
         arg[k] = 0;
       }
     }
     const LevelDesc& L = p.lv[l];
-    const int s = q & (kStages - 1);
+    const int s = q % kStages;
     mbar_wait(&bar[s], (uint32_t)(q / kStages) & 1u);
-    float4 v[kChunkRows];
+    float v[kChunkRows][CPL];
     {
-      const float4* src = reinterpret_cast<const float4*>(ring + s * kChunkFloats) + lane;
+      const vec_t* src = reinterpret_cast<const vec_t*>(ring + s * ChunkFloats) + lane;
 #pragma unroll
-      for (int r = 0; r < kChunkRows; ++r) v[r] = src[r * (kTileA / 4)];
+      for (int r = 0; r < kChunkRows; ++r) vec_unpack<CPL>(src[r * 32], v[r]);
     }
     __syncwarp();  // every lane holds its copy: the stage may be refilled
     if (pq < total_q) issue();
 
-    const bool active = 4 * lane < nA;
-    const int anchor0 = L.anchor_off + cell0 + 4 * lane;
+    const bool active = CPL * lane < nA;
+    const int anchor0 = L.anchor_off + cell0 + CPL * lane;
     if (j < 4) {
-      float t[kRegMax];
 #pragma unroll
-      for (int r = 0; r < kRegMax; ++r) t[r] = v[r].x;
-      const float dx = dfl16(t);
+      for (int k = 0; k < CPL; ++k) {
+        float t[kRegMax];
 #pragma unroll
-      for (int r = 0; r < kRegMax; ++r) t[r] = v[r].y;
-      const float dy = dfl16(t);
+        for (int r = 0; r < kRegMax; ++r) t[r] = v[r][k];
+        const float dk = dfl16(t);
 #pragma unroll
-      for (int r = 0; r < kRegMax; ++r) t[r] = v[r].z;
-      const float dz = dfl16(t);
-#pragma unroll
-      for (int r = 0; r < kRegMax; ++r) t[r] = v[r].w;
-      const float dw = dfl16(t);
-#pragma unroll
-      for (int side = 0; side < 4; ++side)
-        if (j == side) {
-          d[side][0] = dx;
-          d[side][1] = dy;
-          d[side][2] = dz;
-          d[side][3] = dw;
-        }
+        for (int side = 0; side < 4; ++side)
+          if (j == side) d[side][k] = dk;
+      }
     } else {
       const int c0 = kChunkRows * (j - 4);
       const int rows = min(kChunkRows, nc - c0);
@@ -289,31 +322,25 @@ __global__ void __launch_bounds__(kWarps * 32, 1) yolov8_decode_stream_kernel(co
 #pragma unroll
           for (int r = 0; r < kChunkRows; ++r) {
             if (r < rows) {
-              float4 o;
-              o.x = sigmoid_precise(v[r].x);
-              o.y = sigmoid_precise(v[r].y);
-              o.z = sigmoid_precise(v[r].z);
-              o.w = sigmoid_precise(v[r].w);
-              *reinterpret_cast<float4*>(yc + (int64_t)r * p.A) = o;
+              float o[CPL];
+#pragma unroll
+              for (int k = 0; k < CPL; ++k) o[k] = sigmoid_precise(v[r][k]);
+              *reinterpret_cast<vec_t*>(yc + (int64_t)r * p.A) = vec_pack<CPL>(o);
             }
           }
         }
       } else if (rows == kChunkRows) {
 #pragma unroll
         for (int r = 0; r < kChunkRows; ++r) {
-          class_step(v[r].x, c0 + r, best[0], arg[0], prev[0]);
-          class_step(v[r].y, c0 + r, best[1], arg[1], prev[1]);
-          class_step(v[r].z, c0 + r, best[2], arg[2], prev[2]);
-          class_step(v[r].w, c0 + r, best[3], arg[3], prev[3]);
+#pragma unroll
+          for (int k = 0; k < CPL; ++k) class_step(v[r][k], c0 + r, best[k], arg[k], prev[k]);
         }
       } else {
 #pragma unroll
         for (int r = 0; r < kChunkRows; ++r) {
           if (r < rows) {
-            class_step(v[r].x, c0 + r, best[0], arg[0], prev[0]);
-            class_step(v[r].y, c0 + r, best[1], arg[1], prev[1]);
-            class_step(v[r].z, c0 + r, best[2], arg[2], prev[2]);
-            class_step(v[r].w, c0 + r, best[3], arg[3], prev[3]);
+#pragma unroll
+            for (int k = 0; k < CPL; ++k) class_step(v[r][k], c0 + r, best[k], arg[k], prev[k]);
           }
         }
       }
@@ -321,27 +348,36 @@ __global__ void __launch_bounds__(kWarps * 32, 1) yolov8_decode_stream_kernel(co
 
     if (++j == nchunks) {  // tile complete
       j = 0;
-      g += stride_tiles;
-      CellBox box[4];
+      ++r;
+      CellBox box[CPL];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) box[k] = cell_box(cell0 + 4 * lane + k, L.w, L.stride, d[0][k], d[1][k], d[2][k], d[3][k]);
+      for (int k = 0; k < CPL; ++k) box[k] = cell_box(cell0 + CPL * lane + k, L.w, L.stride, d[0][k], d[1][k], d[2][k], d[3][k]);
       if (FULL) {
         if (active) {
           float* yb = p.y + (int64_t)b * (4 + nc) * p.A + anchor0;
-          *reinterpret_cast<float4*>(yb) = make_float4(box[0].cx, box[1].cx, box[2].cx, box[3].cx);
-          *reinterpret_cast<float4*>(yb + (int64_t)p.A) = make_float4(box[0].cy, box[1].cy, box[2].cy, box[3].cy);
-          *reinterpret_cast<float4*>(yb + 2 * (int64_t)p.A) = make_float4(box[0].w, box[1].w, box[2].w, box[3].w);
-          *reinterpret_cast<float4*>(yb + 3 * (int64_t)p.A) = make_float4(box[0].h, box[1].h, box[2].h, box[3].h);
+          float o[CPL];
+#pragma unroll
+          for (int k = 0; k < CPL; ++k) o[k] = box[k].cx;
+          *reinterpret_cast<vec_t*>(yb) = vec_pack<CPL>(o);
+#pragma unroll
+          for (int k = 0; k < CPL; ++k) o[k] = box[k].cy;
+          *reinterpret_cast<vec_t*>(yb + (int64_t)p.A) = vec_pack<CPL>(o);
+#pragma unroll
+          for (int k = 0; k < CPL; ++k) o[k] = box[k].w;
+          *reinterpret_cast<vec_t*>(yb + 2 * (int64_t)p.A) = vec_pack<CPL>(o);
+#pragma unroll
+          for (int k = 0; k < CPL; ++k) o[k] = box[k].h;
+          *reinterpret_cast<vec_t*>(yb + 3 * (int64_t)p.A) = vec_pack<CPL>(o);
         }
       } else {
-        const float* col = L.ptr + (int64_t)b * L.batch_stride + (int64_t)(4 * kRegMax) * L.chan_stride + cell0 + 4 * lane;
-        bool cand[4];
-        float score[4];
-        int cls[4];
-        unsigned m[4];
+        const float* col = L.ptr + (int64_t)b * L.batch_stride + (int64_t)(4 * kRegMax) * L.chan_stride + cell0 + CPL * lane;
+        bool cand[CPL];
+        float score[CPL];
+        int cls[CPL];
+        unsigned m[CPL];
         int total = 0;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < CPL; ++k) {
           cand[k] = false;
           score[k] = 0.f;
           cls[k] = 0;
@@ -355,7 +391,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) yolov8_decode_stream_kernel(co
           base = __shfl_sync(0xffffffffu, base, 0);
           const unsigned lt = (1u << lane) - 1u;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
+          for (int k = 0; k < CPL; ++k) {
             if (cand[k]) {
               const int slot = base + __popc(m[k] & lt);
               const int anchor = anchor0 + k;
@@ -445,12 +481,12 @@ static EncodeTiledFn encode_tiled_fn() {
 }
 
 // (cell, channel, image) view of one level; box = 128 cells x 16 channels x 1 image, zero fill out of range
-static bool make_level_tmap(CUtensorMap* tm, const LevelDesc& L, int C, int B) {
+static bool make_level_tmap(CUtensorMap* tm, const LevelDesc& L, int C, int B, int tile_a) {
   EncodeTiledFn enc = encode_tiled_fn();
   if (!enc) return false;
   cuuint64_t dims[3] = {(cuuint64_t)L.hw, (cuuint64_t)C, (cuuint64_t)B};
   cuuint64_t strides[2] = {(cuuint64_t)L.chan_stride * 4u, (cuuint64_t)L.batch_stride * 4u};
-  cuuint32_t box[3] = {(cuuint32_t)kTileA, (cuuint32_t)kChunkRows, 1u};
+  cuuint32_t box[3] = {(cuuint32_t)tile_a, (cuuint32_t)kChunkRows, 1u};
   cuuint32_t estr[3] = {1u, 1u, 1u};
   if (B == 1) strides[1] = (cuuint64_t)L.chan_stride * 4u * (cuuint64_t)C;  // unused dimension: any valid stride
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(L.ptr), dims, strides, box, estr,
@@ -459,26 +495,86 @@ static bool make_level_tmap(CUtensorMap* tm, const LevelDesc& L, int C, int B) {
   return r == CUDA_SUCCESS;
 }
 
+static int decode_cpl() {  // cells per lane of the streaming kernel (CVPP_DECODE_CPL=4 selects the 14-warp variant)
+  const char* e = getenv("CVPP_DECODE_CPL");
+  return (e && e[0] == '4') ? 4 : 2;
+}
+
+// Launch shape of the streaming kernel.  A warp streams whole tiles, so an SM with T tiles and W warps runs
+// ceil(T / W) rounds and the last one may be mostly idle: W is chosen in 9..14 to fill the rounds (measured at
+// C2: 2 stages x 12 warps x 4 KB = 96 KB in flight per SM is the sweet spot - more requests in flight only queue
+// in the memory system and lower the delivered bandwidth).  Small batches get few warps per CTA, spread over
+// every SM, and a deeper ring (latency- rather than bandwidth-bound).  CVPP_DECODE_STAGES / CVPP_DECODE_WARPS
+// override the choice (tuning knobs, tools/bench_paths.py).
+static void pick_shape(int total_tiles, int sms, int cpl, int* stages, int* warps, int* grid) {
+  const char* es = getenv("CVPP_DECODE_STAGES");
+  const char* ew = getenv("CVPP_DECODE_WARPS");
+  if (cpl == 4) {
+    *stages = 2;
+    *warps = 14;
+  } else if (total_tiles <= 4 * sms) {
+    *stages = 6;
+    *warps = (total_tiles + sms - 1) / sms;
+  } else {
+    const int T = (total_tiles + sms - 1) / sms;
+    int best_w = 12, best_slots = ((T + 11) / 12) * 12;
+    for (int w = 9; w <= 14; ++w) {
+      const int slots = ((T + w - 1) / w) * w;
+      if (slots < best_slots) {
+        best_slots = slots;
+        best_w = w;
+      }
+    }
+    *stages = 2;
+    *warps = best_w;
+  }
+  if (es && cpl != 4) *stages = atoi(es) == 3 ? 3 : atoi(es) == 6 ? 6 : 2;
+  if (ew && atoi(ew) >= 1 && atoi(ew) <= kMaxWarps) *warps = atoi(ew);
+  const int g = (total_tiles + *warps - 1) / *warps;
+  *grid = g < sms ? g : sms;
+}
+
+template <bool FULL, int CPL, int STAGES>
+static int launch_stream(DecodeParams& p, const DeviceInfo& di, int grid, int warps, size_t smem, cudaStream_t stream) {
+  auto kern = yolov8_decode_stream_kernel<FULL, CPL, STAGES>;
+  static unsigned long long attr_done = 0;  // one per template instantiation
+  int rc = ensure_smem_attr(reinterpret_cast<const void*>(kern), di.max_smem, di.device, &attr_done);
+  if (rc != CVPP_OK) return rc;
+  kern<<<grid, warps * 32, smem, stream>>>(p);
+  return CVPP_OK;
+}
+
 template <bool FULL>
 static int launch_decode(DecodeParams& p, bool tma_ok, cudaStream_t stream) {
   DeviceInfo di;
   int rc = device_info(&di);
   if (rc != CVPP_OK) return rc;
-  const int sms = di.sms, max_smem = di.max_smem;
-  const size_t smem = (size_t)kWarps * kStages * kChunkFloats * sizeof(float) + (size_t)kWarps * kStages * sizeof(uint64_t);
+  const int max_smem = di.max_smem;
+  const int cpl = decode_cpl();
+  const int tile_a = 32 * cpl;
+  // tiling of every level for the chosen tile width
+  int tiles = 0;
+  for (int l = 0; l < p.num_levels; ++l) {
+    p.lv[l].tile_off = tiles;
+    tiles += (p.lv[l].hw + tile_a - 1) / tile_a;
+  }
+  p.tiles_per_image = tiles;
+  p.total_tiles = tiles * p.B;
+  int stages, warps, grid;
+  pick_shape(p.total_tiles, di.sms, cpl, &stages, &warps, &grid);
+  const size_t smem = (size_t)warps * stages * kChunkRows * tile_a * sizeof(float) + (size_t)warps * stages * sizeof(uint64_t);
   if (tma_ok && smem <= (size_t)max_smem) {
     const int C = 4 * kRegMax + p.nc;
-    for (int l = 0; l < p.num_levels && tma_ok; ++l) tma_ok = make_level_tmap(&p.tmap[l], p.lv[l], C, p.B);
+    for (int l = 0; l < p.num_levels && tma_ok; ++l) tma_ok = make_level_tmap(&p.tmap[l], p.lv[l], C, p.B, tile_a);
   } else {
     tma_ok = false;
   }
   if (tma_ok) {
-    auto kern = yolov8_decode_stream_kernel<FULL>;
-    static unsigned long long attr_done = 0;  // one per template instantiation
-    rc = ensure_smem_attr(reinterpret_cast<const void*>(kern), (int)smem, di.device, &attr_done);
+    if (cpl == 4) rc = launch_stream<FULL, 4, 2>(p, di, grid, warps, smem, stream);
+    else if (stages == 2) rc = launch_stream<FULL, 2, 2>(p, di, grid, warps, smem, stream);
+    else if (stages == 3) rc = launch_stream<FULL, 2, 3>(p, di, grid, warps, smem, stream);
+    else rc = launch_stream<FULL, 2, 6>(p, di, grid, warps, smem, stream);
     if (rc != CVPP_OK) return rc;
-    int grid = p.total_tiles < sms ? p.total_tiles : sms;
-    kern<<<grid, kWarps * 32, smem, stream>>>(p);
   } else {
     dim3 grid((p.A + 127) / 128, p.B);
     yolov8_decode_generic_kernel<FULL><<<grid, 128, 0, stream>>>(p);
@@ -536,7 +632,6 @@ int yolov8_decode_launch(const float* const* level_ptr, const int64_t* batch_str
     L.anchor_off = (int)A;
     L.tile_off = tiles;
     A += L.hw;
-    tiles += (L.hw + kTileA - 1) / kTileA;
     if ((reinterpret_cast<uintptr_t>(L.ptr) & 15u) || (L.batch_stride & 3) || (L.chan_stride & 3) || (L.hw & 3))
       tma_ok = false;  // bulk copies need 16-byte aligned rows
   }
