@@ -161,6 +161,8 @@ __device__ __forceinline__ uint32_t lowest_bits(uint32_t m, int room) {
   return o;
 }
 
+constexpr int kPairMaxBoxes = 11;  // 55 pairs: two ballot words
+
 // Resolve word w of segment [s, e): returns the kept mask (identical in all lanes).  All 32 lanes call.
 // Pair (i, j) of the word is tested once, by lane i at rotation t = (j - i) mod 32, t = 1..16, so the
 // 496 pairs cost 16 rounds of 32 parallel tests; a ballot per round routes each verdict to the
@@ -173,6 +175,46 @@ __device__ __forceinline__ uint32_t resolve_word(int w, int s, int e, const BoxV
   const uint32_t inmask = seg_mask_of_word(w, s, e);
   uint32_t am = alive[w] & inmask;
   if (am == 0 || (am & (am - 1)) == 0) return am;  // zero or one live box: nothing to resolve
+  {
+    // few live boxes in one contiguous run (the usual state of a freshly sorted small class): lane = PAIR.
+    // The k (k - 1) / 2 <= 55 pairs are enumerated row-major over the upper triangle (row a holds b = a + 1 ..
+    // k - 1), tested in at most two 32-lane rounds, and lane a cuts its column mask out of the ballot words.
+    const int lo = __ffs(am) - 1, k = __popc(am);
+    const uint32_t run = am >> lo;
+    if (k <= kPairMaxBoxes && (run & (run + 1u)) == 0u) {
+      const int P = (k * (k - 1)) >> 1;
+      uint64_t ww = 0;
+      for (int r = 0; (r << 5) < P; ++r) {
+        const int q = lane + (r << 5);
+        bool sup = false;
+        if (q < P) {
+          int a = 0, rem = q;
+          while (rem >= k - 1 - a) {
+            rem -= k - 1 - a;
+            ++a;
+          }
+          const int i = base + lo + a, j = i + 1 + rem;
+          sup = suppresses(bv.load_box(i), bv.load_area(i), bv.load_box(j), bv.load_area(j), t);
+        }
+        ww |= (uint64_t)__ballot_sync(0xffffffffu, sup) << (r << 5);
+      }
+      if (ww == 0ull) return am;  // nobody suppresses anybody
+      uint32_t col = 0;
+      if (lane < k - 1) {
+        const int off = lane * (k - 1) - ((lane * (lane - 1)) >> 1);
+        const int len = k - 1 - lane;
+        col = ((uint32_t)(ww >> off) & ((1u << len) - 1u)) << (lo + lane + 1);
+      }
+      uint32_t it = __ballot_sync(0xffffffffu, col != 0u);  // rows (ranks) that suppress somebody
+      while (it) {
+        const int a = __ffs(it) - 1;
+        it &= it - 1;
+        const uint32_t c = __shfl_sync(0xffffffffu, col, a);
+        if ((am >> (lo + a)) & 1u) am &= ~c;
+      }
+      return am;
+    }
+  }
   const float4 bi = bv.load_box(base + lane);
   const float ai = bv.load_area(base + lane);
   const bool me = (am >> lane) & 1u;
@@ -192,6 +234,7 @@ __device__ __forceinline__ uint32_t resolve_word(int w, int s, int e, const BoxV
     if (j > lane) col |= bit;
     else row |= bit;
   }
+  if (__ballot_sync(0xffffffffu, (col | row) != 0u) == 0u) return am;  // nobody suppresses anybody
   // replay the greedy order on bitmasks: a live box kills the later boxes in its column mask and every
   // later box whose row mask names it
   uint32_t rem = am;
@@ -1048,6 +1091,7 @@ __global__ void __launch_bounds__(kN2Threads, 1) nms2_kernel(const __grid_consta
       __syncthreads();
       tb = sh_i0;
       __syncthreads();
+      N2_MARK(10);
     }
     // ---- class histogram -> 32-aligned segments -> scatter -> per-class sort
     for (int c = tid; c < nc; c += kN2Threads) {
@@ -1163,6 +1207,7 @@ __global__ void __launch_bounds__(kN2Threads, 1) nms2_kernel(const __grid_consta
                  trick || sh_maxt > 32 * kCoopMinWords);
   }
   __syncthreads();
+  N2_MARK(11);
   if (attempt == 0) {
     int ns = 0;
     for (int base = 0; base < nwords; base += kN2Threads) {

@@ -27,13 +27,13 @@
 
 namespace cvpp {
 
-constexpr int kYaTileA = 128;
 constexpr int kYaChunkRows = 16;
 constexpr int kYaStages = 2;
-constexpr int kYaWarpsV7 = 14;    // 14 x 16 KB rings = 224 KB
-constexpr int kYaWarpsV3 = 12;    // 12 x 16 KB rings + 12 x 2 KB hit buffers
+// CPL = cells per lane: tiles of 32 * CPL cells, chunks of 16 rows x 32 * CPL cells (4 KB at CPL 2, 8 KB at CPL 4).
+// The per-chunk arithmetic is latency-bound per warp (fewer warps are slower for both modes, unlike the YOLOv8
+// kernel), so the default is CPL 2: half the per-thread state and twice the warps.
+constexpr int ya_max_warps(int mode, int cpl) { return cpl == 4 ? (mode == 0 ? 14 : 12) : (mode == 0 ? 24 : 20); }
 constexpr int kYaHitCap = 224;    // V3: per-warp staging of candidate records (12 B each, see V3Stage)
-constexpr int kYaChunkFloats = kYaChunkRows * kYaTileA;
 constexpr int kYaMaxLevels = 4;
 constexpr int MODE_V7 = 0;
 constexpr int MODE_V3 = 1;
@@ -51,10 +51,11 @@ struct YaLevel {
 };
 
 struct YaParams {
-  CUtensorMap tmap[kYaMaxLevels];       // box 128 cells x 16 rows x 1 image
-  CUtensorMap tmap_tail[kYaMaxLevels];  // box 128 cells x tail_rows x 1 image: the last chunk of an anchor reads
+  CUtensorMap tmap[kYaMaxLevels];       // box tile_a cells x 16 rows x 1 image
+  CUtensorMap tmap_tail[kYaMaxLevels];  // box tile_a cells x tail_rows x 1 image: the last chunk of an anchor reads
                                         // exactly the rows that are left ((5 + nc) mod 16), not 16
   int tail_rows;
+  int tile_a;           // cells per tile (32 * CPL)
   YaLevel lv[kYaMaxLevels];
   int num_levels, B, nc, tiles_per_image, total_tiles;
   int merged;           // V3: Decoder flattens the batch (yolov3_decode.py:47-50): one output "image"
@@ -167,8 +168,8 @@ __device__ __forceinline__ void ya_tile_info(const YaParams& p, int g, int& b, i
     if (q < p.num_levels && j >= p.lv[q].tile_off) l = q;
   const int t = j - p.lv[l].tile_off;
   a = t / p.lv[l].tiles_per_anchor;
-  cell0 = (t - a * p.lv[l].tiles_per_anchor) * kYaTileA;
-  nA = min(kYaTileA, p.lv[l].hw - cell0);
+  cell0 = (t - a * p.lv[l].tiles_per_anchor) * p.tile_a;
+  nA = min(p.tile_a, p.lv[l].hw - cell0);
 }
 
 // ---- V3 candidate staging ---------------------------------------------------------------------------
@@ -222,40 +223,59 @@ __device__ __forceinline__ void v3_flush(const V3Stage& st, const YaParams& p, i
 }
 
 // class rows [RBEGIN, rows) of one 16-row chunk; FULL: rows == 16 at compile time
-template <int MODE, int RBEGIN, bool FULL>
-__device__ __forceinline__ void ya_class_rows(const float4 (&v)[kYaChunkRows], int rows, int c_first, float (&best)[4],
-                                              int (&arg)[4], float (&prev)[4], const float (&so)[4], const float (&cut)[4],
-                                              unsigned& boxed, const V3Stage& st, const YaParams& p, int ob,
+template <int MODE, int CPL, int RBEGIN, bool FULL>
+__device__ __forceinline__ void ya_class_rows(const float (&v)[kYaChunkRows][CPL], int rows, int c_first, float (&best)[CPL],
+                                              int (&arg)[CPL], float (&prev)[CPL], const float (&so)[CPL],
+                                              const float (&cut)[CPL], unsigned& boxed, const V3Stage& st, const YaParams& p, int ob,
                                               int anchor_base, int a, int cell0, int hw) {
   const int lane = threadIdx.x & 31;
 #pragma unroll
   for (int r = RBEGIN; r < kYaChunkRows; ++r) {
     if (FULL || r < rows) {
       const int c = c_first + (r - RBEGIN);
-      const float x[4] = {v[r].x, v[r].y, v[r].z, v[r].w};
+      const float(&x)[CPL] = v[r];
       if (MODE == MODE_V7) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) v7_class_step(x[k], c, best[k], arg[k], prev[k]);
+        for (int k = 0; k < CPL; ++k) v7_class_step(x[k], c, best[k], arg[k], prev[k]);
       } else {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < CPL; ++k) {
           if (x[k] >= cut[k]) {
             const int pos = atomicAdd(st.count, 1);
             st.rec_x[pos] = make_float2(x[k], so[k]);
-            st.rec_m[pos] = ((uint32_t)c << 8) | (uint32_t)(4 * lane + k);
+            st.rec_m[pos] = ((uint32_t)c << 8) | (uint32_t)(CPL * lane + k);
             boxed |= 1u << k;
           }
         }
         __syncwarp();
-        if (*st.count > kYaHitCap - 4 * 32) v3_flush(st, p, ob, anchor_base, a, cell0, hw);  // room for one more row
+        if (*st.count > kYaHitCap - CPL * 32) v3_flush(st, p, ob, anchor_base, a, cell0, hw);  // room for one more row
       }
     }
   }
 }
 
-template <int MODE>
-__global__ void __launch_bounds__((MODE == MODE_V7 ? kYaWarpsV7 : kYaWarpsV3) * 32, 1)
+template <int CPL>
+struct YaVec;
+template <>
+struct YaVec<4> {
+  typedef float4 type;
+  static __device__ __forceinline__ void unpack(const float4& q, float (&o)[4]) {
+    o[0] = q.x; o[1] = q.y; o[2] = q.z; o[3] = q.w;
+  }
+};
+template <>
+struct YaVec<2> {
+  typedef float2 type;
+  static __device__ __forceinline__ void unpack(const float2& q, float (&o)[2]) {
+    o[0] = q.x; o[1] = q.y;
+  }
+};
+
+template <int MODE, int CPL>
+__global__ void __launch_bounds__(ya_max_warps(MODE, CPL) * 32, 1)
 yolo_anchor_stream_kernel(const __grid_constant__ YaParams p) {
+  constexpr int kYaTileA = 32 * CPL;
+  constexpr int kYaChunkFloats = kYaChunkRows * kYaTileA;
   const int kYaWarps = blockDim.x >> 5;  // picked by the host (ya_pick_warps)
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -307,13 +327,13 @@ yolo_anchor_stream_kernel(const __grid_constant__ YaParams p) {
   };
   for (int q = 0; q < kYaStages && q < total_q; ++q) issue();
 
-  float t5[5][4];          // tx, ty, tw, th, tobj logits of the lane's 4 cells
-  float best[4], prev[4];  // V7: running class scan
-  int arg[4];
-  float so[4], cut[4];     // V3: sigmoid(obj), per-cell class logit cut
+  float t5[5][CPL];            // tx, ty, tw, th, tobj logits of the lane's CPL cells
+  float best[CPL], prev[CPL];  // V7: running class scan
+  int arg[CPL];
+  float so[CPL], cut[CPL];     // V3: sigmoid(obj), per-cell class logit cut
   unsigned boxed = 0;      // V3: cells that pushed a record (their box is written at the end of the tile)
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
+  for (int k = 0; k < CPL; ++k) {
     best[k] = prev[k] = -INFINITY;
     arg[k] = 0;
     so[k] = 0.0f;
@@ -326,49 +346,48 @@ yolo_anchor_stream_kernel(const __grid_constant__ YaParams p) {
     const YaLevel& L = p.lv[l];
     const int s = q & (kYaStages - 1);
     mbar_wait(&bar[s], (uint32_t)(q / kYaStages) & 1u);
-    float4 v[kYaChunkRows];
+    float v[kYaChunkRows][CPL];
     {
-      const float4* src = reinterpret_cast<const float4*>(ring + s * kYaChunkFloats) + lane;
+      typedef typename YaVec<CPL>::type vec_t;
+      const vec_t* src = reinterpret_cast<const vec_t*>(ring + s * kYaChunkFloats) + lane;
 #pragma unroll
-      for (int r = 0; r < kYaChunkRows; ++r) v[r] = src[r * (kYaTileA / 4)];
+      for (int r = 0; r < kYaChunkRows; ++r) YaVec<CPL>::unpack(src[r * 32], v[r]);
     }
     __syncwarp();
     if (pq < total_q) issue();
 
     // rows of this chunk are attributes [16 j, 16 j + 16) of the anchor: 0..4 box/obj, 5.. classes
-    const bool active = 4 * lane < nA;
+    const bool active = CPL * lane < nA;
     const int ob = p.merged ? 0 : b;
     const int anchor_base = L.anchor_off + b * L.image_stride;
     if (j == 0) {
 #pragma unroll
       for (int r = 0; r < 5; ++r) {
-        t5[r][0] = v[r].x;
-        t5[r][1] = v[r].y;
-        t5[r][2] = v[r].z;
-        t5[r][3] = v[r].w;
+#pragma unroll
+        for (int k = 0; k < CPL; ++k) t5[r][k] = v[r][k];
       }
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
+      for (int k = 0; k < CPL; ++k) {
         best[k] = prev[k] = -INFINITY;
         arg[k] = 0;
       }
       boxed = 0;
       if (MODE == MODE_V3) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < CPL; ++k) {
           so[k] = sigmoid_precise(t5[4][k]);
           cut[k] = active ? v3_logit_cut(so[k], p.conf_thres) : INFINITY;
         }
       }
       if (attrs >= kYaChunkRows)
-        ya_class_rows<MODE, 5, true>(v, kYaChunkRows, 0, best, arg, prev, so, cut, boxed, st, p, ob, anchor_base, a, cell0, L.hw);
+        ya_class_rows<MODE, CPL, 5, true>(v, kYaChunkRows, 0, best, arg, prev, so, cut, boxed, st, p, ob, anchor_base, a, cell0, L.hw);
       else
-        ya_class_rows<MODE, 5, false>(v, attrs, 0, best, arg, prev, so, cut, boxed, st, p, ob, anchor_base, a, cell0, L.hw);
+        ya_class_rows<MODE, CPL, 5, false>(v, attrs, 0, best, arg, prev, so, cut, boxed, st, p, ob, anchor_base, a, cell0, L.hw);
     } else if (j < nchunks - 1) {
-      ya_class_rows<MODE, 0, true>(v, kYaChunkRows, kYaChunkRows * j - 5, best, arg, prev, so, cut, boxed, st, p, ob,
+      ya_class_rows<MODE, CPL, 0, true>(v, kYaChunkRows, kYaChunkRows * j - 5, best, arg, prev, so, cut, boxed, st, p, ob,
                                    anchor_base, a, cell0, L.hw);
     } else {
-      ya_class_rows<MODE, 0, false>(v, attrs - kYaChunkRows * j, kYaChunkRows * j - 5, best, arg, prev, so, cut, boxed, st, p,
+      ya_class_rows<MODE, CPL, 0, false>(v, attrs - kYaChunkRows * j, kYaChunkRows * j - 5, best, arg, prev, so, cut, boxed, st, p,
                                     ob, anchor_base, a, cell0, L.hw);
     }
 
@@ -378,25 +397,25 @@ yolo_anchor_stream_kernel(const __grid_constant__ YaParams p) {
       if (MODE == MODE_V3) {
         v3_flush(st, p, ob, anchor_base, a, cell0, L.hw);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < CPL; ++k) {
           if (boxed & (1u << k)) {
-            const int cell = cell0 + 4 * lane + k;
+            const int cell = cell0 + CPL * lane + k;
             p.box_dense[(int64_t)ob * p.A + anchor_base + ya_local_index<MODE_V3>(a, cell, L.hw)] =
                 v3_box(t5[0][k], t5[1][k], t5[2][k], t5[3][k], cell, L.w, L.h, L.aw[a], L.ah[a]);
           }
         }
       } else {
-        const float* col = L.ptr + (int64_t)b * L.batch_stride + (int64_t)(a * attrs + 5) * L.chan_stride + cell0 + 4 * lane;
-        V7Cell cell[4];
-        unsigned m[4];
+        const float* col = L.ptr + (int64_t)b * L.batch_stride + (int64_t)(a * attrs + 5) * L.chan_stride + cell0 + CPL * lane;
+        V7Cell cell[CPL];
+        unsigned m[CPL];
         int total = 0;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < CPL; ++k) {
           cell[k].cand = false;
           if (active) {
             v7_finalize(t5[4][k], best[k], arg[k], prev[k], col + k, L.chan_stride, nc, p.conf_thres, cell[k]);
             if (cell[k].cand)
-              cell[k].box = v7_box(t5[0][k], t5[1][k], t5[2][k], t5[3][k], cell0 + 4 * lane + k, L.w, L.h, L.aw[a], L.ah[a]);
+              cell[k].box = v7_box(t5[0][k], t5[1][k], t5[2][k], t5[3][k], cell0 + CPL * lane + k, L.w, L.h, L.aw[a], L.ah[a]);
           }
           m[k] = __ballot_sync(0xffffffffu, cell[k].cand);
           total += __popc(m[k]);
@@ -407,10 +426,10 @@ yolo_anchor_stream_kernel(const __grid_constant__ YaParams p) {
           base = __shfl_sync(0xffffffffu, base, 0);
           const unsigned lt = (1u << lane) - 1u;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
+          for (int k = 0; k < CPL; ++k) {
             if (cell[k].cand) {
               const int slot = base + __popc(m[k] & lt);
-              const int anchor = anchor_base + ya_local_index<MODE_V7>(a, cell0 + 4 * lane + k, L.hw);
+              const int anchor = anchor_base + ya_local_index<MODE_V7>(a, cell0 + CPL * lane + k, L.hw);
               if (slot < p.max_cand)
                 p.cand_key[(int64_t)ob * p.max_cand + slot] =
                     key_pack((uint32_t)cell[k].cls, __float_as_uint(cell[k].score), (uint32_t)anchor);
@@ -511,30 +530,35 @@ static YaEncodeTiledFn ya_encode_fn() {
   return fn;
 }
 
-static int ya_pick_warps(int mode) {
+static int ya_pick_cpl() {  // CVPP_YA_CPL=4 selects the 128-cell-tile variant (kept for comparison)
+  const char* e = getenv("CVPP_YA_CPL");
+  return (e && e[0] == '4') ? 4 : 2;
+}
+
+static int ya_pick_warps(int mode, int cpl) {
   const char* e = getenv("CVPP_YA_WARPS");
-  const int cap = mode == MODE_V7 ? kYaWarpsV7 : kYaWarpsV3;
+  const int cap = ya_max_warps(mode, cpl);
   if (e && atoi(e) >= 1 && atoi(e) <= cap) return atoi(e);
   return cap;
 }
 
-static size_t ya_smem_bytes(int mode, int warps) {
-  size_t s = (size_t)warps * kYaStages * kYaChunkFloats * sizeof(float) + (size_t)warps * kYaStages * sizeof(uint64_t);
+static size_t ya_smem_bytes(int mode, int warps, int cpl) {
+  size_t s = (size_t)warps * kYaStages * kYaChunkRows * 32 * cpl * sizeof(float) + (size_t)warps * kYaStages * sizeof(uint64_t);
   if (mode == MODE_V3) s += (size_t)warps * (kYaHitCap * (sizeof(float2) + sizeof(uint32_t)) + sizeof(int));
   return s;
 }
 
-template <int MODE>
+template <int MODE, int CPL>
 static int ya_launch_mode(YaParams& stream_p, bool have_stream, YaParams& gen_p, int gen_anchors, int B, size_t smem,
                           const DeviceInfo& di, cudaStream_t stream) {
-  const int kYaWarps = ya_pick_warps(MODE);
+  const int kYaWarps = ya_pick_warps(MODE, CPL);
   if (have_stream) {
     static unsigned long long attr_done = 0;
-    int rc = ensure_smem_attr(reinterpret_cast<const void*>(yolo_anchor_stream_kernel<MODE>), di.max_smem, di.device, &attr_done);
+    int rc = ensure_smem_attr(reinterpret_cast<const void*>(yolo_anchor_stream_kernel<MODE, CPL>), di.max_smem, di.device, &attr_done);
     if (rc != CVPP_OK) return rc;
     const int want = (stream_p.total_tiles + kYaWarps - 1) / kYaWarps;
     const int grid = want < di.sms ? want : di.sms;
-    yolo_anchor_stream_kernel<MODE><<<grid, kYaWarps * 32, smem, stream>>>(stream_p);
+    yolo_anchor_stream_kernel<MODE, CPL><<<grid, kYaWarps * 32, smem, stream>>>(stream_p);
     CVPP_CUDA_TRY(cudaGetLastError());
   }
   if (gen_anchors > 0) {
@@ -571,6 +595,7 @@ int yolo_anchor_decode_launch(int mode, const float* const* level_ptr, const int
     return CVPP_ERR_ALIGNMENT;
   }
   const bool merged = mode == MODE_V3 && merge_batch;
+  const int cpl = ya_pick_cpl(), tile_a = 32 * cpl;
   YaLevel lv[kYaMaxLevels];
   bool tma_level[kYaMaxLevels];
   int64_t A = 0;
@@ -603,7 +628,7 @@ int yolo_anchor_decode_launch(int mode, const float* const* level_ptr, const int
     L.anchor_off = (int)(merged ? A * B : A);
     L.image_stride = merged ? 3 * L.hw : 0;
     L.tile_off = 0;
-    L.tiles_per_anchor = (L.hw + kYaTileA - 1) / kYaTileA;
+    L.tiles_per_anchor = (L.hw + tile_a - 1) / tile_a;
     A += 3 * (int64_t)L.hw;
     tma_level[l] = !force_generic && !((reinterpret_cast<uintptr_t>(L.ptr) & 15u) || (L.batch_stride & 3) ||
                                        (L.chan_stride & 3) || (L.hw & 3));
@@ -620,7 +645,7 @@ int yolo_anchor_decode_launch(int mode, const float* const* level_ptr, const int
   DeviceInfo di;
   int rc = device_info(&di);
   if (rc != CVPP_OK) return rc;
-  const size_t smem = ya_smem_bytes(mode, ya_pick_warps(mode));
+  const size_t smem = ya_smem_bytes(mode, ya_pick_warps(mode, cpl), cpl);
   const bool tma_avail = smem <= (size_t)di.max_smem && ya_encode_fn();
 
   alignas(64) YaParams sp{}, gp{};
@@ -636,6 +661,7 @@ int yolo_anchor_decode_launch(int mode, const float* const* level_ptr, const int
     q->aux_dense = reinterpret_cast<float2*>(aux_dense);
     q->max_cand = max_cand;
     q->tail_rows = attrs % kYaChunkRows ? attrs % kYaChunkRows : kYaChunkRows;
+    q->tile_a = tile_a;
   }
   int gen_anchors = 0, tiles = 0;
   for (int l = 0; l < num_levels; ++l) {
@@ -645,7 +671,7 @@ int yolo_anchor_decode_launch(int mode, const float* const* level_ptr, const int
       cuuint64_t dims[3] = {(cuuint64_t)L.hw, (cuuint64_t)(3 * attrs), (cuuint64_t)B};
       cuuint64_t strides[2] = {(cuuint64_t)L.chan_stride * 4u, (cuuint64_t)L.batch_stride * 4u};
       if (B == 1) strides[1] = (cuuint64_t)L.chan_stride * 4u * (cuuint64_t)(3 * attrs);
-      cuuint32_t box[3] = {(cuuint32_t)kYaTileA, (cuuint32_t)kYaChunkRows, 1u};
+      cuuint32_t box[3] = {(cuuint32_t)tile_a, (cuuint32_t)kYaChunkRows, 1u};
       cuuint32_t estr[3] = {1u, 1u, 1u};
       ok = ya_encode_fn()(&sp.tmap[sp.num_levels], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(L.ptr), dims,
                           strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
@@ -669,8 +695,12 @@ int yolo_anchor_decode_launch(int mode, const float* const* level_ptr, const int
   }
   sp.tiles_per_image = tiles;
   sp.total_tiles = tiles * B;
-  if (mode == MODE_V7) return ya_launch_mode<MODE_V7>(sp, sp.num_levels > 0, gp, gen_anchors, B, smem, di, stream);
-  return ya_launch_mode<MODE_V3>(sp, sp.num_levels > 0, gp, gen_anchors, B, smem, di, stream);
+  if (cpl == 4) {
+    if (mode == MODE_V7) return ya_launch_mode<MODE_V7, 4>(sp, sp.num_levels > 0, gp, gen_anchors, B, smem, di, stream);
+    return ya_launch_mode<MODE_V3, 4>(sp, sp.num_levels > 0, gp, gen_anchors, B, smem, di, stream);
+  }
+  if (mode == MODE_V7) return ya_launch_mode<MODE_V7, 2>(sp, sp.num_levels > 0, gp, gen_anchors, B, smem, di, stream);
+  return ya_launch_mode<MODE_V3, 2>(sp, sp.num_levels > 0, gp, gen_anchors, B, smem, di, stream);
 }
 
 // ---- predict_bounding_bbox (dense), core/predict/yolov3_decode.py:12-29 -----------------------------

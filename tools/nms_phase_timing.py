@@ -23,6 +23,8 @@ _lib.lib().cvpp_debug_n2_timing(buf)
 t16 = np.array(buf[:]).reshape(64, 16)
 t = t16[:, :8]
 print('  class sorts', ((t16[:,8]-t16[:,2])/1.965e3).mean(), 'big classes', ((t16[:,9]-t16[:,8])/1.965e3).mean(), 'gather', ((t16[:,3]-t16[:,9])/1.965e3).mean())
+print('  prefix hist+bin', ((t16[:,10]-t16[:,0])/1.965e3).mean(), 'class hist+segments', ((t16[:,1]-t16[:,10])/1.965e3).mean())
+print('  suppress_all', ((t16[:,11]-t16[:,3])/1.965e3).mean(), 'survivor count', ((t16[:,4]-t16[:,11])/1.965e3).mean())
 d = np.diff(t, axis=1) / 1.965e3   # us at 1965 MHz
 names = ["hist+scan", "scatter", "class sort+gather", "suppress", "select", "final sort", "output"]
 for i, nme in enumerate(names):
