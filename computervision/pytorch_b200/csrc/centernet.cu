@@ -303,6 +303,7 @@ __global__ void __launch_bounds__(kCtThreads, 3) centernet_tiles_kernel(const __
   int* wcnt = &sh_wcnt[warp];
   if (lane == 0) *wcnt = 0;
   __syncwarp();
+  const uint64_t policy = l2_policy_evict_first();
 
   const int stride = gridDim.x * kWarps;
   const int first = p.tile_lo + blockIdx.x * kWarps + warp;
@@ -326,7 +327,7 @@ __global__ void __launch_bounds__(kCtThreads, 3) centernet_tiles_kernel(const __
 #pragma unroll
     for (int u = 0; u < kCtUnroll; ++u) {
       const int idx = u * 32 + lane;
-      cur[u] = idx < n4 ? __ldg(src + idx) : kNone;
+      cur[u] = idx < n4 ? ldg_stream_f4(src + idx, policy) : kNone;
     }
     float thr_b = thr;
     int thr_bpf = cn_enc(-INFINITY);
@@ -339,7 +340,7 @@ __global__ void __launch_bounds__(kCtThreads, 3) centernet_tiles_kernel(const __
 #pragma unroll
       for (int u = 0; u < kCtUnroll; ++u) {
         const int idx = it + 32 * kCtUnroll + u * 32 + lane;
-        nxt[u] = idx < n4 ? __ldg(src + idx) : kNone;
+        nxt[u] = idx < n4 ? ldg_stream_f4(src + idx, policy) : kNone;
       }
 #pragma unroll
       for (int u = 0; u < kCtUnroll; ++u) {

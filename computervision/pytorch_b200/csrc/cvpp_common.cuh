@@ -39,6 +39,24 @@ int ensure_smem_attr(const void* func, int bytes, int device, unsigned long long
     if (_e != cudaSuccess) return ::cvpp::cuda_fail(_e, #expr); \
   } while (0)
 
+// ---- single-use (streamed) global loads ------------------------------------------------------
+// Inputs that are read exactly once carry an L2 evict-first policy: hundreds of MB of streamed predictions
+// then do not displace what the next kernel needs from L2 (candidate keys, dense boxes, its code).
+#ifdef __CUDACC__
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ float4 ldg_stream_f4(const float4* p, uint64_t policy) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p), "l"(policy));
+  return v;
+}
+#endif
+
 // ---- candidate keys --------------------------------------------------------------------------
 // class-major packing: [class:12 | inv_score:31 | anchor:21]
 __host__ __device__ __forceinline__ uint64_t key_pack(uint32_t cls, uint32_t score_bits, uint32_t anchor) {

@@ -74,7 +74,8 @@ ssd_decode_filter_kernel(const float4* __restrict__ loc, const float* __restrict
       const int n4 = total >> 2;
       const float4* s4 = reinterpret_cast<const float4*>(src);
       float4* d4 = reinterpret_cast<float4*>(sm);
-      for (int i = tid; i < n4; i += kSsdThreads) d4[i] = __ldg(s4 + i);
+      const uint64_t policy = l2_policy_evict_first();
+      for (int i = tid; i < n4; i += kSsdThreads) d4[i] = ldg_stream_f4(s4 + i, policy);
       for (int i = (n4 << 2) + tid; i < total; i += kSsdThreads) sm[i] = __ldg(src + i);
     } else {
       for (int i = tid; i < total; i += kSsdThreads) sm[i] = __ldg(src + i);

@@ -68,10 +68,19 @@ struct YaParams {
   int max_cand;
 };
 
-__device__ __forceinline__ void ya_tma_load_3d(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, uint64_t* bar) {
+// single-use input: L2 evict-first (see yolov8_decode.cu)
+__device__ __forceinline__ uint64_t ya_evict_first_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+
+__device__ __forceinline__ void ya_tma_load_3d(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, uint64_t* bar,
+                                               uint64_t policy) {
   asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4, %5}], [%2], %6;"
+      ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "l"(policy)
       : "memory");
 }
 
@@ -306,6 +315,7 @@ yolo_anchor_stream_kernel(const __grid_constant__ YaParams p) {
   const int n_tiles = first < p.total_tiles ? (p.total_tiles - first + stride_tiles - 1) / stride_tiles : 0;
   const int total_q = n_tiles * nchunks;
 
+  const uint64_t policy = ya_evict_first_policy();
   int pq = 0, pj = 0, pg = first, pb = 0, pl = 0, pa = 0, pcell0 = 0;
   auto issue = [&]() {
     if (pj == 0) {
@@ -317,7 +327,7 @@ yolo_anchor_stream_kernel(const __grid_constant__ YaParams p) {
       const bool tail = pj == nchunks - 1;
       mbar_arrive_expect_tx(fb, (uint32_t)((tail ? p.tail_rows : kYaChunkRows) * kYaTileA * sizeof(float)));
       ya_tma_load_3d(ring + (pq & (kYaStages - 1)) * kYaChunkFloats, tail ? &p.tmap_tail[pl] : &p.tmap[pl], pcell0,
-                     pa * attrs + kYaChunkRows * pj, pb, fb);
+                     pa * attrs + kYaChunkRows * pj, pb, fb, policy);
     }
     ++pq;
     if (++pj == nchunks) {

@@ -179,10 +179,20 @@ __device__ __forceinline__ bool finalize_cell(float best, int arg_in, float prev
 // -----------------------------------------------------------------------------------------------
 // TMA-streamed persistent kernel: independent warps, private tensor-map TMA rings
 // -----------------------------------------------------------------------------------------------
-__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, uint64_t* bar) {
+// The head outputs are read exactly once: the loads carry an L2 evict-first policy so that 310 MB of streamed
+// input does not push the candidate keys, the dense boxes and the NMS kernel's CODE out of L2.
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, uint64_t* bar,
+                                            uint64_t policy) {
   asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4, %5}], [%2], %6;"
+      ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "l"(policy)
       : "memory");
 }
 
@@ -252,6 +262,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) yolov8_decode_stream_kernel
   auto tile_of = [&](int r) { return r * stride_tiles + (r < full_rounds ? first : last_slot); };
   const int total_q = n_tiles * nchunks;
 
+  const uint64_t policy = l2_evict_first_policy();
   // producer cursor (runs kStages chunks ahead of the consumer cursor)
   int pq = 0, pj = 0, pr = 0, pb = 0, pl = 0, pcell0 = 0;
   auto issue = [&]() {
@@ -262,7 +273,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) yolov8_decode_stream_kernel
     if (lane == 0) {
       uint64_t* fb = &bar[pq % kStages];
       mbar_arrive_expect_tx(fb, (uint32_t)(ChunkFloats * sizeof(float)));
-      tma_load_3d(ring + (pq % kStages) * ChunkFloats, &p.tmap[pl], pcell0, kChunkRows * pj, pb, fb);
+      tma_load_3d(ring + (pq % kStages) * ChunkFloats, &p.tmap[pl], pcell0, kChunkRows * pj, pb, fb, policy);
     }
     ++pq;
     if (++pj == nchunks) {
