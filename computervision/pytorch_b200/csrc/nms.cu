@@ -804,6 +804,7 @@ namespace cvpp {
 constexpr int kN2Threads = 1024;
 constexpr int kN2Warps = kN2Threads / 32;
 constexpr int kN2Bins = 4096;
+constexpr int kN2DirectSel = 1024;   // survivors up to this count skip the bin selection: one block sort
 constexpr int kN2SmallMax = 256;     // coordinate-trick images up to this size are handled by one warp
 constexpr int kN2WarpSortMax = 256;  // keys per class a single warp sorts in registers (E <= 8)
 
@@ -847,6 +848,19 @@ __device__ __forceinline__ void warp_sort_segment(uint64_t* seg, int t) {
 #pragma unroll
   for (int e = 0; e < E; ++e)
     if ((e * 32 + lane) < t) seg[e * 32 + lane] = x[e];
+  __syncwarp();
+}
+
+// t <= 32 distinct keys: lane i counts the keys below its own (broadcast shared-memory reads) and stores its
+// key at that rank - about 4 t instructions instead of the 15-stage shuffle network (classes of the score
+// prefix hold ~8 keys).
+__device__ __forceinline__ void warp_rank_sort_32(uint64_t* seg, int t) {
+  const int lane = threadIdx.x & 31;
+  const uint64_t mine = lane < t ? seg[lane] : ~0ull;
+  int rank = 0;
+  for (int j = 0; j < t; ++j) rank += seg[j] < mine ? 1 : 0;
+  __syncwarp();
+  if (lane < t) seg[rank] = mine;
   __syncwarp();
 }
 
@@ -1016,7 +1030,7 @@ __global__ void __launch_bounds__(kN2Threads, 1) nms2_kernel(const __grid_consta
   }
 
   N2_MARK(0);
-  int npos = 0, nwords = 0;
+  int npos = 0, nwords = 0, n_surv = 0;
   // attempt 0: score-prefix subset (only when the output is score-ordered, capped, and the image is large);
   // attempt 1: every candidate
   int attempt = (!trick && cap > 0 && n > 2 * cap + 256) ? 0 : 1;
@@ -1155,7 +1169,7 @@ __global__ void __launch_bounds__(kN2Threads, 1) nms2_kernel(const __grid_consta
       if (t <= 0) continue;
       if (t <= kN2WarpSortMax) {
         uint64_t* seg = ckey + s;
-        if (t <= 32) warp_sort_segment<1>(seg, t);
+        if (t <= 32) warp_rank_sort_32(seg, t);
         else if (t <= 64) warp_sort_segment<2>(seg, t);
         else if (t <= 128) warp_sort_segment<4>(seg, t);
         else warp_sort_segment<8>(seg, t);
@@ -1208,18 +1222,31 @@ __global__ void __launch_bounds__(kN2Threads, 1) nms2_kernel(const __grid_consta
   }
   __syncthreads();
   N2_MARK(11);
-  if (attempt == 0) {
-    int ns = 0;
-    for (int base = 0; base < nwords; base += kN2Threads) {
-      int total = 0;
-      block_excl_scan(base + tid < nwords ? __popc(alive[base + tid]) : 0, sh_scan, &total);
-      ns += total;
-    }
-    if (ns >= cap) break;  // the subset already holds the global top max_det survivors
-    attempt = 1;
-    tb = kN2Bins - 1;
+  if (p.order == CVPP_ORDER_SCORE_DESC && !trick) {
+    // compact the survivors' score-major keys behind the (dead) boxes: their count decides attempt 0, and up
+    // to kN2DirectSel of them are sorted directly by the output stage (a warp covers exactly one alive word)
+    uint64_t* sel = reinterpret_cast<uint64_t*>(reinterpret_cast<int*>(sh_box) + kN2Bins);
+    if (tid == 0) sh_kept = 0;
     __syncthreads();
-    continue;
+    for (int i0 = warp << 5; i0 < npos; i0 += kN2Threads) {
+      const uint32_t word = alive[i0 >> 5];
+      if (word == 0u) continue;
+      int base = 0;
+      if (lane == 0) base = atomicAdd(&sh_kept, __popc(word));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if ((word >> lane) & 1u) {
+        const int pos = base + __popc(word & ((1u << lane) - 1u));
+        if (pos < kN2DirectSel) sel[pos] = key_to_score_major(ckey[i0 + lane]);
+      }
+    }
+    __syncthreads();
+    n_surv = sh_kept;
+    if (attempt == 0 && n_surv < cap) {  // the subset does not hold the global top max_det survivors: redo in full
+      attempt = 1;
+      tb = kN2Bins - 1;
+      __syncthreads();
+      continue;
+    }
   }
   break;
   }
@@ -1235,6 +1262,28 @@ __global__ void __launch_bounds__(kN2Threads, 1) nms2_kernel(const __grid_consta
     // (boxes and areas are dead: the histogram and the selected keys reuse their memory)
     int* hist = reinterpret_cast<int*>(sh_box);                               // kN2Bins ints
     uint64_t* sel = reinterpret_cast<uint64_t*>(hist + kN2Bins);              // up to cap_pos keys (16 B/pos - 16 KB)
+    if (n_surv <= kN2DirectSel) {
+      // few survivors (the usual case after the score-prefix shortcut): they are already compacted - one sort
+      const int P = pow2_ceil(n_surv < 32 ? 32 : n_surv);
+      for (int i = n_surv + tid; i < P; i += kN2Threads) sel[i] = ~0ull;
+      __syncthreads();
+      N2_MARK(5);
+      block_sort_smem_max8(sel, P);
+      N2_MARK(6);
+      const int n_kept = (p.max_det > 0 && p.max_det < n_surv) ? p.max_det : n_surv;
+      const int n_rows = min(n_kept, p.max_out);
+      for (int o = tid; o < n_rows; o += kN2Threads) {
+        const uint64_t k = sel[o];
+        const uint32_t anchor = (uint32_t)(k >> 12) & 0x1fffffu;
+        ob[o] = dense[anchor];
+        os[o] = __uint_as_float(0x7fffffffu - (uint32_t)(k >> 33));
+        oc[o] = (int32_t)(k & 0xfffu);
+        oa[o] = (int32_t)anchor;
+      }
+      N2_MARK(7);
+      if (tid == 0) p.det_count[b] = n_kept;
+      return;
+    }
     for (int i = tid; i < kN2Bins; i += kN2Threads) hist[i] = 0;
     if (tid == 0) {
       sh_i0 = kN2Bins - 1;
