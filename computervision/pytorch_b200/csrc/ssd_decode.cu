@@ -10,6 +10,8 @@
 // thread-per-prior global read would be strided); thread-per-prior then reads its row conflict-free
 // ((nc+1) odd), runs the softmax, decodes the box once, and emits one key per class above the threshold
 // (one ballot + warp-aggregated atomic per class with any hit).
+#include <cstdlib>
+
 #include "cvpp_common.cuh"
 
 namespace cvpp {
@@ -174,6 +176,225 @@ ssd_decode_filter_kernel(const float4* __restrict__ loc, const float* __restrict
     if (gbase + i < max_cand) cand_key[(int64_t)b * max_cand + gbase + i] = sh_key[i];
 }
 
+// -----------------------------------------------------------------------------------------------
+// Streaming version (default): persistent CTAs of independent warps, as in yolov8_decode.cu.  A warp owns tiles of
+// 32 consecutive priors of one image; the tile's conf rows are ONE contiguous run of 128 (nc + 1) bytes that a
+// single 1-D bulk copy (TMA engine, L2 evict-first) lands in the warp's private 3-stage ring, so two tiles are in
+// flight while one is evaluated and no CTA barrier is ever met.  (The block-synchronous version above loads,
+// waits and then computes: 2.1 TB/s.)  Same two phases, same arithmetic; keys are staged per warp and leave
+// with one reservation per tile.
+constexpr int kSsdTile = 32;        // priors per tile (one per lane)
+constexpr int kSsdStages = 2;
+constexpr int kSsdWarpKeys = 96;    // per-warp key stage: at most 32 keys are appended per step
+constexpr int kSsdPairCap = 128;    // per-warp (listed prior, class) pairs awaiting exact evaluation
+constexpr int kSsdMaxWarps = 32;    // the per-tile arithmetic is a latency chain: many warps, small tiles
+
+struct SsdParams {
+  const float4* loc;
+  const float* conf;
+  const float4* priors;
+  int P, nc, B;
+  float conf_thres;
+  uint64_t* cand_key;
+  int32_t* cand_count;
+  float4* box_dense;
+  int max_cand;
+  int tiles_per_image, total_tiles;
+};
+
+// NC1 > 0: nc + 1 known at compile time (21 for VOC) - the per-prior loops unroll and their loads overlap
+template <int NC1>
+__global__ void __launch_bounds__(kSsdMaxWarps * 32, 1) ssd_stream_kernel(const __grid_constant__ SsdParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+  const int nc = NC1 > 0 ? NC1 - 1 : p.nc, nc1 = nc + 1, P = p.P;
+  const int chunk_floats = kSsdTile * nc1;
+  float* ring = reinterpret_cast<float*>(smem_raw) + (size_t)warp * kSsdStages * chunk_floats;
+  unsigned char* q = smem_raw + (size_t)warps * kSsdStages * chunk_floats * sizeof(float);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(q) + warp * kSsdStages;
+  q += (size_t)warps * kSsdStages * sizeof(uint64_t);
+  uint64_t* keys = reinterpret_cast<uint64_t*>(q) + warp * kSsdWarpKeys;
+  q += (size_t)warps * kSsdWarpKeys * sizeof(uint64_t);
+  int* list = reinterpret_cast<int*>(q) + warp * kSsdTile;
+  q += (size_t)warps * kSsdTile * sizeof(int);
+  float* cuts = reinterpret_cast<float*>(q) + warp * kSsdTile;
+  q += (size_t)warps * kSsdTile * sizeof(float);
+  float2* msum = reinterpret_cast<float2*>(q) + warp * kSsdTile;
+  q += (size_t)warps * kSsdTile * sizeof(float2);
+  uint16_t* pairs = reinterpret_cast<uint16_t*>(q) + warp * kSsdPairCap;
+
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < kSsdStages; ++s) mbar_init(&bar[s], 1);
+    mbar_fence_init();
+  }
+  __syncwarp();
+  const uint64_t policy = l2_policy_evict_first();
+
+  // tiles of this warp (the last, partial round is dealt SM-minor so that every SM keeps streaming)
+  const int stride_tiles = gridDim.x * warps;
+  const int first = blockIdx.x * warps + warp;
+  const int full_rounds = p.total_tiles / stride_tiles;
+  const int last_slot = warp * gridDim.x + blockIdx.x;
+  const int n_tiles = full_rounds + (full_rounds * stride_tiles + last_slot < p.total_tiles ? 1 : 0);
+  auto tile_of = [&](int r) { return r * stride_tiles + (r < full_rounds ? first : last_slot); };
+  int pr_round = 0;
+  auto issue = [&]() {
+    const int g = tile_of(pr_round);
+    const int b = g / p.tiles_per_image;
+    const int p0 = (g - b * p.tiles_per_image) * kSsdTile;
+    const int rows = min(kSsdTile, P - p0);
+    if (lane == 0) {
+      uint64_t* fb = &bar[pr_round % kSsdStages];
+      const uint32_t bytes = (uint32_t)(rows * nc1) * (uint32_t)sizeof(float);
+      mbar_arrive_expect_tx(fb, bytes);
+      bulk_g2s_hint(ring + (pr_round % kSsdStages) * chunk_floats, p.conf + ((int64_t)b * P + p0) * nc1, bytes, fb, policy);
+    }
+    ++pr_round;
+  };
+  for (int r = 0; r < kSsdStages && r < n_tiles; ++r) issue();
+
+  const unsigned lt = (1u << lane) - 1u;
+  const int grp = lane >> 3, gl = lane & 7;
+  for (int r = 0; r < n_tiles; ++r) {
+    const int g = tile_of(r);
+    const int b = g / p.tiles_per_image;
+    const int p0 = (g - b * p.tiles_per_image) * kSsdTile;
+    const int rows = min(kSsdTile, P - p0);
+    const int s = r % kSsdStages;
+    mbar_wait(&bar[s], (uint32_t)(r / kSsdStages) & 1u);
+    const float* x0 = ring + s * chunk_floats;
+
+    // ---- phase 1: approximate per-prior cut (one prior per lane; odd nc + 1 makes the rows conflict-free)
+    int n_list = 0;
+#pragma unroll
+    for (int u = 0; u < kSsdTile / 32; ++u) {
+      const int row = lane + 32 * u;
+      bool cand = false;
+      float cut = INFINITY;
+      if (row < rows) {
+        const float* x = x0 + row * nc1;
+        float top = -INFINITY;
+        const float kLog2e = 1.4426950408889634f;
+        float sum = 0.0f, m;
+        if (NC1 > 0) {
+          float xv[NC1 > 0 ? NC1 : 1];
+#pragma unroll
+          for (int k = 0; k < NC1; ++k) xv[k] = x[k];
+#pragma unroll
+          for (int k = 1; k < NC1; ++k) top = fmaxf(top, xv[k]);
+          m = fmaxf(xv[0], top);
+          float s0 = 0.0f, s1 = 0.0f;
+#pragma unroll
+          for (int k = 0; k < NC1; ++k) {
+            const float e = ssd_ex2((xv[k] - m) * kLog2e);
+            if (k & 1) s1 += e;
+            else s0 += e;
+          }
+          sum = s0 + s1;
+        } else {
+          for (int k = 1; k < nc1; ++k) top = fmaxf(top, x[k]);
+          m = fmaxf(x[0], top);
+          for (int k = 0; k < nc1; ++k) sum += ssd_ex2((x[k] - m) * kLog2e);
+        }
+        cut = p.conf_thres > 0.0f ? m + __logf(p.conf_thres * sum) - 0.02f : -INFINITY;
+        cand = top >= cut;
+      }
+      const unsigned mk = __ballot_sync(0xffffffffu, cand);
+      if (cand) {
+        const int slot = n_list + __popc(mk & lt);
+        list[slot] = row;
+        cuts[slot] = cut;
+      }
+      n_list += __popc(mk);
+    }
+    __syncwarp();
+
+    // ---- phase 2: exact evaluation of the listed priors.  (a) 8 lanes per prior: the reference's softmax
+    //      maximum and denominator (per-lane partial sums + butterfly, as in the block version); (b) the same lanes
+    //      list the (prior, class) pairs above the cut; (c) the pairs are evaluated 32 at a time at full lane
+    //      efficiency; (d) the box of every prior with a surviving class is decoded once, a lane per prior.
+    int wk_n = 0;
+    auto flush = [&]() {
+      __syncwarp();
+      int base = 0;
+      if (lane == 0) base = atomicAdd(p.cand_count + b, wk_n);
+      base = __shfl_sync(0xffffffffu, base, 0);
+      for (int i = lane; i < wk_n; i += 32)
+        if (base + i < p.max_cand) p.cand_key[(int64_t)b * p.max_cand + base + i] = keys[i];
+      __syncwarp();
+      wk_n = 0;
+    };
+    int n_pairs = 0;
+    unsigned boxed = 0;  // listed priors with at least one surviving class
+    auto eval_pairs = [&]() {
+      __syncwarp();
+      for (int base = 0; base < n_pairs; base += 32) {
+        const int j = base + lane;
+        bool hit = false;
+        uint64_t key = 0;
+        int i = 0;
+        if (j < n_pairs) {
+          const int pc = pairs[j];
+          i = pc >> 8;
+          const int c = pc & 0xff, row = list[i];
+          const float2 ms = msum[i];
+          const float prob = fdiv(expf(fsub(x0[row * nc1 + c], ms.x)), ms.y);  // torch.softmax: exp(x - max) / sum
+          if (prob > p.conf_thres) {
+            hit = true;
+            key = key_pack((uint32_t)(c - 1), __float_as_uint(prob), (uint32_t)(p0 + row));
+          }
+        }
+        const unsigned hm = __ballot_sync(0xffffffffu, hit);
+        if (hm) {
+          boxed |= __reduce_or_sync(0xffffffffu, hit ? (1u << i) : 0u);
+          if (wk_n + __popc(hm) > kSsdWarpKeys) flush();
+          if (hit) keys[wk_n + __popc(hm & lt)] = key;
+          wk_n += __popc(hm);
+        }
+      }
+      __syncwarp();
+      n_pairs = 0;
+    };
+    for (int base = 0; base < n_list; base += 4) {
+      const int i = base + grp;
+      const bool valid = i < n_list;
+      const int row = valid ? list[i] : 0;
+      const float cut = valid ? cuts[i] : INFINITY;
+      const float* x = x0 + row * nc1;
+      float m = -INFINITY;
+      for (int k = gl; k < nc1; k += 8) m = fmaxf(m, x[k]);
+      m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+      m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+      m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4));
+      float sum = 0.0f;
+      for (int k = gl; k < nc1; k += 8) sum = fadd(sum, expf(fsub(x[k], m)));
+      sum = fadd(sum, __shfl_xor_sync(0xffffffffu, sum, 1));
+      sum = fadd(sum, __shfl_xor_sync(0xffffffffu, sum, 2));
+      sum = fadd(sum, __shfl_xor_sync(0xffffffffu, sum, 4));
+      if (valid && gl == 0) msum[i] = make_float2(m, sum);
+      for (int c0 = 0; c0 <= nc; c0 += 8) {  // uniform trip count: ballots inside
+        const int c = c0 + gl;
+        const bool above = valid && c >= 1 && c <= nc && x[c] >= cut;
+        const unsigned am = __ballot_sync(0xffffffffu, above);
+        if (am) {
+          if (n_pairs + __popc(am) > kSsdPairCap) eval_pairs();  // (msum of this pass is visible: __syncwarp inside)
+          if (above) pairs[n_pairs + __popc(am & lt)] = (uint16_t)((i << 8) | c);
+          n_pairs += __popc(am);
+        }
+      }
+    }
+    if (n_pairs) eval_pairs();
+    if (lane < n_list && ((boxed >> lane) & 1u)) {
+      const int pr = p0 + list[lane];
+      p.box_dense[(int64_t)b * P + pr] = ssd_decode_box(p.priors[pr], p.loc[(int64_t)b * P + pr]);
+    }
+    if (wk_n) flush();
+    __syncwarp();  // every lane is done with the stage: it may be refilled
+    if (pr_round < n_tiles) issue();
+  }
+}
+
 __global__ void __launch_bounds__(256)
 ssd_parse_loc_kernel(const float4* __restrict__ loc, const float4* __restrict__ priors, int P, int64_t total,
                      float4* __restrict__ out) {
@@ -200,13 +421,75 @@ int ssd_decode_filter_launch(const float* loc, const float* conf, const float* p
     set_error("ssd_decode_filter: loc, priors and box_dense must be 16-byte aligned");
     return CVPP_ERR_ALIGNMENT;
   }
+  CVPP_CUDA_TRY(cudaMemsetAsync(cand_count, 0, sizeof(int32_t) * (size_t)B, stream));
+  if (B == 0) return CVPP_OK;
+  {
+    // streaming kernel: needs 16-byte aligned conf rows per image and tile (bulk copies) and room for >= 4 warps
+    DeviceInfo di;
+    int rc = device_info(&di);
+    if (rc != CVPP_OK) return rc;
+    const int nc1 = nc + 1;
+    const size_t per_warp = (size_t)kSsdStages * kSsdTile * nc1 * sizeof(float) + kSsdStages * sizeof(uint64_t) +
+                            kSsdWarpKeys * sizeof(uint64_t) + kSsdTile * (sizeof(int) + sizeof(float) + sizeof(float2)) +
+                            kSsdPairCap * sizeof(uint16_t);
+    int wmax = (int)(((size_t)di.max_smem - 1024) / per_warp);
+    if (wmax > kSsdMaxWarps) wmax = kSsdMaxWarps;
+    const bool aligned = (reinterpret_cast<uintptr_t>(conf) & 15u) == 0 && (((int64_t)P * nc1) & 3) == 0;
+    const char* force = getenv("CVPP_SSD_BLOCK_KERNEL");
+    if (aligned && wmax >= 4 && nc <= 255 && !(force && force[0] == '1')) {
+      SsdParams sp{};
+      sp.loc = reinterpret_cast<const float4*>(loc);
+      sp.conf = conf;
+      sp.priors = reinterpret_cast<const float4*>(priors);
+      sp.P = P;
+      sp.nc = nc;
+      sp.B = B;
+      sp.conf_thres = conf_thres;
+      sp.cand_key = cand_key;
+      sp.cand_count = cand_count;
+      sp.box_dense = reinterpret_cast<float4*>(box_dense);
+      sp.max_cand = max_cand;
+      sp.tiles_per_image = (P + kSsdTile - 1) / kSsdTile;
+      sp.total_tiles = sp.tiles_per_image * B;
+      // warps per CTA: fill whole rounds of tiles (see pick_shape in yolov8_decode.cu)
+      int warps = wmax;
+      if (sp.total_tiles <= di.sms * wmax) {
+        warps = (sp.total_tiles + di.sms - 1) / di.sms;
+      } else {
+        const int T = (sp.total_tiles + di.sms - 1) / di.sms;
+        int best = ((T + wmax - 1) / wmax) * wmax;
+        for (int w = wmax - 1; w >= wmax - 4 && w >= 4; --w) {
+          const int slots = ((T + w - 1) / w) * w;
+          if (slots < best) {
+            best = slots;
+            warps = w;
+          }
+        }
+      }
+      const char* ew = getenv("CVPP_SSD_WARPS");
+      if (ew && atoi(ew) >= 1 && atoi(ew) <= wmax) warps = atoi(ew);
+      const int want = (sp.total_tiles + warps - 1) / warps;
+      const int grid = want < di.sms ? want : di.sms;
+      static unsigned long long attr_done = 0;
+      static unsigned long long attr_done21 = 0;
+      if (nc1 == 21) {
+        rc = ensure_smem_attr(reinterpret_cast<const void*>(ssd_stream_kernel<21>), di.max_smem, di.device, &attr_done21);
+        if (rc != CVPP_OK) return rc;
+        ssd_stream_kernel<21><<<grid, warps * 32, per_warp * warps, stream>>>(sp);
+      } else {
+        rc = ensure_smem_attr(reinterpret_cast<const void*>(ssd_stream_kernel<0>), di.max_smem, di.device, &attr_done);
+        if (rc != CVPP_OK) return rc;
+        ssd_stream_kernel<0><<<grid, warps * 32, per_warp * warps, stream>>>(sp);
+      }
+      CVPP_CUDA_TRY(cudaGetLastError());
+      return CVPP_OK;
+    }
+  }
   const size_t smem = (size_t)kSsdThreads * (nc + 1) * sizeof(float);
   if (smem > 48 * 1024) {
     set_error("ssd_decode_filter: nc=%d needs more than 48 KB of staging shared memory", nc);
     return CVPP_ERR_UNSUPPORTED;
   }
-  CVPP_CUDA_TRY(cudaMemsetAsync(cand_count, 0, sizeof(int32_t) * (size_t)B, stream));
-  if (B == 0) return CVPP_OK;
   dim3 grid((unsigned)((P + kSsdThreads - 1) / kSsdThreads), (unsigned)B);
   ssd_decode_filter_kernel<<<grid, kSsdThreads, smem, stream>>>(
       reinterpret_cast<const float4*>(loc), conf, reinterpret_cast<const float4*>(priors), P, nc, conf_thres, cand_key,

@@ -82,3 +82,38 @@ def test_stage_b_exact_on_identical_inputs():
         box, s, c, a = rows[b]
         assert np.array_equal(a.numpy(), prior[o][keep]) and np.array_equal(c.numpy(), cls[o][keep])
         assert np.array_equal(s.numpy(), score[o][keep]) and np.array_equal(box.numpy(), dense[b, prior[o][keep]])
+
+
+@pytest.mark.parametrize("B,P,nc", [(3, 1000, 3),    # nc + 1 = 4: streaming kernel, generic class count, ragged last tile
+                                    (2, 1001, 20),   # P (nc + 1) not a multiple of 4: block kernel (misaligned rows)
+                                    (5, 36, 20),     # fewer tiles than SMs
+                                    (1, 4100, 6)])
+def test_ragged_shapes_vs_oracle(B, P, nc):
+    """Shapes off the VOC fast path: both kernels against the oracle, kept prior indices bit-exact."""
+    rng = np.random.default_rng(100 * B + P + nc)
+    loc = rng.standard_normal((B, P, 4)).astype(np.float32)
+    conf = (rng.standard_normal((B, P, nc + 1)) * 2.0).astype(np.float32)
+    conf[..., 0] += 3.0
+    # score separation as in synth.ssd_head: keep every probability clear of the threshold and of its neighbours
+    cx, cy = rng.random((P,)) * 0.8 + 0.1, rng.random((P,)) * 0.8 + 0.1
+    w, h = rng.random((P,)) * 0.15 + 0.02, rng.random((P,)) * 0.15 + 0.02
+    pri = np.stack([cx - w, cy - h, cx + w, cy + h], 1).astype(np.float32)
+    # threshold in the middle of the widest gap of the probabilities around 0.02: no score sits on the boundary
+    e = np.exp(conf.astype(np.float64) - conf.max(-1, keepdims=True))
+    prob = np.sort((e / e.sum(-1, keepdims=True))[..., 1:].ravel())
+    near = prob[(prob > 0.015) & (prob < 0.025)]
+    k = int(np.argmax(np.diff(near)))
+    thr = float(np.float32((near[k] + near[k + 1]) / 2))
+    assert near[k + 1] - near[k] > 4e-6
+    ref = oracle.ssd_decode(loc, conf, pri, thr, 0.45)
+    cand = ops.ssd_decode_filter(torch.from_numpy(loc).to(DEV), torch.from_numpy(conf).to(DEV),
+                                 torch.from_numpy(pri).to(DEV), thr, max_cand=P * nc)
+    rows = ops.per_class_nms_rows(cand, 0.45)
+    total = 0
+    for b, ((rrows, rprior), (box, score, cls, anchor)) in enumerate(zip(ref, rows)):
+        assert np.array_equal(anchor.numpy(), rprior), b
+        assert np.array_equal(cls.numpy().astype(np.float32), rrows[:, 4])
+        assert np.all(np.abs(score.numpy() - rrows[:, 5]) <= SCORE_RTOL * rrows[:, 5])
+        assert np.all(np.abs(box.numpy() - rrows[:, :4]) <= 1e-5 * np.abs(rrows[:, :4]) + 1e-6)
+        total += len(rprior)
+    assert total > 0
