@@ -289,12 +289,16 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    host_ms = [0.0]
+
     def timed(fn, steps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        h0 = time.perf_counter()
         for _ in range(steps):
             fn()
+        host_ms[0] = 1e3 * (time.perf_counter() - h0) / steps   # host time to ISSUE a step (diagnostic)
         if world > 1:
             torch.cuda.current_stream().wait_event(gdone[0])   # the side-stream gathers belong to the timed region
             torch.cuda.current_stream().wait_event(gdone[1])
@@ -330,6 +334,7 @@ def run_ours(args):
         if stop:
             break
     ms = statistics.median(ms_runs)
+    host_ms_step = host_ms[0]
     det = step()
     cand_mean = float(det.cand_count.float().mean().item())
     kept_mean = float(det.count.float().mean().item())
@@ -478,6 +483,7 @@ def run_ours(args):
                     "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s / K},
             # per step: decode+filter and fused sort+NMS (+ the epilogue / peer-store gather kernel when N > 1)
             "gpu_launches": (2 if world == 1 else 3) * K,
+            "host_issue_ms_per_step": host_ms_step,
             "overlap": None if world == 1 else "epilogue/all-gather of step k on a side stream under the decode of step k+1",
         }
         print(json.dumps(line), flush=True)

@@ -229,12 +229,18 @@ struct EpilogueParams {
 };
 
 __global__ void __launch_bounds__(256) detection_epilogue_kernel(const __grid_constant__ EpilogueParams p) {
-  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= (int64_t)p.B * p.max_out) return;
-  const int b = (int)(t / p.max_out), k = (int)(t - (int64_t)b * p.max_out);
-  const int n = min(p.det_count[b], p.max_out);
+  // The rows of a CTA are one contiguous run of the output: they are staged in shared memory and leave as
+  // coalesced 128-bit stores - into each peer's buffer over NVLink in the gather form (per-element 4-byte
+  // stores at a 28-byte stride made a million tiny NVLink writes per step and dragged the step at 8 GPUs).
+  __shared__ __align__(16) float sh_rows[256 * 7];
+  const int64_t total = (int64_t)p.B * p.max_out;
+  const int64_t t0 = (int64_t)blockIdx.x * blockDim.x;
+  const int64_t t = t0 + threadIdx.x;
+  const bool valid = t < total;
+  const int b = valid ? (int)(t / p.max_out) : 0, k = valid ? (int)(t - (int64_t)b * p.max_out) : 0;
+  const int n = valid ? min(p.det_count[b], p.max_out) : 0;
   float row[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  if (k < n) {
+  if (valid && k < n) {
     float4 bx = p.det_box[t];
     if (p.box_mode != CVPP_BOX_KEEP) {
       const float* L = p.letterbox + 5 * b;
@@ -289,17 +295,29 @@ __global__ void __launch_bounds__(256) detection_epilogue_kernel(const __grid_co
       row[6] = (float)p.det_anchor[t];
     }
   }
-  if (p.n_dst == 0) {
-    float* o = p.rows + t * p.width;
-    for (int c = 0; c < p.width; ++c) o[c] = row[c];
-    if (k == 0 && p.count_out) p.count_out[b] = (float)n;
-    return;
-  }
-  const int64_t at = ((int64_t)p.slot * p.B * p.max_out + t) * p.width;
-  for (int d = 0; d < p.n_dst; ++d) {  // plain stores into peer memory; visible to the peers at kernel end
-    float* o = p.dst[d] + at;
-    for (int c = 0; c < p.width; ++c) o[c] = row[c];
-    if (k == 0) p.dst[d][p.count_off + (int64_t)p.slot * p.B + b] = (float)n;
+  for (int c = 0; c < p.width; ++c) sh_rows[threadIdx.x * p.width + c] = row[c];  // odd width: conflict-free
+  __syncthreads();
+  const int rows_here = (int)min((int64_t)blockDim.x, total - t0);
+  const int floats = rows_here * p.width;
+  const int n_out = p.n_dst == 0 ? 1 : p.n_dst;
+  for (int d = 0; d < n_out; ++d) {
+    float* o = p.n_dst == 0 ? p.rows + t0 * p.width : p.dst[d] + ((int64_t)p.slot * total + t0) * p.width;
+    if ((reinterpret_cast<uintptr_t>(o) & 15u) == 0) {
+      const int nv = floats >> 2;
+      float4* o4 = reinterpret_cast<float4*>(o);
+      const float4* s4 = reinterpret_cast<const float4*>(sh_rows);
+      for (int i = threadIdx.x; i < nv; i += blockDim.x) o4[i] = s4[i];
+      for (int i = (nv << 2) + threadIdx.x; i < floats; i += blockDim.x) o[i] = sh_rows[i];
+    } else {
+      for (int i = threadIdx.x; i < floats; i += blockDim.x) o[i] = sh_rows[i];
+    }
+    if (valid && k == 0) {
+      if (p.n_dst == 0) {
+        if (p.count_out) p.count_out[b] = (float)n;
+      } else {
+        p.dst[d][p.count_off + (int64_t)p.slot * p.B + b] = (float)n;
+      }
+    }
   }
 }
 
