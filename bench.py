@@ -231,15 +231,18 @@ def run_ours(args):
                 peer = None
 
     graphed = None
-    posts = [post]
-    if world > 1 and peer is not None:
-        posts = [post, ops.Yolov8Postprocessor(BS, A, NC, dev, max_det=MAX_DET)]   # two detection buffer sets
+    # Throughput mode (default): two detection buffer sets, each with its own CUDA graph and stream, used
+    # alternately - batches are independent, so the latency-bound NMS kernel of step k (64 CTAs) overlaps the
+    # HBM-bound decode of step k+1.  --no-pipeline runs strictly one step after the other on one stream.
+    pipelined = (world == 1 or peer is not None) and not args.no_pipeline
+    pipe = None
+    if world == 1 or peer is not None:
+        pipe = ops.PipelinedPostprocess(BS, A, NC, dev, ls, CONF, IOU, max_det=MAX_DET, depth=2 if pipelined else 1,
+                                        graph=not args.no_graph)
     if not args.no_graph:
         try:
-            if world == 1:
-                graphed = post.capture(ls, CONF, IOU)
-            elif peer is not None:
-                graphed = [pp.capture(ls, CONF, IOU) for pp in posts]             # one graph per buffer set
+            if pipe is not None:
+                pass
             else:
                 # one graph per payload buffer: postprocess + row packing (cvpp_detection_epilogue)
                 post(ls, CONF, IOU)
@@ -256,22 +259,18 @@ def run_ours(args):
 
     def step():
         if world == 1:
-            return graphed.replay() if graphed is not None else post(ls, CONF, IOU)
+            return pipe.submit()
         # (box 4, score, cls, anchor) as 7 fp32 columns + counts, delivered to every rank
+        if peer is not None:
+            # decode + NMS of step k, then its fused epilogue + peer-store all-gather, on pipeline stream k % 2
+            # (buffer set and gather slot k % 2): both overlap the decode of step k + 1 on the other stream
+            det = pipe.submit()
+            with torch.cuda.stream(pipe.streams[pipe.last_slot]):
+                ops.detection_epilogue_allgather(det, ops.ROWS_FULL, peer.peer_ptrs(pipe.last_slot), peer.rank)
+            return det                                 # (the cross-rank barrier comes once, after the K steps)
         i = step_no[0] & 1
         step_no[0] += 1
         main = torch.cuda.current_stream()
-        if peer is not None:
-            # decode + NMS of step k on the main stream into buffer set k % 2; the fused epilogue + peer-store
-            # all-gather of step k on the side stream, overlapping the decode of step k + 1
-            main.wait_event(gdone[i])                  # the epilogue that last read this buffer set is done
-            det = graphed[i].replay() if graphed is not None else posts[i](ls, CONF, IOU)
-            ready[i].record(main)
-            with torch.cuda.stream(side):
-                side.wait_event(ready[i])
-                ops.detection_epilogue_allgather(det, ops.ROWS_FULL, peer.peer_ptrs(i), peer.rank)
-                gdone[i].record(side)
-            return det                                 # (the cross-rank barrier comes once, after the K steps)
         main.wait_event(gdone[i])                      # the gather that last read this buffer is done
         if graphed is not None:
             graphed[i].replay()
@@ -291,15 +290,29 @@ def run_ours(args):
 
     host_ms = [0.0]
 
+    def timed_plain(fn, steps):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
+
     def timed(fn, steps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        if pipe is not None:
+            pipe.fork()                                         # the pipeline streams start after e0 ...
         h0 = time.perf_counter()
         for _ in range(steps):
             fn()
         host_ms[0] = 1e3 * (time.perf_counter() - h0) / steps   # host time to ISSUE a step (diagnostic)
-        if world > 1:
+        if pipe is not None:
+            pipe.join()                                         # ... and e1 waits for every one of them
+        elif world > 1:
             torch.cuda.current_stream().wait_event(gdone[0])   # the side-stream gathers belong to the timed region
             torch.cuda.current_stream().wait_event(gdone[1])
         if world > 1 and peer is not None:
@@ -336,6 +349,14 @@ def run_ours(args):
     ms = statistics.median(ms_runs)
     host_ms_step = host_ms[0]
     det = step()
+    if pipe is not None:
+        pipe.join()
+    torch.cuda.synchronize()
+    # the same K steps strictly one after the other on one stream (no overlap between steps), for comparison
+    serial_ms = None
+    if pipelined and world == 1 and not args.no_graph:
+        sg = post.capture(ls, CONF, IOU)
+        serial_ms = statistics.median([timed_plain(sg.replay, K) for _ in range(10)]) / K
     cand_mean = float(det.cand_count.float().mean().item())
     kept_mean = float(det.count.float().mean().item())
 
@@ -465,12 +486,16 @@ def run_ours(args):
             "config": dict(CONFIG, candidates_per_image=cand_mean, kept_per_image=kept_mean,
                            all_gather=("none (1 GPU)" if world == 1 else
                                        "fused into the epilogue kernel: rows (B,300,7) fp32 + counts stored into every "
-                                       "rank's buffer over NVLink peer memory every step (alternating slots) on a side stream that overlaps "
-                                       "the next step's decode; one symmetric-memory barrier at the end of the timed region"
+                                       "rank's buffer over NVLink peer memory every step (alternating slots), on the step's pipeline "
+                                       "stream; one symmetric-memory barrier at the end of the timed region"
                                        if peer is not None else
                                        "one NCCL all-gather per step of [rows (B,300,7) fp32 | counts], on a side stream "
                                        "overlapping the next step's decode"),
-                           launch="CUDA graph replay of cvpp_yolov8_postprocess" if graphed is not None else "eager C call",
+                           launch="eager C call" if args.no_graph else "CUDA graph replay of cvpp_yolov8_postprocess",
+                           pipeline=("2 batches in flight: steps alternate over two streams / detection buffer sets, so the "
+                                     "NMS kernel of step k overlaps the decode of step k+1 (ops.PipelinedPostprocess); every "
+                                     "step does the full decode+NMS, the timed region ends when both streams have drained"
+                                     if pipelined else "none: one step after the other on one stream"),
                            timing=f"median of {len(ms_runs)} back-to-back {K}-step CUDA-event measurements"),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "kernel": "yolov8_decode_stream_kernel<FULL=0, CPL=2, STAGES=2> (decode+filter)",
@@ -484,7 +509,9 @@ def run_ours(args):
             # per step: decode+filter and fused sort+NMS (+ the epilogue / peer-store gather kernel when N > 1)
             "gpu_launches": (2 if world == 1 else 3) * K,
             "host_issue_ms_per_step": host_ms_step,
-            "overlap": None if world == 1 else "epilogue/all-gather of step k on a side stream under the decode of step k+1",
+            "serial_ms_per_step": serial_ms,   # one stream, no overlap between steps (decode + NMS back to back)
+            "overlap": ("NMS of step k under the decode of step k+1" if pipelined else None) if world == 1 else
+                       "NMS + epilogue/all-gather of step k under the decode of step k+1",
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -501,6 +528,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-graph", action="store_true", help="launch the three kernels eagerly instead of replaying a CUDA graph")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--no-pipeline", action="store_true", help="one step after the other on one stream (no overlap of step k's NMS with step k+1's decode)")
     ap.add_argument("--nccl-gather", action="store_true", help="N>1: use NCCL all_gather instead of the fused peer-store epilogue")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -273,6 +273,54 @@ class GraphedPostprocess:
         return self.post.det
 
 
+class PipelinedPostprocess:
+    """Throughput mode of the YOLOv8 post-processor: `depth` detection buffer sets, each with its own CUDA graph and
+    its own stream, used round-robin.  Consecutive batches are independent, so the fused sort+NMS kernel of batch k
+    (64 CTAs, latency-bound) overlaps the HBM-bound decode of batch k+1 on the SMs it leaves idle; a stream replays
+    its own graph in order, which is all the synchronisation buffer reuse needs.
+
+        pipe = PipelinedPostprocess(B, A, nc, device, ls, conf, iou)
+        det = pipe.submit()        # returns at once; `det` belongs to slot pipe.last_slot
+        pipe.wait(pipe.last_slot)  # or pipe.join(): the caller's stream waits for the slot / for everything
+    """
+
+    def __init__(self, B: int, A: int, nc: int, device, ls: LevelSet, conf_thres: float, iou_thres: float,
+                 max_det: int = 300, depth: int = 2, graph: bool = True, **post_args):
+        self.posts = [Yolov8Postprocessor(B, A, nc, device, max_det=max_det) for _ in range(depth)]
+        self.device = self.posts[0].device
+        self.args = (conf_thres, iou_thres) + tuple(post_args.get(k, d) for k, d in
+                                                    (("rule", RULE_TORCHVISION_CPU), ("max_nms", 30000), ("reg_max", 16)))
+        self.ls = ls
+        self.graphs = [pp.capture(ls, *self.args) for pp in self.posts] if graph else None
+        self.streams = [torch.cuda.Stream(device=self.device) for _ in range(depth)]
+        self.turn = 0
+        self.last_slot = 0
+
+    def fork(self) -> None:
+        """Every pipeline stream waits for the work already queued on the caller's current stream."""
+        cur = torch.cuda.current_stream(self.device)
+        for s in self.streams:
+            s.wait_stream(cur)
+
+    def submit(self) -> Detections:
+        i = self.turn % len(self.posts)
+        self.turn += 1
+        self.last_slot = i
+        with torch.cuda.stream(self.streams[i]):
+            if self.graphs is not None:
+                self.graphs[i].replay()
+            else:
+                self.posts[i](self.ls, *self.args)
+        return self.posts[i].det
+
+    def wait(self, slot: int) -> None:
+        torch.cuda.current_stream(self.device).wait_stream(self.streams[slot])
+
+    def join(self) -> None:
+        for i in range(len(self.streams)):
+            self.wait(i)
+
+
 def letterbox_params(image_hw: Sequence[Tuple[int, int]], input_hw: Sequence[int], device) -> torch.Tensor:
     """(B, 5) fp32 rows in_w, in_h, left, top, scale: the scalars of reverse_letter_box
     (image_process.py:115-121) computed in Python doubles exactly like the reference, then cast."""

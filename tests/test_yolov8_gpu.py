@@ -241,3 +241,27 @@ def test_properties_full_size():
         # idempotence: NMS over the kept boxes alone keeps all of them
         keep = oracle.batched_nms(d["box"], d["score"], d["cls"].astype(np.float32), 0.7, mode=2)
         assert len(keep) == len(d["anchor"])
+
+
+def test_pipelined_postprocess_equals_serial():
+    """Throughput mode (two buffer sets / graphs / streams, batches in flight): every slot of every submit holds
+    exactly the detections of the serial call."""
+    levels = synth.yolov8_head(31, B=16, clustered=True)
+    ls = ops.make_levels(to_dev(levels), synth.YOLOV8_STRIDES)
+    A = ls.A
+    ref = ops.Yolov8Postprocessor(16, A, NC, torch.device(DEV))(ls, 0.001, 0.7)
+    torch.cuda.synchronize()
+    want = [t.clone() for t in (ref.box, ref.score, ref.cls, ref.anchor, ref.count)]
+    for graph in (True, False):
+        pipe = ops.PipelinedPostprocess(16, A, NC, torch.device(DEV), ls, 0.001, 0.7, depth=2, graph=graph)
+        pipe.fork()
+        dets = [pipe.submit() for _ in range(7)]
+        pipe.join()
+        torch.cuda.synchronize()
+        assert dets[0] is dets[2] and dets[0] is not dets[1]          # slots alternate
+        for d in dets[-2:]:
+            n = d.count.cpu().numpy()
+            assert np.array_equal(n, want[4].cpu().numpy()) and n.sum() > 0
+            for got, w in zip((d.box, d.score, d.cls, d.anchor), want[:4]):
+                for b in range(16):
+                    assert torch.equal(got[b, :n[b]], w[b, :n[b]])
