@@ -1369,6 +1369,7 @@ __global__ void __launch_bounds__(kN2Threads, 1) nms2_kernel(const __grid_consta
     oc[o] = (int32_t)(k & 0xfffu);
     oa[o] = (int32_t)anchor;
   }
+  N2_MARK(7);
   if (tid == 0) p.det_count[b] = n_kept;
 }
 
