@@ -178,14 +178,119 @@ def run_reference_arm(args):
 # -------------------------------------------------------------------------------------------------
 # GPU arm
 # -------------------------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(gpu_index: int):
+    """Pin this process (and therefore the first-touch placement of its pinned host buffers) to the CPUs NVML reports
+    as local to the GPU: on a two-socket box every rank otherwise allocates on the node it happens to start on and
+    the H2D copies of 4-8 ranks share one socket's memory controllers / the inter-socket link."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        n_words = (os.cpu_count() + 63) // 64
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = [64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1]
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return f"{len(allowed)} CPUs local to GPU {gpu_index} ({allowed[0]}..{allowed[-1]})"
+    except Exception as e:  # diagnostic only
+        return f"unavailable ({type(e).__name__})"
+    return "unavailable"
+
+
+def synth_levels_device(torch, dev, seed: int, B: int):
+    """SURVEY §8d YOLOv8 distribution, generated on the device."""
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    levels = []
+    for h, w in SIZES:
+        x = torch.randn((B, 4 * REG_MAX + NC, h, w), generator=g, device=dev, dtype=torch.float32)
+        x[:, :4 * REG_MAX] *= 3.0
+        x[:, 4 * REG_MAX:] *= 4.3155
+        x[:, 4 * REG_MAX:] += -18.19
+        levels.append(x)
+    return levels
+
+
+def reference_on_gpu(torch, ops, levels, post, n_reps: int = 3):
+    """The bar the reference's own stack sets on this GPU: the reference's op sequence
+    in eager ATen + torchvision's sm_100 NMS kernel on CUDA tensors (oracle/eager_gpu.py, pinned bit for bit against
+    the reference's fixtures on CPU by tests/test_eager_ref.py) - test infrastructure, timed beside the product on
+    the same inputs, with the kept sets compared."""
+    from oracle import eager_gpu
+
+    def run():
+        y = eager_gpu.detect_tail(levels, STRIDES, NC, REG_MAX)
+        return eager_gpu.non_max_suppression(y, CONF, IOU, MAX_DET, nc=NC)
+
+    run()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(n_reps):
+        rows, anchors = run()
+    e1.record()
+    torch.cuda.synchronize()
+    wall = (time.perf_counter() - t0) / n_reps
+    ms = e0.elapsed_time(e1) / n_reps
+    y = eager_gpu.detect_tail(levels, STRIDES, NC, REG_MAX)
+    e0.record()
+    for _ in range(n_reps):
+        eager_gpu.detect_tail(levels, STRIDES, NC, REG_MAX)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_dec = e0.elapsed_time(e1) / n_reps
+    ls = ops.make_levels(levels, STRIDES)
+    same = {}
+    for name, rule in (("rule_torchvision_cpu", ops.RULE_TORCHVISION_CPU), ("rule_torchvision_cuda", ops.RULE_TORCHVISION_CUDA)):
+        det = post(ls, CONF, IOU, rule=rule)
+        torch.cuda.synchronize()
+        cnt = det.count.tolist()
+        eq = sum(int(n == len(a) and bool(torch.equal(det.anchor[b, :n].long(), a))) for b, (n, a) in enumerate(zip(cnt, anchors)))
+        inter = sum(len(set(det.anchor[b, :n].tolist()) & set(a.tolist())) for b, (n, a) in enumerate(zip(cnt, anchors)))
+        same[name] = {"images_with_identical_kept_list": eq, "of": len(cnt),
+                      "kept_in_common": inter, "kept_reference": sum(len(a) for a in anchors)}
+    del y
+    return {"value": BS / (ms * 1e-3), "unit": UNIT, "ms_per_batch": ms, "wall_ms_per_batch": 1e3 * wall,
+            "decode_ms": ms_dec, "reps": n_reps,
+            "what": "eager torch restatement of Detect tail + non_max_suppression (oracle/eager_gpu.py) calling "
+                    "torchvision.ops.batched_nms on CUDA tensors: the reference stack's own Blackwell-compiled kernel",
+            "kept_sets_vs_product": same,
+            "note": "torchvision's CUDA kernel compares the fp32 IoU with float(thr) and is compiled with FMA "
+                    "contraction; the product reproduces the CPU kernel ((double)iou > thr, no contraction), which is "
+                    "what the oracle pins - near-threshold pairs may differ between the two torchvision kernels"}
+
+
+def c1_cpu_latency(levels_np_bs1, reps: int = 50):
+    """C1 beside the GPU bs=1 latency: the CPU port on the same single image, 1 thread and all threads (p50 us)."""
+    import oracle
+    out = {}
+    for tag, n in (("threads_1", 1), ("threads_all", 0)):
+        oracle.set_threads(n)
+        lat = []
+        for i in range(reps + 5):
+            t0 = time.perf_counter()
+            y = oracle.yolov8_decode(levels_np_bs1, STRIDES, NC)
+            oracle.yolov8_nms(y, 0.25, IOU, MAX_DET, nc=NC)
+            if i >= 5:
+                lat.append(1e6 * (time.perf_counter() - t0))
+        lat.sort()
+        out[tag] = {"p50_us": lat[len(lat) // 2], "p95_us": lat[int(len(lat) * 0.95)], "reps": reps,
+                    "threads": 1 if n == 1 else oracle.max_threads()}
+    oracle.set_threads(0)
+    return out
+
+
 def run_ours(args):
+    world = env_int("WORLD_SIZE", 1)
+    rank = env_int("RANK", 0)
+    local_rank = env_int("LOCAL_RANK", 0)
+    numa = bind_to_gpu_numa_node(local_rank) if not args.no_numa_bind else "disabled (--no-numa-bind)"
     import torch
     import torch.distributed as dist
     from computervision.pytorch_b200 import ops
 
-    world = env_int("WORLD_SIZE", 1)
-    rank = env_int("RANK", 0)
-    local_rank = env_int("LOCAL_RANK", 0)
     if world != args.gpus and world > 1:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     if args.gpus > 1 and world == 1:
@@ -196,22 +301,33 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    # synthetic head, generated on the device (SURVEY §8d distribution), seed = base + rank
-    g = torch.Generator(device=dev)
-    g.manual_seed(1234 + rank)
-    levels = []
-    for h, w in SIZES:
-        x = torch.randn((BS, 4 * REG_MAX + NC, h, w), generator=g, device=dev, dtype=torch.float32)
-        x[:, :4 * REG_MAX] *= 3.0
-        x[:, 4 * REG_MAX:] *= 4.3155
-        x[:, 4 * REG_MAX:] += -18.19
-        levels.append(x)
-    ls = ops.make_levels(levels, STRIDES)
-    post = ops.Yolov8Postprocessor(BS, A, NC, dev, max_det=MAX_DET)
-
     from computervision.pytorch_b200 import distributed as cvd
-    if world > 1:
-        # the detection all-gather of step k runs on a side stream and overlaps the decode of step k+1:
+    peer = None
+    if world > 1 and not args.nccl_gather:
+        try:   # fused epilogue + all-gather over NVLink peer stores (no NCCL kernel next to the decode)
+            peer = cvd.PeerGather(BS, MAX_DET, 7, dev, depth=max(2, args.pipeline_depth))
+        except Exception as e:
+            print(f"[bench] symmetric-memory peer gather unavailable ({e}); using NCCL all_gather", file=sys.stderr)
+            peer = None
+
+    # Throughput mode (default): --pipeline-depth (3) slots, each with its OWN input buffers (a distinct synthetic
+    # batch per slot, seed = base + 16 * rank + slot), detection buffers, CUDA graph and stream, used round-robin -
+    # batches are independent, so the latency-bound NMS kernel of step k (64 CTAs) overlaps the HBM-bound decode of the
+    # next steps.  --no-pipeline runs strictly one step after the other on one stream.
+    use_pipe = world == 1 or peer is not None
+    pipelined = use_pipe and not args.no_pipeline
+    depth = args.pipeline_depth if pipelined else 1
+    n_sets = depth if use_pipe else 2
+    inputs = [synth_levels_device(torch, dev, 1234 + 16 * rank + s, BS) for s in range(n_sets)]
+    level_sets = [ops.make_levels(lv, STRIDES) for lv in inputs]
+    levels, ls = inputs[0], level_sets[0]
+    post = ops.Yolov8Postprocessor(BS, A, NC, dev, max_det=MAX_DET)
+    pipe = None
+    graphed = None
+    if use_pipe:
+        pipe = ops.PipelinedPostprocess(BS, A, NC, dev, level_sets, CONF, IOU, max_det=MAX_DET, graph=not args.no_graph)
+    else:
+        # NCCL fallback: the all-gather of step k runs on a side stream and overlaps the decode of step k+1:
         # two alternating payload buffers [rows (B,300,7) | counts (B)], ONE collective per step
         side = torch.cuda.Stream(device=dev)
         n_pay = BS * MAX_DET * 7 + BS
@@ -222,53 +338,37 @@ def run_ours(args):
         for e in gdone:
             e.record()
         step_no = [0]
-        peer = None
-        if not args.nccl_gather:
-            try:   # fused epilogue + all-gather over NVLink peer stores (no NCCL kernel next to the decode)
-                peer = cvd.PeerGather(BS, MAX_DET, 7, dev, depth=max(2, args.pipeline_depth))
-            except Exception as e:
-                print(f"[bench] symmetric-memory peer gather unavailable ({e}); using NCCL all_gather", file=sys.stderr)
-                peer = None
+        if not args.no_graph:
+            post(ls, CONF, IOU)
+            torch.cuda.synchronize()
+            graphed = []
+            for i in range(2):
+                gph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gph):
+                    ops.detection_epilogue(post(level_sets[i], CONF, IOU), ops.ROWS_FULL, out=pay[i], packed=True)
+                graphed.append(gph)
 
-    graphed = None
-    # Throughput mode (default): --pipeline-depth (3) detection buffer sets, each with its own CUDA graph and stream,
-    # used round-robin - batches are independent, so the latency-bound NMS kernel of step k (64 CTAs) overlaps the
-    # HBM-bound decode of the next steps (measured: depth 1 78 us/step, 2 60 us, 3 54 us, 4 54 us).
-    # --no-pipeline runs strictly one step after the other on one stream.
-    pipelined = (world == 1 or peer is not None) and not args.no_pipeline
-    pipe = None
-    if world == 1 or peer is not None:
-        pipe = ops.PipelinedPostprocess(BS, A, NC, dev, ls, CONF, IOU, max_det=MAX_DET, depth=args.pipeline_depth if pipelined else 1,
-                                        graph=not args.no_graph)
-    if not args.no_graph:
-        try:
-            if pipe is not None:
-                pass
-            else:
-                # one graph per payload buffer: postprocess + row packing (cvpp_detection_epilogue)
-                post(ls, CONF, IOU)
-                torch.cuda.synchronize()
-                graphed = []
-                for i in range(2):
-                    gph = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(gph):
-                        ops.detection_epilogue(post(ls, CONF, IOU), ops.ROWS_FULL, out=pay[i], packed=True)
-                    graphed.append(gph)
-        except Exception as e:  # report, fall back to the eager C call
-            print(f"[bench] CUDA graph capture failed ({e}); using eager launches", file=sys.stderr)
-            graphed = None
+    consume_tok = torch.zeros((1,), dtype=torch.float32, device=dev)
 
-    def step():
+    def step(consumable=False):
+        """One pass of the hot path over one batch.  consumable=True (N > 1, peer gather): the gather slot is fenced
+        by cross-rank barriers on BOTH sides of the stores, and a token consumer reads the gathered counts - the rate
+        at which a reader can actually use every step's all-gather."""
         if world == 1:
             return pipe.submit()
-        # (box 4, score, cls, anchor) as 7 fp32 columns + counts, delivered to every rank
         if peer is not None:
-            # decode + NMS of step k, then its fused epilogue + peer-store all-gather, on pipeline stream k % 2
-            # (buffer set and gather slot k % 2): both overlap the decode of step k + 1 on the other stream
+            # decode + NMS of step k, then its fused epilogue + peer-store all-gather, on the slot's pipeline stream
+            # (buffer set and gather slot k % depth): both overlap the decode of the next steps on the other streams
             det = pipe.submit()
-            with torch.cuda.stream(pipe.streams[pipe.last_slot]):
-                ops.detection_epilogue_allgather(det, ops.ROWS_FULL, peer.peer_ptrs(pipe.last_slot), peer.rank)
-            return det                                 # (the cross-rank barrier comes once, after the K steps)
+            slot = pipe.last_slot
+            with torch.cuda.stream(pipe.streams[slot]):
+                if consumable:
+                    peer.barrier(slot)      # every rank has finished reading what this slot held (depth steps ago)
+                ops.detection_epilogue_allgather(det, ops.ROWS_FULL, peer.peer_ptrs(slot), peer.rank)
+                if consumable:
+                    peer.barrier(slot)      # every rank's rows have landed in every buffer
+                    consume_tok.add_(peer.view_counts_f32(slot).sum())   # the token consumer
+            return det
         i = step_no[0] & 1
         step_no[0] += 1
         main = torch.cuda.current_stream()
@@ -276,7 +376,7 @@ def run_ours(args):
         if graphed is not None:
             graphed[i].replay()
         else:
-            ops.detection_epilogue(post(ls, CONF, IOU), ops.ROWS_FULL, out=pay[i], packed=True)
+            ops.detection_epilogue(post(level_sets[i], CONF, IOU), ops.ROWS_FULL, out=pay[i], packed=True)
         ready[i].record(main)
         with torch.cuda.stream(side):
             side.wait_event(ready[i])
@@ -327,6 +427,19 @@ def run_ours(args):
             ms = float(t.item())
         return ms
 
+    def repeat_timed(fn, K, budget_s=1.5, max_runs=50):
+        runs = []
+        t_end = time.perf_counter() + budget_s
+        while True:
+            runs.append(timed(fn, K))
+            stop = time.perf_counter() > t_end or len(runs) >= max_runs
+            if world > 1:
+                f = torch.tensor([int(stop)], device=dev)
+                dist.broadcast(f, 0)
+                stop = bool(f.item())
+            if stop:
+                return runs
+
     W, K = max(args.warmup, 3), args.steps
     for _ in range(W):
         step()
@@ -336,19 +449,41 @@ def run_ours(args):
         sampler.start()
         time.sleep(0.25)
     # keep the timed region long enough for nvidia-smi to see it: repeat the K-step measurement
-    ms_runs = []
-    t_end = time.perf_counter() + 1.5
-    while True:
-        ms_runs.append(timed(step, K))
-        stop = time.perf_counter() > t_end or len(ms_runs) >= 50
-        if world > 1:
-            f = torch.tensor([int(stop)], device=dev)
-            dist.broadcast(f, 0)
-            stop = bool(f.item())
-        if stop:
-            break
+    ms_runs = repeat_timed(step, K)
     ms = statistics.median(ms_runs)
     host_ms_step = host_ms[0]
+
+    # ---- N > 1: the rate at which every step's gather is CONSUMABLE (barriers on both sides of the stores + a
+    #      token reader), and a check of what landed against NCCL's all_gather of the same rows
+    ms_consumable, gather_verified = None, None
+    if world > 1 and peer is not None:
+        for _ in range(W):
+            step(True)
+        barrier()
+        ms_consumable = statistics.median(repeat_timed(lambda: step(True), K, budget_s=0.8, max_runs=20)) / K
+        det = step(True)
+        slot = pipe.last_slot
+        pipe.join()
+        packed = ops.detection_epilogue(det, ops.ROWS_FULL, packed=True)
+        ref_rows, ref_counts = cvd.unpack_detections(cvd.gather_packed(packed), BS, MAX_DET, 7)
+        rows_g, counts_g = peer.view(slot)
+        torch.cuda.synchronize()
+        ok = bool(torch.equal(rows_g, ref_rows) and torch.equal(counts_g, ref_counts) and int(ref_counts.sum()) > 0)
+        t = torch.tensor([int(ok)], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        gather_verified = bool(t.item())
+        if not gather_verified:
+            raise SystemExit("[bench] the peer-store all-gather does not match NCCL all_gather_into_tensor")
+    elif world > 1:
+        torch.cuda.current_stream().wait_event(gdone[0])
+        torch.cuda.current_stream().wait_event(gdone[1])
+        torch.cuda.synchronize()
+        i = (step_no[0] - 1) & 1
+        ok = bool(torch.equal(gout[i][rank], pay[i]))
+        t = torch.tensor([int(ok)], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        gather_verified = bool(t.item())
+
     det = step()
     if pipe is not None:
         pipe.join()
@@ -366,31 +501,34 @@ def run_ours(args):
     # Each stage is launched K times back to back between two events on the launching stream (the
     # current torch stream): the average launch duration without the dependency gap of a mixed sequence.
     # (The stage is replayed from a one-launch CUDA graph: an eager call of the Python wrapper costs more host
-    # time than the 25 us NMS kernel runs, which would time the host, not the kernel.)
-    def burst(fn):
-        for _ in range(3):
-            fn()
-        torch.cuda.synchronize()
-        if args.no_graph:
-            replay = fn
-        else:
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+    # time than the 25 us NMS kernel runs, which would time the host, not the kernel.)  The decode launches
+    # alternate over the distinct input sets, so no launch re-reads what the previous one left in L2.
+    def burst(fns):
+        reps = []
+        for fn in fns:
+            for _ in range(3):
                 fn()
-            replay = g.replay
-            replay()
+            torch.cuda.synchronize()
+            if args.no_graph:
+                reps.append(fn)
+            else:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    fn()
+                g.replay()
+                reps.append(g.replay)
         barrier()
         a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        for _ in range(K):
-            replay()
+        for i in range(K):
+            reps[i % len(reps)]()
         b_.record()
         barrier()
         return a.elapsed_time(b_) / K
 
-    ms_dec = burst(lambda: ops.yolov8_decode_filter(ls, NC, CONF))
+    ms_dec = burst([(lambda l=l: ops.yolov8_decode_filter(l, NC, CONF)) for l in level_sets])
     cand_fixed = ops.yolov8_decode_filter(ls, NC, CONF)
-    ms_nms = burst(lambda: ops.sort_nms(cand_fixed, IOU, max_det=MAX_DET, max_nms=30000))
+    ms_nms = burst([lambda: ops.sort_nms(cand_fixed, IOU, max_det=MAX_DET, max_nms=30000)])
     if world > 1:
         t = torch.tensor([ms_dec, ms_nms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -420,52 +558,130 @@ def run_ours(args):
         bs1 = {"p50_us": lat[len(lat) // 2], "p95_us": lat[int(len(lat) * 0.95)], "reps": len(lat),
                "config": "bs=1, conf=0.25, iou=0.7 (BASELINE.json configs[0] shape), graph replay, L2 flushed",
                "kept": int(post1.det.count.item())}
+        if world == 1 and not args.no_cpu:
+            bs1["cpu_port"] = c1_cpu_latency([l.cpu().numpy() for l in lv1])
+            bs1["cpu_port"]["what"] = "the same image through the oracle/ C port of the reference path (BASELINE configs[0])"
         del flush
 
-    # ---- e2e: pinned host buffers -> device -> kernels -> host
-    host_levels = [torch.empty(l.shape, dtype=l.dtype).pin_memory() for l in levels]
-    for hl, l in zip(host_levels, levels):
-        hl.copy_(l)
-    dev_in = [torch.empty_like(l) for l in levels]
-    ls_in = ops.make_levels(dev_in, STRIDES)
-    h_box = torch.empty((BS, MAX_DET, 4), dtype=torch.float32).pin_memory()
-    h_score = torch.empty((BS, MAX_DET), dtype=torch.float32).pin_memory()
-    h_cls = torch.empty((BS, MAX_DET), dtype=torch.int32).pin_memory()
-    h_anchor = torch.empty((BS, MAX_DET), dtype=torch.int32).pin_memory()
-    h_count = torch.empty((BS,), dtype=torch.int32).pin_memory()
+    # ---- e2e: pinned host buffers -> device -> kernels -> host, through the public pipelined call:
+    #      a copy stream refills slot s's input buffers from pinned host memory (after `consumed[s]`, i.e. as soon as
+    #      the slot's previous decode has read them), submit(ready) runs decode + NMS on the slot's stream, the
+    #      detections leave for pinned host memory on the same stream, and the host reads them one slot-turn later.
+    host_sets = [[torch.empty(l.shape, dtype=l.dtype).pin_memory() for l in lv] for lv in inputs[:2]]
+    for hs, lv in zip(host_sets, inputs):
+        for hl, l in zip(hs, lv):
+            hl.copy_(l)
     h2d = sum(l.numel() * 4 for l in levels)
-    d2h = sum(t.numel() * t.element_size() for t in (h_box, h_score, h_cls, h_anchor, h_count))
+    n_slots = depth if pipe is not None else 1
+    h_out = [dict(box=torch.empty((BS, MAX_DET, 4), dtype=torch.float32).pin_memory(),
+                  score=torch.empty((BS, MAX_DET), dtype=torch.float32).pin_memory(),
+                  cls=torch.empty((BS, MAX_DET), dtype=torch.int32).pin_memory(),
+                  anchor=torch.empty((BS, MAX_DET), dtype=torch.int32).pin_memory(),
+                  count=torch.empty((BS,), dtype=torch.int32).pin_memory()) for _ in range(n_slots)]
+    d2h = sum(t.numel() * t.element_size() for t in h_out[0].values())
 
-    def e2e_step():
-        for d, h in zip(dev_in, host_levels):
+    def d2h_copy(dt, ho):
+        ho["box"].copy_(dt.box, non_blocking=True)
+        ho["score"].copy_(dt.score, non_blocking=True)
+        ho["cls"].copy_(dt.cls, non_blocking=True)
+        ho["anchor"].copy_(dt.anchor, non_blocking=True)
+        ho["count"].copy_(dt.count, non_blocking=True)
+
+    def e2e_serial_step(k):
+        for d, h in zip(levels, host_sets[k & 1]):
             d.copy_(h, non_blocking=True)
-        dt = post(ls_in, CONF, IOU)
-        h_box.copy_(dt.box, non_blocking=True)
-        h_score.copy_(dt.score, non_blocking=True)
-        h_cls.copy_(dt.cls, non_blocking=True)
-        h_anchor.copy_(dt.anchor, non_blocking=True)
-        h_count.copy_(dt.count, non_blocking=True)
+        d2h_copy(post(ls, CONF, IOU), h_out[0])
         torch.cuda.current_stream().synchronize()   # the caller reads the detections
+        return int(h_out[0]["count"][0])
 
-    for _ in range(2):
-        e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(K):
-        e2e_step()
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
+    def run_e2e(step_fn, drain):
+        for k in range(3):
+            step_fn(k)
+        drain()
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(K):
+            step_fn(k)
+        drain()
+        barrier()
+        el = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([el], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            el = float(t.item())
+        return el
+
+    e2e_serial_s = run_e2e(e2e_serial_step, lambda: torch.cuda.synchronize())
+    e2e_s, e2e_mode = e2e_serial_s, "serial: copy in, one call, copy out, synchronize - every step"
+    if pipe is not None and pipelined:
+        copy_stream = torch.cuda.Stream(device=dev)
+        ready = [torch.cuda.Event() for _ in range(depth)]
+        done = [torch.cuda.Event() for _ in range(depth)]
+        pending = [False] * depth
+        sink = [0]
+
+        def e2e_pipe_step(k):
+            slot = pipe.next_slot
+            if pending[slot]:
+                done[slot].synchronize()                       # the caller reads the slot's previous detections
+                sink[0] += int(h_out[slot]["count"][0])
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(pipe.consumed[slot])    # the slot's previous decode is done with its inputs
+                for d, h in zip(inputs[slot], host_sets[k & 1]):
+                    d.copy_(h, non_blocking=True)
+                ready[slot].record(copy_stream)
+            dt = pipe.submit(ready[slot])
+            with torch.cuda.stream(pipe.streams[slot]):
+                d2h_copy(dt, h_out[slot])
+                done[slot].record()
+            pending[slot] = True
+
+        def e2e_drain():
+            for s in range(depth):
+                if pending[s]:
+                    done[s].synchronize()
+                    sink[0] += int(h_out[s]["count"][0])
+                    pending[s] = False
+            torch.cuda.synchronize()
+
+        e2e_s = run_e2e(e2e_pipe_step, e2e_drain)
+        e2e_mode = (f"pipelined through ops.PipelinedPostprocess ({depth} slots): H2D of step k+1 on a copy stream behind "
+                    "`consumed[slot]`, D2H on the slot's stream, the host reads each slot one turn later")
+
+    # ---- the other configurations, measured in this run (decode kernel vs its roofline, whole path)
+    paths = None
+    if world == 1 and rank == 0 and not args.no_paths:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_paths
+        del host_sets
+        torch.cuda.empty_cache()
+        paths = bench_paths.collect(iters=30, device=dev)
+
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+
+    # ---- BASELINE configs[4]: YOLOv7 bs=1024 image-sharded over the ranks + compact detection all-gather (strong scaling)
+    c5 = None
+    if not args.no_c5:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_c5
+        del inputs, level_sets, levels, ls, pipe
+        torch.cuda.empty_cache()
+        c5 = bench_c5.run_c5(rank, world, dev, steps=max(10, min(K, 20)), warmup=3, peak_gbs=peak,
+                             cpu_sample=(16 if world == 1 and not args.no_cpu else 0))
+        inputs = [synth_levels_device(torch, dev, 1234 + 16 * rank, BS)]
+
+    ref_gpu = None
+    if world == 1 and rank == 0 and not args.no_reference_gpu:
+        try:
+            ref_gpu = reference_on_gpu(torch, ops, inputs[0], post)
+        except Exception as e:  # torchvision missing / broken on the box: say so, do not fail the bench
+            ref_gpu = {"unavailable": f"{type(e).__name__}: {e}"}
 
     if rank == 0:
-        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-        if os.path.exists(peaks_path):
-            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-        else:
-            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
         alg_bytes = BS * (HEAD_BYTES_PER_IMAGE + CAND_BYTES * cand_mean)
         achieved = alg_bytes / (ms_dec * 1e-3) / 1e9
         traffic = None
@@ -480,25 +696,30 @@ def run_ours(args):
             v, reps, cores = cpu_port_images_per_s(synth_levels_numpy(1234, BS), budget_s=args.cpu_seconds)
             cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": f"{reps} reps x {BS} images of the same workload (oracle/ C port, {cores} host threads)"}
+        if world == 1:
+            gather_txt = "none (1 GPU)"
+        elif peer is not None:
+            gather_txt = ("fused into the epilogue kernel: rows (B,300,7) fp32 + counts stored into every rank's buffer over "
+                          "NVLink peer memory every step (one gather slot per pipeline slot), on the step's pipeline stream; "
+                          "`value` is free-running (one symmetric-memory barrier at the end of the timed region), "
+                          "`ms_per_step_barrier_each_step` fences every step's slot on both sides and reads it")
+        else:
+            gather_txt = ("one NCCL all-gather per step of [rows (B,300,7) fp32 | counts], on a side stream overlapping the "
+                          "next step's decode")
         line = {
             "metric": METRIC, "value": world * BS * K / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": dict(CONFIG, candidates_per_image=cand_mean, kept_per_image=kept_mean,
-                           all_gather=("none (1 GPU)" if world == 1 else
-                                       "fused into the epilogue kernel: rows (B,300,7) fp32 + counts stored into every "
-                                       "rank's buffer over NVLink peer memory every step (alternating slots), on the step's pipeline "
-                                       "stream; one symmetric-memory barrier at the end of the timed region"
-                                       if peer is not None else
-                                       "one NCCL all-gather per step of [rows (B,300,7) fp32 | counts], on a side stream "
-                                       "overlapping the next step's decode"),
-                           launch="eager C call" if args.no_graph else "CUDA graph replay of cvpp_yolov8_postprocess",
-                           pipeline=(f"{args.pipeline_depth} batches in flight: steps go round-robin over {args.pipeline_depth} streams / "
-                                     "detection buffer sets, so the NMS kernel of step k overlaps the decode of the next steps "
-                                     "(ops.PipelinedPostprocess); every step does the full decode+NMS, the timed region ends "
-                                     "when every stream has drained"
+            "config": dict(CONFIG, candidates_per_image=cand_mean, kept_per_image=kept_mean, all_gather=gather_txt,
+                           launch="eager C call" if args.no_graph else "CUDA graph replay of cvpp_yolov8_postprocess_ev",
+                           inputs=f"{n_sets} distinct synthetic batches per GPU, one per pipeline slot, rotated every step",
+                           pipeline=(f"{depth} batches in flight: steps go round-robin over {depth} slots (own input buffers, "
+                                     "detection buffers, graph, stream), so the NMS kernel of step k overlaps the decode of the "
+                                     "next steps (ops.PipelinedPostprocess); every step does the full decode+NMS on its own "
+                                     "batch, the timed region ends when every stream has drained"
                                      if pipelined else "none: one step after the other on one stream"),
-                           timing=f"median of {len(ms_runs)} back-to-back {K}-step CUDA-event measurements"),
+                           timing=f"median of {len(ms_runs)} back-to-back {K}-step CUDA-event measurements",
+                           numa=numa),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "kernel": "yolov8_decode_stream_kernel<FULL=0, CPL=2, STAGES=2> (decode+filter)",
                          "ms_per_launch": ms_dec, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src},
@@ -507,13 +728,21 @@ def run_ours(args):
             "cpu_baseline": cpu,
             "clocks": clocks,
             "e2e": {"value": world * BS * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s / K},
+                    "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s / K, "mode": e2e_mode,
+                    "h2d_GBps_per_gpu": h2d * K / e2e_s / 1e9,
+                    "serial_value": world * BS * K / e2e_serial_s, "serial_ms_per_step": 1e3 * e2e_serial_s / K},
             # per step: decode+filter and fused sort+NMS (+ the epilogue / peer-store gather kernel when N > 1)
             "gpu_launches": (2 if world == 1 else 3) * K,
             "host_issue_ms_per_step": host_ms_step,
             "serial_ms_per_step": serial_ms,   # one stream, no overlap between steps (decode + NMS back to back)
             "overlap": ("NMS of step k under the decode of step k+1" if pipelined else None) if world == 1 else
                        "NMS + epilogue/all-gather of step k under the decode of step k+1",
+            "gather_verified": gather_verified,
+            "ms_per_step_barrier_each_step": ms_consumable,
+            "value_barrier_each_step": (world * BS / (ms_consumable * 1e-3)) if ms_consumable else None,
+            "paths": paths,
+            "c5": c5,
+            "reference_gpu": ref_gpu,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -533,6 +762,10 @@ def main():
     ap.add_argument("--pipeline-depth", type=int, default=3, help="batches in flight in throughput mode")
     ap.add_argument("--no-pipeline", action="store_true", help="one step after the other on one stream (no overlap of step k's NMS with step k+1's decode)")
     ap.add_argument("--nccl-gather", action="store_true", help="N>1: use NCCL all_gather instead of the fused peer-store epilogue")
+    ap.add_argument("--no-paths", action="store_true", help="skip the C3/C4/C5-shard/YOLOv3 `paths` leg")
+    ap.add_argument("--no-c5", action="store_true", help="skip the BASELINE configs[4] (YOLOv7 bs=1024 sharded) leg")
+    ap.add_argument("--no-reference-gpu", action="store_true", help="skip the eager-torch + torchvision-on-CUDA bar")
+    ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the process to the GPU's local CPUs")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(_HERE, "libcvpp.so")
 
 CVPP_OK = 0
-RULE_TORCHVISION_CPU, RULE_COORD_TRICK, RULE_PER_CLASS = 0, 1, 2
+RULE_TORCHVISION_CPU, RULE_COORD_TRICK, RULE_PER_CLASS, RULE_TORCHVISION_CUDA = 0, 1, 2, 3
 ORDER_SCORE_DESC, ORDER_CLASS_MAJOR = 0, 1
 ROWS_YOLOV8, ROWS_SSD, ROWS_YOLOV7, ROWS_FULL, ROWS_COCO, ROWS_VOC = 0, 1, 2, 3, 4, 5
 BOX_KEEP, BOX_CORRECT, BOX_NORMALISE_CORRECT = 0, 1, 2
@@ -38,6 +38,7 @@ _PROTOS = {
     "cvpp_yolov8_decode_full": (c_int, [P(c_vp), P(c_i64), P(c_i64), P(c_int), P(c_int), P(c_f32), c_int, c_int,
                                         c_int, c_int, c_vp, c_vp]),
     "cvpp_pred_filter": (c_int, [c_vp, c_int, c_int, c_int, c_i64, c_f32, c_vp, c_vp, c_vp, c_int, c_vp]),
+    "cvpp_keep_classes": (c_int, [c_vp, c_vp, c_int, c_int, P(ctypes.c_int32), c_int, c_vp]),
     "cvpp_sort_workspace_bytes": (c_size, [c_int, c_int]),
     "cvpp_segmented_sort": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_size, c_vp]),
     "cvpp_nms_workspace_bytes": (c_size, [c_int, c_int, c_int]),
@@ -50,6 +51,9 @@ _PROTOS = {
     "cvpp_yolov8_postprocess": (c_int, [P(c_vp), P(c_i64), P(c_i64), P(c_int), P(c_int), P(c_f32), c_int, c_int,
                                         c_int, c_int, c_f32, c_f64, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp,
                                         c_vp, c_vp, c_vp, c_vp, c_size, c_vp]),
+    "cvpp_yolov8_postprocess_ev": (c_int, [P(c_vp), P(c_i64), P(c_i64), P(c_int), P(c_int), P(c_f32), c_int, c_int,
+                                           c_int, c_int, c_f32, c_f64, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp,
+                                           c_vp, c_vp, c_vp, c_vp, c_size, c_vp, c_vp]),
     "cvpp_centernet_workspace_bytes": (c_size, [c_int, c_int, c_int, c_int, c_int]),
     "cvpp_centernet_decode": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_f32, c_int, c_int, c_f32, c_vp, c_vp,
                                       c_vp, c_vp, c_vp, c_vp, c_vp, c_size, c_vp]),
@@ -68,6 +72,10 @@ _PROTOS = {
     "cvpp_centernet_suppress": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp]),
     "cvpp_detection_epilogue_allgather": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_i64, c_int, c_int,
                                                   c_vp, P(c_vp), c_int, c_int, c_vp]),
+    "cvpp_detection_epilogue_compact": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_i64, c_int, c_int,
+                                                c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
+    "cvpp_topk_workspace_bytes": (c_size, [c_int, c_int]),
+    "cvpp_topk": (c_int, [c_vp, c_int, c_i64, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_size, c_vp]),
     "cvpp_detection_epilogue": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_i64, c_int, c_int, c_vp,
                                         c_vp, c_vp, c_vp]),
 }

@@ -65,14 +65,11 @@ class CenterNetA:
     @staticmethod
     def _top_k(scores, k):
         """(B, H, W, C) scores -> (topk_scores, inds int32, classes, ys, xs), flat index order
-        (y*W + x)*C + c as in the reference.  Library top-k; the fused kernel selects peaks itself."""
+        (y*W + x)*C + c as in the reference (:328-338).  cvpp_topk: exact radix select, equal scores ordered
+        by the lower flat index (torch.topk leaves ties unspecified) - the rule of the fused decode."""
         B, H, W, C = scores.size()
-        topk_scores, topk_inds = torch.topk(scores.reshape(B, -1), k=k, largest=True, sorted=True)
-        clses = topk_inds % C
-        pixel = torch.div(topk_inds, C, rounding_mode="floor")
-        ys = torch.div(pixel, W, rounding_mode="floor")
-        xs = pixel % W
-        return topk_scores, (ys * W + xs).to(torch.int32), clses, ys, xs
+        val, _, clses, ys, xs, pixel = ops.topk(scores.reshape(B, -1).float(), k, split=(C, W))
+        return val, pixel, clses, ys, xs
 
     @staticmethod
     def _suppress_redundant_centers(heatmap, pool_size=3):

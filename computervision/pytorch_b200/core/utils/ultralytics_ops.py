@@ -3,7 +3,7 @@
 
 `non_max_suppression` keeps the reference signature.  It runs two CUDA kernels through the C ABI
 (confidence filter -> fused per-class sort + class-aware NMS) and reads the per-image counts back once;
-there is no per-image Python loop and no torchvision call.  The dead branches of the reference that no
+per-image results are views of one row buffer (no per-image kernels) and there is no torchvision call.  The dead branches of the reference that no
 caller reaches (multi_label, autolabelling `labels`, merge-NMS) raise NotImplementedError instead of
 silently doing something else; `agnostic` is accepted and ignored exactly like the reference, whose
 class-offset line is commented out (:243-247); `max_time_img` is accepted and ignored (the wall-clock
@@ -30,8 +30,12 @@ def xywh2xyxy(x):
 
 
 def _rows_from_detections(prediction: torch.Tensor, det: ops.Detections, nc: int, nm: int) -> List[torch.Tensor]:
-    """(n_i, 6 + nm) rows [x1, y1, x2, y2, conf, cls, masks...] per image, like reference :226,257."""
+    """(n_i, 6 + nm) rows [x1, y1, x2, y2, conf, cls, masks...] per image, like reference :226,257: ONE epilogue
+    kernel assembles the (B, max_det, 6) rows on the device, one device->host read fetches the counts, and every
+    image's result is a view of that buffer (mask columns, which no caller of the reference uses, are appended
+    per image)."""
     B = prediction.shape[0]
+    rows = ops.detection_epilogue(det, ops.ROWS_YOLOV8)
     counts = det.count.tolist()          # the one device->host read
     cap = det.box.shape[1]
     empty = torch.zeros((0, 6 + nm), device=prediction.device)
@@ -40,10 +44,8 @@ def _rows_from_detections(prediction: torch.Tensor, det: ops.Detections, nc: int
         if n <= 0:
             continue
         n = min(n, cap)
-        cols = [det.box[b, :n], det.score[b, :n, None], det.cls[b, :n, None].to(torch.float32)]
-        if nm:
-            cols.append(prediction[b, 4 + nc:, det.anchor[b, :n].long()].T)
-        out[b] = torch.cat(cols, 1)
+        out[b] = rows[b, :n] if not nm else \
+            torch.cat((rows[b, :n], prediction[b, 4 + nc:, det.anchor[b, :n].long()].T), 1)
     return out
 
 
@@ -87,23 +89,10 @@ def non_max_suppression(
 
     cand = ops.pred_filter(prediction, nc, conf_thres)
     if classes is not None:
-        _keep_classes(cand, classes)
+        ops.keep_classes(cand, classes)      # reference :229-230
     det = ops.sort_nms(cand, iou_thres, rule, ops.ORDER_SCORE_DESC, max_det=max_det, max_nms=max_nms, max_out=max_det)
     rows = _rows_from_detections(prediction.contiguous(), det, nc, nm)
     if return_anchors:
         counts = det.count.tolist()
         return rows, [det.anchor[b, :n] for b, n in enumerate(counts)]
     return rows
-
-
-def _keep_classes(cand: ops.Candidates, classes: Sequence[int]) -> None:
-    """`x = x[(x[:, 5:6] == classes).any(1)]` (reference :229-230) applied to the candidate keys on
-    the device: keys of other classes are pushed behind the kept ones and the counts shrink."""
-    key = cand.key
-    B, M = key.shape
-    cls = (key >> 52) & 0xFFF
-    valid = torch.arange(M, device=key.device)[None, :] < cand.count[:, None].clamp(max=M)
-    want = torch.isin(cls, torch.as_tensor(list(classes), device=key.device)) & valid
-    order = torch.argsort((~want).to(torch.uint8), dim=1, stable=True)
-    cand.key.copy_(torch.gather(key, 1, order))
-    cand.count.copy_(want.sum(1).to(torch.int32))

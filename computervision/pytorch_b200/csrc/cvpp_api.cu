@@ -57,6 +57,8 @@ int yolov8_decode_launch(const float* const* level_ptr, const int64_t* batch_str
                          float* box_dense, int max_cand, float* y, int force_generic, cudaStream_t stream);
 int pred_filter_launch(const float* pred, int B, int channels, int nc, int64_t A, float conf_thres, uint64_t* cand_key,
                        int32_t* cand_count, float* box_dense, int max_cand, cudaStream_t stream);
+int keep_classes_launch(uint64_t* cand_key, int32_t* cand_count, int B, int max_cand, const int32_t* classes, int n_classes,
+                        cudaStream_t stream);
 size_t segsort_workspace_bytes(int B, int max_cand);
 int segsort_launch(uint64_t* keys, int32_t* cand_count, int B, int max_cand, int rule, int max_nms, void* workspace,
                    size_t workspace_bytes, cudaStream_t stream);
@@ -104,9 +106,18 @@ int detection_epilogue_launch(const float* det_box, const float* det_score, cons
                               int max_out, int64_t A, int layout, int box_mode, const float* letterbox, float* rows,
                               float* count_out, float* const* peer_dst, int n_peers, int slot, cudaStream_t stream);
 
+int detection_epilogue_compact_launch(const float* det_box, const float* det_score, const int32_t* det_cls,
+                                      const int32_t* det_anchor, const int32_t* det_count, const float* aux_dense, int B,
+                                      int max_out, int64_t A, int layout, int box_mode, const float* letterbox, float* rows,
+                                      int64_t row_capacity, int32_t* row_offset, int32_t* overflow, cudaStream_t stream);
 int letterbox_reverse_launch(const float* boxes, int64_t n, int xywh, float in_w, float in_h, float left, float top,
                              float scale, float* out, cudaStream_t stream);
 int centernet_suppress_launch(const float* heat, int B, int H, int W, int C, float* out, cudaStream_t stream);
+
+size_t topk_workspace_bytes(int B, int K);
+int topk_launch(const float* scores, int B, long long N, int K, int C, int W, float* out_val, long long* out_idx,
+                long long* out_cls, long long* out_y, long long* out_x, int32_t* out_pixel, void* workspace,
+                size_t workspace_bytes, cudaStream_t stream);
 
 static int force_generic() {
   const char* e = getenv("CVPP_FORCE_GENERIC");
@@ -171,6 +182,11 @@ int cvpp_pred_filter(const float* pred, int B, int channels, int nc, int64_t A, 
                             (cudaStream_t)stream);
 }
 
+int cvpp_keep_classes(uint64_t* cand_key, int32_t* cand_count, int B, int max_cand, const int32_t* classes, int n_classes,
+                      cvpp_stream_t stream) {
+  return keep_classes_launch(cand_key, cand_count, B, max_cand, classes, n_classes, (cudaStream_t)stream);
+}
+
 size_t cvpp_sort_workspace_bytes(int B, int max_cand) {
   if (B < 0 || max_cand < 1) return 0;
   return segsort_workspace_bytes(B, max_cand);
@@ -219,12 +235,12 @@ size_t cvpp_yolov8_workspace_bytes(int B, int64_t A, int max_cand, int nc) {
   return s;
 }
 
-int cvpp_yolov8_postprocess(const float* const* level_ptr, const int64_t* batch_stride, const int64_t* chan_stride,
+int cvpp_yolov8_postprocess_ev(const float* const* level_ptr, const int64_t* batch_stride, const int64_t* chan_stride,
                             const int* level_h, const int* level_w, const float* level_stride, int num_levels, int B,
                             int nc, int reg_max, float conf_thres, double iou_thres, int rule, int max_det, int max_nms,
                             int max_cand, float* det_box, float* det_score, int32_t* det_cls, int32_t* det_anchor,
                             int32_t* det_count, int32_t* cand_count_out, void* workspace, size_t workspace_bytes,
-                            cvpp_stream_t stream) {
+                            cvpp_event_t inputs_consumed, cvpp_stream_t stream) {
   if (!level_h || !level_w || num_levels < 1 || num_levels > CVPP_MAX_LEVELS) {
     set_error("yolov8_postprocess: bad level description");
     return CVPP_ERR_INVALID_ARG;
@@ -233,6 +249,11 @@ int cvpp_yolov8_postprocess(const float* const* level_ptr, const int64_t* batch_
   for (int l = 0; l < num_levels; ++l) A += (int64_t)level_h[l] * level_w[l];
   if (max_det < 1 || max_cand < 1) {
     set_error("yolov8_postprocess: max_det and max_cand must be >= 1");
+    return CVPP_ERR_INVALID_ARG;
+  }
+  if ((int64_t)max_cand < A) {
+    set_error("yolov8_postprocess: max_cand=%d < A=%lld could overflow the candidate buffer (keys would be dropped in a "
+              "nondeterministic order); pass max_cand >= A", max_cand, (long long)A);
     return CVPP_ERR_INVALID_ARG;
   }
   if (!workspace || workspace_bytes < cvpp_yolov8_workspace_bytes(B, A, max_cand, nc)) {
@@ -253,10 +274,28 @@ int cvpp_yolov8_postprocess(const float* const* level_ptr, const int64_t* batch_
   int rc = cvpp_yolov8_decode_filter(level_ptr, batch_stride, chan_stride, level_h, level_w, level_stride, num_levels,
                                      B, nc, reg_max, conf_thres, cand_key, cand_count, box_dense, max_cand, stream);
   if (rc != CVPP_OK) return rc;
+  if (inputs_consumed) {  // the head tensors have no reader after the decode kernel
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    CVPP_CUDA_TRY(cudaStreamIsCapturing((cudaStream_t)stream, &cap));
+    CVPP_CUDA_TRY(cudaEventRecordWithFlags((cudaEvent_t)inputs_consumed, (cudaStream_t)stream,
+                                           cap == cudaStreamCaptureStatusActive ? cudaEventRecordExternal : cudaEventRecordDefault));
+  }
   // (the fused kernel also copies the candidate counts out: no separate device-to-device copy node)
   return sort_nms_launch(cand_key, cand_count, box_dense, B, max_cand, A, nc, iou_thres, rule, CVPP_ORDER_SCORE_DESC,
                          max_det, max_nms, max_det, det_box, det_score, det_cls, det_anchor, det_count, sn_ws, sn_bytes,
                          (cudaStream_t)stream, cand_count_out);
+}
+
+int cvpp_yolov8_postprocess(const float* const* level_ptr, const int64_t* batch_stride, const int64_t* chan_stride,
+                            const int* level_h, const int* level_w, const float* level_stride, int num_levels, int B,
+                            int nc, int reg_max, float conf_thres, double iou_thres, int rule, int max_det, int max_nms,
+                            int max_cand, float* det_box, float* det_score, int32_t* det_cls, int32_t* det_anchor,
+                            int32_t* det_count, int32_t* cand_count_out, void* workspace, size_t workspace_bytes,
+                            cvpp_stream_t stream) {
+  return cvpp_yolov8_postprocess_ev(level_ptr, batch_stride, chan_stride, level_h, level_w, level_stride, num_levels, B, nc,
+                                    reg_max, conf_thres, iou_thres, rule, max_det, max_nms, max_cand, det_box, det_score,
+                                    det_cls, det_anchor, det_count, cand_count_out, workspace, workspace_bytes, nullptr,
+                                    stream);
 }
 
 size_t cvpp_centernet_workspace_bytes(int B, int H, int W, int nc, int K) {
@@ -338,6 +377,15 @@ int cvpp_detection_epilogue(const float* det_box, const float* det_score, const 
                                    box_mode, letterbox, rows, count_out, nullptr, 0, 0, (cudaStream_t)stream);
 }
 
+int cvpp_detection_epilogue_compact(const float* det_box, const float* det_score, const int32_t* det_cls,
+                                    const int32_t* det_anchor, const int32_t* det_count, const float* aux_dense, int B,
+                                    int max_out, int64_t A, int layout, int box_mode, const float* letterbox, float* rows,
+                                    int64_t row_capacity, int32_t* row_offset, int32_t* overflow, cvpp_stream_t stream) {
+  return detection_epilogue_compact_launch(det_box, det_score, det_cls, det_anchor, det_count, aux_dense, B, max_out, A,
+                                           layout, box_mode, letterbox, rows, row_capacity, row_offset, overflow,
+                                           (cudaStream_t)stream);
+}
+
 int cvpp_detection_epilogue_allgather(const float* det_box, const float* det_score, const int32_t* det_cls,
                                       const int32_t* det_anchor, const int32_t* det_count, const float* aux_dense, int B,
                                       int max_out, int64_t A, int layout, int box_mode, const float* letterbox,
@@ -357,6 +405,19 @@ int cvpp_letterbox_reverse(const float* boxes, int64_t n, int xywh, float in_w, 
 
 int cvpp_centernet_suppress(const float* heat, int B, int H, int W, int C, float* out, cvpp_stream_t stream) {
   return centernet_suppress_launch(heat, B, H, W, C, out, (cudaStream_t)stream);
+}
+
+size_t cvpp_topk_workspace_bytes(int B, int K) {
+  if (B < 0 || K < 1) return 0;
+  return topk_workspace_bytes(B, K);
+}
+
+int cvpp_topk(const float* scores, int B, int64_t N, int K, int C, int W, float* out_val, int64_t* out_idx, int64_t* out_cls,
+              int64_t* out_y, int64_t* out_x, int32_t* out_pixel, void* workspace, size_t workspace_bytes,
+              cvpp_stream_t stream) {
+  return topk_launch(scores, B, (long long)N, K, C, W, out_val, reinterpret_cast<long long*>(out_idx),
+                     reinterpret_cast<long long*>(out_cls), reinterpret_cast<long long*>(out_y),
+                     reinterpret_cast<long long*>(out_x), out_pixel, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 }  // extern "C"

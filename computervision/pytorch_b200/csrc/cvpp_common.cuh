@@ -17,6 +17,8 @@
 // torchvision.ops.batched_nms on CPU switches to the per-class branch when boxes.numel() > 4000
 // (torchvision/ops/boxes.py:80), i.e. more than 1000 boxes.
 #define CVPP_TRICK_MAX_BOXES 1000
+// ... and on CUDA tensors when boxes.numel() > 20000, i.e. more than 5000 boxes (same line).
+#define CVPP_TRICK_MAX_BOXES_CUDA 5000
 
 namespace cvpp {
 
@@ -76,7 +78,8 @@ __host__ __device__ __forceinline__ uint64_t key_from_score_major(uint64_t k) {
 }
 
 __host__ __device__ __forceinline__ bool rule_uses_trick(int rule, int n) {
-  return rule == CVPP_NMS_RULE_COORD_TRICK || (rule == CVPP_NMS_RULE_TORCHVISION_CPU && n <= CVPP_TRICK_MAX_BOXES);
+  return rule == CVPP_NMS_RULE_COORD_TRICK || (rule == CVPP_NMS_RULE_TORCHVISION_CPU && n <= CVPP_TRICK_MAX_BOXES) ||
+         (rule == CVPP_NMS_RULE_TORCHVISION_CUDA && n <= CVPP_TRICK_MAX_BOXES_CUDA);
 }
 
 #ifdef __CUDACC__

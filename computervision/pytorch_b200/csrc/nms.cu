@@ -685,7 +685,7 @@ static int nms_prepare(NmsParams& p, size_t& smem, const uint64_t* sorted_key, c
     set_error("nms: Invalid IoU %f, valid values are between 0.0 and 1.0", iou_thres);
     return CVPP_ERR_INVALID_ARG;
   }
-  if (rule < 0 || rule > 2 || order < 0 || order > 1) {
+  if (rule < 0 || rule > 3 || order < 0 || order > 1) {
     set_error("nms: unknown rule %d / order %d", rule, order);
     return CVPP_ERR_INVALID_ARG;
   }
@@ -1409,7 +1409,7 @@ int sort_nms_launch(const uint64_t* cand_key, const int32_t* cand_count, const f
     set_error("sort_nms: Invalid IoU %f, valid values are between 0.0 and 1.0", iou_thres);
     return CVPP_ERR_INVALID_ARG;
   }
-  if (rule < 0 || rule > 2 || order < 0 || order > 1) {
+  if (rule < 0 || rule > 3 || order < 0 || order > 1) {
     set_error("sort_nms: unknown rule %d / order %d", rule, order);
     return CVPP_ERR_INVALID_ARG;
   }

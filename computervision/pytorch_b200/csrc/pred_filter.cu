@@ -71,4 +71,71 @@ int pred_filter_launch(const float* pred, int B, int channels, int nc, int64_t A
   return CVPP_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// keep_classes: `x = x[(x[:, 5:6] == classes).any(1)]` (core/utils/ultralytics_ops.py:229-230) on the candidate
+// keys: keys whose class bit is not set in the mask are dropped, in place, one CTA per image.  The keys are an
+// unordered set (the sort comes later), so the compaction need not be stable; a chunk is read into registers
+// before anything of it is overwritten, and the write cursor never passes the read cursor.
+// ---------------------------------------------------------------------------------------------------
+struct ClassMask {
+  uint32_t w[CVPP_MAX_CLASSES / 32];
+};
+
+__global__ void __launch_bounds__(1024) keep_classes_kernel(uint64_t* __restrict__ cand_key, int32_t* __restrict__ cand_count,
+                                                            int max_cand, const __grid_constant__ ClassMask mask) {
+  __shared__ int sh_warp[32];
+  __shared__ int sh_base;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint64_t* keys = cand_key + (int64_t)b * max_cand;
+  const int n = min(max(cand_count[b], 0), max_cand);
+  if (tid == 0) sh_base = 0;
+  __syncthreads();
+  for (int i0 = 0; i0 < n; i0 += 1024) {
+    const int i = i0 + tid;
+    uint64_t k = 0;
+    bool keep = false;
+    if (i < n) {
+      k = keys[i];
+      const uint32_t c = key_cls(k);
+      keep = (mask.w[c >> 5] >> (c & 31)) & 1u;
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) sh_warp[warp] = __popc(bal);
+    __syncthreads();   // every key of the chunk is in a register now
+    int woff = 0, total = 0;
+    for (int q = 0; q < 32; ++q) {
+      const int u = sh_warp[q];
+      if (q < warp) woff += u;
+      total += u;
+    }
+    const int base = sh_base;
+    if (keep) keys[base + woff + __popc(bal & ((1u << lane) - 1u))] = k;
+    __syncthreads();
+    if (tid == 0) sh_base = base + total;
+    __syncthreads();
+  }
+  if (tid == 0) cand_count[b] = sh_base;
+}
+
+int keep_classes_launch(uint64_t* cand_key, int32_t* cand_count, int B, int max_cand, const int32_t* classes, int n_classes,
+                        cudaStream_t stream) {
+  if (!cand_key || !cand_count || (n_classes > 0 && !classes)) {
+    set_error("keep_classes: NULL pointer argument");
+    return CVPP_ERR_INVALID_ARG;
+  }
+  if (B < 0 || max_cand < 1 || n_classes < 0) {
+    set_error("keep_classes: bad sizes (B=%d max_cand=%d n_classes=%d)", B, max_cand, n_classes);
+    return CVPP_ERR_INVALID_ARG;
+  }
+  ClassMask m{};
+  for (int i = 0; i < n_classes; ++i) {
+    const int c = classes[i];
+    if (c >= 0 && c < CVPP_MAX_CLASSES) m.w[c >> 5] |= 1u << (c & 31);  // ids outside the key range match nothing
+  }
+  if (B == 0) return CVPP_OK;
+  keep_classes_kernel<<<B, 1024, 0, stream>>>(cand_key, cand_count, max_cand, m);
+  CVPP_CUDA_TRY(cudaGetLastError());
+  return CVPP_OK;
+}
+
 }  // namespace cvpp

@@ -228,6 +228,63 @@ struct EpilogueParams {
   int64_t A;
 };
 
+// one caller-facing row of detection t = b * max_out + k (k < det_count[b]) in the layout / box mode of p
+__device__ __forceinline__ void epilogue_row(const EpilogueParams& p, int b, int64_t t, float (&row)[7]) {
+  float4 bx = p.det_box[t];
+  if (p.box_mode != CVPP_BOX_KEEP) {
+    const float* L = p.letterbox + 5 * b;
+    const float in_w = L[0], in_h = L[1], left = L[2], top = L[3], scale = L[4];
+    if (p.box_mode == CVPP_BOX_NORMALISE_CORRECT) {  // yolo_v8.py:233-234
+      bx.x = fdiv(bx.x, in_w);
+      bx.z = fdiv(bx.z, in_w);
+      bx.y = fdiv(bx.y, in_h);
+      bx.w = fdiv(bx.w, in_h);
+    }
+    // (x1y1 + x2y2) / 2, x2y2 - x1y1 (yolo_v7.py:416-417), then c -/+ wh / 2 (image_process.py:80-83)
+    const float cx = fmul(fadd(bx.x, bx.z), 0.5f), cy = fmul(fadd(bx.y, bx.w), 0.5f);
+    const float hw = fmul(fsub(bx.z, bx.x), 0.5f), hh = fmul(fsub(bx.w, bx.y), 0.5f);
+    // * input size, - padding, * scale (image_process.py:85-96); without letterbox the table holds
+    // (image_w, image_h, 0, 0, 1) and the same sequence is image_process.py:178-181 bit for bit
+    bx.x = fmul(fsub(fmul(fsub(cx, hw), in_w), left), scale);
+    bx.z = fmul(fsub(fmul(fadd(cx, hw), in_w), left), scale);
+    bx.y = fmul(fsub(fmul(fsub(cy, hh), in_h), top), scale);
+    bx.w = fmul(fsub(fmul(fadd(cy, hh), in_h), top), scale);
+  }
+  row[0] = bx.x;
+  row[1] = bx.y;
+  row[2] = bx.z;
+  row[3] = bx.w;
+  const float cls = (float)p.det_cls[t];
+  if (p.layout == CVPP_ROWS_YOLOV8) {  // x1,y1,x2,y2,conf,cls
+    row[4] = p.det_score[t];
+    row[5] = cls;
+  } else if (p.layout == CVPP_ROWS_SSD) {  // x1,y1,x2,y2,label,conf
+    row[4] = cls;
+    row[5] = p.det_score[t];
+  } else if (p.layout == CVPP_ROWS_YOLOV7) {  // x1,y1,x2,y2,obj,class_conf,class_pred
+    const float2 a = p.aux_dense[(int64_t)b * p.A + p.det_anchor[t]];
+    row[4] = a.x;
+    row[5] = a.y;
+    row[6] = cls;
+  } else if (p.layout == CVPP_ROWS_COCO) {  // x,y,w,h,score,cls (yolo_v8.py:364-372: right - left, bottom - top in fp32)
+    row[2] = fsub(bx.z, bx.x);
+    row[3] = fsub(bx.w, bx.y);
+    row[4] = p.det_score[t];
+    row[5] = cls;
+  } else if (p.layout == CVPP_ROWS_VOC) {  // cls,score,int(left),int(top),int(right),int(bottom) (yolo_v8.py:286-296)
+    row[0] = cls;
+    row[1] = p.det_score[t];
+    row[2] = truncf(bx.x);
+    row[3] = truncf(bx.y);
+    row[4] = truncf(bx.z);
+    row[5] = truncf(bx.w);
+  } else {  // CVPP_ROWS_FULL: x1,y1,x2,y2,score,cls,anchor
+    row[4] = p.det_score[t];
+    row[5] = cls;
+    row[6] = (float)p.det_anchor[t];
+  }
+}
+
 __global__ void __launch_bounds__(256) detection_epilogue_kernel(const __grid_constant__ EpilogueParams p) {
   // The rows of a CTA are one contiguous run of the output: they are staged in shared memory and leave as
   // coalesced 128-bit stores - into each peer's buffer over NVLink in the gather form (per-element 4-byte
@@ -240,61 +297,7 @@ __global__ void __launch_bounds__(256) detection_epilogue_kernel(const __grid_co
   const int b = valid ? (int)(t / p.max_out) : 0, k = valid ? (int)(t - (int64_t)b * p.max_out) : 0;
   const int n = valid ? min(p.det_count[b], p.max_out) : 0;
   float row[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  if (valid && k < n) {
-    float4 bx = p.det_box[t];
-    if (p.box_mode != CVPP_BOX_KEEP) {
-      const float* L = p.letterbox + 5 * b;
-      const float in_w = L[0], in_h = L[1], left = L[2], top = L[3], scale = L[4];
-      if (p.box_mode == CVPP_BOX_NORMALISE_CORRECT) {  // yolo_v8.py:233-234
-        bx.x = fdiv(bx.x, in_w);
-        bx.z = fdiv(bx.z, in_w);
-        bx.y = fdiv(bx.y, in_h);
-        bx.w = fdiv(bx.w, in_h);
-      }
-      // (x1y1 + x2y2) / 2, x2y2 - x1y1 (yolo_v7.py:416-417), then c -/+ wh / 2 (image_process.py:80-83)
-      const float cx = fmul(fadd(bx.x, bx.z), 0.5f), cy = fmul(fadd(bx.y, bx.w), 0.5f);
-      const float hw = fmul(fsub(bx.z, bx.x), 0.5f), hh = fmul(fsub(bx.w, bx.y), 0.5f);
-      // * input size, - padding, * scale (image_process.py:85-96); without letterbox the table holds
-      // (image_w, image_h, 0, 0, 1) and the same sequence is image_process.py:178-181 bit for bit
-      bx.x = fmul(fsub(fmul(fsub(cx, hw), in_w), left), scale);
-      bx.z = fmul(fsub(fmul(fadd(cx, hw), in_w), left), scale);
-      bx.y = fmul(fsub(fmul(fsub(cy, hh), in_h), top), scale);
-      bx.w = fmul(fsub(fmul(fadd(cy, hh), in_h), top), scale);
-    }
-    row[0] = bx.x;
-    row[1] = bx.y;
-    row[2] = bx.z;
-    row[3] = bx.w;
-    const float cls = (float)p.det_cls[t];
-    if (p.layout == CVPP_ROWS_YOLOV8) {  // x1,y1,x2,y2,conf,cls
-      row[4] = p.det_score[t];
-      row[5] = cls;
-    } else if (p.layout == CVPP_ROWS_SSD) {  // x1,y1,x2,y2,label,conf
-      row[4] = cls;
-      row[5] = p.det_score[t];
-    } else if (p.layout == CVPP_ROWS_YOLOV7) {  // x1,y1,x2,y2,obj,class_conf,class_pred
-      const float2 a = p.aux_dense[(int64_t)b * p.A + p.det_anchor[t]];
-      row[4] = a.x;
-      row[5] = a.y;
-      row[6] = cls;
-    } else if (p.layout == CVPP_ROWS_COCO) {  // x,y,w,h,score,cls (yolo_v8.py:364-372: right - left, bottom - top in fp32)
-      row[2] = fsub(bx.z, bx.x);
-      row[3] = fsub(bx.w, bx.y);
-      row[4] = p.det_score[t];
-      row[5] = cls;
-    } else if (p.layout == CVPP_ROWS_VOC) {  // cls,score,int(left),int(top),int(right),int(bottom) (yolo_v8.py:286-296)
-      row[0] = cls;
-      row[1] = p.det_score[t];
-      row[2] = truncf(bx.x);
-      row[3] = truncf(bx.y);
-      row[4] = truncf(bx.z);
-      row[5] = truncf(bx.w);
-    } else {  // CVPP_ROWS_FULL: x1,y1,x2,y2,score,cls,anchor
-      row[4] = p.det_score[t];
-      row[5] = cls;
-      row[6] = (float)p.det_anchor[t];
-    }
-  }
+  if (valid && k < n) epilogue_row(p, b, t, row);
   for (int c = 0; c < p.width; ++c) sh_rows[threadIdx.x * p.width + c] = row[c];  // odd width: conflict-free
   __syncthreads();
   const int rows_here = (int)min((int64_t)blockDim.x, total - t0);
@@ -379,6 +382,132 @@ int detection_epilogue_launch(const float* det_box, const float* det_score, cons
   p.A = A;
   const int64_t total = (int64_t)B * max_out;
   detection_epilogue_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(p);
+  CVPP_CUDA_TRY(cudaGetLastError());
+  return CVPP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Compact epilogue (the all-gather payload of heads WITHOUT a max_det cap - YOLOv7 / SSD / YOLOv3):
+// the rows of image b start at row_offset[b] = sum over b' < b of min(det_count[b'], max_out), no padding.
+// Kernel 1 (one CTA): exclusive scan of the clamped counts -> row_offset[0..B], overflow flag when the total
+// exceeds the row capacity.  Kernel 2: grid (ceil(max_out / 256), B); a CTA past the image's count exits at once.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) row_offsets_kernel(const int32_t* __restrict__ det_count, int B, int max_out,
+                                                           int64_t row_capacity, int32_t* __restrict__ row_offset,
+                                                           int32_t* __restrict__ overflow) {
+  __shared__ int sh_warp[32];
+  __shared__ int sh_base;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) sh_base = 0;
+  __syncthreads();
+  for (int b0 = 0; b0 < B; b0 += 1024) {
+    const int b = b0 + tid;
+    const int v = b < B ? min(max(det_count[b], 0), max_out) : 0;
+    int incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int u = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += u;
+    }
+    if (lane == 31) sh_warp[warp] = incl;
+    __syncthreads();
+    int woff = 0, total = 0;
+    for (int q = 0; q < 32; ++q) {
+      const int u = sh_warp[q];
+      if (q < warp) woff += u;
+      total += u;
+    }
+    const int base = sh_base;
+    if (b < B) row_offset[b] = base + woff + incl - v;
+    __syncthreads();
+    if (tid == 0) sh_base = base + total;
+    __syncthreads();
+  }
+  if (tid == 0) {
+    row_offset[B] = sh_base;
+    if (overflow) *overflow = (int64_t)sh_base > row_capacity ? 1 : 0;
+  }
+}
+
+__global__ void __launch_bounds__(256) detection_epilogue_compact_kernel(const __grid_constant__ EpilogueParams p,
+                                                                         const int32_t* __restrict__ row_offset,
+                                                                         int64_t row_capacity) {
+  __shared__ __align__(16) float sh_rows[256 * 7];
+  const int b = blockIdx.y;
+  const int n = min(max(p.det_count[b], 0), p.max_out);
+  const int k0 = blockIdx.x * 256;
+  if (k0 >= n) return;
+  const int k = k0 + threadIdx.x;
+  float row[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (k < n) epilogue_row(p, b, (int64_t)b * p.max_out + k, row);
+  for (int c = 0; c < p.width; ++c) sh_rows[threadIdx.x * p.width + c] = row[c];
+  __syncthreads();
+  const int64_t first = (int64_t)row_offset[b] + k0;
+  int64_t rows_here = min(256, n - k0);
+  if (first + rows_here > row_capacity) rows_here = row_capacity > first ? row_capacity - first : 0;  // overflow: truncated
+  const int floats = (int)rows_here * p.width;
+  float* o = p.rows + first * p.width;
+  // the run starts at an arbitrary row: peel to the first 16-byte boundary, then 128-bit stores
+  const int head = min(floats, (int)(((16u - (uint32_t)(reinterpret_cast<uintptr_t>(o) & 15u)) & 15u) >> 2));
+  for (int i = threadIdx.x; i < head; i += 256) o[i] = sh_rows[i];
+  const int nv = (floats - head) >> 2;
+  float4* o4 = reinterpret_cast<float4*>(o + head);
+  for (int i = threadIdx.x; i < nv; i += 256) {
+    const float* s = sh_rows + head + 4 * i;
+    o4[i] = make_float4(s[0], s[1], s[2], s[3]);
+  }
+  for (int i = head + (nv << 2) + threadIdx.x; i < floats; i += 256) o[i] = sh_rows[i];
+}
+
+int detection_epilogue_compact_launch(const float* det_box, const float* det_score, const int32_t* det_cls,
+                                      const int32_t* det_anchor, const int32_t* det_count, const float* aux_dense, int B,
+                                      int max_out, int64_t A, int layout, int box_mode, const float* letterbox, float* rows,
+                                      int64_t row_capacity, int32_t* row_offset, int32_t* overflow, cudaStream_t stream) {
+  if (!det_box || !det_score || !det_cls || !det_anchor || !det_count || !rows || !row_offset) {
+    set_error("detection_epilogue_compact: NULL pointer argument");
+    return CVPP_ERR_INVALID_ARG;
+  }
+  if (B < 0 || B > 65535 || max_out < 1 || row_capacity < 0 || layout < CVPP_ROWS_YOLOV8 || layout > CVPP_ROWS_VOC ||
+      box_mode < CVPP_BOX_KEEP || box_mode > CVPP_BOX_NORMALISE_CORRECT) {
+    set_error("detection_epilogue_compact: bad sizes (B=%d, B <= 65535) / layout %d / box_mode %d", B, layout, box_mode);
+    return CVPP_ERR_INVALID_ARG;
+  }
+  if ((int64_t)B * max_out > 0x7fffffffll) {
+    set_error("detection_epilogue_compact: B * max_out must fit 31 bits");
+    return CVPP_ERR_INVALID_ARG;
+  }
+  if (layout == CVPP_ROWS_YOLOV7 && (!aux_dense || A < 1)) {
+    set_error("detection_epilogue_compact: the YOLOv7 layout needs aux_dense (B, A, 2)");
+    return CVPP_ERR_INVALID_ARG;
+  }
+  if (box_mode != CVPP_BOX_KEEP && !letterbox) {
+    set_error("detection_epilogue_compact: box_mode %d needs the (B, 5) letterbox table", box_mode);
+    return CVPP_ERR_INVALID_ARG;
+  }
+  if ((reinterpret_cast<uintptr_t>(det_box) & 15u) || (reinterpret_cast<uintptr_t>(rows) & 3u)) {
+    set_error("detection_epilogue_compact: det_box must be 16-byte aligned");
+    return CVPP_ERR_ALIGNMENT;
+  }
+  row_offsets_kernel<<<1, 1024, 0, stream>>>(det_count, B, max_out, row_capacity, row_offset, overflow);
+  CVPP_CUDA_TRY(cudaGetLastError());
+  if (B == 0) return CVPP_OK;
+  EpilogueParams p{};
+  p.det_box = reinterpret_cast<const float4*>(det_box);
+  p.det_score = det_score;
+  p.det_cls = det_cls;
+  p.det_anchor = det_anchor;
+  p.det_count = det_count;
+  p.aux_dense = reinterpret_cast<const float2*>(aux_dense);
+  p.letterbox = letterbox;
+  p.rows = rows;
+  p.B = B;
+  p.max_out = max_out;
+  p.layout = layout;
+  p.box_mode = box_mode;
+  p.width = (layout == CVPP_ROWS_YOLOV7 || layout == CVPP_ROWS_FULL) ? 7 : 6;
+  p.A = A;
+  const dim3 grid((unsigned)((max_out + 255) / 256), (unsigned)B);
+  detection_epilogue_compact_kernel<<<grid, 256, 0, stream>>>(p, row_offset, row_capacity);
   CVPP_CUDA_TRY(cudaGetLastError());
   return CVPP_OK;
 }

@@ -127,6 +127,11 @@ class PeerGather:
         rows = s[: self.n_rows].reshape(self.world * self.b_local, self.max_det, self.width)
         return rows, s[self.n_rows:].to(torch.int32)
 
+    def view_counts_f32(self, i: int) -> torch.Tensor:
+        """The (world*B,) per-image counts of slot i as stored (fp32), a view - no conversion kernel."""
+        s = self.buf[(i % self.depth) * self.slot_elems:]
+        return s[self.n_rows: self.n_rows + self.world * self.b_local]
+
 
 def split_rows(rows_all: torch.Tensor, counts_all: torch.Tensor) -> List[torch.Tensor]:
     """Per-image (n_i, W) views of the gathered rows (one host read of the counts)."""

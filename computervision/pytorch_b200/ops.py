@@ -11,7 +11,7 @@ import torch
 from . import _lib
 from ._lib import (BOX_CORRECT, BOX_KEEP, BOX_NORMALISE_CORRECT, ORDER_CLASS_MAJOR, ORDER_SCORE_DESC,  # noqa: F401
                    ROWS_COCO, ROWS_FULL, ROWS_SSD, ROWS_VOC, ROWS_YOLOV7, ROWS_YOLOV8, RULE_COORD_TRICK, RULE_PER_CLASS,
-                   RULE_TORCHVISION_CPU, check)
+                   RULE_TORCHVISION_CPU, RULE_TORCHVISION_CUDA, check)
 
 c_vp = ctypes.c_void_p
 
@@ -154,6 +154,16 @@ def pred_filter(pred: torch.Tensor, nc: int, conf_thres: float, max_cand: Option
     return Candidates(key, count, box_dense, max_cand, A, nc)
 
 
+def keep_classes(c: Candidates, classes: Sequence[int]) -> None:
+    """cvpp_keep_classes: drop (in place) the candidate keys whose class is not in `classes`."""
+    ids = [int(v) for v in classes]
+    arr = (ctypes.c_int32 * max(len(ids), 1))(*ids)
+    dev = c.key.device
+    with torch.cuda.device(dev):
+        check(_lib.lib().cvpp_keep_classes(_ptr(c.key), _ptr(c.count), int(c.key.shape[0]), c.max_cand, arr, len(ids),
+                                           _stream(dev)))
+
+
 def segmented_sort(c: Candidates, rule: int = RULE_TORCHVISION_CPU, max_nms: int = 0) -> None:
     """Sorts c.key in place (and truncates c.count to max_nms when max_nms > 0)."""
     l = _lib.lib()
@@ -212,14 +222,19 @@ def sort_nms(c: Candidates, iou_thres: float, rule: int = RULE_TORCHVISION_CPU, 
 
 
 class Yolov8Postprocessor:
-    """Pre-allocated buffers + one C call (cvpp_yolov8_postprocess) per batch: decode+filter, sort, NMS.
+    """Pre-allocated buffers + one C call (cvpp_yolov8_postprocess_ev) per batch: decode+filter, sort, NMS.
 
     `capture()` records that call into a CUDA graph bound to one LevelSet (fixed input buffers), so a
-    steady-state step is a single graph launch - the form to use for bs=1 latency."""
+    steady-state step is a single graph launch - the form to use for bs=1 latency.
+    max_cand defaults to A (one key per anchor at most); smaller values are rejected because an overflowing
+    candidate buffer would drop keys in a nondeterministic order."""
 
     def __init__(self, B: int, A: int, nc: int, device, max_det: int = 300, max_cand: Optional[int] = None):
         self.B, self.A, self.nc, self.max_det = int(B), int(A), int(nc), int(max_det)
         self.max_cand = int(max_cand or A)
+        if self.max_cand < self.A:
+            raise ValueError(f"max_cand={self.max_cand} < A={self.A}: the candidate buffer could overflow "
+                             "(every anchor can pass the confidence filter)")
         self.device = torch.device(device)
         if self.device.index is None:
             self.device = torch.device("cuda", torch.cuda.current_device())
@@ -238,22 +253,30 @@ class Yolov8Postprocessor:
                           _ptr(self.ws), self.ws_bytes)
 
     def __call__(self, ls: LevelSet, conf_thres: float, iou_thres: float, rule: int = RULE_TORCHVISION_CPU,
-                 max_nms: int = 30000, reg_max: int = 16) -> Detections:
+                 max_nms: int = 30000, reg_max: int = 16, consumed: Optional[torch.cuda.Event] = None) -> Detections:
+        """`consumed` (optional CUDA event) is recorded right after the decode kernel, the last reader of `ls`."""
         if ls.B != self.B or ls.A != self.A or ls.C != 4 * reg_max + self.nc:
             raise ValueError("level set does not match the shapes this post-processor was built for")
         dev = self.device
+        if ls.device != dev:
+            raise ValueError(f"level set lives on {ls.device}, this post-processor on {dev}")
         if torch.cuda.current_device() != dev.index:
             with torch.cuda.device(dev):
-                return self.__call__(ls, conf_thres, iou_thres, rule, max_nms, reg_max)
-        check(self._lib.cvpp_yolov8_postprocess(
+                return self.__call__(ls, conf_thres, iou_thres, rule, max_nms, reg_max, consumed)
+        ev = c_vp(0)
+        if consumed is not None:
+            if not consumed.cuda_event:          # torch creates the handle lazily, on the first record
+                consumed.record()
+            ev = c_vp(consumed.cuda_event)
+        check(self._lib.cvpp_yolov8_postprocess_ev(
             ls.ptr, ls.batch_stride, ls.chan_stride, ls.h, ls.w, ls.stride, ls.n, self.B, self.nc, reg_max,
             float(conf_thres), float(iou_thres), rule, self.max_det, int(max_nms), self.max_cand, *self._out_args,
-            c_vp(torch.cuda.current_stream().cuda_stream)))
+            ev, c_vp(torch.cuda.current_stream().cuda_stream)))
         return self.det
 
     def capture(self, ls: LevelSet, conf_thres: float, iou_thres: float, rule: int = RULE_TORCHVISION_CPU,
-                max_nms: int = 30000, reg_max: int = 16) -> "GraphedPostprocess":
-        return GraphedPostprocess(self, ls, (conf_thres, iou_thres, rule, max_nms, reg_max))
+                max_nms: int = 30000, reg_max: int = 16, consumed: Optional[torch.cuda.Event] = None) -> "GraphedPostprocess":
+        return GraphedPostprocess(self, ls, (conf_thres, iou_thres, rule, max_nms, reg_max, consumed))
 
 
 class GraphedPostprocess:
@@ -274,27 +297,67 @@ class GraphedPostprocess:
 
 
 class PipelinedPostprocess:
-    """Throughput mode of the YOLOv8 post-processor: `depth` detection buffer sets, each with its own CUDA graph and
-    its own stream, used round-robin.  Consecutive batches are independent, so the fused sort+NMS kernel of batch k
-    (64 CTAs, latency-bound) overlaps the HBM-bound decode of batch k+1 on the SMs it leaves idle; a stream replays
-    its own graph in order, which is all the synchronisation buffer reuse needs.
+    """Throughput mode of the YOLOv8 post-processor: `depth` slots, each with its own INPUT buffers (one LevelSet per
+    slot), detection buffers, CUDA graph and stream, used round-robin.  Consecutive batches are independent, so the
+    fused sort+NMS kernel of batch k (64 CTAs, latency-bound) overlaps the HBM-bound decode of batch k+1 on the SMs
+    it leaves idle.
 
-        pipe = PipelinedPostprocess(B, A, nc, device, ls, conf, iou)
-        det = pipe.submit()        # returns at once; `det` belongs to slot pipe.last_slot
-        pipe.wait(pipe.last_slot)  # or pipe.join(): the caller's stream waits for the slot / for everything
-    """
+    Synchronisation with the producer of the head tensors (the network, or an H2D copy):
+      * `submit(ready)` makes the slot's stream wait for `ready` (an event the producer recorded after writing the
+        slot's inputs; None = the inputs were written on the current stream before fork()/submit order holds);
+      * `consumed[slot]` is recorded right after the slot's decode kernel (inside the replayed graph, as an external
+        event-record node): the producer waits on it before overwriting that slot's inputs - while the slot's NMS
+        may still be running;
+      * `wait(slot)` / `join()`: the caller's stream waits for the slot's detections / for everything.
 
-    def __init__(self, B: int, A: int, nc: int, device, ls: LevelSet, conf_thres: float, iou_thres: float,
-                 max_det: int = 300, depth: int = 2, graph: bool = True, **post_args):
+        pipe = PipelinedPostprocess(B, A, nc, device, [ls0, ls1, ls2], conf, iou)
+        for k, batch in enumerate(batches):
+            slot = pipe.next_slot
+            with torch.cuda.stream(producer):
+                producer.wait_event(pipe.consumed[slot])     # slot's previous decode is done with the buffers
+                write(batch, into=inputs[slot]); ready = torch.cuda.Event(); ready.record(producer)
+            det = pipe.submit(ready)                          # returns at once
+        pipe.join()
+
+    A single LevelSet may be passed instead of a list: every slot then reads the SAME buffers (static-input
+    benchmarking only - a real producer could not refill them while another slot's decode is in flight)."""
+
+    def __init__(self, B: int, A: int, nc: int, device, inputs, conf_thres: float, iou_thres: float,
+                 max_det: int = 300, depth: Optional[int] = None, graph: bool = True, **post_args):
+        if isinstance(inputs, LevelSet):
+            depth = int(depth or 2)
+            inputs = [inputs] * depth
+            self.static_input = True
+        else:
+            inputs = list(inputs)
+            if depth is not None and int(depth) != len(inputs):
+                raise ValueError(f"depth={depth} but {len(inputs)} input level sets were given (one per slot)")
+            depth = len(inputs)
+            self.static_input = False
+        if depth < 1:
+            raise ValueError("at least one slot is needed")
+        self.inputs = inputs
         self.posts = [Yolov8Postprocessor(B, A, nc, device, max_det=max_det) for _ in range(depth)]
         self.device = self.posts[0].device
         self.args = (conf_thres, iou_thres) + tuple(post_args.get(k, d) for k, d in
                                                     (("rule", RULE_TORCHVISION_CPU), ("max_nms", 30000), ("reg_max", 16)))
-        self.ls = ls
-        self.graphs = [pp.capture(ls, *self.args) for pp in self.posts] if graph else None
+        self.consumed = [torch.cuda.Event() for _ in range(depth)]
+        with torch.cuda.device(self.device):
+            for e in self.consumed:
+                e.record()                  # creates the handle; "consumed" holds before the first use of a slot
+        self.graphs = [pp.capture(ls, *self.args, consumed=e) for pp, ls, e in zip(self.posts, inputs, self.consumed)] \
+            if graph else None
         self.streams = [torch.cuda.Stream(device=self.device) for _ in range(depth)]
         self.turn = 0
         self.last_slot = 0
+
+    @property
+    def ls(self) -> LevelSet:
+        return self.inputs[0]
+
+    @property
+    def next_slot(self) -> int:
+        return self.turn % len(self.posts)
 
     def fork(self) -> None:
         """Every pipeline stream waits for the work already queued on the caller's current stream."""
@@ -302,15 +365,18 @@ class PipelinedPostprocess:
         for s in self.streams:
             s.wait_stream(cur)
 
-    def submit(self) -> Detections:
+    def submit(self, ready: Optional[torch.cuda.Event] = None) -> Detections:
         i = self.turn % len(self.posts)
         self.turn += 1
         self.last_slot = i
-        with torch.cuda.stream(self.streams[i]):
+        st = self.streams[i]
+        if ready is not None:
+            st.wait_event(ready)
+        with torch.cuda.stream(st):
             if self.graphs is not None:
                 self.graphs[i].replay()
             else:
-                self.posts[i](self.ls, *self.args)
+                self.posts[i](self.inputs[i], *self.args, consumed=self.consumed[i])
         return self.posts[i].det
 
     def wait(self, slot: int) -> None:
@@ -588,6 +654,38 @@ def detection_epilogue(det: Detections, layout: int, box_mode: int = BOX_KEEP, l
     return flat if packed else flat.reshape(B, max_out, width)
 
 
+def detection_epilogue_compact(det: Detections, layout: int, row_capacity: int, box_mode: int = BOX_KEEP,
+                               letterbox: Optional[torch.Tensor] = None, aux_dense: Optional[torch.Tensor] = None,
+                               out: Optional[torch.Tensor] = None, row_offset: Optional[torch.Tensor] = None,
+                               overflow: Optional[torch.Tensor] = None):
+    """cvpp_detection_epilogue_compact: rows of all images back to back (no padding).  Returns
+    (rows (row_capacity, W) float32, row_offset (B + 1,) int32, overflow (1,) int32) - all on the device, nothing is
+    read back; image b owns rows[row_offset[b]:row_offset[b + 1]]."""
+    B, max_out = int(det.box.shape[0]), int(det.box.shape[1])
+    dev = det.box.device
+    width = 7 if layout in (ROWS_YOLOV7, ROWS_FULL) else 6
+    row_capacity = int(row_capacity)
+    if out is None:
+        out = torch.empty((max(row_capacity, 1), width), dtype=torch.float32, device=dev)
+    if out.numel() < row_capacity * width or out.dtype != torch.float32 or not out.is_contiguous():
+        raise ValueError("`out` is too small / not contiguous float32 for this row capacity")
+    if row_offset is None:
+        row_offset = torch.empty((B + 1,), dtype=torch.int32, device=dev)
+    if overflow is None:
+        overflow = torch.empty((1,), dtype=torch.int32, device=dev)
+    A = int(aux_dense.shape[1]) if aux_dense is not None else 0
+    if letterbox is not None:
+        letterbox = letterbox.to(device=dev, dtype=torch.float32).contiguous()
+        if tuple(letterbox.shape) != (B, 5):
+            raise ValueError("letterbox must be (B, 5)")
+    with torch.cuda.device(dev):
+        check(_lib.lib().cvpp_detection_epilogue_compact(_ptr(det.box), _ptr(det.score), _ptr(det.cls), _ptr(det.anchor),
+                                                         _ptr(det.count), _ptr(aux_dense), B, max_out, A, int(layout),
+                                                         int(box_mode), _ptr(letterbox), _ptr(out), row_capacity,
+                                                         _ptr(row_offset), _ptr(overflow), _stream(dev)))
+    return out, row_offset, overflow
+
+
 def detection_epilogue_allgather(det: Detections, layout: int, peer_ptrs: Sequence[int], rank: int,
                                  box_mode: int = BOX_KEEP, letterbox: Optional[torch.Tensor] = None,
                                  aux_dense: Optional[torch.Tensor] = None) -> None:
@@ -635,6 +733,36 @@ def centernet_suppress(heat: torch.Tensor) -> torch.Tensor:
     with torch.cuda.device(heat.device):
         check(_lib.lib().cvpp_centernet_suppress(_ptr(heat), B, H, W, C, _ptr(out), _stream(heat.device)))
     return out
+
+
+def topk(scores: torch.Tensor, k: int, split: Optional[Tuple[int, int]] = None):
+    """cvpp_topk: scores (B, N) float32 -> (values (B, k), indices (B, k) int64), scores descending, equal scores by
+    the lower flat index.  split=(C, W) also returns the reference's index split (CenterNetA._top_k,
+    centernet.py:331-337): (values, indices, cls, ys, xs, pixel) with pixel = y*W + x as int32."""
+    _require_cuda(scores, "scores")
+    if scores.dim() != 2:
+        raise ValueError(f"scores must be (B, N), got {tuple(scores.shape)}")
+    scores = scores.contiguous()
+    B, N = int(scores.shape[0]), int(scores.shape[1])
+    k = int(k)
+    if k < 1 or k > N:
+        raise RuntimeError("selected index k out of range")      # torch.topk's message for the same misuse
+    dev = scores.device
+    l = _lib.lib()
+    nbytes = int(l.cvpp_topk_workspace_bytes(B, k))
+    ws = torch.empty((max(nbytes, 1),), dtype=torch.uint8, device=dev)
+    val = torch.empty((B, k), dtype=torch.float32, device=dev)
+    idx = torch.empty((B, k), dtype=torch.int64, device=dev)
+    cls = ys = xs = pix = None
+    C = W = 0
+    if split is not None:
+        C, W = int(split[0]), int(split[1])
+        cls, ys, xs = (torch.empty((B, k), dtype=torch.int64, device=dev) for _ in range(3))
+        pix = torch.empty((B, k), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        check(l.cvpp_topk(_ptr(scores), B, N, k, C, W, _ptr(val), _ptr(idx), _ptr(cls), _ptr(ys), _ptr(xs), _ptr(pix),
+                          _ptr(ws), nbytes, _stream(dev)))
+    return (val, idx) if split is None else (val, idx, cls, ys, xs, pix)
 
 
 def correct_boxes_params(image_hw: Sequence[Tuple[int, int]], input_hw: Sequence[int], letterbox_image: bool,

@@ -35,6 +35,7 @@ extern "C" {
 #endif
 
 typedef void* cvpp_stream_t;
+typedef void* cvpp_event_t; /* a cudaEvent_t / CUevent handle owned by the caller */
 
 #if defined(__GNUC__)
 #define CVPP_API __attribute__((visibility("default")))
@@ -55,7 +56,9 @@ enum {
 enum {
   CVPP_NMS_RULE_TORCHVISION_CPU = 0, /* per image: n > 1000 -> per-class ("vanilla") else coordinate trick */
   CVPP_NMS_RULE_COORD_TRICK = 1,     /* boxes + cls * (max_coord + 1), one class-agnostic pass          */
-  CVPP_NMS_RULE_PER_CLASS = 2        /* per-class nms on raw boxes (also what YOLOv7/SSD/YOLOv3 do)      */
+  CVPP_NMS_RULE_PER_CLASS = 2,       /* per-class nms on raw boxes (also what YOLOv7/SSD/YOLOv3 do)      */
+  CVPP_NMS_RULE_TORCHVISION_CUDA = 3 /* batched_nms's switch for CUDA tensors: n > 5000 -> per-class else trick
+                                        (boxes.numel() > 20000, torchvision/ops/boxes.py:80); same IoU test    */
 };
 
 /* output order of cvpp_nms */
@@ -126,6 +129,14 @@ CVPP_API int cvpp_pred_filter(const float* pred, int B, int channels, int nc, in
                      cvpp_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Class filter on candidate keys, in place: keeps the keys whose class id is in `classes` (HOST array of
+ * n_classes ids) and rewrites cand_count.  A count above max_cand (an overflowed filter) is clamped first.
+ * Replaces: x = x[(x[:, 5:6] == torch.tensor(classes)).any(1)]   core/utils/ultralytics_ops.py:229-230
+ * ------------------------------------------------------------------------------------------- */
+CVPP_API int cvpp_keep_classes(uint64_t* cand_key, int32_t* cand_count, int B, int max_cand, const int32_t* classes,
+                               int n_classes, cvpp_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Segmented sort of candidate keys, one segment per image (kernel 2).
  * Replaces: x[:, 4].argsort(descending=True)[:max_nms]   core/utils/ultralytics_ops.py:240
  *           the stable descending sort inside torchvision nms (per class)
@@ -183,7 +194,8 @@ CVPP_API int cvpp_sort_nms(const uint64_t* cand_key, const int32_t* cand_count, 
  * The whole YOLOv8 path in one call: decode+filter -> fused sort+NMS (cvpp_sort_nms) on `stream`.
  * Replaces Detect.forward eval tail + non_max_suppression as chained by YOLOv8.decode_box
  * (core/algorithms/yolo_v8.py:222-227).  Scratch buffers are carved from `workspace`
- * (cvpp_yolov8_workspace_bytes).  max_cand = A is always sufficient.
+ * (cvpp_yolov8_workspace_bytes).  max_cand must be >= A (one key per anchor at most): a smaller buffer could
+ * overflow and drop keys in a nondeterministic order, so it is rejected with CVPP_ERR_INVALID_ARG.
  * ------------------------------------------------------------------------------------------- */
 CVPP_API size_t cvpp_yolov8_workspace_bytes(int B, int64_t A, int max_cand, int nc);
 CVPP_API int cvpp_yolov8_postprocess(const float* const* level_ptr, const int64_t* batch_stride,
@@ -193,6 +205,20 @@ CVPP_API int cvpp_yolov8_postprocess(const float* const* level_ptr, const int64_
                             int max_cand, float* det_box, float* det_score, int32_t* det_cls,
                             int32_t* det_anchor, int32_t* det_count, int32_t* cand_count_out,
                             void* workspace, size_t workspace_bytes, cvpp_stream_t stream);
+
+/* The same call for pipelined callers (several batches in flight on different streams): `inputs_consumed`
+ * (nullable) is recorded on `stream` right after the decode+filter kernel - the last reader of the head
+ * tensors - so the producer of the NEXT batch may overwrite them while this batch's sort+NMS still runs.
+ * Under stream capture the record becomes an external event-record node (cudaEventRecordExternal), so the
+ * event can be waited on from outside the replayed graph. */
+CVPP_API int cvpp_yolov8_postprocess_ev(const float* const* level_ptr, const int64_t* batch_stride,
+                            const int64_t* chan_stride, const int* level_h, const int* level_w,
+                            const float* level_stride, int num_levels, int B, int nc, int reg_max,
+                            float conf_thres, double iou_thres, int rule, int max_det, int max_nms,
+                            int max_cand, float* det_box, float* det_score, int32_t* det_cls,
+                            int32_t* det_anchor, int32_t* det_count, int32_t* cand_count_out,
+                            void* workspace, size_t workspace_bytes, cvpp_event_t inputs_consumed,
+                            cvpp_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * CenterNet decode (kernel 4): heatmap peaks + top-K + box assembly + score mask + optional
@@ -329,6 +355,20 @@ CVPP_API int cvpp_detection_epilogue(const float* det_box, const float* det_scor
                                      float* rows, float* count_out, cvpp_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Compact detection epilogue: the same rows, WITHOUT padding - image b's rows start at
+ * row_offset[b] = sum over b' < b of min(det_count[b'], max_out); row_offset has B + 1 entries (the last one
+ * is the total).  This is the all-gather payload of the heads that have no max_det cap (YOLOv7._nms
+ * core/algorithms/yolo_v7.py:348-422, Ssd.decode_boxes ssd.py:236-288, yolo3_nms core/utils/nms.py:54-84):
+ * ranks exchange row_offset[B] first, or pass a fixed row_capacity and check `overflow` (nullable, one int32:
+ * 1 when the total exceeds row_capacity; rows beyond the capacity are not written).  B <= 65535.
+ * ------------------------------------------------------------------------------------------- */
+CVPP_API int cvpp_detection_epilogue_compact(const float* det_box, const float* det_score, const int32_t* det_cls,
+                                             const int32_t* det_anchor, const int32_t* det_count,
+                                             const float* aux_dense, int B, int max_out, int64_t A, int layout,
+                                             int box_mode, const float* letterbox, float* rows, int64_t row_capacity,
+                                             int32_t* row_offset, int32_t* overflow, cvpp_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Detection epilogue fused with the evaluation all-gather: the same rows as
  * cvpp_detection_epilogue, but every row (and the per-image count) is stored straight into the gather
  * buffer of EVERY rank through NVLink peer mappings - one kernel, no NCCL launch, no staging copy.
@@ -361,6 +401,21 @@ CVPP_API int cvpp_letterbox_reverse(const float* boxes, int64_t n, int xywh, flo
  * ------------------------------------------------------------------------------------------- */
 CVPP_API int cvpp_centernet_suppress(const float* heat, int B, int H, int W, int C, float* out,
                                      cvpp_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Per-row top-K of a (B, N) fp32 score matrix, sorted: scores descending, EQUAL scores by the lower
+ * flat index (the rule of cvpp_centernet_decode; torch.topk leaves it unspecified), NaN first.
+ * Replaces: CenterNetA._top_k   core/algorithms/centernet.py:328-338
+ *           (torch.topk(scores.view(B, -1), K) + the index split into class / y / x / y*W+x).
+ * out_val (B, K) fp32, out_idx (B, K) int64 flat indices.  With C > 0 the index is also split like the
+ * reference, each output nullable: out_cls = idx % C, pixel = idx / C, out_y = pixel / W,
+ * out_x = pixel % W (int64, like torch) and out_pixel = y*W + x (int32, reference :337).
+ * 1 <= K <= min(N, 4096), N < 2^32.  workspace: cvpp_topk_workspace_bytes(B, K).
+ * ------------------------------------------------------------------------------------------- */
+CVPP_API size_t cvpp_topk_workspace_bytes(int B, int K);
+CVPP_API int cvpp_topk(const float* scores, int B, int64_t N, int K, int C, int W, float* out_val, int64_t* out_idx,
+                       int64_t* out_cls, int64_t* out_y, int64_t* out_x, int32_t* out_pixel, void* workspace,
+                       size_t workspace_bytes, cvpp_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -80,7 +80,8 @@ def nms(boxes, scores, iou_threshold: float) -> np.ndarray:
 
 
 def batched_nms(boxes, scores, idxs, iou_threshold: float, mode: int = 0) -> np.ndarray:
-    """torchvision.ops.batched_nms (CPU) restated. mode 0=CPU rule, 1=trick, 2=vanilla."""
+    """torchvision.ops.batched_nms (CPU) restated. mode 0=CPU rule, 1=trick, 2=vanilla, 3=the branch switch
+    torchvision applies to CUDA tensors (numel > 20000 -> vanilla, boxes.py:80) with the CPU kernel's IoU test."""
     boxes = _f32(boxes).reshape(-1, 4)
     scores = _f32(scores).reshape(-1)
     idxs = _f32(idxs).reshape(-1)
@@ -212,6 +213,16 @@ def centernet_decode(pred, K: int, conf: float, pool_mode: int = 0, use_nms: boo
                                _ptr(score, _f32p), _ptr(cls, _i32p), _ptr(pix, _i32p), _ptr(cnt, _i32p))
     return [(box[b, :cnt[b]].copy(), score[b, :cnt[b]].copy(), cls[b, :cnt[b]].copy(), pix[b, :cnt[b]].copy())
             for b in range(B)]
+
+
+def topk(scores, k: int):
+    """torch.topk(scores.view(B, -1), k, largest=True, sorted=True) (centernet.py:330) with the product's tie rule
+    made explicit: equal scores are ordered by the lower flat index (stable descending sort).
+    Returns (values (B, k) float32, indices (B, k) int64)."""
+    s = _f32(scores)
+    s = s.reshape(s.shape[0], -1)
+    idx = np.argsort(-s.astype(np.float64), axis=1, kind="stable")[:, :k].astype(np.int64)
+    return np.take_along_axis(s, idx, axis=1), idx
 
 
 # --------------------------------------------------------------------------

@@ -170,7 +170,8 @@ ORC_API int64_t orc_nms(const float* boxes, const float* scores, int64_t n, doub
 /* torchvision.ops.batched_nms — torchvision/ops/boxes.py:51-120             */
 /* idxs are class ids stored as float (the reference passes x[:, 5]).        */
 /* mode: 0 = torchvision's CPU rule (numel > 4000 -> vanilla else trick),    */
-/*       1 = coordinate trick, 2 = vanilla.                                  */
+/*       1 = coordinate trick, 2 = vanilla, 3 = the switch torchvision uses  */
+/*       for CUDA tensors (numel > 20000 -> vanilla), CPU kernel arithmetic. */
 /* ------------------------------------------------------------------------- */
 static int cmp_float_asc(const void* a, const void* b) {
   float x = *(const float*)a, y = *(const float*)b;
@@ -180,7 +181,7 @@ static int cmp_float_asc(const void* a, const void* b) {
 ORC_API int64_t orc_batched_nms(const float* boxes, const float* scores, const float* idxs, int64_t n,
                                 double iou_threshold, int mode, int64_t* keep) {
   if (n <= 0) return 0;
-  int vanilla = (mode == 2) || (mode == 0 && n * 4 > 4000);
+  int vanilla = (mode == 2) || (mode == 0 && n * 4 > 4000) || (mode == 3 && n * 4 > 20000);
   if (!vanilla) {
     /* _batched_nms_coordinate_trick (boxes.py:83-100) */
     float maxc = boxes[0];

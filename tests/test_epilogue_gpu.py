@@ -41,3 +41,29 @@ def test_bad_peer_list_is_rejected():
         ops.detection_epilogue_allgather(det, ops.ROWS_FULL, [0], 0)
     with pytest.raises(RuntimeError):
         ops.detection_epilogue_allgather(det, ops.ROWS_FULL, [1] * 17, 0)
+
+
+@pytest.mark.parametrize("layout,width,mode", [(ops.ROWS_FULL, 7, ops.BOX_KEEP), (ops.ROWS_YOLOV8, 6, ops.BOX_NORMALISE_CORRECT),
+                                               (ops.ROWS_VOC, 6, ops.BOX_NORMALISE_CORRECT)])
+def test_compact_epilogue_is_the_padded_rows_without_the_padding(layout, width, mode):
+    """cvpp_detection_epilogue_compact: image b's rows at row_offset[b], bit-identical to the padded epilogue's rows;
+    offsets = exclusive scan of min(count, max_out); the overflow flag and the truncation at the row capacity."""
+    B, md = 7, 300
+    pred = torch.from_numpy(synth.yolov8_pred(11, B, 8400, nc=80)).to(DEV)
+    pred[3, 4:] = 0.0                                                     # an image without detections
+    det = ops.sort_nms(ops.pred_filter(pred, 80, 0.01), 0.7, max_det=md, max_nms=30000)
+    table = ops.correct_boxes_params([(480, 640), (375, 500)] * 3 + [(640, 640)], (640, 640), True, DEV)
+    ref = ops.detection_epilogue(det, layout, mode, table if mode != ops.BOX_KEEP else None)
+    counts = np.minimum(det.count.cpu().numpy(), md)
+    total = int(counts.sum())
+    assert counts[3] == 0 and total > 300
+    for cap in (total, total + 5, total - 100):
+        rows, off, ovf = ops.detection_epilogue_compact(det, layout, cap, mode, table if mode != ops.BOX_KEEP else None)
+        torch.cuda.synchronize()
+        off = off.cpu().numpy()
+        assert np.array_equal(off, np.concatenate([[0], np.cumsum(counts)]).astype(np.int32))
+        assert int(ovf.item()) == int(total > cap)
+        for b in range(B):
+            lo, hi = int(off[b]), min(int(off[b + 1]), cap)
+            if hi > lo:
+                assert torch.equal(rows[lo:hi, :width], ref[b, :hi - lo])

@@ -265,3 +265,59 @@ def test_pipelined_postprocess_equals_serial():
             for got, w in zip((d.box, d.score, d.cls, d.anchor), want[:4]):
                 for b in range(16):
                     assert torch.equal(got[b, :n[b]], w[b, :n[b]])
+
+
+def test_pipelined_postprocess_distinct_batches_with_a_producer():
+    """One input buffer set per slot, refilled by a producer stream with a DIFFERENT batch every step: the producer
+    waits on `consumed[slot]` before overwriting a slot's inputs and hands `ready` to submit().  Every step's
+    detections must equal the serial result of ITS batch (a missing handshake shows as detections of a
+    neighbouring batch)."""
+    dev = torch.device(DEV)
+    B, steps, depth = 8, 9, 3
+    batches = [to_dev(synth.yolov8_head(100 + k, B=B, clustered=bool(k & 1))) for k in range(4)]
+    serial = ops.Yolov8Postprocessor(B, 8400, NC, dev)
+    want = []
+    for lv in batches:
+        d = serial(ops.make_levels(lv, synth.YOLOV8_STRIDES), 0.001, 0.7)
+        torch.cuda.synchronize()
+        want.append((d.count.clone(), d.anchor.clone(), d.cls.clone(), d.box.clone()))
+    assert not torch.equal(want[0][1], want[1][1])
+    for graph in (True, False):
+        slots_in = [[torch.empty_like(t) for t in batches[0]] for _ in range(depth)]
+        pipe = ops.PipelinedPostprocess(B, 8400, NC, dev, [ops.make_levels(s, synth.YOLOV8_STRIDES) for s in slots_in],
+                                        0.001, 0.7, graph=graph)
+        assert not pipe.static_input and len(pipe.streams) == depth
+        producer = torch.cuda.Stream(device=dev)
+        got = []
+        for k in range(steps):
+            slot = pipe.next_slot
+            with torch.cuda.stream(producer):
+                producer.wait_event(pipe.consumed[slot])
+                for dst, src in zip(slots_in[slot], batches[k % len(batches)]):
+                    dst.copy_(src, non_blocking=True)
+                ready = torch.cuda.Event()
+                ready.record(producer)
+            det = pipe.submit(ready)
+            # snapshot the slot's detections on its own stream before the slot is reused
+            with torch.cuda.stream(pipe.streams[slot]):
+                got.append((det.count.clone(), det.anchor.clone(), det.cls.clone(), det.box.clone()))
+        pipe.join()
+        torch.cuda.synchronize()
+        for k, g in enumerate(got):
+            w = want[k % len(batches)]
+            assert torch.equal(g[0], w[0]), (graph, k)
+            for b, n in enumerate(w[0].tolist()):
+                assert torch.equal(g[1][b, :n], w[1][b, :n]) and torch.equal(g[2][b, :n], w[2][b, :n])
+                assert torch.equal(g[3][b, :n], w[3][b, :n])
+
+
+def test_postprocessor_rejects_small_candidate_buffers_and_foreign_devices():
+    with pytest.raises(ValueError):
+        ops.Yolov8Postprocessor(2, 8400, NC, torch.device(DEV), max_cand=1000)
+    levels = synth.yolov8_head(3, B=2)
+    ls = ops.make_levels(to_dev(levels), synth.YOLOV8_STRIDES)
+    post = ops.Yolov8Postprocessor(2, 8400, NC, torch.device(DEV))
+    post.max_cand = 100                                   # bypass the Python check: the C ABI must refuse too
+    from computervision.pytorch_b200._lib import CvppError
+    with pytest.raises(CvppError):
+        post(ls, 0.001, 0.7)

@@ -18,6 +18,16 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 from computervision.pytorch_b200 import ops  # noqa: E402
+from computervision.pytorch_b200.core.utils.anchor import generate_ssd_anchor_v2  # noqa: E402
+
+# the reference's config constants (configs/ssd_cfg.py, yolo7_cfg.py, yolo3 cfg): SSD300 prior recipe, YOLOv7 anchors in
+# the order of anchors_mask ((6,7,8),(3,4,5),(0,1,2)), YOLOv3 anchors in level order
+SSD_SIZES, SSD_FEATS = (30, 60, 111, 162, 213, 264, 315), (38, 19, 10, 5, 3, 1)
+SSD_RATIOS = ((1, 2, 0.5), (1, 2, 0.5, 3, 1.0 / 3), (1, 2, 0.5, 3, 1.0 / 3), (1, 2, 0.5, 3, 1.0 / 3), (1, 2, 0.5), (1, 2, 0.5))
+YOLOV7_LEVEL_ANCHORS = np.array([142, 110, 192, 243, 459, 401, 36, 75, 76, 55, 72, 146, 12, 16, 19, 36, 40, 28],
+                                np.float32).reshape(-1, 2)
+YOLOV3_LEVEL_ANCHORS = np.array([116, 90, 156, 198, 373, 326, 30, 61, 62, 45, 59, 119, 10, 13, 16, 30, 33, 23],
+                                np.float32).reshape(-1, 2)
 
 DEV = torch.device("cuda:0")
 PEAK = 6504.1
@@ -46,7 +56,7 @@ def report(name, B, bytes_per_image, ms_decode, ms_total, extra=None):
             "decode_GBps": round(gbs, 1), "decode_frac_of_hbm_peak": round(gbs / PEAK, 4),
             "images_per_s": round(B / (ms_total * 1e-3), 1), "bytes_per_image": bytes_per_image}
     line.update(extra or {})
-    print(json.dumps(line), flush=True)
+    return line
 
 
 def gen():
@@ -70,7 +80,7 @@ def bench_yolov8(iters, B=64):
     ms_dec = timed(lambda: ops.yolov8_decode_filter(ls, 80, 0.001), iters)
     ms_tot = timed(lambda: post(ls, 0.001, 0.7), iters)
     cand = float(c.count.float().mean())
-    report("yolov8_C2", B, 144 * 8400 * 4 + 24 * cand, ms_dec, ms_tot, {"cand_per_image": cand})
+    return report("yolov8_C2", B, 144 * 8400 * 4 + 24 * cand, ms_dec, ms_tot, {"cand_per_image": cand})
 
 
 def bench_centernet(iters, B=64):
@@ -81,11 +91,10 @@ def bench_centernet(iters, B=64):
     pred[..., 82:] = torch.rand((B, 128, 128, 2), generator=g, device=DEV) * 20
     ms = timed(lambda: ops.centernet_decode(pred, 100, 0.001), iters)
     ms_nms = timed(lambda: ops.centernet_decode(pred, 100, 0.001, use_nms=True), iters)
-    report("centernet_C3", B, 128 * 128 * 84 * 4, ms, ms, {"total_ms_with_diou_nms": round(ms_nms, 4)})
+    return report("centernet_C3", B, 128 * 128 * 84 * 4, ms, ms, {"total_ms_with_diou_nms": round(ms_nms, 4)})
 
 
 def bench_ssd(iters, B=128):
-    import oracle
     g = gen()
     P = 8732
     loc = torch.randn((B, P, 4), generator=g, device=DEV)
@@ -95,7 +104,7 @@ def bench_ssd(iters, B=128):
     cls = torch.randint(1, 21, (B, P), generator=g, device=DEV)
     val = conf[..., 0] + torch.randn((B, P), generator=g, device=DEV) * 2.0 + 2.0
     conf.scatter_(2, cls.unsqueeze(2), torch.where(boost, val, conf.gather(2, cls.unsqueeze(2)).squeeze(2)).unsqueeze(2))
-    pri = torch.from_numpy(oracle.ssd_priors()).to(DEV)
+    pri = torch.from_numpy(generate_ssd_anchor_v2((300, 300), SSD_SIZES, SSD_FEATS, SSD_RATIOS)).to(DEV)
     c = ops.ssd_decode_filter(loc, conf, pri, 0.001, max_cand=32768)
     ms_dec = timed(lambda: ops.ssd_decode_filter(loc, conf, pri, 0.001, max_cand=32768), iters)
 
@@ -103,20 +112,23 @@ def bench_ssd(iters, B=128):
         cc = ops.ssd_decode_filter(loc, conf, pri, 0.001, max_cand=32768)
         ops.sort_nms(cc, 0.5, ops.RULE_PER_CLASS, ops.ORDER_CLASS_MAJOR, max_det=0, max_out=4096)
     ms_tot = timed(full, iters)
-    report("ssd_C4", B, 873200, ms_dec, ms_tot, {"cand_per_image": float(c.count.float().mean())})
+    return report("ssd_C4", B, 873200, ms_dec, ms_tot, {"cand_per_image": float(c.count.float().mean())})
 
 
-def bench_yolov7(iters, B=128):
-    import oracle
-    g = gen()
+def yolov7_inputs(B, g):
     levels = []
     for s in (20, 40, 80):
         x = torch.randn((B, 3, 85, s, s), generator=g, device=DEV)
         x[:, :, 4] = x[:, :, 4] * 3.0 - 9.0
         x[:, :, 5:] = x[:, :, 5:] * 2.0 - 1.0
         levels.append(x.reshape(B, 255, s, s))
+    return levels
+
+
+def bench_yolov7(iters, B=128):
+    levels = yolov7_inputs(B, gen())
     ls = ops.make_levels(levels)
-    anchors = oracle.yolov7_level_anchors()
+    anchors = YOLOV7_LEVEL_ANCHORS
     c = ops.yolov7_decode_filter(ls, 80, anchors, (640, 640), 0.001)
     ms_dec = timed(lambda: ops.yolov7_decode_filter(ls, 80, anchors, (640, 640), 0.001), iters)
 
@@ -124,11 +136,10 @@ def bench_yolov7(iters, B=128):
         cc = ops.yolov7_decode_filter(ls, 80, anchors, (640, 640), 0.001)
         ops.sort_nms(cc, 0.3, ops.RULE_PER_CLASS, ops.ORDER_CLASS_MAJOR, max_det=0, max_out=8192)
     ms_tot = timed(full, iters)
-    report("yolov7_C5_shard", B, 25200 * 85 * 4, ms_dec, ms_tot, {"cand_per_image": float(c.count.float().mean())})
+    return report("yolov7_C5_shard", B, 25200 * 85 * 4, ms_dec, ms_tot, {"cand_per_image": float(c.count.float().mean())})
 
 
 def bench_yolov3(iters, B=256):
-    import oracle
     g = gen()
     levels = []
     for s in (13, 26, 52):
@@ -138,7 +149,7 @@ def bench_yolov3(iters, B=256):
         x[:, :, 5:] = x[:, :, 5:] * 2.0 - 3.0
         levels.append(x.reshape(B, 75, s, s))
     ls = ops.make_levels(levels)
-    anchors = np.array(oracle.YOLOV3_ANCHORS, np.float32).reshape(-1, 2)
+    anchors = YOLOV3_LEVEL_ANCHORS
     c = ops.yolov3_decode_filter(ls, 20, anchors, (416, 416), 0.001, max_cand=16384)
     ms_dec = timed(lambda: ops.yolov3_decode_filter(ls, 20, anchors, (416, 416), 0.001, max_cand=16384), iters)
 
@@ -146,7 +157,23 @@ def bench_yolov3(iters, B=256):
         cc = ops.yolov3_decode_filter(ls, 20, anchors, (416, 416), 0.001, max_cand=16384)
         ops.sort_nms(cc, 0.5, ops.RULE_PER_CLASS, ops.ORDER_CLASS_MAJOR, max_det=0, max_out=8192)
     ms_tot = timed(full, iters)
-    report("yolov3_voc", B, 10647 * 25 * 4, ms_dec, ms_tot, {"cand_per_image": float(c.count.float().mean())})
+    return report("yolov3_voc", B, 10647 * 25 * 4, ms_dec, ms_tot, {"cand_per_image": float(c.count.float().mean())})
+
+
+TABLE = {"yolov8": bench_yolov8, "centernet": bench_centernet, "ssd": bench_ssd, "yolov7": bench_yolov7,
+         "yolov3": bench_yolov3}
+
+
+def collect(iters=30, only=("centernet", "ssd", "yolov7", "yolov3"), device=None):
+    """bench.py's `paths` key: one dict per configuration, measured in the calling process."""
+    global DEV
+    if device is not None:
+        DEV = torch.device(device)
+    out = []
+    for name in only:
+        out.append(TABLE[name](iters))
+        torch.cuda.empty_cache()
+    return out
 
 
 if __name__ == "__main__":
@@ -154,7 +181,5 @@ if __name__ == "__main__":
     ap.add_argument("--iters", type=int, default=50)
     ap.add_argument("--only", default="yolov8,centernet,ssd,yolov7,yolov3")
     a = ap.parse_args()
-    table = {"yolov8": bench_yolov8, "centernet": bench_centernet, "ssd": bench_ssd, "yolov7": bench_yolov7,
-             "yolov3": bench_yolov3}
     for name in a.only.split(","):
-        table[name](a.iters)
+        print(json.dumps(TABLE[name](a.iters)), flush=True)
