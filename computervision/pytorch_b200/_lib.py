@@ -74,6 +74,7 @@ _PROTOS = {
                                                   c_vp, P(c_vp), c_int, c_int, c_vp]),
     "cvpp_detection_epilogue_compact": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_i64, c_int, c_int,
                                                 c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
+    "cvpp_voc_match": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_f64, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "cvpp_topk_workspace_bytes": (c_size, [c_int, c_int]),
     "cvpp_topk": (c_int, [c_vp, c_int, c_i64, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_size, c_vp]),
     "cvpp_detection_epilogue": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_i64, c_int, c_int, c_vp,

@@ -119,6 +119,10 @@ int topk_launch(const float* scores, int B, long long N, int K, int C, int W, fl
                 long long* out_cls, long long* out_y, long long* out_x, int32_t* out_pixel, void* workspace,
                 size_t workspace_bytes, cudaStream_t stream);
 
+int voc_match_launch(const float* det_rows, const int32_t* det_offset, const float* gt_box, const int32_t* gt_cls,
+                     const int32_t* gt_difficult, const int32_t* gt_offset, int B, double min_overlap, int32_t* flag,
+                     int32_t* best_gt, double* ovmax, int32_t* claim_ws, cudaStream_t stream);
+
 static int force_generic() {
   const char* e = getenv("CVPP_FORCE_GENERIC");
   return e && e[0] == '1';
@@ -405,6 +409,13 @@ int cvpp_letterbox_reverse(const float* boxes, int64_t n, int xywh, float in_w, 
 
 int cvpp_centernet_suppress(const float* heat, int B, int H, int W, int C, float* out, cvpp_stream_t stream) {
   return centernet_suppress_launch(heat, B, H, W, C, out, (cudaStream_t)stream);
+}
+
+int cvpp_voc_match(const float* det_rows, const int32_t* det_offset, const float* gt_box, const int32_t* gt_cls,
+                   const int32_t* gt_difficult, const int32_t* gt_offset, int B, double min_overlap, int32_t* flag,
+                   int32_t* best_gt, double* ovmax, int32_t* claim_ws, cvpp_stream_t stream) {
+  return voc_match_launch(det_rows, det_offset, gt_box, gt_cls, gt_difficult, gt_offset, B, min_overlap, flag, best_gt, ovmax,
+                          claim_ws, (cudaStream_t)stream);
 }
 
 size_t cvpp_topk_workspace_bytes(int B, int K) {

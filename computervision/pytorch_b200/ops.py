@@ -765,6 +765,35 @@ def topk(scores: torch.Tensor, k: int, split: Optional[Tuple[int, int]] = None):
     return (val, idx) if split is None else (val, idx, cls, ys, xs, pix)
 
 
+def voc_match(det_rows: torch.Tensor, det_offset: torch.Tensor, gt_box: torch.Tensor, gt_cls: torch.Tensor,
+              gt_difficult: torch.Tensor, gt_offset: torch.Tensor, min_overlap: float):
+    """cvpp_voc_match: det_rows (N, 6) float32 VOC rows, det_offset (B+1,) int32, gt_box (G, 4) float32, gt_cls /
+    gt_difficult (G,) int32, gt_offset (B+1,) int32 - all on the device -> (flag (N,) int32: 1 TP / 2 FP / 0 difficult
+    match, best_gt (N,) int32, ovmax (N,) float64)."""
+    _require_cuda(det_rows, "det_rows")
+    _require_cuda(gt_box, "gt_box")
+    dev = det_rows.device
+    for t, name in ((det_offset, "det_offset"), (gt_cls, "gt_cls"), (gt_difficult, "gt_difficult"), (gt_offset, "gt_offset")):
+        if t.dtype != torch.int32 or t.device != dev:
+            raise ValueError(f"{name} must be an int32 tensor on {dev}")
+    det_rows, gt_box = det_rows.contiguous(), gt_box.contiguous()
+    B = int(det_offset.numel()) - 1
+    if B < 0 or int(gt_offset.numel()) != B + 1 or det_rows.dim() != 2 or det_rows.shape[1] != 6:
+        raise ValueError("expected det_rows (N, 6) and offsets with B + 1 entries each")
+    N, G = int(det_rows.shape[0]), int(gt_box.shape[0])
+    flag = torch.empty((max(N, 1),), dtype=torch.int32, device=dev)
+    best = torch.empty((max(N, 1),), dtype=torch.int32, device=dev)
+    ov = torch.empty((max(N, 1),), dtype=torch.float64, device=dev)
+    claim = torch.empty((max(G, 1),), dtype=torch.int32, device=dev)
+    if gt_box.numel() == 0:
+        gt_box = torch.zeros((1, 4), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(_lib.lib().cvpp_voc_match(_ptr(det_rows), _ptr(det_offset.contiguous()), _ptr(gt_box), _ptr(gt_cls.contiguous()),
+                                        _ptr(gt_difficult.contiguous()), _ptr(gt_offset.contiguous()), B, float(min_overlap),
+                                        _ptr(flag), _ptr(best), _ptr(ov), _ptr(claim), _stream(dev)))
+    return flag[:N], best[:N], ov[:N]
+
+
 def correct_boxes_params(image_hw: Sequence[Tuple[int, int]], input_hw: Sequence[int], letterbox_image: bool,
                          device) -> torch.Tensor:
     """The (B, 5) table cvpp_detection_epilogue wants for yolo_correct_boxes (image_process.py:161-181)."""

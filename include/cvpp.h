@@ -417,6 +417,21 @@ CVPP_API int cvpp_topk(const float* scores, int B, int64_t N, int K, int C, int 
                        int64_t* out_cls, int64_t* out_y, int64_t* out_x, int32_t* out_pixel, void* workspace,
                        size_t workspace_bytes, cvpp_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Matching of detections to ground truth for the VOC-style mAP, one CTA per image.
+ * Replaces the per-detection loop of get_map   core/metrics/mAP.py:441-520 (best-overlap search :486-503 with the
+ * "+1" pixel convention in double precision, first maximum wins; MINOVERLAP / difficult / `used` logic :508-520).
+ * det_rows (N, 6) fp32 in the CVPP_ROWS_VOC layout (cls, score, l, t, r, b), image b owning rows
+ * det_offset[b] .. det_offset[b+1] (what cvpp_detection_epilogue_compact writes), every (image, class) group in
+ * descending score order; gt_box (G, 4) l,t,r,b fp32 (16-byte aligned), gt_cls / gt_difficult (G) int32, image b
+ * owning gt_offset[b] .. gt_offset[b+1].  Outputs per detection: flag 1 = true positive, 2 = false positive,
+ * 0 = matched a difficult box (counts as neither); best_gt = index of the best box within the image's list (-1:
+ * no box of the class overlaps); ovmax (double, -1 when none).  claim_ws: G int32 of scratch.
+ * ------------------------------------------------------------------------------------------- */
+CVPP_API int cvpp_voc_match(const float* det_rows, const int32_t* det_offset, const float* gt_box, const int32_t* gt_cls,
+                            const int32_t* gt_difficult, const int32_t* gt_offset, int B, double min_overlap,
+                            int32_t* flag, int32_t* best_gt, double* ovmax, int32_t* claim_ws, cvpp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -225,6 +225,45 @@ def topk(scores, k: int):
     return np.take_along_axis(s, idx, axis=1), idx
 
 
+def voc_match(det_rows, det_counts, gt_boxes, gt_cls, gt_diff, gt_counts, min_overlap: float):
+    """The matching loop of get_map (core/metrics/mAP.py:441-520) restated per image in Python floats:
+    det_rows (N, 6) VOC rows in file / line order -> flag (N,) 1 = TP, 2 = FP, 0 = matched a difficult box.
+    Within an image the processing order of a class is the line order (module docstring of csrc/map_match.cu)."""
+    det_rows = np.asarray(det_rows, np.float32).reshape(-1, 6)
+    flag = np.zeros(len(det_rows), np.int32)
+    d0 = g0 = 0
+    for nd, ng in zip(det_counts, gt_counts):
+        used = [False] * int(ng)
+        for d in range(d0, d0 + int(nd)):
+            c = int(det_rows[d, 0])
+            bb = [float(v) for v in det_rows[d, 2:6]]
+            ovmax, match = -1, -1
+            for g in range(int(ng)):
+                if int(gt_cls[g0 + g]) != c:
+                    continue
+                bbgt = [float(v) for v in gt_boxes[g0 + g]]
+                bi = [max(bb[0], bbgt[0]), max(bb[1], bbgt[1]), min(bb[2], bbgt[2]), min(bb[3], bbgt[3])]
+                iw = bi[2] - bi[0] + 1
+                ih = bi[3] - bi[1] + 1
+                if iw > 0 and ih > 0:
+                    ua = (bb[2] - bb[0] + 1) * (bb[3] - bb[1] + 1) + (bbgt[2] - bbgt[0] + 1) * (bbgt[3] - bbgt[1] + 1) - iw * ih
+                    ov = iw * ih / ua
+                    if ov > ovmax:
+                        ovmax, match = ov, g
+            if ovmax >= min_overlap:
+                if not int(gt_diff[g0 + match]):
+                    if not used[match]:
+                        flag[d] = 1
+                        used[match] = True
+                    else:
+                        flag[d] = 2
+            else:
+                flag[d] = 2
+        d0 += int(nd)
+        g0 += int(ng)
+    return flag
+
+
 # --------------------------------------------------------------------------
 # SSD
 # --------------------------------------------------------------------------
