@@ -35,6 +35,12 @@ _PROTOS = {
     "cvpp_error_name": (ctypes.c_char_p, [c_int]),
     "cvpp_yolov8_decode_filter": (c_int, [P(c_vp), P(c_i64), P(c_i64), P(c_int), P(c_int), P(c_f32), c_int, c_int,
                                           c_int, c_int, c_f32, c_vp, c_vp, c_vp, c_int, c_vp]),
+    "cvpp_yolov8_head_decode_filter": (c_int, [P(c_vp), P(c_vp), P(c_vp), P(c_vp), P(c_vp), P(c_vp), P(c_int), P(c_int),
+                                               P(c_f32), c_int, c_int, c_int, c_int, c_int, c_int, c_f32, c_vp, c_vp, c_vp,
+                                               c_int, c_vp]),
+    "cvpp_yolov8_head_decode_filter_x": (c_int, [P(c_vp), P(c_vp), P(c_vp), P(c_vp), P(c_vp), P(c_vp), P(c_int), P(c_int),
+                                                 P(c_f32), c_int, c_int, c_int, c_int, c_int, c_int, c_f32, c_vp, c_vp, c_vp,
+                                                 c_int, c_vp, c_vp]),
     "cvpp_yolov8_decode_full": (c_int, [P(c_vp), P(c_i64), P(c_i64), P(c_int), P(c_int), P(c_f32), c_int, c_int,
                                         c_int, c_int, c_vp, c_vp]),
     "cvpp_pred_filter": (c_int, [c_vp, c_int, c_int, c_int, c_i64, c_f32, c_vp, c_vp, c_vp, c_int, c_vp]),

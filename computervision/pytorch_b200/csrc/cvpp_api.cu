@@ -123,6 +123,12 @@ int voc_match_launch(const float* det_rows, const int32_t* det_offset, const flo
                      const int32_t* gt_difficult, const int32_t* gt_offset, int B, double min_overlap, int32_t* flag,
                      int32_t* best_gt, double* ovmax, int32_t* claim_ws, cudaStream_t stream);
 
+int yolov8_head_fused_launch(const float* const* box_feat, const float* const* cls_feat, const float* const* box_w,
+                             const float* const* box_b, const float* const* cls_w, const float* const* cls_b,
+                             const int* level_h, const int* level_w, const float* level_stride, int num_levels, int B, int c2,
+                             int c3, int nc, int reg_max, float conf_thres, uint64_t* cand_key, int32_t* cand_count,
+                             float* box_dense, int max_cand, float* head_out, cudaStream_t stream);
+
 static int force_generic() {
   const char* e = getenv("CVPP_FORCE_GENERIC");
   return e && e[0] == '1';
@@ -163,6 +169,27 @@ int cvpp_yolov8_decode_filter(const float* const* level_ptr, const int64_t* batc
   return yolov8_decode_launch(level_ptr, batch_stride, chan_stride, level_h, level_w, level_stride, num_levels, B, nc,
                               reg_max, conf_thres, cand_key, cand_count, box_dense, max_cand, nullptr, force_generic(),
                               (cudaStream_t)stream);
+}
+
+int cvpp_yolov8_head_decode_filter(const float* const* box_feat, const float* const* cls_feat, const float* const* box_w,
+                                   const float* const* box_b, const float* const* cls_w, const float* const* cls_b,
+                                   const int* level_h, const int* level_w, const float* level_stride, int num_levels, int B,
+                                   int c2, int c3, int nc, int reg_max, float conf_thres, uint64_t* cand_key,
+                                   int32_t* cand_count, float* box_dense, int max_cand, cvpp_stream_t stream) {
+  return yolov8_head_fused_launch(box_feat, cls_feat, box_w, box_b, cls_w, cls_b, level_h, level_w, level_stride, num_levels,
+                                  B, c2, c3, nc, reg_max, conf_thres, cand_key, cand_count, box_dense, max_cand, nullptr,
+                                  (cudaStream_t)stream);
+}
+
+int cvpp_yolov8_head_decode_filter_x(const float* const* box_feat, const float* const* cls_feat, const float* const* box_w,
+                                     const float* const* box_b, const float* const* cls_w, const float* const* cls_b,
+                                     const int* level_h, const int* level_w, const float* level_stride, int num_levels, int B,
+                                     int c2, int c3, int nc, int reg_max, float conf_thres, uint64_t* cand_key,
+                                     int32_t* cand_count, float* box_dense, int max_cand, float* head_out,
+                                     cvpp_stream_t stream) {
+  return yolov8_head_fused_launch(box_feat, cls_feat, box_w, box_b, cls_w, cls_b, level_h, level_w, level_stride, num_levels,
+                                  B, c2, c3, nc, reg_max, conf_thres, cand_key, cand_count, box_dense, max_cand, head_out,
+                                  (cudaStream_t)stream);
 }
 
 int cvpp_yolov8_decode_full(const float* const* level_ptr, const int64_t* batch_stride, const int64_t* chan_stride,

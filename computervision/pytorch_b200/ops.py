@@ -127,6 +127,61 @@ def yolov8_decode_filter(ls: LevelSet, nc: int, conf_thres: float, reg_max: int 
     return Candidates(key, count, box_dense, max_cand, ls.A, nc)
 
 
+def yolov8_head_decode_filter(box_feats: Sequence[torch.Tensor], cls_feats: Sequence[torch.Tensor],
+                              box_w: Sequence[torch.Tensor], box_b: Sequence[torch.Tensor], cls_w: Sequence[torch.Tensor],
+                              cls_b: Sequence[torch.Tensor], strides: Sequence[float], conf_thres: float,
+                              reg_max: int = 16, max_cand: Optional[int] = None, return_head: bool = False):
+    """cvpp_yolov8_head_decode_filter: the head's last 1x1 convolutions + decode + confidence filter in ONE tcgen05
+    kernel.  Per level: box_feats[l] (B, c2, H, W), cls_feats[l] (B, c3, H, W) - the inputs of cv2[l][2] / cv3[l][2]
+    (modules.py:423-425); box_w[l] (4*reg_max, c2[, 1, 1]), box_b[l] (4*reg_max,), cls_w[l] (nc, c3[, 1, 1]), cls_b[l] (nc,).
+    return_head=True also returns the materialised head x_cat (B, 4*reg_max + nc, A) (cvpp_yolov8_head_decode_filter_x)."""
+    n = len(box_feats)
+    if not (n == len(cls_feats) == len(box_w) == len(box_b) == len(cls_w) == len(cls_b) == len(strides)) or n < 1 or n > 4:
+        raise ValueError("between 1 and 4 levels, with one feature pair / weight set / stride each")
+    keep = []
+
+    def prep(t, what):
+        _require_cuda(t, what)
+        t = t.contiguous()
+        keep.append(t)
+        return t
+    bf = [prep(t, f"box_feats[{i}]") for i, t in enumerate(box_feats)]
+    cf = [prep(t, f"cls_feats[{i}]") for i, t in enumerate(cls_feats)]
+    B, c2, c3 = int(bf[0].shape[0]), int(bf[0].shape[1]), int(cf[0].shape[1])
+    bw = [prep(t.reshape(t.shape[0], -1), f"box_w[{i}]") for i, t in enumerate(box_w)]
+    cw = [prep(t.reshape(t.shape[0], -1), f"cls_w[{i}]") for i, t in enumerate(cls_w)]
+    bb = [prep(t.reshape(-1), f"box_b[{i}]") for i, t in enumerate(box_b)]
+    cb = [prep(t.reshape(-1), f"cls_b[{i}]") for i, t in enumerate(cls_b)]
+    nc = int(cw[0].shape[0])
+    hs, ws = [], []
+    dev = bf[0].device
+    for i in range(n):
+        if bf[i].dim() != 4 or cf[i].dim() != 4 or tuple(bf[i].shape[2:]) != tuple(cf[i].shape[2:]) or \
+                bf[i].shape[0] != B or cf[i].shape[0] != B or bf[i].shape[1] != c2 or cf[i].shape[1] != c3:
+            raise ValueError(f"level {i}: expected box features (B, {c2}, H, W) and class features (B, {c3}, H, W)")
+        if tuple(bw[i].shape) != (4 * reg_max, c2) or tuple(cw[i].shape) != (nc, c3) or bb[i].numel() != 4 * reg_max or \
+                cb[i].numel() != nc:
+            raise ValueError(f"level {i}: weight / bias shapes do not match the features")
+        if any(t.device != dev for t in (bf[i], cf[i], bw[i], cw[i], bb[i], cb[i])):
+            raise ValueError("all tensors must live on the same device")
+        hs.append(int(bf[i].shape[2]))
+        ws.append(int(bf[i].shape[3]))
+    A = sum(h * w for h, w in zip(hs, ws))
+    max_cand = int(max_cand or A)
+    key = torch.empty((B, max_cand), dtype=torch.int64, device=dev)
+    count = torch.empty((B,), dtype=torch.int32, device=dev)
+    box_dense = torch.empty((B, A, 4), dtype=torch.float32, device=dev)
+    arr = lambda ts: (c_vp * n)(*[t.data_ptr() for t in ts])   # noqa: E731
+    head = torch.empty((B, 4 * reg_max + nc, A), dtype=torch.float32, device=dev) if return_head else None
+    with torch.cuda.device(dev):
+        check(_lib.lib().cvpp_yolov8_head_decode_filter_x(
+            arr(bf), arr(cf), arr(bw), arr(bb), arr(cw), arr(cb), (ctypes.c_int * n)(*hs), (ctypes.c_int * n)(*ws),
+            (ctypes.c_float * n)(*[float(s) for s in strides]), n, B, c2, c3, nc, int(reg_max), float(conf_thres),
+            _ptr(key), _ptr(count), _ptr(box_dense), max_cand, _ptr(head), _stream(dev)))
+    cand = Candidates(key, count, box_dense, max_cand, A, nc)
+    return (cand, head) if return_head else cand
+
+
 def yolov8_decode_full(ls: LevelSet, nc: int, reg_max: int = 16) -> torch.Tensor:
     if ls.C != 4 * reg_max + nc:
         raise ValueError(f"head has {ls.C} channels, expected 4*{reg_max}+{nc}")

@@ -112,6 +112,32 @@ CVPP_API int cvpp_yolov8_decode_filter(const float* const* level_ptr, const int6
                               float conf_thres, uint64_t* cand_key, int32_t* cand_count, float* box_dense,
                               int max_cand, cvpp_stream_t stream);
 
+/* The same candidates straight from the INPUTS of the head's last 1x1 convolutions: the
+ * convolutions  nn.Conv2d(c2, 4 * reg_max, 1)  and  nn.Conv2d(c3, nc, 1)   core/models/yolov8/modules.py:423-425
+ * and their concatenation (:431) run on the tensor cores inside the decode kernel (tcgen05.mma kind::tf32, fp32
+ * accumulators in TMEM, the decode as the TMEM epilogue), so the (B, 4*reg_max + nc, A) head tensor never exists in HBM.
+ * box_feat[l] (B, c2, H_l, W_l) / cls_feat[l] (B, c3, H_l, W_l): contiguous NCHW fp32 device tensors, 16-byte aligned,
+ * H*W a multiple of 4; box_w[l] (4*reg_max, c2), box_b[l] (4*reg_max), cls_w[l] (nc, c3), cls_b[l] (nc): device
+ * pointers to the conv weights / biases (the pointer ARRAYS are host arrays).  c2, c3 multiples of 16; nc <= 192.
+ * Arithmetic: products of TF32-truncated operands accumulated in fp32 (what cuDNN computes for the reference's fp32
+ * conv under torch's default allow_tf32), bias added in fp32, then bit for bit the code of cvpp_yolov8_decode_filter.
+ * Outputs exactly as cvpp_yolov8_decode_filter. */
+CVPP_API int cvpp_yolov8_head_decode_filter(const float* const* box_feat, const float* const* cls_feat,
+                              const float* const* box_w, const float* const* box_b, const float* const* cls_w,
+                              const float* const* cls_b, const int* level_h, const int* level_w,
+                              const float* level_stride, int num_levels, int B, int c2, int c3, int nc, int reg_max,
+                              float conf_thres, uint64_t* cand_key, int32_t* cand_count, float* box_dense,
+                              int max_cand, cvpp_stream_t stream);
+
+/* ... and the variant that ALSO materialises the head, head_out (B, 4*reg_max + nc, A) = the reference's x_cat
+ * (modules.py:438), for callers that need the raw logits as well (Detect.forward returns (y, x), the loss consumes x). */
+CVPP_API int cvpp_yolov8_head_decode_filter_x(const float* const* box_feat, const float* const* cls_feat,
+                              const float* const* box_w, const float* const* box_b, const float* const* cls_w,
+                              const float* const* cls_b, const int* level_h, const int* level_w,
+                              const float* level_stride, int num_levels, int B, int c2, int c3, int nc, int reg_max,
+                              float conf_thres, uint64_t* cand_key, int32_t* cand_count, float* box_dense,
+                              int max_cand, float* head_out, cvpp_stream_t stream);
+
 /* Same decode, but writes the full y (B, 4+nc, A) = [cx,cy,w,h, sigmoid(cls)] like
  * Detect.forward (modules.py:444) for callers that want the dense tensor. */
 CVPP_API int cvpp_yolov8_decode_full(const float* const* level_ptr, const int64_t* batch_stride,

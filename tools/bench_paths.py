@@ -160,11 +160,44 @@ def bench_yolov3(iters, B=256):
     return report("yolov3_voc", B, 10647 * 25 * 4, ms_dec, ms_tot, {"cand_per_image": float(c.count.float().mean())})
 
 
-TABLE = {"yolov8": bench_yolov8, "centernet": bench_centernet, "ssd": bench_ssd, "yolov7": bench_yolov7,
+def bench_head_fused(iters, B=64):
+    """SURVEY §8f rank 3 at the C2 shape: the head's last 1x1 convolutions fused with decode + filter (tcgen05) vs the
+    unfused pair (cuDNN convolutions writing the (B,144,A) head + the streaming decode kernel re-reading it)."""
+    g = gen()
+    sizes = ((80, 80), (40, 40), (20, 20))
+    bf = [torch.randn((B, 64, h, w), generator=g, device=DEV) for h, w in sizes]
+    cf = [torch.randn((B, 80, h, w), generator=g, device=DEV) for h, w in sizes]
+    bw = [torch.randn((64, 64), generator=g, device=DEV) * 0.375 for _ in sizes]          # box logits ~ N(0, 3^2)
+    cw = [torch.randn((80, 80), generator=g, device=DEV) * 0.4825 for _ in sizes]         # class logits ~ N(-18.19, 4.3155^2)
+    bb = [torch.zeros((64,), device=DEV) for _ in sizes]
+    cb = [torch.full((80,), -18.19, device=DEV) for _ in sizes]
+    strides = (8.0, 16.0, 32.0)
+    fused = lambda: ops.yolov8_head_decode_filter(bf, cf, bw, bb, cw, cb, strides, 0.001)   # noqa: E731
+    c = fused()
+    ms_fused = timed(fused, iters)
+    w4 = [(a[:, :, None, None].contiguous(), b[:, :, None, None].contiguous()) for a, b in zip(bw, cw)]
+
+    def conv_only():
+        return [torch.cat((torch.nn.functional.conv2d(x, wa, ba), torch.nn.functional.conv2d(y, wb, bb_)), 1)
+                for x, y, (wa, wb), ba, bb_ in zip(bf, cf, w4, bb, cb)]
+
+    def unfused():
+        return ops.yolov8_decode_filter(ops.make_levels(conv_only(), strides), 80, 0.001)
+    ms_conv = timed(conv_only, iters)
+    ms_unfused = timed(unfused, iters)
+    cand = float(c.count.float().mean())
+    return report("yolov8_head_fused_C2", B, 144 * 8400 * 4 + 24 * cand, ms_fused, ms_fused,
+                  {"cand_per_image": cand, "unfused_ms": round(ms_unfused, 4), "unfused_conv_cat_ms": round(ms_conv, 4),
+                   "speedup_vs_unfused": round(ms_unfused / ms_fused, 2),
+                   "note": "inputs = the features BEFORE the last 1x1 convs; bytes = (c2 + c3) x A x 4 per image; the unfused "
+                           "path additionally writes and re-reads the 4.84 MB/image head (torch conv2d = cuDNN, allow_tf32 default)"})
+
+
+TABLE = {"head_fused": bench_head_fused, "yolov8": bench_yolov8, "centernet": bench_centernet, "ssd": bench_ssd, "yolov7": bench_yolov7,
          "yolov3": bench_yolov3}
 
 
-def collect(iters=30, only=("centernet", "ssd", "yolov7", "yolov3"), device=None):
+def collect(iters=30, only=("centernet", "ssd", "yolov7", "yolov3", "head_fused"), device=None):
     """bench.py's `paths` key: one dict per configuration, measured in the calling process."""
     global DEV
     if device is not None:
