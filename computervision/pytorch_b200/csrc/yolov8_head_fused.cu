@@ -14,21 +14,29 @@
 //   * A operand = the activations exactly as the previous layer left them, NCHW: cells are contiguous, so a tile is
 //     "MN-major"; 3-D tensor-map TMA loads of [32 cells x 16 channels] with the 32-byte-atom 128-byte swizzle
 //     (CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B = UMMA SWIZZLE_128B_BASE32B, the one layout the tensor core takes for an
-//     MN-major 32-bit operand) land in the canonical UMMA layout (4 atoms of 32 cells per 128-cell tile), 8-stage
-//     ring of 8 KB chunks, L2 evict-first;
-//   * B operand = the conv weights (n, k), K-major, written ONCE per level into shared memory in the swizzled
-//     canonical layout by the epilogue warps;
-//   * one elected thread issues the MMAs (two K = 8 steps per chunk), tcgen05.commit releases ring stages and
-//     publishes the accumulator (two TMEM accumulator stages of 64 + nc columns);
-//   * epilogue = two groups of four warps alternating over tiles: thread t owns TMEM lane t = cell t of the tile,
-//     pulls its 64 box logits and nc class logits with tcgen05.ld (32x32b.x16), adds the bias and runs EXACTLY the
-//     per-cell code of the streaming decode kernel (yolov8_cell.cuh) - DFL integral, class argmax with first-index
-//     tie repair, sigmoid, threshold, warp-aggregated candidate append.
-// Warp roles: 0 = TMA producer, 1 = TMEM allocator + MMA issuer, 2..9 = epilogue.  Persistent, one CTA per SM;
-// tiles are dealt level by level (the weights of one level are resident at a time).
+//     MN-major 32-bit operand) land in the canonical UMMA layout (4 atoms of 32 cells per 128-cell tile), a ring of
+//     16 KB stages (32 channels) as deep as shared memory allows, L2 evict-first;
+//   * B operand = the conv weights (n, k), K-major: 2-D tensor-map TMA loads of [32 k x N rows] with the plain 128-byte
+//     swizzle are the canonical layout as they land; two weight buffers alternate by level, so there is no CTA-wide
+//     barrier after the set-up (the first version staged weights by hand behind __syncthreads: 10 us of the kernel);
+//   * two MMA warps (box branch N = 64, class branch N = nc_pad), each running its loop warp-uniformly with one elected
+//     lane issuing (four K = 8 steps per stage); tcgen05.commit releases ring stages and publishes the branch's
+//     accumulator columns (two TMEM accumulator stages of 64 + nc columns); each loads its own weights by TMA;
+//   * epilogue = two groups of eight warps alternating over tiles; in a group, TMEM lane t = cell t of the tile is
+//     served by TWO threads: one of a "box warp" pulls the 64 box logits with tcgen05.ld (32x32b.x16), adds the bias and
+//     runs the DFL integral + anchor arithmetic (it starts when the box branch is done, under the class MMAs), one of
+//     a "class warp" pulls the nc class logits and runs the argmax with first-index tie repair, sigmoid, threshold and
+//     the warp-aggregated candidate append (the box reaches it through shared memory + a 64-thread named barrier) -
+//     EXACTLY the per-cell code of the streaming decode kernel (yolov8_cell.cuh).
+// Warp roles: 0 = TMA producer (activations only: one 4-D UTMALDG per 16 KB stage), 1 / 2 = MMA issuers (1 also owns the
+// TMEM allocation), 3 idle, 4..19 = epilogue.  Persistent, one CTA per SM; tiles are dealt level by level.
+// Measured steps (C2 shape, 64 images, us): one thread issuing under `if (lane == 0)` 80 (every UTMALDG / UTCHMMA wrapped in
+// an elect + R2UR waterfall) -> warp-uniform loops with elect.sync 66.7 -> weights off the producer's path 65.5 -> two MMA
+// warps (see DESIGN); the pure TMA stream of the same ring runs in 47.6.
 // HBM-bound like the decode: (c2 + c3) * A * 4 bytes per image (4 838 400 B for the n model) - but the producing
 // convolution's 4.8 MB/image write and the decode's re-read of it are gone.
 #include <cuda.h>
+#include <cstdlib>
 
 #include "cvpp_common.cuh"
 #include "yolov8_cell.cuh"
@@ -37,12 +45,12 @@ namespace cvpp {
 
 constexpr int kHfTileM = 128;        // cells per tile (UMMA M)
 constexpr int kHfAtomCells = 32;     // cells per 128-byte swizzle atom row
-constexpr int kHfChunkK = 16;        // channels per ring stage (two K = 8 MMA steps)
-constexpr int kHfStages = 8;
-constexpr int kHfStageBytes = kHfTileM * kHfChunkK * 4;  // 8192
-constexpr int kHfAtomBytes = kHfChunkK * 128;            // one 32-cell atom of a stage: 2048
+constexpr int kHfChunkK = 32;        // channels per ring stage (up to four K = 8 MMA steps) = one 128-byte K atom of the weights
+constexpr int kHfMaxStages = 12;                        // ring stages actually used: as many as shared memory holds (host)
+constexpr int kHfStageBytes = kHfTileM * kHfChunkK * 4;  // 16384
+constexpr int kHfAtomBytes = kHfChunkK * 128;            // one 32-cell atom of a stage: 4096
 constexpr int kHfBoxN = 4 * kRegMax;                     // 64
-constexpr int kHfThreads = 320;                          // 2 + 8 warps
+constexpr int kHfThreads = 640;                          // 4 + 16 warps (warp 3 idles: the epilogue warps keep warp % 4 = TMEM lane quarter)
 constexpr int kHfAccCols = 256;                          // TMEM columns per accumulator stage (64 + nc_pad <= 256)
 
 struct HeadLevel {
@@ -55,11 +63,14 @@ struct HeadLevel {
   int anchor_off;
   int tiles_per_image;
   int tile_base;        // tiles of the earlier levels (all images): rotates the deal so that every SM stays busy
+  int one_tma;          // H*W is a multiple of 32: the feature maps have the 4-D (cell in atom, channel, atom, image) tensor map
 };
 
 struct HeadParams {
   CUtensorMap tmap_box[CVPP_MAX_LEVELS];  // (cell, channel, image) of the box-branch features, box 32 x 16 x 1, SWIZZLE_128B
   CUtensorMap tmap_cls[CVPP_MAX_LEVELS];
+  CUtensorMap tmap_wbox[CVPP_MAX_LEVELS];  // (k, n) conv weights, box 32 k x 64 rows, SWIZZLE_128B: lands in the K-major UMMA layout
+  CUtensorMap tmap_wcls[CVPP_MAX_LEVELS];  // box 32 k x nc_pad rows (rows >= nc and k >= c3 zero-filled)
   HeadLevel lv[CVPP_MAX_LEVELS];
   int num_levels, B, c2, c3, nc, nc_pad, A;
   float conf_thres;
@@ -68,14 +79,51 @@ struct HeadParams {
   float4* box_dense;
   int max_cand;
   int w_box_bytes, w_cls_bytes;  // shared-memory footprint of one level's weights
+  int stages_box;                // of which the box branch's ring (the rest is the class branch's)
+  int stages;                    // ring depth (8 KB each): the bytes in flight per SM that keep HBM busy
+  int w_level_bytes;             // footprint of one level's weights: box W + cls W
+  int debug;                     // CVPP_HEAD_DEBUG (measurement only): 1 = no MMAs (pure TMA stream), 2 = epilogue releases at once, 4 = no candidate append
+  int w_bufs;                    // weight buffers: 2 (alternating by level) when shared memory allows, else 1 (the wide models)
   float* head_out;               // optional (B, 64 + nc, A): the materialised head x_cat (modules.py:438), for callers that want it
 };
 
 // ---- PTX wrappers ----------------------------------------------------------------------------------------------
+#ifdef CVPP_NMS_TIMING   // the instrumented build (make timing): a timeline of CTA 0 (clock64 stamps, fire-and-forget stores)
+__device__ long long g_hf_tl[8][512];   // [0] producer: chunk issued  [1] mma: chunk's operands landed  [2] mma: chunk committed
+                                        // [3] box warp (quarter 0): accumulator seen full  [4] ... released  [5] kernel start / end
+__device__ unsigned long long g_hf_cta[256][4];   // per CTA: globaltimer at start / first operands landed / last tile's accumulator / end
+__device__ __forceinline__ unsigned long long hf_gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define HF_STAMP(row, idx) do { if (blockIdx.x == 0 && (idx) < 512) g_hf_tl[row][idx] = clock64(); } while (0)
+#define HF_CTA(k) do { if (blockIdx.x < 256) g_hf_cta[blockIdx.x][k] = hf_gtime(); } while (0)
+#else
+#define HF_CTA(k) do {} while (0)
+#define HF_STAMP(row, idx) do {} while (0)
+#endif
+#define HF_WAIT(slot, stmt) do { stmt; } while (0)
 __device__ __forceinline__ void hf_mbar_wait(uint64_t* bar, uint32_t parity) {
   // bounded spin: a protocol bug traps (the launch fails) instead of hanging the device
   for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins)
     if (spins > (1u << 28)) __trap();
+}
+// the epilogue warps wait for most of a tile period: poll with a back-off so that they do not take issue slots from the
+// one thread that feeds the tensor core
+__device__ __forceinline__ void hf_mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins) {
+    __nanosleep(40);
+    if (spins > (1u << 26)) __trap();
+  }
+}
+// one lane of a CONVERGED warp: the warp runs the role's loop uniformly (descriptors and addresses live in uniform registers)
+// and only the issue is predicated; `if (lane == 0)` around the whole loop makes the compiler wrap every UTMALDG / UTCHMMA in
+// an elect + R2UR waterfall (~25 instructions, ~100 cycles per MMA on a scheduler shared with four epilogue warps)
+__device__ __forceinline__ bool hf_elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void hf_mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -113,6 +161,21 @@ __device__ __forceinline__ void hf_tma_load_3d(void* dst, const CUtensorMap* tm,
       : "memory");
 }
 
+__device__ __forceinline__ void hf_tma_load_4d(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, uint64_t* bar,
+                                               uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
+      ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(policy)
+      : "memory");
+}
+
+__device__ __forceinline__ void hf_tma_load_2d(void* dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+
 // UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor): start address, leading / stride byte offsets in 16-byte
 // units, version 1 (Blackwell), layout type 2 = SWIZZLE_128B (16-byte chunks), 1 = SWIZZLE_128B_BASE32B (32-byte chunks:
 // the ONLY layout the tensor core accepts for an MN-major 32-bit operand - with type 2 the MMA silently yields zeros,
@@ -128,48 +191,51 @@ __device__ __forceinline__ uint32_t umma_idesc_tf32(int m, int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
-// weights (n_rows, k) row-major in global -> K-major canonical layout with the 128-byte swizzle:
-// [ceil(k / 32) atoms][n_pad rows][128 B], 16-byte chunk index XOR (row % 8); rows >= n_rows and columns >= k are zero.
-__device__ __forceinline__ void hf_stage_weights(float* dst, const float* __restrict__ w, int n_rows, int n_pad, int k, int tid, int nthreads) {
-  const int atoms = (k + 31) >> 5;
-  const int total = atoms * n_pad * 32;
-  for (int i = tid; i < total; i += nthreads) {
-    const int kk = i & 31, n = (i >> 5) % n_pad, a = (i >> 5) / n_pad;
-    const int kg = (a << 5) + kk;
-    const float v = (n < n_rows && kg < k) ? __ldg(w + (int64_t)n * k + kg) : 0.0f;
-    const int off = (a * n_pad + n) * 32 + ((((kk >> 2) ^ (n & 7)) << 2) | (kk & 3));
-    dst[off] = v;
-  }
-}
-
+template <bool HEAD_OUT>
 __global__ void __launch_bounds__(kHfThreads, 1) yolov8_head_fused_kernel(const __grid_constant__ HeadParams p) {
   extern __shared__ unsigned char smem_dyn[];
   // the 128-byte swizzle pattern is anchored at 1024-byte boundaries: align the carve-up by hand (1 KB of slack is allocated)
   unsigned char* smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
-  // layout: [ring kHfStages x 8 KB | box W | cls W | bias (64 + nc_pad) | barriers | tmem slot]
+  // layout: [ring p.stages x 16 KB | 2 x (box W | cls W) | barriers | tmem slot | box hand-over slots]
   unsigned char* ring = smem_raw;
-  float* w_box = reinterpret_cast<float*>(smem_raw + kHfStages * kHfStageBytes);
-  float* w_cls = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(w_box) + p.w_box_bytes);
-  float* bias = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(w_cls) + p.w_cls_bytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(bias + kHfBoxN + p.nc_pad);
-  uint64_t* full = bars;                      // [kHfStages] TMA -> MMA
-  uint64_t* empty = bars + kHfStages;         // [kHfStages] MMA -> TMA
-  uint64_t* acc_full = bars + 2 * kHfStages;  // [2] MMA -> epilogue
-  uint64_t* acc_empty = acc_full + 2;         // [2] epilogue -> MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  const uint32_t n_stages = (uint32_t)p.stages;
+  unsigned char* w_region = smem_raw + n_stages * kHfStageBytes;  // weight buffer of level l: w_region + (l % w_bufs) * w_level_bytes
+  uint64_t* bars = reinterpret_cast<uint64_t*>(w_region + (size_t)p.w_bufs * p.w_level_bytes);
+  uint64_t* full = bars;                         // [kHfMaxStages] TMA -> MMA
+  uint64_t* empty = bars + kHfMaxStages;         // [kHfMaxStages] MMA -> TMA
+  // per branch (0 = box, 1 = class) x 2 stages / buffers:
+  uint64_t* acc_full = bars + 2 * kHfMaxStages;  // [2][2] MMA -> epilogue: the branch's accumulator columns are complete
+  uint64_t* acc_empty = acc_full + 4;            // [2][2] epilogue -> MMA
+  uint64_t* w_full = acc_empty + 4;              // [2][2] TMA -> MMA: the level's weights of the branch have landed
+  uint64_t* w_empty = w_full + 4;                // [2][2] MMA -> TMA: every MMA that reads the buffer has completed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_empty + 4);
+  float4* box_sh = reinterpret_cast<float4*>(reinterpret_cast<unsigned char*>(tmem_slot) + 16);  // [2 groups][2 slots][128 cells]
 
+  if (threadIdx.x == 0) { HF_STAMP(5, 0); HF_CTA(0); }
+  uint32_t dbg_chunk = 0;  // chunk counter of the instrumented build
+  (void)dbg_chunk;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int nchunk_box = p.c2 / kHfChunkK, nchunk_cls = p.c3 / kHfChunkK;
+  const int nchunk_box = (p.c2 + kHfChunkK - 1) / kHfChunkK, nchunk_cls = (p.c3 + kHfChunkK - 1) / kHfChunkK;
   const int nchunks = nchunk_box + nchunk_cls;
 
+  if (warp == 0 && lane == 1) {
+    for (int l = 0; l < p.num_levels; ++l) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmap_box[l]) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmap_cls[l]) : "memory");
+    }
+  }
+  if (warp == 1 && lane == 1) asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmap_wbox[0]) : "memory");
+  if (warp == 2 && lane == 1) asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmap_wcls[0]) : "memory");
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < kHfStages; ++s) {
+    for (uint32_t s = 0; s < n_stages; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
-    for (int a = 0; a < 2; ++a) {
+    for (int a = 0; a < 4; ++a) {
       mbar_init(&acc_full[a], 1);
-      mbar_init(&acc_empty[a], 4);  // one arrive per epilogue warp of the group
+      mbar_init(&acc_empty[a], 4);  // one arrive per epilogue warp of the group and branch
+      mbar_init(&w_full[a], 1);
+      mbar_init(&w_empty[a], 1);
     }
     mbar_fence_init();
   }
@@ -183,7 +249,12 @@ __global__ void __launch_bounds__(kHfThreads, 1) yolov8_head_fused_kernel(const 
   const uint32_t tmem_base = *tmem_slot;
 
   // running pipeline state (identical sequences in every role)
-  uint32_t q = 0;     // ring chunk counter
+  // Two rings, one per branch: box stages [0, n_box), class stages [n_box, n_stages).  Each MMA warp then sees EVERY phase of
+  // the barriers it waits on, in order (with one shared ring a warp skips the other branch's fills, and a parity wait
+  // cannot tell a stage that is one fill behind from one that is one fill ahead: measured as rare launch failures).
+  const uint32_t n_box = (uint32_t)p.stages_box, n_cls = n_stages - n_box;
+  uint32_t stage = 0, phase = 0;    // MMA warps: position in their own ring; producer: position in the box ring
+  uint32_t stage_c = 0, phase_c = 0;  // producer: position in the class ring
   uint32_t tile_i = 0;  // CTA-local tile counter (accumulator stage = tile_i & 1)
   const uint64_t policy = l2_policy_evict_first();
   const uint32_t idesc_box = umma_idesc_tf32(kHfTileM, kHfBoxN);
@@ -191,17 +262,13 @@ __global__ void __launch_bounds__(kHfThreads, 1) yolov8_head_fused_kernel(const 
 
   for (int l = 0; l < p.num_levels; ++l) {
     const HeadLevel& L = p.lv[l];
-    // (A) every MMA of the previous level has completed (the epilogue waited for each accumulator)
-    __syncthreads();
-    if (warp >= 2) {
-      const int t = tid - 64;
-      hf_stage_weights(w_box, L.box_w, kHfBoxN, kHfBoxN, p.c2, t, kHfThreads - 64);
-      hf_stage_weights(w_cls, L.cls_w, p.nc, p.nc_pad, p.c3, t, kHfThreads - 64);
-      for (int i = t; i < kHfBoxN + p.nc_pad; i += kHfThreads - 64)
-        bias[i] = i < kHfBoxN ? __ldg(L.box_b + i) : (i - kHfBoxN < p.nc ? __ldg(L.cls_b + i - kHfBoxN) : 0.0f);
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA's async proxy
-    }
-    __syncthreads();  // (B)
+    // The conv weights of level l live in buffer l % w_bufs, loaded by the producer's TMA (no CTA-wide barrier anywhere
+    // after the set-up: the roles only meet on mbarriers).
+    const int wbuf_i = p.w_bufs == 2 ? (l & 1) : 0;
+    const uint32_t wbuf_par = (uint32_t)(p.w_bufs == 2 ? (l >> 1) : l) & 1u;
+    unsigned char* w_buf = w_region + (size_t)wbuf_i * p.w_level_bytes;
+    const float* __restrict__ bias_box = L.box_b;   // biases straight from global memory (L1-resident broadcast loads)
+    const float* __restrict__ bias_cls = L.cls_b;
 
     const int n_tiles = L.tiles_per_image * p.B;
     // deal: tile t of the level goes to CTA (t + tile_base) % grid
@@ -210,140 +277,259 @@ __global__ void __launch_bounds__(kHfThreads, 1) yolov8_head_fused_kernel(const 
 
     if (warp == 0) {
       // ===================== TMA producer =====================
-      if (lane == 0) {
+      // (ring position = (stage, parity) counters carried across tiles and levels: no division on the issue path)
+      {
+        const CUtensorMap* tm_box = &p.tmap_box[l];
+        const CUtensorMap* tm_cls = &p.tmap_cls[l];
         for (int t = first; t < n_tiles; t += gridDim.x) {
           const int b = t / L.tiles_per_image, cell0 = (t - b * L.tiles_per_image) * kHfTileM;
-          for (int c = 0; c < nchunks; ++c, ++q) {
-            const uint32_t s = q % kHfStages;
-            hf_mbar_wait(&empty[s], ((q / kHfStages) & 1u) ^ 1u);
-            mbar_arrive_expect_tx(&full[s], kHfStageBytes);
-            const CUtensorMap* tm = c < nchunk_box ? &p.tmap_box[l] : &p.tmap_cls[l];
-            const int ch = (c < nchunk_box ? c : c - nchunk_box) * kHfChunkK;
-            unsigned char* dst = ring + s * kHfStageBytes;
+          for (int c = 0; c < nchunks; ++c) {
+            const bool is_box = c < nchunk_box;
+            const uint32_t st = is_box ? stage : n_box + stage_c;
+            hf_mbar_wait(&empty[st], (is_box ? phase : phase_c) ^ 1u);
+            const CUtensorMap* tm = is_box ? tm_box : tm_cls;
+            const int ch = (is_box ? c : c - nchunk_box) * kHfChunkK;
+            unsigned char* dst = ring + st * kHfStageBytes;
+            if (hf_elect_one()) {
+              mbar_arrive_expect_tx(&full[st], kHfStageBytes);   // channels past the last one are zero-filled and still counted
+              if (L.one_tma) {
+                // one instruction per stage: (cell in atom, channel, atom, image) view, box 32 x 32 x 4 x 1
+                hf_tma_load_4d(dst, tm, 0, ch, cell0 / kHfAtomCells, b, &full[st], policy);
+              } else {
 #pragma unroll
-            for (int a = 0; a < kHfTileM / kHfAtomCells; ++a)
-              hf_tma_load_3d(dst + a * kHfAtomBytes, tm, cell0 + a * kHfAtomCells, ch, b, &full[s], policy);
+                for (int a = 0; a < kHfTileM / kHfAtomCells; ++a)
+                  hf_tma_load_3d(dst + a * kHfAtomBytes, tm, cell0 + a * kHfAtomCells, ch, b, &full[st], policy);
+              }
+            }
+            __syncwarp();
+            if (lane == 0) HF_STAMP(0, dbg_chunk);
+            ++dbg_chunk;
+            if (is_box) {
+              if (++stage == n_box) {
+                stage = 0;
+                phase ^= 1u;
+              }
+            } else if (++stage_c == n_cls) {
+              stage_c = 0;
+              phase_c ^= 1u;
+            }
           }
         }
       }
-      __syncwarp();
-    } else if (warp == 1) {
-      // ===================== MMA issuer =====================
-      if (lane == 0) {
-        const uint32_t wb = smem_u32(w_box), wc = smem_u32(w_cls);
+    } else if (warp == 1 || warp == 2) {
+      // ===================== MMA issuers: warp 1 = box branch (N = 64), warp 2 = class branch (N = nc_pad) ===========
+      // Two issuing warps on two schedulers: one warp's serial loop (wait, fence, elect, 4 UTCHMMA, UTCBAR: ~100
+      // instructions per stage, sharing its scheduler with four epilogue warps) took 750 cycles per stage - more than
+      // the 530 the memory stream needs.  Each branch has its own accumulator columns, weights and barriers, so the box
+      // epilogue also starts while the class MMAs of the same tile are still running.
+      //   A (MN-major, 32-byte-chunk swizzle): atoms of 32 cells [32 rows x 128 B] 4096 B apart (LBO), the 4-row K groups of
+      //     the swizzle atom 512 B apart (SBO); a K = 8 step = 1024 B further into every atom;
+      //   B (K-major, 128-byte swizzle): [K atom = chunk][row][128 B], 8-row groups 1024 B apart (SBO), K step = 32 B.
+      {
+        const bool is_box = warp == 1;
+        const int role = is_box ? 0 : 1;
+        const int my_chunks = is_box ? nchunk_box : nchunk_cls;
+        const int skip_before = is_box ? 0 : nchunk_box;   // (chunk numbering of the instrumented build)
+        const uint32_t ring0 = is_box ? 0u : n_box, my_stages = is_box ? n_box : n_cls;
+        const int ksteps = (is_box ? p.c2 : p.c3) >> 3;
+        const int n_rows = is_box ? kHfBoxN : p.nc_pad;
+        const uint32_t my_w_off = is_box ? 0u : (uint32_t)p.w_box_bytes, my_w_bytes = (uint32_t)(is_box ? p.w_box_bytes : p.w_cls_bytes);
+        const uint32_t idesc = is_box ? idesc_box : idesc_cls;
+        const uint32_t atom16 = (uint32_t)(n_rows * 128) >> 4;
+        const uint64_t a_desc0 = umma_desc(smem_u32(ring), kHfAtomBytes, 512, kUmmaSw128Base32);
+        const uint64_t b_desc0 = umma_desc(smem_u32(w_buf + my_w_off), 16, 1024, kUmmaSw128);
+        uint64_t* my_w_full = w_full + 2 * role;
+        uint64_t* my_w_empty = w_empty + 2 * role;
+        uint64_t* my_acc_full = acc_full + 2 * role;
+        uint64_t* my_acc_empty = acc_empty + 2 * role;
+        // The conv weights are this warp's own TMA loads (the producer only streams activations): level 0 (and every level
+        // when there is one buffer) on entry; with two buffers, level l + 1 once the first tile of level l is in flight,
+        // after the MMAs of level l - 1 - the last readers of that buffer - have completed (w_empty, committed below).
+        auto load_weights = [&](int wl) {
+          const int buf = p.w_bufs == 2 ? (wl & 1) : 0;
+          const uint32_t use = (uint32_t)(p.w_bufs == 2 ? (wl >> 1) : wl);   // how many times the buffer was filled before
+          if (use) hf_mbar_wait(&my_w_empty[buf], (use & 1u) ^ 1u);
+          unsigned char* wb = w_region + (size_t)buf * p.w_level_bytes + my_w_off;
+          if (hf_elect_one()) {
+            mbar_arrive_expect_tx(&my_w_full[buf], my_w_bytes);
+            const CUtensorMap* tm = is_box ? &p.tmap_wbox[wl] : &p.tmap_wcls[wl];
+            for (int a = 0; a < my_chunks; ++a) hf_tma_load_2d(wb + a * (n_rows * 128), tm, a * 32, 0, &my_w_full[buf]);
+          }
+          __syncwarp();
+        };
+        if (l == 0 || p.w_bufs == 1) load_weights(l);
+        bool next_pending = p.w_bufs == 2 && l + 1 < p.num_levels;
+        hf_mbar_wait(&my_w_full[wbuf_i], wbuf_par);   // this level's weights have landed
+        tcgen05_fence_after();
         for (int t = first; t < n_tiles; t += gridDim.x, ++tile_i) {
           const uint32_t acc = tile_i & 1u;
-          hf_mbar_wait(&acc_empty[acc], ((tile_i >> 1) & 1u) ^ 1u);
+          hf_mbar_wait(&my_acc_empty[acc], ((tile_i >> 1) & 1u) ^ 1u);
           tcgen05_fence_after();
-          const uint32_t d_box = tmem_base + acc * kHfAccCols, d_cls = d_box + kHfBoxN;
-          for (int c = 0; c < nchunks; ++c, ++q) {
-            const uint32_t s = q % kHfStages;
-            hf_mbar_wait(&full[s], (q / kHfStages) & 1u);
+          const uint32_t d = tmem_base + acc * kHfAccCols + (is_box ? 0u : (uint32_t)kHfBoxN);
+          for (int cc = 0; cc < my_chunks; ++cc) {
+            const int nks = min(4, ksteps - 4 * cc);   // K = 8 steps with real channels
+            const uint32_t st = ring0 + stage;
+            const uint64_t a_desc = a_desc0 + (uint64_t)(st * (kHfStageBytes >> 4));
+            const uint64_t b_desc = b_desc0 + (uint64_t)(cc * atom16);
+            hf_mbar_wait(&full[st], phase);
+            if (lane == 0) HF_STAMP(1, dbg_chunk + skip_before + cc);
+            if (dbg_chunk == 0 && cc == 0 && is_box && lane == 0) HF_CTA(1);
             tcgen05_fence_after();
-            const uint32_t a_base = smem_u32(ring + s * kHfStageBytes);
-            const bool is_box = c < nchunk_box;
-            const int cc = is_box ? c : c - nchunk_box;
+            if (hf_elect_one()) {
+              if (p.debug & 1) {
+                hf_mbar_arrive(&empty[st]);
+              } else {
 #pragma unroll
-            for (int ks = 0; ks < kHfChunkK / 8; ++ks) {
-              const int kk = cc * (kHfChunkK / 8) + ks;  // K = 8 step index within the branch
-              // A: MN-major, 32-byte-chunk swizzle: atoms of 32 cells [16 rows x 128 B] 2048 B apart (LBO), the 4-row K
-              // groups of the swizzle atom 512 B apart (SBO); a K = 8 step is two of them = 1024 B
-              const uint64_t a_desc = umma_desc(a_base + ks * 1024, kHfAtomBytes, 512, kUmmaSw128Base32);
-              // B: K-major, [atom][row][128 B]: 8-row groups 1024 B apart (SBO), K step = 32 B inside the 128-byte row
-              const uint32_t n_pad = is_box ? kHfBoxN : p.nc_pad;
-              const uint32_t b_addr = (is_box ? wb : wc) + (kk >> 2) * n_pad * 128 + (kk & 3) * 32;
-              const uint64_t b_desc = umma_desc(b_addr, 16, 1024, kUmmaSw128);
-              tcgen05_mma_tf32(is_box ? d_box : d_cls, a_desc, b_desc, is_box ? idesc_box : idesc_cls, kk > 0 ? 1u : 0u);
+                for (int ks = 0; ks < 4; ++ks)
+                  if (ks < nks) tcgen05_mma_tf32(d, a_desc + (uint64_t)(ks * 64), b_desc + (uint64_t)(ks * 2), idesc, (cc | ks) ? 1u : 0u);
+                tcgen05_commit(&empty[st]);  // the stage is free once these MMAs have read it
+              }
             }
-            tcgen05_commit(&empty[s]);  // the stage is free once these MMAs have read it
+            __syncwarp();
+            if (lane == 0) HF_STAMP(2, dbg_chunk + skip_before + cc);
+            if (++stage == my_stages) {
+              stage = 0;
+              phase ^= 1u;
+            }
           }
-          tcgen05_commit(&acc_full[acc]);  // accumulator complete
+          dbg_chunk += nchunks;
+          if (hf_elect_one()) tcgen05_commit(&my_acc_full[acc]);  // this branch's accumulator columns are complete
+          __syncwarp();
+          if (lane == 0 && !is_box) HF_CTA(2);
+          if (next_pending) {
+            load_weights(l + 1);
+            next_pending = false;
+          }
         }
+        if (next_pending) load_weights(l + 1);
+        if (hf_elect_one()) tcgen05_commit(&my_w_empty[wbuf_i]);     // every MMA reading this level's weights is done once this arrives
+        __syncwarp();
       }
       __syncwarp();
-    } else {
-      // ===================== epilogue: 2 groups x 4 warps, group g takes the tiles with tile_i % 2 == g ==========
-      const int group = (warp - 2) >> 2;
+    } else if (warp >= 4) {
+      // ===================== epilogue: 2 groups x (4 box warps + 4 class warps); group g takes the tiles with
+      //                       tile_i % 2 == g; the box warp and the class warp of a TMEM lane quarter meet on a named barrier
+      const int e = warp - 4;
+      const int group = e >> 3;
+      const bool cls_role = (e >> 2) & 1;
       const int quarter = warp & 3;  // TMEM lanes [32 * quarter, +32) are the ones this warp may read
+      const int pair_bar = 1 + group * 4 + quarter;
       for (int t = first; t < n_tiles; t += gridDim.x, ++tile_i) {
         if ((int)(tile_i & 1u) != group) continue;
         const uint32_t acc = tile_i & 1u;
         const int b = t / L.tiles_per_image, cell0 = (t - b * L.tiles_per_image) * kHfTileM;
-        hf_mbar_wait(&acc_full[acc], (tile_i >> 1) & 1u);
+        float4* slot = box_sh + ((group * 2 + ((tile_i >> 1) & 1u)) * kHfTileM + quarter * 32 + lane);
+        uint64_t* my_acc_empty = acc_empty + 2 * (int)cls_role + acc;
+        hf_mbar_wait_relaxed(&acc_full[2 * (int)cls_role + acc], (tile_i >> 1) & 1u);
+        if (!cls_role && quarter == 0 && lane == 0) HF_STAMP(3, tile_i);
         tcgen05_fence_after();
+        if (p.debug & 2) {
+          __syncwarp();
+          if (lane == 0) hf_mbar_arrive(my_acc_empty);
+          continue;
+        }
         const uint32_t trow = tmem_base + acc * kHfAccCols + ((uint32_t)(quarter * 32) << 16);
         const int cell = cell0 + quarter * 32 + lane;
-        float v[16];
-        float d[4];
-#pragma unroll
-        for (int side = 0; side < 4; ++side) {
-          tcgen05_ld16(trow + side * 16, v);
-#pragma unroll
-          for (int k = 0; k < 16; ++k) v[k] = fadd(v[k], bias[side * 16 + k]);
-          if (p.head_out && cell < L.hw) {
-#pragma unroll
-            for (int k = 0; k < 16; ++k)
-              p.head_out[((int64_t)b * (kHfBoxN + p.nc) + side * 16 + k) * p.A + L.anchor_off + cell] = v[k];
-          }
-          d[side] = dfl16(v);
-        }
-        float best = -INFINITY, prev = -INFINITY;
-        int arg = 0;
-        for (int c0 = 0; c0 < p.nc; c0 += 16) {
-          tcgen05_ld16(trow + kHfBoxN + c0, v);
-#pragma unroll
-          for (int k = 0; k < 16; ++k) {
-            if (c0 + k < p.nc) {
-              const float x = fadd(v[k], bias[kHfBoxN + c0 + k]);
-              if (p.head_out && cell < L.hw) p.head_out[((int64_t)b * (kHfBoxN + p.nc) + kHfBoxN + c0 + k) * p.A + L.anchor_off + cell] = x;
-              class_step(x, c0 + k, best, arg, prev);
-            }
-          }
-        }
         const bool active = cell < L.hw;
-        float score = sigmoid_precise(best);
-        bool cand = active && score > p.conf_thres;
-        // an EARLIER class whose sigmoid rounds to the same float takes the reference's first-index argmax: redo the
-        // scan on sigmoid values (warp-collective TMEM loads, so the whole warp joins when any lane needs it)
-        if (__any_sync(0xffffffffu, cand && sigmoid_precise(prev) >= score)) {
-          float bs = -1.0f;
-          int ba = 0;
+        float v[16];
+        if (!cls_role) {
+          // ---- box warp: 4 x (16 bins -> DFL integral), anchor + stride -> xyxy, handed to the class warp through smem
+          float d[4];
+#pragma unroll
+          for (int side = 0; side < 4; ++side) {
+            tcgen05_ld16(trow + side * 16, v);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) v[k] = fadd(v[k], __ldg(bias_box + side * 16 + k));
+            if (HEAD_OUT) {
+              if (active) {
+#pragma unroll
+                for (int k = 0; k < 16; ++k)
+                  p.head_out[((int64_t)b * (kHfBoxN + p.nc) + side * 16 + k) * p.A + L.anchor_off + cell] = v[k];
+              }
+            }
+            d[side] = dfl16(v);
+          }
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) hf_mbar_arrive(my_acc_empty);
+          if (quarter == 0 && lane == 0) HF_STAMP(4, tile_i);
+          const CellBox bx = cell_box(active ? cell : 0, L.w, L.stride, d[0], d[1], d[2], d[3]);
+          *slot = make_float4(bx.x1, bx.y1, bx.x2, bx.y2);
+          asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");  // the class warp may read the slot
+        } else {
+          // ---- class warp: running argmax over the class logits, sigmoid, threshold, candidate append
+          float best = -INFINITY, prev = -INFINITY;
+          int arg = 0;
           for (int c0 = 0; c0 < p.nc; c0 += 16) {
             tcgen05_ld16(trow + kHfBoxN + c0, v);
+            if (c0 + 16 <= p.nc) {
 #pragma unroll
-            for (int k = 0; k < 16; ++k) {
-              if (c0 + k < p.nc) {
-                const float sv = sigmoid_precise(fadd(v[k], bias[kHfBoxN + c0 + k]));
-                if (sv > bs) {
-                  bs = sv;
-                  ba = c0 + k;
+              for (int k = 0; k < 16; ++k) {
+                v[k] = fadd(v[k], __ldg(bias_cls + c0 + k));
+                class_step(v[k], c0 + k, best, arg, prev);
+              }
+            } else {
+#pragma unroll
+              for (int k = 0; k < 16; ++k) {
+                if (c0 + k < p.nc) {
+                  v[k] = fadd(v[k], __ldg(bias_cls + c0 + k));
+                  class_step(v[k], c0 + k, best, arg, prev);
                 }
               }
             }
+            if (HEAD_OUT) {
+              if (active) {
+#pragma unroll
+                for (int k = 0; k < 16; ++k)
+                  if (c0 + k < p.nc) p.head_out[((int64_t)b * (kHfBoxN + p.nc) + kHfBoxN + c0 + k) * p.A + L.anchor_off + cell] = v[k];
+              }
+            }
           }
-          if (cand && sigmoid_precise(prev) >= score) {
-            score = bs;
-            arg = ba;
+          float score = sigmoid_precise(best);
+          bool cand = active && score > p.conf_thres;
+          // an EARLIER class whose sigmoid rounds to the same float takes the reference's first-index argmax: redo the
+          // scan on sigmoid values (warp-collective TMEM loads, so the whole warp joins when any lane needs it)
+          if (__any_sync(0xffffffffu, cand && sigmoid_precise(prev) >= score)) {
+            float bs = -1.0f;
+            int ba = 0;
+            for (int c0 = 0; c0 < p.nc; c0 += 16) {
+              tcgen05_ld16(trow + kHfBoxN + c0, v);
+#pragma unroll
+              for (int k = 0; k < 16; ++k) {
+                if (c0 + k < p.nc) {
+                  const float sv = sigmoid_precise(fadd(v[k], __ldg(bias_cls + c0 + k)));
+                  if (sv > bs) {
+                    bs = sv;
+                    ba = c0 + k;
+                  }
+                }
+              }
+            }
+            if (cand && sigmoid_precise(prev) >= score) {
+              score = bs;
+              arg = ba;
+            }
           }
-        }
-        // the accumulator stage can be overwritten: every lane of this warp has its values in registers
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) hf_mbar_arrive(&acc_empty[acc]);
-
-        const CellBox bx = cell_box(active ? cell : 0, L.w, L.stride, d[0], d[1], d[2], d[3]);
-        const unsigned m = __ballot_sync(0xffffffffu, cand);
-        if (m) {
-          int base = 0;
-          if (lane == 0) base = atomicAdd(p.cand_count + b, __popc(m));
-          base = __shfl_sync(0xffffffffu, base, 0);
-          if (cand) {
-            const int slot = base + __popc(m & ((1u << lane) - 1u));
-            const int anchor = L.anchor_off + cell;
-            if (slot < p.max_cand)
-              p.cand_key[(int64_t)b * p.max_cand + slot] = key_pack((uint32_t)arg, __float_as_uint(score), (uint32_t)anchor);
-            p.box_dense[(int64_t)b * p.A + anchor] = make_float4(bx.x1, bx.y1, bx.x2, bx.y2);
+          // the accumulator stage can be overwritten: every lane of this warp has its values in registers
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) hf_mbar_arrive(my_acc_empty);
+          if (quarter == 0 && lane == 0) HF_STAMP(6, tile_i);
+          asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");  // the box warp has written the slot
+          const unsigned m = (p.debug & 4) ? 0u : __ballot_sync(0xffffffffu, cand);
+          if (m) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(p.cand_count + b, __popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (cand) {
+              const int slot_i = base + __popc(m & ((1u << lane) - 1u));
+              const int anchor = L.anchor_off + cell;
+              if (slot_i < p.max_cand)
+                p.cand_key[(int64_t)b * p.max_cand + slot_i] = key_pack((uint32_t)arg, __float_as_uint(score), (uint32_t)anchor);
+              p.box_dense[(int64_t)b * p.A + anchor] = *slot;
+            }
           }
+          if (quarter == 0 && lane == 0) HF_STAMP(7, tile_i);
         }
       }
     }
@@ -351,11 +537,21 @@ __global__ void __launch_bounds__(kHfThreads, 1) yolov8_head_fused_kernel(const 
 
   tcgen05_fence_before();
   __syncthreads();
+  if (tid == 0) { HF_STAMP(5, 1); HF_CTA(3); }
   if (warp == 1) {
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
+
+#ifdef CVPP_NMS_TIMING
+extern "C" __attribute__((visibility("default"))) int cvpp_debug_hf_timing(long long* out) {
+  return (int)cudaMemcpyFromSymbol(out, g_hf_tl, sizeof(long long) * 8 * 512);
+}
+extern "C" __attribute__((visibility("default"))) int cvpp_debug_hf_cta(unsigned long long* out) {
+  return (int)cudaMemcpyFromSymbol(out, g_hf_cta, sizeof(unsigned long long) * 256 * 4);
+}
+#endif
 
 // ---------------------------------------------------------------------------------------------------------------
 typedef CUresult (*HfEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -374,17 +570,42 @@ static HfEncodeTiledFn hf_encode_fn() {
   return fn;
 }
 
-// (cell, channel, image) view of a contiguous (B, C, H, W) feature map; box = 32 cells x 16 channels x 1 image with the
+// (cell, channel, image) view of a contiguous (B, C, H, W) feature map; box = 32 cells x 32 channels x 1 image with the
 // 32-byte-atom 128-byte swizzle (the UMMA canonical MN-major atom for 32-bit operands), zero fill past the last cell
 static bool hf_make_tmap(CUtensorMap* tm, const float* ptr, int hw, int C, int B) {
   HfEncodeTiledFn enc = hf_encode_fn();
   if (!enc) return false;
+  if (hw % kHfAtomCells == 0) {
+    // whole atoms only: split the cell index into (cell in atom, atom) so that ONE box of 32 x 32 channels x 4 atoms lands as
+    // [atom][channel][32 cells] - the stage layout - with a single instruction; atoms past the last one are zero-filled
+    cuuint64_t dims[4] = {(cuuint64_t)kHfAtomCells, (cuuint64_t)C, (cuuint64_t)(hw / kHfAtomCells), (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)hw * 4u, (cuuint64_t)kHfAtomCells * 4u, (cuuint64_t)hw * 4u * (cuuint64_t)C};
+    cuuint32_t box[4] = {(cuuint32_t)kHfAtomCells, (cuuint32_t)kHfChunkK, (cuuint32_t)(kHfTileM / kHfAtomCells), 1u};
+    cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  }
   cuuint64_t dims[3] = {(cuuint64_t)hw, (cuuint64_t)C, (cuuint64_t)B};
   cuuint64_t strides[2] = {(cuuint64_t)hw * 4u, (cuuint64_t)hw * 4u * (cuuint64_t)C};
   cuuint32_t box[3] = {(cuuint32_t)kHfAtomCells, (cuuint32_t)kHfChunkK, 1u};
   cuuint32_t estr[3] = {1u, 1u, 1u};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+// (k, n) view of row-major conv weights (n_rows, k); box = 32 k x box_rows with the 16-byte-chunk 128-byte swizzle: exactly
+// the K-major canonical UMMA layout [row][128 B]; rows past n_rows and columns past k are zero-filled
+static bool hf_make_wmap(CUtensorMap* tm, const float* ptr, int k, int n_rows, int box_rows) {
+  HfEncodeTiledFn enc = hf_encode_fn();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)n_rows};
+  cuuint64_t strides[1] = {(cuuint64_t)k * 4u};
+  cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
@@ -411,8 +632,9 @@ int yolov8_head_fused_launch(const float* const* box_feat, const float* const* c
     set_error("yolov8 head: reg_max=%d is not compiled in (reference hard-codes 16, modules.py:413)", reg_max);
     return CVPP_ERR_UNSUPPORTED;
   }
-  if (c2 < kHfChunkK || c3 < kHfChunkK || (c2 % kHfChunkK) || (c3 % kHfChunkK) || c2 > 1024 || c3 > 1024) {
-    set_error("yolov8 head: c2=%d / c3=%d must be multiples of %d (the reference's widths are 64 / 80..320)", c2, c3, kHfChunkK);
+  if (c2 < kHfChunkK || c3 < kHfChunkK || (c2 % 16) || (c3 % 16) || c2 > 1024 || c3 > 1024) {
+    set_error("yolov8 head: c2=%d / c3=%d must be multiples of 16, at least %d (the reference's widths are 64 / 80..320)", c2, c3,
+              kHfChunkK);
     return CVPP_ERR_UNSUPPORTED;
   }
   if (!(conf_thres >= 0.0f && conf_thres <= 1.0f)) {
@@ -454,6 +676,7 @@ int yolov8_head_fused_launch(const float* const* box_feat, const float* const* c
     L.cls_w = cls_w[l];
     L.cls_b = cls_b[l];
     L.hw = level_h[l] * level_w[l];
+    L.one_tma = (L.hw % kHfAtomCells) == 0;
     L.w = level_w[l];
     L.stride = level_stride[l];
     L.anchor_off = (int)A;
@@ -461,8 +684,9 @@ int yolov8_head_fused_launch(const float* const* box_feat, const float* const* c
     L.tile_base = tiles;
     tiles += L.tiles_per_image * B;
     A += L.hw;
-    if ((reinterpret_cast<uintptr_t>(box_feat[l]) & 15u) || (reinterpret_cast<uintptr_t>(cls_feat[l]) & 15u) || (L.hw & 3)) {
-      set_error("yolov8 head: level %d feature maps must be 16-byte aligned with H*W a multiple of 4 (TMA rows)", l);
+    if ((reinterpret_cast<uintptr_t>(box_feat[l]) & 15u) || (reinterpret_cast<uintptr_t>(cls_feat[l]) & 15u) || (L.hw & 3) ||
+        (reinterpret_cast<uintptr_t>(box_w[l]) & 15u) || (reinterpret_cast<uintptr_t>(cls_w[l]) & 15u)) {
+      set_error("yolov8 head: level %d feature maps / weights must be 16-byte aligned with H*W a multiple of 4 (TMA rows)", l);
       return CVPP_ERR_ALIGNMENT;
     }
   }
@@ -474,22 +698,51 @@ int yolov8_head_fused_launch(const float* const* box_feat, const float* const* c
   CVPP_CUDA_TRY(cudaMemsetAsync(cand_count, 0, sizeof(int32_t) * (size_t)B, stream));
   if (B == 0) return CVPP_OK;
   for (int l = 0; l < num_levels; ++l) {
-    if (!hf_make_tmap(&p.tmap_box[l], box_feat[l], p.lv[l].hw, c2, B) || !hf_make_tmap(&p.tmap_cls[l], cls_feat[l], p.lv[l].hw, c3, B)) {
+    if (!hf_make_tmap(&p.tmap_box[l], box_feat[l], p.lv[l].hw, c2, B) || !hf_make_tmap(&p.tmap_cls[l], cls_feat[l], p.lv[l].hw, c3, B) ||
+        !hf_make_wmap(&p.tmap_wbox[l], box_w[l], c2, kHfBoxN, kHfBoxN) || !hf_make_wmap(&p.tmap_wcls[l], cls_w[l], c3, nc, p.nc_pad)) {
       set_error("yolov8 head: cuTensorMapEncodeTiled failed for level %d", l);
       return CVPP_ERR_CUDA;
     }
   }
-  const size_t smem = (size_t)kHfStages * kHfStageBytes + p.w_box_bytes + p.w_cls_bytes + (size_t)(kHfBoxN + p.nc_pad) * 4 +
-                      (2 * kHfStages + 4) * sizeof(uint64_t) + 16 + 1024;
-  if (smem > (size_t)di.max_smem) {
-    set_error("yolov8 head: c2=%d c3=%d nc=%d need %zu bytes of shared memory, the device has %d", c2, c3, nc, smem, di.max_smem);
+  p.w_level_bytes = p.w_box_bytes + p.w_cls_bytes;   // multiples of 1024 each: the swizzle atoms stay aligned
+  const size_t misc = (2 * kHfMaxStages + 16) * sizeof(uint64_t) + 16 + 4 * kHfTileM * sizeof(float4) + 1024;
+  // two weight buffers (the next level's weights land while this level computes) when that leaves a ring of >= 4 stages,
+  // else one (the m/l/x widths: 127 KB of weights per level at c3 = 320)
+  p.w_bufs = 2 * (size_t)p.w_level_bytes + misc + 4 * kHfStageBytes <= (size_t)di.max_smem ? 2 : 1;
+  const size_t fixed = (size_t)p.w_bufs * p.w_level_bytes + misc;
+  // ring depth: whatever shared memory is left, at most kHfMaxStages (HBM wants ~100+ KB in flight per SM), at least 4
+  int stages = fixed + 4 * kHfStageBytes <= (size_t)di.max_smem ? (int)(((size_t)di.max_smem - fixed) / kHfStageBytes) : 0;
+  if (stages > kHfMaxStages) stages = kHfMaxStages;
+  if (const char* e = getenv("CVPP_HEAD_STAGES")) {  // tuning knob
+    const int v = atoi(e);
+    if (v >= 4 && v <= stages) stages = v;
+  }
+  if (stages < 4) {
+    set_error("yolov8 head: c2=%d c3=%d nc=%d leave no room for the activation ring in %d bytes of shared memory", c2, c3, nc,
+              di.max_smem);
     return CVPP_ERR_UNSUPPORTED;
   }
-  static unsigned long long attr_done = 0;
-  rc = ensure_smem_attr(reinterpret_cast<const void*>(yolov8_head_fused_kernel), di.max_smem, di.device, &attr_done);
-  if (rc != CVPP_OK) return rc;
+  p.stages = stages;
+  {  // split in proportion to the branches' chunks per tile, at least two stages each
+    const int cb = (c2 + kHfChunkK - 1) / kHfChunkK, cc = (c3 + kHfChunkK - 1) / kHfChunkK;
+    int sb = (stages * cb + (cb + cc) / 2) / (cb + cc);
+    if (sb < 2) sb = 2;
+    if (sb > stages - 2) sb = stages - 2;
+    p.stages_box = sb;
+  }
+  if (const char* e = getenv("CVPP_HEAD_DEBUG")) p.debug = atoi(e);
+  const size_t smem = fixed + (size_t)stages * kHfStageBytes;
+  static unsigned long long attr_done[2] = {0, 0};
   const int grid = tiles < di.sms ? tiles : di.sms;
-  yolov8_head_fused_kernel<<<grid, kHfThreads, smem, stream>>>(p);
+  if (head_out) {
+    rc = ensure_smem_attr(reinterpret_cast<const void*>(yolov8_head_fused_kernel<true>), di.max_smem, di.device, &attr_done[1]);
+    if (rc != CVPP_OK) return rc;
+    yolov8_head_fused_kernel<true><<<grid, kHfThreads, smem, stream>>>(p);
+  } else {
+    rc = ensure_smem_attr(reinterpret_cast<const void*>(yolov8_head_fused_kernel<false>), di.max_smem, di.device, &attr_done[0]);
+    if (rc != CVPP_OK) return rc;
+    yolov8_head_fused_kernel<false><<<grid, kHfThreads, smem, stream>>>(p);
+  }
   CVPP_CUDA_TRY(cudaGetLastError());
   return CVPP_OK;
 }

@@ -1,4 +1,7 @@
-set -x
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_head_fused_gpu.py -q -m gpu --timeout=120 > gpurun_out/r2_c4_tests.log 2>&1; tail -30 gpurun_out/r2_c4_tests.log
-timeout 200 python tools/bench_paths.py --only head_fused,yolov8 --iters 50 > gpurun_out/r2_c4_head_paths.jsonl 2>&1; cat gpurun_out/r2_c4_head_paths.jsonl
+L=gpurun_out/r2_d10.log
+: > $L
+timeout 600 python -m pytest tests/test_head_fused_gpu.py -q -m gpu --timeout=300 2>&1 | tail -5 >> $L
+for dbg in 0 0 2 1 3; do echo "dbg $dbg" >> $L; CVPP_HEAD_DEBUG=$dbg timeout 200 python tools/bench_paths.py --only head_fused --iters 50 2>&1 | tail -3 | cut -c1-130 >> $L; done
+cat $L
+for dbg in 0; do CVPP_HEAD_DEBUG=$dbg timeout 200 python tools/head_fused_timing.py > gpurun_out/r2_head_timing_dbg$dbg.log 2>&1; echo "== dbg $dbg"; grep "decode_ms\|kernel cycles\|lag\|landed (as\|steady\|^end\|^first" gpurun_out/r2_head_timing_dbg$dbg.log; done

@@ -14,6 +14,8 @@ struct Variant {
   int b_lbo, b_sbo, b_kstep;
   int a_major_bit;             // instruction descriptor bit 15
   int a_layout;                // 0: [4 atoms][K rows][128 B] swizzled (MN-major); 1: K-major swizzled [M rows][K*4 B] (needs transposed data)
+  int reps;
+  int commit_each;             // 1: tcgen05.commit to a scratch mbarrier after every pair of MMAs (as a pipelined kernel does per stage)
   int swz;                     // layout type field of A (2 = 128B, 1 = 128B base 32B); B always uses 2
 };
 
@@ -66,6 +68,7 @@ __global__ void __launch_bounds__(128) probe(const float* __restrict__ X /*[K][M
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   if (tid == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar + 1)));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -76,15 +79,22 @@ __global__ void __launch_bounds__(128) probe(const float* __restrict__ X /*[K][M
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = *slot;
+  long long t0 = 0;
   if (tid == 0) {
+    t0 = clock64();
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)v.a_major_bit << 15) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+    for (int rep = 0; rep < v.reps; ++rep) {
     for (int ks = 0; ks < K / 8; ++ks) {
       const uint64_t da = desc(smem_u32(sa) + ks * v.a_kstep, v.a_lbo, v.a_sbo, v.swz);
       const uint64_t db = desc(smem_u32(sb) + ks * v.b_kstep, v.b_lbo, v.b_sbo, 2);
-      const uint32_t acc = ks > 0;
+      const uint32_t acc = ks > 0 && rep == 0 ? 1u : (rep > 0 ? (ks > 0) : 0u);
       asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
                    ::"r"(tmem), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
     }
+    if (v.commit_each) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar + 1)) : "memory");
+    }
+    const long long t_issue = clock64() - t0;
+    if (v.reps > 1) printf("   issue loop alone: %lld cycles (%.1f per pair)\n", t_issue, (double)t_issue / v.reps);
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
   }
   // wait
@@ -94,6 +104,7 @@ __global__ void __launch_bounds__(128) probe(const float* __restrict__ X /*[K][M
       asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(0u) : "memory");
     if (!ok && tid == 0) printf("TIMEOUT waiting for the MMA commit\n");
   }
+  if (tid == 0 && v.reps > 1) printf("   %d x %d MMAs (M=128 N=%d K=8): %lld cycles -> %.1f cycles per MMA\n", v.reps, K / 8, N, clock64() - t0, (double)(clock64() - t0) / (v.reps * (K / 8)));
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
   for (int c0 = 0; c0 < N; c0 += 16) {
@@ -128,14 +139,17 @@ int main() {
   cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768);
   Variant vs[] = {
       // a_lbo a_sbo a_kstep  b_lbo b_sbo b_kstep a_major a_layout swz
-      {K * 128, 1024, 1024, 16, 1024, 32, 1, 0, 2},   // the design: MN-major A
-      {1024, K * 128, 1024, 16, 1024, 32, 1, 0, 2},   // LBO / SBO swapped for A
-      {K * 128, 1024, 1024, 0, 1024, 32, 1, 0, 2},    // B LBO = 0
-      {16, 1024, 32, 16, 1024, 32, 0, 1, 2},          // control: both K-major (classic layout)
-      {0, 1024, 32, 0, 1024, 32, 0, 1, 2},            // control with LBO 0
-      {K * 128, 512, 1024, 16, 1024, 32, 1, 2, 1},    // MN-major A, SWIZZLE_128B_BASE32B (layout type 1), 4-row K groups 512 B apart
-      {512, K * 128, 1024, 16, 1024, 32, 1, 2, 1},    // ... LBO / SBO swapped
-      {K * 128, 1024, 1024, 16, 1024, 32, 1, 2, 1},   // ... SBO = 1024
+      {K * 128, 1024, 1024, 16, 1024, 32, 1, 0, 1, 0, 2},   // the design: MN-major A
+      {1024, K * 128, 1024, 16, 1024, 32, 1, 0, 1, 0, 2},   // LBO / SBO swapped for A
+      {K * 128, 1024, 1024, 0, 1024, 32, 1, 0, 1, 0, 2},    // B LBO = 0
+      {16, 1024, 32, 16, 1024, 32, 0, 1, 1, 0, 2},          // control: both K-major (classic layout)
+      {0, 1024, 32, 0, 1024, 32, 0, 1, 1, 0, 2},            // control with LBO 0
+      {K * 128, 512, 1024, 16, 1024, 32, 1, 2, 1, 0, 1},    // MN-major A, SWIZZLE_128B_BASE32B (layout type 1), 4-row K groups 512 B apart
+      {512, K * 128, 1024, 16, 1024, 32, 1, 2, 1, 0, 1},    // ... LBO / SBO swapped
+      {K * 128, 1024, 1024, 16, 1024, 32, 1, 2, 1, 0, 1},   // ... SBO = 1024
+      {16, 1024, 32, 16, 1024, 32, 0, 1, 200, 0, 2},          // timing: K-major A
+      {K * 128, 512, 1024, 16, 1024, 32, 1, 2, 200, 0, 1},    // timing: MN-major A (BASE32B)
+      {K * 128, 512, 1024, 16, 1024, 32, 1, 2, 200, 1, 1},    // timing: MN-major A + a commit after every pair
   };
   for (size_t i = 0; i < sizeof(vs) / sizeof(vs[0]); ++i) {
     cudaMemset(dO, 0xff, ref.size() * 4);
