@@ -364,7 +364,8 @@ def run_ours(args):
             with torch.cuda.stream(pipe.streams[slot]):
                 if consumable:
                     peer.barrier(slot)      # every rank has finished reading what this slot held (depth steps ago)
-                ops.detection_epilogue_allgather(det, ops.ROWS_FULL, peer.peer_ptrs(slot), peer.rank)
+                ops.detection_epilogue_allgather(det, ops.ROWS_FULL, peer.peer_ptrs(slot), peer.rank,
+                                                 multicast_ptr=(0 if args.no_multicast else peer.multicast_ptr(slot)))
                 if consumable:
                     peer.barrier(slot)      # every rank's rows have landed in every buffer
                     consume_tok.add_(peer.view_counts_f32(slot).sum())   # the token consumer
@@ -648,6 +649,14 @@ def run_ours(args):
         e2e_mode = (f"pipelined through ops.PipelinedPostprocess ({depth} slots): H2D of step k+1 on a copy stream behind "
                     "`consumed[slot]`, D2H on the slot's stream, the host reads each slot one turn later")
 
+    # ---- the ceiling of e2e: the same pinned host buffers copied to the device by every rank at once and nothing else
+    # (8 GPUs of one box share the host's memory / PCIe fabric: the per-GPU H2D rate falls as ranks are added)
+    def h2d_only(k):
+        for d, h in zip(levels, host_sets[k & 1]):
+            d.copy_(h, non_blocking=True)
+    h2d_s = run_e2e(h2d_only, lambda: torch.cuda.synchronize())
+    h2d_ceiling_gbs = h2d * K / h2d_s / 1e9
+
     # ---- the other configurations, measured in this run (decode kernel vs its roofline, whole path)
     paths = None
     if world == 1 and rank == 0 and not args.no_paths:
@@ -699,7 +708,9 @@ def run_ours(args):
         if world == 1:
             gather_txt = "none (1 GPU)"
         elif peer is not None:
-            gather_txt = ("fused into the epilogue kernel: rows (B,300,7) fp32 + counts stored into every rank's buffer over "
+            gather_txt = (("NVSwitch multicast (one multimem.st per 16 B, replicated by the switch into every rank's buffer) - "
+                           if (peer.multicast_ptr(0) and not args.no_multicast) else "N unicast peer stores - ") +
+                          "fused into the epilogue kernel: rows (B,300,7) fp32 + counts stored into every rank's buffer over "
                           "NVLink peer memory every step (one gather slot per pipeline slot), on the step's pipeline stream; "
                           "`value` is free-running (one symmetric-memory barrier at the end of the timed region), "
                           "`ms_per_step_barrier_each_step` fences every step's slot on both sides and reads it")
@@ -730,6 +741,9 @@ def run_ours(args):
             "e2e": {"value": world * BS * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s / K, "mode": e2e_mode,
                     "h2d_GBps_per_gpu": h2d * K / e2e_s / 1e9,
+                    "h2d_only_GBps_per_gpu": h2d_ceiling_gbs,
+                    "ceiling": {"value": world * BS * K / h2d_s, "unit": UNIT,
+                                "what": "the step's H2D copies alone, all ranks at once (host memory / PCIe fabric of the box)"},
                     "serial_value": world * BS * K / e2e_serial_s, "serial_ms_per_step": 1e3 * e2e_serial_s / K},
             # per step: decode+filter and fused sort+NMS (+ the epilogue / peer-store gather kernel when N > 1)
             "gpu_launches": (2 if world == 1 else 3) * K,
@@ -762,6 +776,7 @@ def main():
     ap.add_argument("--pipeline-depth", type=int, default=3, help="batches in flight in throughput mode")
     ap.add_argument("--no-pipeline", action="store_true", help="one step after the other on one stream (no overlap of step k's NMS with step k+1's decode)")
     ap.add_argument("--nccl-gather", action="store_true", help="N>1: use NCCL all_gather instead of the fused peer-store epilogue")
+    ap.add_argument("--no-multicast", action="store_true", help="N>1 peer gather: N unicast peer stores instead of one multimem.st through the NVSwitch")
     ap.add_argument("--no-paths", action="store_true", help="skip the C3/C4/C5-shard/YOLOv3 `paths` leg")
     ap.add_argument("--no-c5", action="store_true", help="skip the BASELINE configs[4] (YOLOv7 bs=1024 sharded) leg")
     ap.add_argument("--no-reference-gpu", action="store_true", help="skip the eager-torch + torchvision-on-CUDA bar")

@@ -78,6 +78,8 @@ _PROTOS = {
     "cvpp_centernet_suppress": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp]),
     "cvpp_detection_epilogue_allgather": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_i64, c_int, c_int,
                                                   c_vp, P(c_vp), c_int, c_int, c_vp]),
+    "cvpp_detection_epilogue_multicast": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_i64, c_int, c_int,
+                                                  c_vp, c_vp, c_int, c_int, c_vp]),
     "cvpp_detection_epilogue_compact": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_i64, c_int, c_int,
                                                 c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
     "cvpp_voc_match": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_f64, c_vp, c_vp, c_vp, c_vp, c_vp]),

@@ -293,6 +293,8 @@ constexpr int kCtThreads = 256;
 constexpr int kCtUnroll = 4;
 
 __global__ void __launch_bounds__(kCtThreads, 3) centernet_tiles_kernel(const __grid_constant__ CnParams p) {
+  pdl_trigger();
+  pdl_wait();  // the sampled bounds / zeroed lists of centernet_sample_bound_kernel
   __shared__ uint64_t sh_keys[kCtThreads / 32][kCtKeyStage];
   __shared__ int sh_wcnt[kCtThreads / 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -378,6 +380,7 @@ constexpr int kCsSamples = 4096;
 constexpr int kCsTop = 6;
 
 __global__ void __launch_bounds__(256) centernet_sample_bound_kernel(const CnParams p) {
+  pdl_trigger();  // the tile kernel may be scheduled; it waits for this grid in pdl_wait()
   __shared__ int sh_hist[1024];  // logit bins of 1/16 over [-32, 32)
   __shared__ int sh_coarse[16];  // sums of 64 bins
   const int b = blockIdx.x;
@@ -434,6 +437,8 @@ __global__ void __launch_bounds__(256) centernet_sample_bound_kernel(const CnPar
 
 // images whose list overflowed in the tile kernel are reset and flagged for the exact row kernel
 __global__ void centernet_redo_mark_kernel(const CnParams p) {
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.x;
   // overflowed list, or fewer than K keys above the guessed bound (and the map has at least K cells at all)
   const int n_keys = p.list_count[b * kCnPad];
@@ -451,6 +456,8 @@ __global__ void centernet_redo_mark_kernel(const CnParams p) {
 }
 
 __global__ void __launch_bounds__(kCnAThreads, 2) centernet_peaks_kernel(const __grid_constant__ CnParams p) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int W = p.W, nc = p.nc, Cf = p.nc + 4;
   const int row_floats = W * Cf;
@@ -615,6 +622,7 @@ __device__ __forceinline__ void diou_greedy_block(const float4* box, int n, floa
 // pass B
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kCnThreads, 1) centernet_finalize_kernel(const __grid_constant__ CnParams p) {
+  pdl_wait();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);  // [key_cap]
   __shared__ float4 sbox[kCnThreads];
@@ -633,17 +641,38 @@ __global__ void __launch_bounds__(kCnThreads, 1) centernet_finalize_kernel(const
   const unsigned long long tau = p.tau[b * kCnPad];
   const uint64_t* src = p.list + (size_t)b * p.list_cap;
 
-  // keep the keys that can still be among the K best, compacted into the sort buffer
+  // keep the keys that can still be among the K best, compacted into the sort buffer.  tau alone is loose (it is only
+  // tightened by rows that hold K peaks): the image's histogram counts EVERY emitted key (best score bin first), so the
+  // first bin at which the cumulative count reaches K bounds the K best exactly - a few hundred keys are sorted instead
+  // of the whole list (the sort was most of this kernel's 16 us).
+  static_assert(kCnThreads >= kCnBins, "one histogram bin per thread");
+  __shared__ int sh_bin_cut;
+  {
+    const int mine = tid < kCnBins ? (int)__ldcg(p.hist + (size_t)b * kCnBins + tid) : 0;
+    int incl = mine;
+    for (int d = 1; d < 32; d <<= 1) {
+      const int u = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += u;
+    }
+    if (lane == 31) sh_warp[warp] = incl;
+    if (tid == 0) {
+      sh_bin_cut = kCnBins - 1;  // fewer than K keys in all: take everything
+      sh_cnt = 0;
+    }
+    __syncthreads();
+    for (int q = 0; q < warp; ++q) incl += sh_warp[q];
+    if (incl >= p.K && incl - mine < p.K) sh_bin_cut = tid;  // one thread at most
+    __syncthreads();
+  }
+  const int bin_cut = sh_bin_cut;
   uint64_t* buf = (p.sort_cap <= p.key_cap) ? keys : p.ws_sort + (size_t)b * p.sort_cap;
-  if (tid == 0) sh_cnt = 0;
-  __syncthreads();
   for (int t0 = 0; t0 < m; t0 += kCnThreads) {
     const int t = t0 + tid;
     uint64_t k = 0;
     bool take = false;
     if (t < m) {
       k = src[t];
-      take = k <= tau;
+      take = k <= tau && cn_score_bin(k) <= bin_cut;
     }
     const unsigned mk = __ballot_sync(0xffffffffu, take);
     if (mk) {
@@ -913,11 +942,10 @@ int centernet_launch(const float* pred, int B, int H, int W, int nc, int K, floa
       pb2.tile_lo = 0;
       const int warps_needed = (p.total_tiles + kW - 1) / kW;
       const int grid_t = warps_needed < ctas_per_sm * di.sms ? warps_needed : ctas_per_sm * di.sms;
-      centernet_tiles_kernel<<<grid_t, kCtThreads, 0, stream>>>(pb2);
-      CVPP_CUDA_TRY(cudaGetLastError());
+      CVPP_CUDA_TRY(launch_pdl(centernet_tiles_kernel, dim3(grid_t), dim3(kCtThreads), 0, stream, pb2));
     }
-    centernet_redo_mark_kernel<<<B, 256, 0, stream>>>(p);  // flags (and resets) the images whose list overflowed
-    CVPP_CUDA_TRY(cudaGetLastError());
+    // flags (and resets) the images whose list overflowed
+    CVPP_CUDA_TRY(launch_pdl(centernet_redo_mark_kernel, dim3(B), dim3(256), 0, stream, p));
     tiles_done = true;
   }
   CnParams pr = p;  // the exact row kernel: everything when the tile kernel could not run, else only flagged images
@@ -947,8 +975,7 @@ int centernet_launch(const float* pred, int B, int H, int W, int nc, int K, floa
   const int rows = B * H;
   const int ctas_per_sm = (2 * (smem_a + 1024) <= (size_t)di.max_smem + 1024) ? 2 : 1;
   const int grid_a = rows < ctas_per_sm * di.sms ? rows : ctas_per_sm * di.sms;
-  centernet_peaks_kernel<<<grid_a, kCnAThreads, smem_a, stream>>>(pr);
-  CVPP_CUDA_TRY(cudaGetLastError());
+  CVPP_CUDA_TRY(launch_pdl(centernet_peaks_kernel, dim3(grid_a), dim3(kCnAThreads), smem_a, stream, pr));
 
   // pass B shared memory: sort buffer when it fits (<= 16384 keys), else the global scratch rows
   CnParams pb = p;
@@ -962,8 +989,7 @@ int centernet_launch(const float* pred, int B, int H, int W, int nc, int K, floa
   }
   rc = ensure_smem_attr(reinterpret_cast<const void*>(centernet_finalize_kernel), bytes_b, di.device, &done_b);
   if (rc != CVPP_OK) return rc;
-  centernet_finalize_kernel<<<B, kCnThreads, smem_b, stream>>>(pb);
-  CVPP_CUDA_TRY(cudaGetLastError());
+  CVPP_CUDA_TRY(launch_pdl(centernet_finalize_kernel, dim3(B), dim3(kCnThreads), smem_b, stream, pb));
   return CVPP_OK;
 }
 

@@ -104,7 +104,7 @@ int gather_feat_launch(const float* feat, const void* ind, int ind_is_int64, con
 int detection_epilogue_launch(const float* det_box, const float* det_score, const int32_t* det_cls,
                               const int32_t* det_anchor, const int32_t* det_count, const float* aux_dense, int B,
                               int max_out, int64_t A, int layout, int box_mode, const float* letterbox, float* rows,
-                              float* count_out, float* const* peer_dst, int n_peers, int slot, cudaStream_t stream);
+                              float* count_out, float* const* peer_dst, float* mc_dst, int n_peers, int slot, cudaStream_t stream);
 
 int detection_epilogue_compact_launch(const float* det_box, const float* det_score, const int32_t* det_cls,
                                       const int32_t* det_anchor, const int32_t* det_count, const float* aux_dense, int B,
@@ -405,7 +405,7 @@ int cvpp_detection_epilogue(const float* det_box, const float* det_score, const 
                             int max_out, int64_t A, int layout, int box_mode, const float* letterbox, float* rows,
                             float* count_out, cvpp_stream_t stream) {
   return detection_epilogue_launch(det_box, det_score, det_cls, det_anchor, det_count, aux_dense, B, max_out, A, layout,
-                                   box_mode, letterbox, rows, count_out, nullptr, 0, 0, (cudaStream_t)stream);
+                                   box_mode, letterbox, rows, count_out, nullptr, nullptr, 0, 0, (cudaStream_t)stream);
 }
 
 int cvpp_detection_epilogue_compact(const float* det_box, const float* det_score, const int32_t* det_cls,
@@ -426,7 +426,23 @@ int cvpp_detection_epilogue_allgather(const float* det_box, const float* det_sco
     return CVPP_ERR_INVALID_ARG;
   }
   return detection_epilogue_launch(det_box, det_score, det_cls, det_anchor, det_count, aux_dense, B, max_out, A, layout,
-                                   box_mode, letterbox, nullptr, nullptr, peer_dst, n_peers, rank, (cudaStream_t)stream);
+                                   box_mode, letterbox, nullptr, nullptr, peer_dst, nullptr, n_peers, rank, (cudaStream_t)stream);
+}
+
+int cvpp_detection_epilogue_multicast(const float* det_box, const float* det_score, const int32_t* det_cls,
+                                      const int32_t* det_anchor, const int32_t* det_count, const float* aux_dense, int B,
+                                      int max_out, int64_t A, int layout, int box_mode, const float* letterbox,
+                                      float* mc_dst, int n_ranks, int rank, cvpp_stream_t stream) {
+  if (n_ranks < 1 || !mc_dst) {
+    set_error("detection_epilogue_multicast: n_ranks must be >= 1 and mc_dst a multicast address");
+    return CVPP_ERR_INVALID_ARG;
+  }
+  if (reinterpret_cast<uintptr_t>(mc_dst) & 15u) {
+    set_error("detection_epilogue_multicast: mc_dst must be 16-byte aligned");
+    return CVPP_ERR_ALIGNMENT;
+  }
+  return detection_epilogue_launch(det_box, det_score, det_cls, det_anchor, det_count, aux_dense, B, max_out, A, layout,
+                                   box_mode, letterbox, nullptr, nullptr, nullptr, mc_dst, n_ranks, rank, (cudaStream_t)stream);
 }
 
 int cvpp_letterbox_reverse(const float* boxes, int64_t n, int xywh, float in_w, float in_h, float left, float top,

@@ -41,6 +41,31 @@ int ensure_smem_attr(const void* func, int bytes, int device, unsigned long long
     if (_e != cudaSuccess) return ::cvpp::cuda_fail(_e, #expr); \
   } while (0)
 
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------
+// A chain of short dependent kernels pays ~2 us of launch latency per link.  launch_pdl() marks a launch as a
+// programmatic dependent of the previous kernel in the stream: it is scheduled as soon as every CTA of that kernel has
+// executed pdl_trigger() (or exited), and its threads block in pdl_wait() until that kernel has completed and its
+// writes are visible - so the launch latency (and whatever runs above pdl_wait) overlaps the predecessor.  Without
+// a trigger in the predecessor, or after a non-kernel stream operation, the launch is an ordinary ordered launch.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+#endif
+
 // ---- single-use (streamed) global loads ------------------------------------------------------
 // Inputs that are read exactly once carry an L2 evict-first policy: hundreds of MB of streamed predictions
 // then do not displace what the next kernel needs from L2 (candidate keys, dense boxes, its code).

@@ -946,6 +946,8 @@ __global__ void __launch_bounds__(kN2Threads, 1) nms2_kernel(const __grid_consta
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.x;
+  // launched with programmatic stream serialisation: nothing the producer kernel wrote is read above this line
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   int n = p.cand_count[b];
   if (tid == 0 && p.cand_count_out) p.cand_count_out[b] = n;
   if (n > p.max_cand) n = p.max_cand;
@@ -1499,7 +1501,22 @@ int sort_nms_launch(const uint64_t* cand_key, const int32_t* cand_count, const f
   }
   rc = ensure_smem_attr(reinterpret_cast<const void*>(nms2_kernel), attr_bytes, di.device, &attr_done);
   if (rc != CVPP_OK) return rc;
-  nms2_kernel<<<B, kN2Threads, smem, stream>>>(p);
+  {
+    // programmatic dependent launch: when the previous operation in the stream is a kernel that executes
+    // griddepcontrol.launch_dependents (the decode kernels do), this grid is scheduled while that one still runs and
+    // waits at griddepcontrol.wait; otherwise this is an ordinary stream-ordered launch
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)B);
+    cfg.blockDim = dim3(kN2Threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CVPP_CUDA_TRY(cudaLaunchKernelEx(&cfg, nms2_kernel, p));
+  }
   CVPP_CUDA_TRY(cudaGetLastError());
   return CVPP_OK;
 }

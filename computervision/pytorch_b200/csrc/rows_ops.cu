@@ -222,6 +222,9 @@ struct EpilogueParams {
   // into EVERY destination buffer dst[d] (peer-mapped device pointers, one per rank, own rank included) at
   // this rank's slot: rows at dst[d] + (slot * B + b) * max_out * width, counts at dst[d] + count_off + slot * B.
   float* dst[CVPP_MAX_PEERS];
+  // NVSwitch multicast form: ONE multimem.st per 16 bytes to the multicast address of the same buffer; the switch
+  // replicates it into every rank's copy, so a row leaves this GPU once instead of n_dst times.  n_dst still gives the layout.
+  float* mc;
   int n_dst, slot;
   int64_t count_off;
   int B, max_out, layout, box_mode, width;
@@ -302,6 +305,28 @@ __global__ void __launch_bounds__(256) detection_epilogue_kernel(const __grid_co
   __syncthreads();
   const int rows_here = (int)min((int64_t)blockDim.x, total - t0);
   const int floats = rows_here * p.width;
+  if (p.mc) {
+    float* o = p.mc + ((int64_t)p.slot * total + t0) * p.width;
+    if ((reinterpret_cast<uintptr_t>(o) & 15u) == 0) {
+      const int nv = floats >> 2;
+      const float4* s4 = reinterpret_cast<const float4*>(sh_rows);
+      for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+        const float4 q = s4[i];
+        asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + 4 * i), "f"(q.x), "f"(q.y), "f"(q.z),
+                     "f"(q.w)
+                     : "memory");
+      }
+      for (int i = (nv << 2) + threadIdx.x; i < floats; i += blockDim.x)
+        asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(o + i), "f"(sh_rows[i]) : "memory");
+    } else {
+      for (int i = threadIdx.x; i < floats; i += blockDim.x)
+        asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(o + i), "f"(sh_rows[i]) : "memory");
+    }
+    if (valid && k == 0)
+      asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(p.mc + p.count_off + (int64_t)p.slot * p.B + b), "f"((float)n)
+                   : "memory");
+    return;
+  }
   const int n_out = p.n_dst == 0 ? 1 : p.n_dst;
   for (int d = 0; d < n_out; ++d) {
     float* o = p.n_dst == 0 ? p.rows + t0 * p.width : p.dst[d] + ((int64_t)p.slot * total + t0) * p.width;
@@ -327,8 +352,8 @@ __global__ void __launch_bounds__(256) detection_epilogue_kernel(const __grid_co
 int detection_epilogue_launch(const float* det_box, const float* det_score, const int32_t* det_cls,
                               const int32_t* det_anchor, const int32_t* det_count, const float* aux_dense, int B,
                               int max_out, int64_t A, int layout, int box_mode, const float* letterbox, float* rows,
-                              float* count_out, float* const* peer_dst, int n_peers, int slot, cudaStream_t stream) {
-  if (n_peers < 0 || n_peers > CVPP_MAX_PEERS || (n_peers > 0 && (!peer_dst || slot < 0 || slot >= n_peers))) {
+                              float* count_out, float* const* peer_dst, float* mc_dst, int n_peers, int slot, cudaStream_t stream) {
+  if (n_peers < 0 || n_peers > CVPP_MAX_PEERS || (n_peers > 0 && ((!peer_dst && !mc_dst) || slot < 0 || slot >= n_peers))) {
     set_error("detection_epilogue: bad peer list (n_peers=%d slot=%d)", n_peers, slot);
     return CVPP_ERR_INVALID_ARG;
   }
@@ -366,7 +391,8 @@ int detection_epilogue_launch(const float* det_box, const float* det_score, cons
   p.count_out = count_out;
   p.n_dst = n_peers;
   p.slot = slot;
-  for (int d = 0; d < n_peers; ++d) {
+  p.mc = mc_dst;
+  for (int d = 0; d < n_peers && !mc_dst; ++d) {
     if (!peer_dst[d]) {
       set_error("detection_epilogue: peer destination %d is NULL", d);
       return CVPP_ERR_INVALID_ARG;

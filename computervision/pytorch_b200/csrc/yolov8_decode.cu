@@ -175,6 +175,9 @@ __device__ __forceinline__ float2 vec_pack<2>(const float (&o)[2]) {
 template <bool FULL, int CPL, int STAGES>
 __global__ void __launch_bounds__(kMaxWarps * 32, 1) yolov8_decode_stream_kernel(const __grid_constant__ DecodeParams p) {
   constexpr int kStages = STAGES;
+  // programmatic dependent launch: the sort+NMS kernel that follows in the stream may be scheduled now (its CTAs park on
+  // griddepcontrol.wait until this grid has completed and flushed): its launch latency and prologue leave the critical path
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int Warps = blockDim.x >> 5;  // chosen by the host so that the tiles of an SM fill whole rounds
   constexpr int TileA = 32 * CPL;            // cells per tile
   constexpr int ChunkFloats = kChunkRows * TileA;

@@ -114,10 +114,19 @@ class PeerGather:
         self.buf.zero_()
         self.handle = symm.rendezvous(self.buf, group)
         self._ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        # NVSwitch multicast mapping of the same buffer (0 when the box / driver has no NVLS support)
+        try:
+            self._mc = int(getattr(self.handle, "multicast_ptr", 0) or 0)
+        except Exception:
+            self._mc = 0
 
     def peer_ptrs(self, i: int) -> List[int]:
         off = 4 * (i % self.depth) * self.slot_elems
         return [p + off for p in self._ptrs]
+
+    def multicast_ptr(self, i: int) -> int:
+        """Multicast address of slot i (0 = not available: use peer_ptrs)."""
+        return self._mc + 4 * (i % self.depth) * self.slot_elems if self._mc else 0
 
     def barrier(self, i: int = 0) -> None:
         self.handle.barrier(channel=i % self.depth)

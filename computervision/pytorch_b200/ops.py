@@ -743,15 +743,24 @@ def detection_epilogue_compact(det: Detections, layout: int, row_capacity: int, 
 
 def detection_epilogue_allgather(det: Detections, layout: int, peer_ptrs: Sequence[int], rank: int,
                                  box_mode: int = BOX_KEEP, letterbox: Optional[torch.Tensor] = None,
-                                 aux_dense: Optional[torch.Tensor] = None) -> None:
+                                 aux_dense: Optional[torch.Tensor] = None, multicast_ptr: int = 0) -> None:
     """cvpp_detection_epilogue_allgather: rows + counts stored into every rank's gather buffer (peer-mapped
-    device pointers `peer_ptrs`, one per rank) at slot `rank`.  See distributed.PeerGather."""
+    device pointers `peer_ptrs`, one per rank) at slot `rank`.  With `multicast_ptr` (the NVSwitch multicast address of
+    the same buffer, PeerGather.multicast_ptr(i)) the rows leave the GPU once as multimem.st
+    (cvpp_detection_epilogue_multicast).  See distributed.PeerGather."""
     B, max_out = int(det.box.shape[0]), int(det.box.shape[1])
     dev = det.box.device
     A = int(aux_dense.shape[1]) if aux_dense is not None else 0
     n = len(peer_ptrs)
     if letterbox is not None:
         letterbox = letterbox.to(device=dev, dtype=torch.float32).contiguous()
+    if multicast_ptr:
+        with torch.cuda.device(dev):
+            check(_lib.lib().cvpp_detection_epilogue_multicast(_ptr(det.box), _ptr(det.score), _ptr(det.cls), _ptr(det.anchor),
+                                                               _ptr(det.count), _ptr(aux_dense), B, max_out, A, int(layout),
+                                                               int(box_mode), _ptr(letterbox), ctypes.c_void_p(int(multicast_ptr)),
+                                                               n, int(rank), _stream(dev)))
+        return
     arr = (c_vp * n)(*[int(p) for p in peer_ptrs])
     with torch.cuda.device(dev):
         check(_lib.lib().cvpp_detection_epilogue_allgather(_ptr(det.box), _ptr(det.score), _ptr(det.cls), _ptr(det.anchor),

@@ -411,6 +411,17 @@ CVPP_API int cvpp_detection_epilogue_allgather(const float* det_box, const float
                                                int box_mode, const float* letterbox, float* const* peer_dst,
                                                int n_peers, int rank, cvpp_stream_t stream);
 
+/* Same gather, through the NVSwitch: mc_dst is the MULTICAST address of the symmetric gather buffer (one
+ * CUmulticastObject bound to every rank's copy - torch symmetric memory exposes it as `multicast_ptr`); every 16
+ * bytes leave this GPU once as a `multimem.st` and the switch writes them into all n_ranks copies (own rank
+ * included).  Same layout, same visibility rule as cvpp_detection_epilogue_allgather.  Needs NVLS-capable
+ * hardware (an NVSwitch box); CVPP_ERR_INVALID_ARG when mc_dst is NULL. */
+CVPP_API int cvpp_detection_epilogue_multicast(const float* det_box, const float* det_score, const int32_t* det_cls,
+                                               const int32_t* det_anchor, const int32_t* det_count,
+                                               const float* aux_dense, int B, int max_out, int64_t A, int layout,
+                                               int box_mode, const float* letterbox, float* mc_dst, int n_ranks,
+                                               int rank, cvpp_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * reverse_letter_box (core/utils/image_process.py:100-129) on n boxes (n, 4): xywh != 0 converts (cx,cy,w,h)
  * to corners first; then * (in_w, in_h), - (left, top), * scale, one fp32 rounding per step.  The five scalars

@@ -16,8 +16,14 @@ B, MD = 4, 40
 pred = torch.from_numpy(synth.yolov8_pred(100 + rank, B, 8400, nc=80)).to(dev)
 det = ops.sort_nms(ops.pred_filter(pred, 80, 0.05), 0.7, max_det=MD, max_nms=30000)
 pg = cvd.PeerGather(B, MD, 7, dev)
-for i in range(3):                      # alternate the slots, reuse one of them
-    ops.detection_epilogue_allgather(det, ops.ROWS_FULL, pg.peer_ptrs(i), pg.rank)
+for i in range(6):                      # alternate the slots, reuse them; the last three through the NVSwitch multicast address
+    mc = pg.multicast_ptr(i) if i >= 3 else 0
+    if i >= 3 and not mc:
+        break
+    pg.barrier(i)                       # nobody still reads what the slot held
+    pg.buf[(i % pg.depth) * pg.slot_elems:][: pg.slot_elems].fill_(-1.0)
+    pg.barrier(i)
+    ops.detection_epilogue_allgather(det, ops.ROWS_FULL, pg.peer_ptrs(i), pg.rank, multicast_ptr=mc)
     pg.barrier(i)
     rows, counts = pg.view(i)
     packed = ops.detection_epilogue(det, ops.ROWS_FULL, packed=True)
@@ -27,5 +33,6 @@ for i in range(3):                      # alternate the slots, reuse one of them
     assert torch.equal(counts, ref_counts), (rank, i)
 dist.barrier()
 if rank == 0:
-    print(f"peer gather ok on {world} ranks: {int(ref_counts.sum())} rows identical to NCCL all_gather")
+    print(f"peer gather ok on {world} ranks: {int(ref_counts.sum())} rows identical to NCCL all_gather "
+          f"(unicast peer stores{' and multimem.st multicast' if pg.multicast_ptr(0) else '; no multicast address on this box'})")
 dist.destroy_process_group()
