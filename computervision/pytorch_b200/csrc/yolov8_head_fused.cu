@@ -28,11 +28,14 @@
 //     a "class warp" pulls the nc class logits and runs the argmax with first-index tie repair, sigmoid, threshold and
 //     the warp-aggregated candidate append (the box reaches it through shared memory + a 64-thread named barrier) -
 //     EXACTLY the per-cell code of the streaming decode kernel (yolov8_cell.cuh).
-// Warp roles: 0 = TMA producer (activations only: one 4-D UTMALDG per 16 KB stage), 1 / 2 = MMA issuers (1 also owns the
-// TMEM allocation), 3 idle, 4..19 = epilogue.  Persistent, one CTA per SM; tiles are dealt level by level.
+// Warp roles: 0 / 3 = TMA producers of the box / class branch (activations only: one 4-D UTMALDG per 16 KB stage into the
+// branch's own ring), 1 / 2 = MMA issuers of the box / class branch (1 also owns the TMEM allocation), 4..19 = epilogue.  Persistent, one CTA per SM; tiles are dealt level by level.
 // Measured steps (C2 shape, 64 images, us): one thread issuing under `if (lane == 0)` 80 (every UTMALDG / UTCHMMA wrapped in
 // an elect + R2UR waterfall) -> warp-uniform loops with elect.sync 66.7 -> weights off the producer's path 65.5 -> two MMA
-// warps (see DESIGN); the pure TMA stream of the same ring runs in 47.6.
+// warps, one ring per branch 58.2 -> one producer per ring + the class scan shared with the box warps 56.8 (0.85 of the
+// measured HBM peak); the same rings with the MMAs and the epilogue switched off (CVPP_HEAD_DEBUG=3) stream in 49.2, with
+// the MMAs on and the epilogue off (=2) in 50.8: what is left is issue-slot contention between the sixteen epilogue warps
+// and the four single-lane roles that share their schedulers.
 // HBM-bound like the decode: (c2 + c3) * A * 4 bytes per image (4 838 400 B for the n model) - but the producing
 // convolution's 4.8 MB/image write and the decode's re-read of it are gone.
 #include <cuda.h>
@@ -50,8 +53,13 @@ constexpr int kHfMaxStages = 12;                        // ring stages actually 
 constexpr int kHfStageBytes = kHfTileM * kHfChunkK * 4;  // 16384
 constexpr int kHfAtomBytes = kHfChunkK * 128;            // one 32-cell atom of a stage: 4096
 constexpr int kHfBoxN = 4 * kRegMax;                     // 64
-constexpr int kHfThreads = 640;                          // 4 + 16 warps (warp 3 idles: the epilogue warps keep warp % 4 = TMEM lane quarter)
+constexpr int kHfThreads = 640;                          // 4 + 16 warps (the epilogue warps keep warp % 4 = TMEM lane quarter)
 constexpr int kHfAccCols = 256;                          // TMEM columns per accumulator stage (64 + nc_pad <= 256)
+
+struct HfSlot {   // what a box warp hands to the class warp of the same cells
+  float4 box;     // decoded xyxy
+  float4 part;    // its share of the class scan: (best logit, class index as bits, largest logit before it, -)
+};
 
 struct HeadLevel {
   const float* box_w;   // (64, c2) row-major
@@ -82,6 +90,7 @@ struct HeadParams {
   int stages_box;                // of which the box branch's ring (the rest is the class branch's)
   int stages;                    // ring depth (8 KB each): the bytes in flight per SM that keep HBM busy
   int w_level_bytes;             // footprint of one level's weights: box W + cls W
+  int cls_split;                 // classes [cls_split, nc) are scanned by the box warps (multiple of 16, or nc = none)
   int debug;                     // CVPP_HEAD_DEBUG (measurement only): 1 = no MMAs (pure TMA stream), 2 = epilogue releases at once, 4 = no candidate append
   int w_bufs;                    // weight buffers: 2 (alternating by level) when shared memory allows, else 1 (the wide models)
   float* head_out;               // optional (B, 64 + nc, A): the materialised head x_cat (modules.py:438), for callers that want it
@@ -209,7 +218,7 @@ __global__ void __launch_bounds__(kHfThreads, 1) yolov8_head_fused_kernel(const 
   uint64_t* w_full = acc_empty + 4;              // [2][2] TMA -> MMA: the level's weights of the branch have landed
   uint64_t* w_empty = w_full + 4;                // [2][2] MMA -> TMA: every MMA that reads the buffer has completed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_empty + 4);
-  float4* box_sh = reinterpret_cast<float4*>(reinterpret_cast<unsigned char*>(tmem_slot) + 16);  // [2 groups][2 slots][128 cells]
+  HfSlot* box_sh = reinterpret_cast<HfSlot*>(reinterpret_cast<unsigned char*>(tmem_slot) + 16);  // [2 groups][2 slots][128 cells]
 
   if (threadIdx.x == 0) { HF_STAMP(5, 0); HF_CTA(0); }
   uint32_t dbg_chunk = 0;  // chunk counter of the instrumented build
@@ -218,11 +227,9 @@ __global__ void __launch_bounds__(kHfThreads, 1) yolov8_head_fused_kernel(const 
   const int nchunk_box = (p.c2 + kHfChunkK - 1) / kHfChunkK, nchunk_cls = (p.c3 + kHfChunkK - 1) / kHfChunkK;
   const int nchunks = nchunk_box + nchunk_cls;
 
-  if (warp == 0 && lane == 1) {
-    for (int l = 0; l < p.num_levels; ++l) {
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmap_box[l]) : "memory");
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmap_cls[l]) : "memory");
-    }
+  if ((warp == 0 || warp == 3) && lane == 1) {
+    for (int l = 0; l < p.num_levels; ++l)
+      asm volatile("prefetch.tensormap [%0];" ::"l"(warp == 0 ? &p.tmap_box[l] : &p.tmap_cls[l]) : "memory");
   }
   if (warp == 1 && lane == 1) asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmap_wbox[0]) : "memory");
   if (warp == 2 && lane == 1) asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmap_wcls[0]) : "memory");
@@ -233,7 +240,8 @@ __global__ void __launch_bounds__(kHfThreads, 1) yolov8_head_fused_kernel(const 
     }
     for (int a = 0; a < 4; ++a) {
       mbar_init(&acc_full[a], 1);
-      mbar_init(&acc_empty[a], 4);  // one arrive per epilogue warp of the group and branch
+      // one arrive per epilogue warp of the group that reads the branch's columns (the box warps also read class columns)
+      mbar_init(&acc_empty[a], (a >= 2 && p.cls_split < p.nc) ? 8 : 4);
       mbar_init(&w_full[a], 1);
       mbar_init(&w_empty[a], 1);
     }
@@ -253,8 +261,7 @@ __global__ void __launch_bounds__(kHfThreads, 1) yolov8_head_fused_kernel(const 
   // the barriers it waits on, in order (with one shared ring a warp skips the other branch's fills, and a parity wait
   // cannot tell a stage that is one fill behind from one that is one fill ahead: measured as rare launch failures).
   const uint32_t n_box = (uint32_t)p.stages_box, n_cls = n_stages - n_box;
-  uint32_t stage = 0, phase = 0;    // MMA warps: position in their own ring; producer: position in the box ring
-  uint32_t stage_c = 0, phase_c = 0;  // producer: position in the class ring
+  uint32_t stage = 0, phase = 0;    // producers and MMA warps: position in their branch's ring
   uint32_t tile_i = 0;  // CTA-local tile counter (accumulator stage = tile_i & 1)
   const uint64_t policy = l2_policy_evict_first();
   const uint32_t idesc_box = umma_idesc_tf32(kHfTileM, kHfBoxN);
@@ -275,20 +282,22 @@ __global__ void __launch_bounds__(kHfThreads, 1) yolov8_head_fused_kernel(const 
     int first = (int)blockIdx.x - (L.tile_base % (int)gridDim.x);
     if (first < 0) first += gridDim.x;
 
-    if (warp == 0) {
-      // ===================== TMA producer =====================
+    if (warp == 0 || warp == 3) {
+      // ===================== TMA producers: warp 0 streams the box branch's activations into the box ring, warp 3 the
+      // class branch's into the class ring.  (One in-order producer over both rings blocked on whichever ring was full
+      // while the other had free stages: 3400 cycles per tile instead of the 2800 the memory system delivers.)
       // (ring position = (stage, parity) counters carried across tiles and levels: no division on the issue path)
       {
-        const CUtensorMap* tm_box = &p.tmap_box[l];
-        const CUtensorMap* tm_cls = &p.tmap_cls[l];
+        const bool is_box = warp == 0;
+        const CUtensorMap* tm = is_box ? &p.tmap_box[l] : &p.tmap_cls[l];
+        const int my_chunks = is_box ? nchunk_box : nchunk_cls;
+        const uint32_t ring0 = is_box ? 0u : n_box, my_stages = is_box ? n_box : n_cls;
         for (int t = first; t < n_tiles; t += gridDim.x) {
           const int b = t / L.tiles_per_image, cell0 = (t - b * L.tiles_per_image) * kHfTileM;
-          for (int c = 0; c < nchunks; ++c) {
-            const bool is_box = c < nchunk_box;
-            const uint32_t st = is_box ? stage : n_box + stage_c;
-            hf_mbar_wait(&empty[st], (is_box ? phase : phase_c) ^ 1u);
-            const CUtensorMap* tm = is_box ? tm_box : tm_cls;
-            const int ch = (is_box ? c : c - nchunk_box) * kHfChunkK;
+          for (int c = 0; c < my_chunks; ++c) {
+            const uint32_t st = ring0 + stage;
+            hf_mbar_wait(&empty[st], phase ^ 1u);
+            const int ch = c * kHfChunkK;
             unsigned char* dst = ring + st * kHfStageBytes;
             if (hf_elect_one()) {
               mbar_arrive_expect_tx(&full[st], kHfStageBytes);   // channels past the last one are zero-filled and still counted
@@ -302,18 +311,13 @@ __global__ void __launch_bounds__(kHfThreads, 1) yolov8_head_fused_kernel(const 
               }
             }
             __syncwarp();
-            if (lane == 0) HF_STAMP(0, dbg_chunk);
-            ++dbg_chunk;
-            if (is_box) {
-              if (++stage == n_box) {
-                stage = 0;
-                phase ^= 1u;
-              }
-            } else if (++stage_c == n_cls) {
-              stage_c = 0;
-              phase_c ^= 1u;
+            if (lane == 0) HF_STAMP(0, dbg_chunk + (is_box ? 0 : nchunk_box) + c);
+            if (++stage == my_stages) {
+              stage = 0;
+              phase ^= 1u;
             }
           }
+          dbg_chunk += nchunks;
         }
       }
     } else if (warp == 1 || warp == 2) {
@@ -418,7 +422,7 @@ __global__ void __launch_bounds__(kHfThreads, 1) yolov8_head_fused_kernel(const 
         if ((int)(tile_i & 1u) != group) continue;
         const uint32_t acc = tile_i & 1u;
         const int b = t / L.tiles_per_image, cell0 = (t - b * L.tiles_per_image) * kHfTileM;
-        float4* slot = box_sh + ((group * 2 + ((tile_i >> 1) & 1u)) * kHfTileM + quarter * 32 + lane);
+        HfSlot* slot = box_sh + ((group * 2 + ((tile_i >> 1) & 1u)) * kHfTileM + quarter * 32 + lane);
         uint64_t* my_acc_empty = acc_empty + 2 * (int)cls_role + acc;
         hf_mbar_wait_relaxed(&acc_full[2 * (int)cls_role + acc], (tile_i >> 1) & 1u);
         if (!cls_role && quarter == 0 && lane == 0) HF_STAMP(3, tile_i);
@@ -426,41 +430,20 @@ __global__ void __launch_bounds__(kHfThreads, 1) yolov8_head_fused_kernel(const 
         if (p.debug & 2) {
           __syncwarp();
           if (lane == 0) hf_mbar_arrive(my_acc_empty);
+          if (!cls_role && p.cls_split < p.nc) {
+            hf_mbar_wait_relaxed(&acc_full[2 + acc], (tile_i >> 1) & 1u);
+            __syncwarp();
+            if (lane == 0) hf_mbar_arrive(&acc_empty[2 + acc]);
+          }
           continue;
         }
         const uint32_t trow = tmem_base + acc * kHfAccCols + ((uint32_t)(quarter * 32) << 16);
         const int cell = cell0 + quarter * 32 + lane;
         const bool active = cell < L.hw;
         float v[16];
-        if (!cls_role) {
-          // ---- box warp: 4 x (16 bins -> DFL integral), anchor + stride -> xyxy, handed to the class warp through smem
-          float d[4];
-#pragma unroll
-          for (int side = 0; side < 4; ++side) {
-            tcgen05_ld16(trow + side * 16, v);
-#pragma unroll
-            for (int k = 0; k < 16; ++k) v[k] = fadd(v[k], __ldg(bias_box + side * 16 + k));
-            if (HEAD_OUT) {
-              if (active) {
-#pragma unroll
-                for (int k = 0; k < 16; ++k)
-                  p.head_out[((int64_t)b * (kHfBoxN + p.nc) + side * 16 + k) * p.A + L.anchor_off + cell] = v[k];
-              }
-            }
-            d[side] = dfl16(v);
-          }
-          tcgen05_fence_before();
-          __syncwarp();
-          if (lane == 0) hf_mbar_arrive(my_acc_empty);
-          if (quarter == 0 && lane == 0) HF_STAMP(4, tile_i);
-          const CellBox bx = cell_box(active ? cell : 0, L.w, L.stride, d[0], d[1], d[2], d[3]);
-          *slot = make_float4(bx.x1, bx.y1, bx.x2, bx.y2);
-          asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");  // the class warp may read the slot
-        } else {
-          // ---- class warp: running argmax over the class logits, sigmoid, threshold, candidate append
-          float best = -INFINITY, prev = -INFINITY;
-          int arg = 0;
-          for (int c0 = 0; c0 < p.nc; c0 += 16) {
+        // running class argmax over the class columns [c_begin, c_end) of this lane's cell (bias added in fp32)
+        auto scan_classes = [&](int c_begin, int c_end, float& best, int& arg, float& prev) {
+          for (int c0 = c_begin; c0 < c_end; c0 += 16) {
             tcgen05_ld16(trow + kHfBoxN + c0, v);
             if (c0 + 16 <= p.nc) {
 #pragma unroll
@@ -483,6 +466,62 @@ __global__ void __launch_bounds__(kHfThreads, 1) yolov8_head_fused_kernel(const 
                 for (int k = 0; k < 16; ++k)
                   if (c0 + k < p.nc) p.head_out[((int64_t)b * (kHfBoxN + p.nc) + kHfBoxN + c0 + k) * p.A + L.anchor_off + cell] = v[k];
               }
+            }
+          }
+        };
+        const int c_split = p.cls_split;  // classes [c_split, nc) are scanned by the box warp (multiple of 16; nc = none)
+        if (!cls_role) {
+          // ---- box warp: 4 x (16 bins -> DFL integral), anchor + stride -> xyxy; then its share of the class scan (the
+          //      class warp alone was the bottleneck: ~5500 cycles per tile against ~2000 here); box and partial scan are
+          //      handed to the class warp through shared memory
+          float d[4];
+#pragma unroll
+          for (int side = 0; side < 4; ++side) {
+            tcgen05_ld16(trow + side * 16, v);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) v[k] = fadd(v[k], __ldg(bias_box + side * 16 + k));
+            if (HEAD_OUT) {
+              if (active) {
+#pragma unroll
+                for (int k = 0; k < 16; ++k)
+                  p.head_out[((int64_t)b * (kHfBoxN + p.nc) + side * 16 + k) * p.A + L.anchor_off + cell] = v[k];
+              }
+            }
+            d[side] = dfl16(v);
+          }
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) hf_mbar_arrive(my_acc_empty);
+          if (quarter == 0 && lane == 0) HF_STAMP(4, tile_i);
+          const CellBox bx = cell_box(active ? cell : 0, L.w, L.stride, d[0], d[1], d[2], d[3]);
+          float pbest = -INFINITY, pprev = -INFINITY;
+          int parg = 0;
+          if (c_split < p.nc) {
+            hf_mbar_wait_relaxed(&acc_full[2 + acc], (tile_i >> 1) & 1u);  // the class branch's columns
+            tcgen05_fence_after();
+            scan_classes(c_split, p.nc, pbest, parg, pprev);
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) hf_mbar_arrive(&acc_empty[2 + acc]);
+          }
+          slot->box = make_float4(bx.x1, bx.y1, bx.x2, bx.y2);
+          slot->part = make_float4(pbest, __int_as_float(parg), pprev, 0.0f);
+          asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");  // the class warp may read the slot
+        } else {
+          // ---- class warp: running argmax over its class logits, merge with the box warp's share, sigmoid, threshold,
+          //      candidate append
+          float best = -INFINITY, prev = -INFINITY;
+          int arg = 0;
+          scan_classes(0, min(c_split, p.nc), best, arg, prev);
+          asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");  // the box warp has written the slot
+          if (c_split < p.nc) {
+            // first-index argmax over the union: the later range wins only when strictly greater; `prev` = the largest
+            // logit BEFORE the winner (all of the earlier range, and the later range's own running maximum before it)
+            const float4 part = slot->part;
+            if (part.x > best) {
+              prev = fmaxf(best, part.z);
+              best = part.x;
+              arg = __float_as_int(part.y);
             }
           }
           float score = sigmoid_precise(best);
@@ -515,7 +554,6 @@ __global__ void __launch_bounds__(kHfThreads, 1) yolov8_head_fused_kernel(const 
           __syncwarp();
           if (lane == 0) hf_mbar_arrive(my_acc_empty);
           if (quarter == 0 && lane == 0) HF_STAMP(6, tile_i);
-          asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");  // the box warp has written the slot
           const unsigned m = (p.debug & 4) ? 0u : __ballot_sync(0xffffffffu, cand);
           if (m) {
             int base = 0;
@@ -526,7 +564,7 @@ __global__ void __launch_bounds__(kHfThreads, 1) yolov8_head_fused_kernel(const 
               const int anchor = L.anchor_off + cell;
               if (slot_i < p.max_cand)
                 p.cand_key[(int64_t)b * p.max_cand + slot_i] = key_pack((uint32_t)arg, __float_as_uint(score), (uint32_t)anchor);
-              p.box_dense[(int64_t)b * p.A + anchor] = *slot;
+              p.box_dense[(int64_t)b * p.A + anchor] = slot->box;
             }
           }
           if (quarter == 0 && lane == 0) HF_STAMP(7, tile_i);
@@ -661,6 +699,14 @@ int yolov8_head_fused_launch(const float* const* box_feat, const float* const* c
   p.box_dense = reinterpret_cast<float4*>(box_dense);
   p.max_cand = max_cand;
   p.head_out = head_out;
+  {
+    const int chunks16 = (nc + 15) / 16, share = (2 * chunks16) / 5;   // ~2/5 of the class columns go to the box warps
+    p.cls_split = share > 0 ? 16 * (chunks16 - share) : nc;
+    if (const char* e = getenv("CVPP_HEAD_SPLIT")) {  // tuning knob: chunks of 16 classes taken by the box warps
+      const int v = atoi(e);
+      if (v >= 0 && v < chunks16) p.cls_split = v > 0 ? 16 * (chunks16 - v) : nc;
+    }
+  }
   p.w_box_bytes = ((c2 + 31) / 32) * kHfBoxN * 128;
   p.w_cls_bytes = ((c3 + 31) / 32) * p.nc_pad * 128;
   int64_t A = 0;
@@ -705,7 +751,7 @@ int yolov8_head_fused_launch(const float* const* box_feat, const float* const* c
     }
   }
   p.w_level_bytes = p.w_box_bytes + p.w_cls_bytes;   // multiples of 1024 each: the swizzle atoms stay aligned
-  const size_t misc = (2 * kHfMaxStages + 16) * sizeof(uint64_t) + 16 + 4 * kHfTileM * sizeof(float4) + 1024;
+  const size_t misc = (2 * kHfMaxStages + 16) * sizeof(uint64_t) + 16 + 4 * kHfTileM * sizeof(HfSlot) + 1024;
   // two weight buffers (the next level's weights land while this level computes) when that leaves a ring of >= 4 stages,
   // else one (the m/l/x widths: 127 KB of weights per level at c3 = 320)
   p.w_bufs = 2 * (size_t)p.w_level_bytes + misc + 4 * kHfStageBytes <= (size_t)di.max_smem ? 2 : 1;
