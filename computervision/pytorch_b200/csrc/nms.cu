@@ -946,8 +946,10 @@ __global__ void __launch_bounds__(kN2Threads, 1) nms2_kernel(const __grid_consta
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.x;
-  // launched with programmatic stream serialisation: nothing the producer kernel wrote is read above this line
-  asm volatile("griddepcontrol.wait;" ::: "memory");
+  // launched with programmatic stream serialisation: nothing the producer kernel wrote is read above this line; the
+  // kernel that follows (the row epilogue) may be scheduled as soon as every CTA of this grid is resident
+  pdl_trigger();
+  pdl_wait();
   int n = p.cand_count[b];
   if (tid == 0 && p.cand_count_out) p.cand_count_out[b] = n;
   if (n > p.max_cand) n = p.max_cand;

@@ -293,6 +293,7 @@ __global__ void __launch_bounds__(256) detection_epilogue_kernel(const __grid_co
   // coalesced 128-bit stores - into each peer's buffer over NVLink in the gather form (per-element 4-byte
   // stores at a 28-byte stride made a million tiny NVLink writes per step and dragged the step at 8 GPUs).
   __shared__ __align__(16) float sh_rows[256 * 7];
+  pdl_wait();  // programmatic dependent of the NMS kernel when it directly follows it in the stream
   const int64_t total = (int64_t)p.B * p.max_out;
   const int64_t t0 = (int64_t)blockIdx.x * blockDim.x;
   const int64_t t = t0 + threadIdx.x;
@@ -407,8 +408,7 @@ int detection_epilogue_launch(const float* det_box, const float* det_score, cons
   p.count_off = (int64_t)n_peers * B * max_out * p.width;
   p.A = A;
   const int64_t total = (int64_t)B * max_out;
-  detection_epilogue_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(p);
-  CVPP_CUDA_TRY(cudaGetLastError());
+  CVPP_CUDA_TRY(launch_pdl(detection_epilogue_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, stream, p));
   return CVPP_OK;
 }
 

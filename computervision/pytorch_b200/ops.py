@@ -378,7 +378,9 @@ class PipelinedPostprocess:
     benchmarking only - a real producer could not refill them while another slot's decode is in flight)."""
 
     def __init__(self, B: int, A: int, nc: int, device, inputs, conf_thres: float, iou_thres: float,
-                 max_det: int = 300, depth: Optional[int] = None, graph: bool = True, **post_args):
+                 max_det: int = 300, depth: Optional[int] = None, graph: bool = True, gather=None,
+                 use_multicast: bool = True, **post_args):
+        self.use_multicast = bool(use_multicast)
         if isinstance(inputs, LevelSet):
             depth = int(depth or 2)
             inputs = [inputs] * depth
@@ -402,6 +404,22 @@ class PipelinedPostprocess:
                 e.record()                  # creates the handle; "consumed" holds before the first use of a slot
         self.graphs = [pp.capture(ls, *self.args, consumed=e) for pp, ls, e in zip(self.posts, inputs, self.consumed)] \
             if graph else None
+        # optional: the slot's graph also holds the fused epilogue + all-gather of the slot's detections into gather slot
+        # `slot` of a distributed.PeerGather (a programmatic dependent launch behind the NMS kernel: no launch gap, and one
+        # graph launch per step on the host instead of a graph launch plus an eager kernel)
+        self.gather = gather
+        self.graphs_gather = None
+        if gather is not None:
+            if gather.depth < depth:
+                raise ValueError(f"the PeerGather has {gather.depth} slots, the pipeline {depth}")
+            if graph:
+                self.graphs_gather = []
+                with torch.cuda.device(self.device):
+                    for i, (pp, ls, e) in enumerate(zip(self.posts, inputs, self.consumed)):
+                        g = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(g):
+                            self._post_and_gather(i)
+                        self.graphs_gather.append(g)
         self.streams = [torch.cuda.Stream(device=self.device) for _ in range(depth)]
         self.turn = 0
         self.last_slot = 0
@@ -420,15 +438,29 @@ class PipelinedPostprocess:
         for s in self.streams:
             s.wait_stream(cur)
 
-    def submit(self, ready: Optional[torch.cuda.Event] = None) -> Detections:
+    def _post_and_gather(self, i: int) -> None:
+        det = self.posts[i](self.inputs[i], *self.args, consumed=self.consumed[i])
+        detection_epilogue_allgather(det, ROWS_FULL, self.gather.peer_ptrs(i), self.gather.rank,
+                                     multicast_ptr=(self.gather.multicast_ptr(i) if self.use_multicast else 0))
+
+    def submit(self, ready: Optional[torch.cuda.Event] = None, gather: bool = False) -> Detections:
+        """gather=True (needs the `gather=` PeerGather of the constructor): the slot's rows + counts are also stored into
+        gather slot `slot` of every rank; fence with gather.barrier(slot) before reading gather.view(slot)."""
         i = self.turn % len(self.posts)
         self.turn += 1
         self.last_slot = i
         st = self.streams[i]
         if ready is not None:
             st.wait_event(ready)
+        if gather and self.gather is None:
+            raise ValueError("submit(gather=True) needs PipelinedPostprocess(..., gather=PeerGather)")
         with torch.cuda.stream(st):
-            if self.graphs is not None:
+            if gather:
+                if self.graphs_gather is not None:
+                    self.graphs_gather[i].replay()
+                else:
+                    self._post_and_gather(i)
+            elif self.graphs is not None:
                 self.graphs[i].replay()
             else:
                 self.posts[i](self.inputs[i], *self.args, consumed=self.consumed[i])

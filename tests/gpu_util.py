@@ -1,8 +1,28 @@
 """Helpers shared by the -m gpu parity tests (they all go through the C ABI via ops.py)."""
+import json
+import os
+
 import numpy as np
 import torch
 
 BOX_RTOL, BOX_ATOL, SCORE_RTOL = 1e-5, 2.5e-4, 1e-5   # see tests/test_oracle_golden.py
+
+
+def record_error(got, ref, what=""):
+    """CVPP_ERR_LOG=<file>: append the largest absolute and relative difference of this comparison (DESIGN.md quotes the
+    measured maxima per path next to the tolerances the tests assert)."""
+    path = os.environ.get("CVPP_ERR_LOG")
+    if not path or np.size(ref) == 0:
+        return
+    got, ref = np.asarray(got, np.float64), np.asarray(ref, np.float64)
+    if got.shape != ref.shape:
+        return
+    d = np.abs(got - ref)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        rel = np.where(np.abs(ref) > 0, d / np.abs(ref), 0.0)
+    with open(path, "a") as f:
+        f.write(json.dumps({"test": os.environ.get("PYTEST_CURRENT_TEST", "").split(" ")[0], "what": what, "n": int(d.size),
+                            "max_abs": float(d.max()), "max_rel": float(rel.max()), "max_ref": float(np.abs(ref).max())}) + "\n")
 
 
 def to_dev(arrays, device="cuda:0"):
@@ -36,11 +56,13 @@ def candidates_to_numpy(c):
 
 def assert_boxes_close(got, ref):
     assert got.shape == ref.shape
+    record_error(got, ref, "box")
     assert np.all(np.abs(got - ref) <= BOX_RTOL * np.abs(ref) + BOX_ATOL), float(np.abs(got - ref).max())
 
 
 def assert_scores_close(got, ref):
     assert got.shape == ref.shape
+    record_error(got, ref, "score")
     assert np.all(np.abs(got - ref) <= SCORE_RTOL * np.abs(ref)), float((np.abs(got - ref) / np.abs(ref)).max())
 
 

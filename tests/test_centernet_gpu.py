@@ -8,7 +8,7 @@ import torch
 
 import oracle
 import synth
-from gpu_util import BOX_ATOL, BOX_RTOL, SCORE_RTOL
+from gpu_util import record_error, BOX_ATOL, BOX_RTOL, SCORE_RTOL
 
 pytestmark = pytest.mark.gpu
 
@@ -26,6 +26,7 @@ def _cfg(nc, inp, use_nms=True):
 
 
 def _close_boxes(a, b, scale=1.0):
+    record_error(a, b, "box")
     return a.shape == b.shape and np.all(np.abs(a - b) <= BOX_RTOL * np.abs(b) + BOX_ATOL * max(scale, 1.0))
 
 
@@ -71,6 +72,7 @@ def test_c3_batch64_vs_oracle(use_nms):
         n = int(cnt[b])
         assert n == len(rs)
         assert np.array_equal(cls[b, :n], rc) and np.array_equal(pix[b, :n], rp)
+        record_error(score[b, :n], rs, "score")
         assert np.all(np.abs(score[b, :n] - rs) <= SCORE_RTOL * rs)
         assert _close_boxes(box[b, :n], rb, 2.0)
         kept_lt_k += n < 100

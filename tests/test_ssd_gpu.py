@@ -8,7 +8,7 @@ import torch
 
 import oracle
 import synth
-from gpu_util import BOX_ATOL, BOX_RTOL, SCORE_RTOL
+from gpu_util import record_error, BOX_ATOL, BOX_RTOL, SCORE_RTOL
 
 pytestmark = pytest.mark.gpu
 
@@ -40,6 +40,8 @@ def test_decode_boxes_vs_reference_fixture(golden_dir):
             ref = g[f"rows_{b}_{ctag}"]
             assert r.dtype == np.float32 and r.shape == ref.shape
             assert np.array_equal(r[:, 4], ref[:, 4])                       # labels, class-major order
+            record_error(r[:, 5], ref[:, 5], "score")
+            record_error(r[:, :4], ref[:, :4], "box")
             assert np.all(np.abs(r[:, 5] - ref[:, 5]) <= SCORE_RTOL * ref[:, 5])
             assert np.all(np.abs(r[:, :4] - ref[:, :4]) <= BOX_RTOL * np.abs(ref[:, :4]) + BOX_ATOL * 2.2)
     res = algo.decode_boxes((tl, tc), 480, 640, 0.99999)

@@ -9,7 +9,7 @@ import torch
 
 import oracle
 import synth
-from gpu_util import BOX_RTOL, SCORE_RTOL, decode_keys
+from gpu_util import record_error, BOX_RTOL, SCORE_RTOL, decode_keys
 
 pytestmark = pytest.mark.gpu
 
@@ -28,6 +28,7 @@ def _cfg(nc=20):
 
 
 def _close(got, ref, rtol, atol=0.0):
+    record_error(got, ref, "box" if atol else "score_or_norm_box")
     return got.shape == ref.shape and bool(np.all(np.abs(got - ref) <= rtol * np.abs(ref) + atol))
 
 
