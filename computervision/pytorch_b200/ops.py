@@ -111,11 +111,20 @@ class Detections:
     cand_count: Optional[torch.Tensor] = None  # (B,) int32 candidates that entered NMS
 
 
+def _check_one_key_per_anchor(max_cand: int, A: int) -> None:
+    """Filters that emit at most one key per anchor: a smaller candidate buffer could overflow, and keys past max_cand are
+    dropped in the (nondeterministic) order of the atomics - wrong detections without an error."""
+    if max_cand < A:
+        raise ValueError(f"max_cand={max_cand} < A={A}: every anchor can pass the confidence filter; an overflowing candidate "
+                         "buffer would silently drop keys in a nondeterministic order")
+
+
 def yolov8_decode_filter(ls: LevelSet, nc: int, conf_thres: float, reg_max: int = 16,
                          max_cand: Optional[int] = None) -> Candidates:
     if ls.C != 4 * reg_max + nc:
         raise ValueError(f"head has {ls.C} channels, expected 4*{reg_max}+{nc}")
     max_cand = int(max_cand or ls.A)
+    _check_one_key_per_anchor(max_cand, ls.A)
     dev = ls.device
     key = torch.empty((ls.B, max_cand), dtype=torch.int64, device=dev)
     count = torch.empty((ls.B,), dtype=torch.int32, device=dev)
@@ -168,6 +177,7 @@ def yolov8_head_decode_filter(box_feats: Sequence[torch.Tensor], cls_feats: Sequ
         ws.append(int(bf[i].shape[3]))
     A = sum(h * w for h, w in zip(hs, ws))
     max_cand = int(max_cand or A)
+    _check_one_key_per_anchor(max_cand, A)
     key = torch.empty((B, max_cand), dtype=torch.int64, device=dev)
     count = torch.empty((B,), dtype=torch.int32, device=dev)
     box_dense = torch.empty((B, A, 4), dtype=torch.float32, device=dev)
@@ -199,6 +209,7 @@ def pred_filter(pred: torch.Tensor, nc: int, conf_thres: float, max_cand: Option
     pred = pred.contiguous()
     B, ch, A = (int(v) for v in pred.shape)
     max_cand = int(max_cand or A)
+    _check_one_key_per_anchor(max_cand, A)
     dev = pred.device
     key = torch.empty((B, max_cand), dtype=torch.int64, device=dev)
     count = torch.empty((B,), dtype=torch.int32, device=dev)

@@ -67,3 +67,48 @@ def test_compact_epilogue_is_the_padded_rows_without_the_padding(layout, width, 
             lo, hi = int(off[b]), min(int(off[b + 1]), cap)
             if hi > lo:
                 assert torch.equal(rows[lo:hi, :width], ref[b, :hi - lo])
+
+
+class _FakeGather:
+    """distributed.PeerGather's surface with the peers emulated by local buffers (one GPU, no process group)."""
+
+    def __init__(self, world, rank, b_local, max_det, width, depth):
+        self.world, self.rank, self.depth = world, rank, depth
+        self.n_rows = world * b_local * max_det * width
+        self.slot_elems = (self.n_rows + world * b_local + 3) & ~3
+        self.bufs = [torch.full((depth * self.slot_elems,), -1.0, device=DEV) for _ in range(world)]
+
+    def peer_ptrs(self, i):
+        return [b.data_ptr() + 4 * (i % self.depth) * self.slot_elems for b in self.bufs]
+
+    def multicast_ptr(self, i):
+        return 0
+
+
+def test_pipelined_postprocess_with_the_gather_in_the_slot_graph():
+    """PipelinedPostprocess(gather=...): decode, NMS and the epilogue + gather stores of a slot replay as ONE CUDA graph
+    (programmatic dependent launches between the kernels).  Every destination buffer must hold, at this rank's place in
+    the slot, exactly the rows the plain epilogue produces from the slot's detections - for every slot, replayed twice."""
+    B, A, nc, md, depth, world, rank = 2, 8400, 80, 40, 3, 3, 1
+    sets = []
+    for s in range(depth):
+        lv = synth.yolov8_head(50 + s, B=B, nc=nc, clustered=True)
+        sets.append(ops.make_levels([torch.from_numpy(np.ascontiguousarray(x)).to(DEV) for x in lv], (8.0, 16.0, 32.0)))
+    fake = _FakeGather(world, rank, B, md, 7, depth)
+    pipe = ops.PipelinedPostprocess(B, A, nc, torch.device(DEV), sets, 0.05, 0.7, max_det=md, gather=fake)
+    per = B * md * 7
+    for turn in range(2 * depth):
+        slot = pipe.next_slot
+        det = pipe.submit(gather=True)
+        pipe.join()
+        torch.cuda.synchronize()
+        ref = ops.detection_epilogue(det, ops.ROWS_FULL, packed=True)
+        assert int(det.count.min()) > 0
+        off = slot * fake.slot_elems
+        for buf in fake.bufs:
+            assert torch.equal(buf[off + rank * per: off + (rank + 1) * per], ref[:per])
+            assert torch.equal(buf[off + fake.n_rows + rank * B: off + fake.n_rows + (rank + 1) * B], ref[per:])
+            other = (rank + 1) % world
+            assert bool((buf[off + other * per: off + (other + 1) * per] == -1.0).all())   # nobody else's place is touched
+    with pytest.raises(ValueError):
+        ops.PipelinedPostprocess(B, A, nc, torch.device(DEV), sets, 0.05, 0.7, max_det=md).submit(gather=True)
