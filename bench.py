@@ -327,7 +327,8 @@ def run_ours(args):
     if use_pipe:
         # N > 1: the fused epilogue + all-gather of a slot is part of the slot's graph (PDL edge behind the NMS kernel)
         pipe = ops.PipelinedPostprocess(BS, A, NC, dev, level_sets, CONF, IOU, max_det=MAX_DET, graph=not args.no_graph,
-                                        gather=(peer if args.graph_gather else None), use_multicast=not args.no_multicast)
+                                        gather=(peer if args.gather_mode != "eager" else None),
+                                        use_multicast=not args.no_multicast, fused_rows=(args.gather_mode == "fused"))
     else:
         # NCCL fallback: the all-gather of step k runs on a side stream and overlaps the decode of step k+1:
         # two alternating payload buffers [rows (B,300,7) | counts (B)], ONE collective per step
@@ -361,7 +362,7 @@ def run_ours(args):
         if peer is not None:
             # decode + NMS of step k, then its fused epilogue + peer-store all-gather, on the slot's pipeline stream
             # (buffer set and gather slot k % depth): both overlap the decode of the next steps on the other streams
-            if not consumable and args.graph_gather:
+            if not consumable and args.gather_mode != "eager":
                 return pipe.submit(gather=True)     # ONE graph launch: decode, NMS, epilogue + gather stores
             det = pipe.submit()
             slot = pipe.last_slot
@@ -714,7 +715,8 @@ def run_ours(args):
         elif peer is not None:
             gather_txt = (("NVSwitch multicast (one multimem.st per 16 B, replicated by the switch into every rank's buffer) - "
                            if (peer.multicast_ptr(0) and not args.no_multicast) else "N unicast peer stores - ") +
-                          "fused into the epilogue kernel: rows (B,300,7) fp32 + counts stored into every rank's buffer over "
+                          f"gather mode `{args.gather_mode}` (fused = written by the NMS kernel's own CTAs, no third launch; eager / "
+                          "graph = the detection_epilogue kernel after / inside the slot's graph): rows (B,300,7) fp32 + counts stored into every rank's buffer over "
                           "NVLink peer memory every step (one gather slot per pipeline slot), on the step's pipeline stream; "
                           "`value` is free-running (one symmetric-memory barrier at the end of the timed region), "
                           "`ms_per_step_barrier_each_step` fences every step's slot on both sides and reads it")
@@ -750,7 +752,7 @@ def run_ours(args):
                                 "what": "the step's H2D copies alone, all ranks at once (host memory / PCIe fabric of the box)"},
                     "serial_value": world * BS * K / e2e_serial_s, "serial_ms_per_step": 1e3 * e2e_serial_s / K},
             # per step: decode+filter and fused sort+NMS (+ the epilogue / peer-store gather kernel when N > 1)
-            "gpu_launches": (2 if world == 1 else 3) * K,
+            "gpu_launches": (2 if (world == 1 or (peer is not None and args.gather_mode == "fused")) else 3) * K,
             "host_issue_ms_per_step": host_ms_step,
             "serial_ms_per_step": serial_ms,   # one stream, no overlap between steps (decode + NMS back to back)
             "overlap": ("NMS of step k under the decode of step k+1" if pipelined else None) if world == 1 else
@@ -780,7 +782,11 @@ def main():
     ap.add_argument("--pipeline-depth", type=int, default=3, help="batches in flight in throughput mode")
     ap.add_argument("--no-pipeline", action="store_true", help="one step after the other on one stream (no overlap of step k's NMS with step k+1's decode)")
     ap.add_argument("--nccl-gather", action="store_true", help="N>1: use NCCL all_gather instead of the fused peer-store epilogue")
-    ap.add_argument("--graph-gather", action="store_true", help="N>1 peer gather: the epilogue kernel is part of the slot's CUDA graph (PDL edge behind the NMS; 12 us instead of 40 us of host issue per step, but 1.5 us/step slower on the device at 8 GPUs) instead of an eager launch after it")
+    ap.add_argument("--gather-mode", default="eager", choices=["fused", "eager", "graph"],
+                    help="N>1 peer gather: eager (default, measured fastest: 58.4 vs 59.5 us/step at 2 GPUs, 59.3 vs 61 at 8) = a third "
+                         "kernel (detection_epilogue) launched after the slot's graph; fused = the NMS kernel's own CTAs write the rows "
+                         "into every rank's buffer (two launches per step, one graph launch, 12 instead of 40 us of host time per step); "
+                         "graph = the epilogue kernel inside the slot's graph behind a PDL edge")
     ap.add_argument("--no-multicast", action="store_true", help="N>1 peer gather: N unicast peer stores instead of one multimem.st through the NVSwitch")
     ap.add_argument("--no-paths", action="store_true", help="skip the C3/C4/C5-shard/YOLOv3 `paths` leg")
     ap.add_argument("--no-c5", action="store_true", help="skip the BASELINE configs[4] (YOLOv7 bs=1024 sharded) leg")

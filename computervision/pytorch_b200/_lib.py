@@ -57,6 +57,9 @@ _PROTOS = {
     "cvpp_yolov8_postprocess": (c_int, [P(c_vp), P(c_i64), P(c_i64), P(c_int), P(c_int), P(c_f32), c_int, c_int,
                                         c_int, c_int, c_f32, c_f64, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp,
                                         c_vp, c_vp, c_vp, c_vp, c_size, c_vp]),
+    "cvpp_yolov8_postprocess_gather": (c_int, [P(c_vp), P(c_i64), P(c_i64), P(c_int), P(c_int), P(c_f32), c_int, c_int,
+                                               c_int, c_int, c_f32, c_f64, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp,
+                                               c_vp, c_vp, c_vp, c_vp, c_size, c_vp, P(c_vp), c_vp, c_int, c_int, c_vp]),
     "cvpp_yolov8_postprocess_ev": (c_int, [P(c_vp), P(c_i64), P(c_i64), P(c_int), P(c_int), P(c_f32), c_int, c_int,
                                            c_int, c_int, c_f32, c_f64, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp,
                                            c_vp, c_vp, c_vp, c_vp, c_size, c_vp, c_vp]),

@@ -72,7 +72,8 @@ size_t sort_nms_workspace_bytes(int B, int max_cand, int nc);
 int sort_nms_launch(const uint64_t* cand_key, const int32_t* cand_count, const float* box_dense, int B, int max_cand, int64_t A,
                     int nc, double iou_thres, int rule, int order, int max_det, int max_nms, int max_out, float* det_box,
                     float* det_score, int32_t* det_cls, int32_t* det_anchor, int32_t* det_count, void* workspace,
-                    size_t workspace_bytes, cudaStream_t stream, int32_t* cand_count_out = nullptr);
+                    size_t workspace_bytes, cudaStream_t stream, int32_t* cand_count_out = nullptr,
+                    float* const* gather_dst = nullptr, float* gather_mc = nullptr, int gather_n = 0, int gather_rank = 0);
 
 size_t centernet_workspace_bytes(int B, int H, int W, int nc, int K);
 int centernet_launch(const float* pred, int B, int H, int W, int nc, int K, float conf, int pool_mode, int use_nms,
@@ -266,12 +267,13 @@ size_t cvpp_yolov8_workspace_bytes(int B, int64_t A, int max_cand, int nc) {
   return s;
 }
 
-int cvpp_yolov8_postprocess_ev(const float* const* level_ptr, const int64_t* batch_stride, const int64_t* chan_stride,
-                            const int* level_h, const int* level_w, const float* level_stride, int num_levels, int B,
-                            int nc, int reg_max, float conf_thres, double iou_thres, int rule, int max_det, int max_nms,
-                            int max_cand, float* det_box, float* det_score, int32_t* det_cls, int32_t* det_anchor,
-                            int32_t* det_count, int32_t* cand_count_out, void* workspace, size_t workspace_bytes,
-                            cvpp_event_t inputs_consumed, cvpp_stream_t stream) {
+static int yolov8_postprocess_impl(const float* const* level_ptr, const int64_t* batch_stride, const int64_t* chan_stride,
+                                   const int* level_h, const int* level_w, const float* level_stride, int num_levels, int B,
+                                   int nc, int reg_max, float conf_thres, double iou_thres, int rule, int max_det, int max_nms,
+                                   int max_cand, float* det_box, float* det_score, int32_t* det_cls, int32_t* det_anchor,
+                                   int32_t* det_count, int32_t* cand_count_out, void* workspace, size_t workspace_bytes,
+                                   cvpp_event_t inputs_consumed, cvpp_stream_t stream, float* const* gather_dst,
+                                   float* gather_mc, int gather_n, int gather_rank) {
   if (!level_h || !level_w || num_levels < 1 || num_levels > CVPP_MAX_LEVELS) {
     set_error("yolov8_postprocess: bad level description");
     return CVPP_ERR_INVALID_ARG;
@@ -314,7 +316,36 @@ int cvpp_yolov8_postprocess_ev(const float* const* level_ptr, const int64_t* bat
   // (the fused kernel also copies the candidate counts out: no separate device-to-device copy node)
   return sort_nms_launch(cand_key, cand_count, box_dense, B, max_cand, A, nc, iou_thres, rule, CVPP_ORDER_SCORE_DESC,
                          max_det, max_nms, max_det, det_box, det_score, det_cls, det_anchor, det_count, sn_ws, sn_bytes,
-                         (cudaStream_t)stream, cand_count_out);
+                         (cudaStream_t)stream, cand_count_out, gather_dst, gather_mc, gather_n, gather_rank);
+}
+
+int cvpp_yolov8_postprocess_ev(const float* const* level_ptr, const int64_t* batch_stride, const int64_t* chan_stride,
+                            const int* level_h, const int* level_w, const float* level_stride, int num_levels, int B,
+                            int nc, int reg_max, float conf_thres, double iou_thres, int rule, int max_det, int max_nms,
+                            int max_cand, float* det_box, float* det_score, int32_t* det_cls, int32_t* det_anchor,
+                            int32_t* det_count, int32_t* cand_count_out, void* workspace, size_t workspace_bytes,
+                            cvpp_event_t inputs_consumed, cvpp_stream_t stream) {
+  return yolov8_postprocess_impl(level_ptr, batch_stride, chan_stride, level_h, level_w, level_stride, num_levels, B, nc,
+                                 reg_max, conf_thres, iou_thres, rule, max_det, max_nms, max_cand, det_box, det_score, det_cls,
+                                 det_anchor, det_count, cand_count_out, workspace, workspace_bytes, inputs_consumed, stream,
+                                 nullptr, nullptr, 0, 0);
+}
+
+int cvpp_yolov8_postprocess_gather(const float* const* level_ptr, const int64_t* batch_stride, const int64_t* chan_stride,
+                                   const int* level_h, const int* level_w, const float* level_stride, int num_levels, int B,
+                                   int nc, int reg_max, float conf_thres, double iou_thres, int rule, int max_det, int max_nms,
+                                   int max_cand, float* det_box, float* det_score, int32_t* det_cls, int32_t* det_anchor,
+                                   int32_t* det_count, int32_t* cand_count_out, void* workspace, size_t workspace_bytes,
+                                   cvpp_event_t inputs_consumed, float* const* peer_dst, float* mc_dst, int n_ranks, int rank,
+                                   cvpp_stream_t stream) {
+  if (n_ranks < 1 || (!peer_dst && !mc_dst)) {
+    set_error("yolov8_postprocess_gather: n_ranks >= 1 and a peer list or a multicast address are needed");
+    return CVPP_ERR_INVALID_ARG;
+  }
+  return yolov8_postprocess_impl(level_ptr, batch_stride, chan_stride, level_h, level_w, level_stride, num_levels, B, nc,
+                                 reg_max, conf_thres, iou_thres, rule, max_det, max_nms, max_cand, det_box, det_score, det_cls,
+                                 det_anchor, det_count, cand_count_out, workspace, workspace_bytes, inputs_consumed, stream,
+                                 peer_dst, mc_dst, n_ranks, rank);
 }
 
 int cvpp_yolov8_postprocess(const float* const* level_ptr, const int64_t* batch_stride, const int64_t* chan_stride,

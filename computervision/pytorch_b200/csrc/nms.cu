@@ -825,6 +825,12 @@ struct Nms2Params {
   int32_t* det_anchor;
   int32_t* det_count;
   int32_t* cand_count_out;  // optional [B]: copy of cand_count (saves the caller a device-to-device copy node)
+  // optional fused row epilogue + all-gather (the CVPP_ROWS_FULL / CVPP_BOX_KEEP form of detection_epilogue_kernel, done
+  // by the image's own CTA once its detections are written: the step has no third launch).  Destination layout as in
+  // cvpp_detection_epilogue_allgather: [n_ranks][B][max_out][7] rows | [n_ranks][B] counts, this rank at slot gather_rank.
+  float* gather_dst[CVPP_MAX_PEERS];  // unicast form: every rank's buffer (peer mappings)
+  float* gather_mc;                   // multicast form: the NVSwitch multicast address of the buffer (one multimem.st)
+  int gather_n, gather_rank;          // gather_n = 0: no fused gather
   int cap_pos;     // class-major positions that fit shared memory (multiple of 32)
   int mask_words;  // cap_pos / 32
   // in-kernel fallback (images that do not fit shared memory, or with more than max_nms candidates): global
@@ -929,8 +935,7 @@ __device__ long long g_n2_t[16 * 64];
 #define N2_MARK(i) do {} while (0)
 #endif
 
-__global__ void __launch_bounds__(kN2Threads, 1) nms2_kernel(const __grid_constant__ Nms2Params p) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+__device__ __forceinline__ void nms2_image(const Nms2Params& p, unsigned char* smem_raw) {
   // layout: [box float4 x cap][key u64 x cap][area f32 x cap][alive u32 x words][seg_begin, seg_end, fill int x nc]
   float4* sh_box = reinterpret_cast<float4*>(smem_raw);
   uint64_t* ckey = reinterpret_cast<uint64_t*>(sh_box + p.cap_pos);
@@ -1272,6 +1277,7 @@ __global__ void __launch_bounds__(kN2Threads, 1) nms2_kernel(const __grid_consta
       for (int i = n_surv + tid; i < P; i += kN2Threads) sel[i] = ~0ull;
       __syncthreads();
       N2_MARK(5);
+      // (2, 4 or 8 keys per thread on fewer warps - fewer block barriers - were measured: 4.7 / 5.0 / 6.0 us vs 5.0)
       block_sort_smem_max8(sel, P);
       N2_MARK(6);
       const int n_kept = (p.max_det > 0 && p.max_det < n_surv) ? p.max_det : n_surv;
@@ -1388,6 +1394,67 @@ int segsort_launch_skip(uint64_t* keys, int32_t* cand_count, int B, int max_cand
                         size_t workspace_bytes, const int32_t* skip, uint64_t* out_keys, int32_t* out_count,
                         cudaStream_t stream);
 
+__global__ void __launch_bounds__(kN2Threads, 1) nms2_kernel(const __grid_constant__ Nms2Params p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  nms2_image(p, smem_raw);
+  if (p.gather_n == 0) return;  // (uniform)
+  // ---- fused row epilogue + all-gather: rows (x1, y1, x2, y2, score, class, anchor) of this image, zero rows past its
+  //      count, staged in shared memory and stored as 128-bit words into every rank's gather buffer
+  __syncthreads();  // every detection of the image has been written by this CTA
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int n = min(__ldcg(p.det_count + b), p.max_out);
+  float* sh = reinterpret_cast<float*>(smem_raw);
+  const int64_t t0 = (int64_t)b * p.max_out;
+  for (int k = tid; k < p.max_out; k += kN2Threads) {
+    float row[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (k < n) {
+      const float4 bx = __ldcg(p.det_box + t0 + k);
+      row[0] = bx.x;
+      row[1] = bx.y;
+      row[2] = bx.z;
+      row[3] = bx.w;
+      row[4] = __ldcg(p.det_score + t0 + k);
+      row[5] = (float)__ldcg(p.det_cls + t0 + k);
+      row[6] = (float)__ldcg(p.det_anchor + t0 + k);
+    }
+#pragma unroll
+    for (int c = 0; c < 7; ++c) sh[k * 7 + c] = row[c];
+  }
+  __syncthreads();
+  const int floats = p.max_out * 7;
+  const int64_t off = ((int64_t)p.gather_rank * gridDim.x + b) * floats;                       // rows of (rank, image b)
+  const int64_t cnt_off = (int64_t)p.gather_n * gridDim.x * floats + (int64_t)p.gather_rank * gridDim.x + b;
+  const bool vec = (floats & 3) == 0;  // every image's block is then 16-byte aligned (the buffers are)
+  if (p.gather_mc) {
+    float* o = p.gather_mc + off;
+    if (vec) {
+      const float4* s4 = reinterpret_cast<const float4*>(sh);
+      for (int i = tid; i < (floats >> 2); i += kN2Threads) {
+        const float4 q = s4[i];
+        asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + 4 * i), "f"(q.x), "f"(q.y), "f"(q.z),
+                     "f"(q.w)
+                     : "memory");
+      }
+    } else {
+      for (int i = tid; i < floats; i += kN2Threads)
+        asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(o + i), "f"(sh[i]) : "memory");
+    }
+    if (tid == 0) asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(p.gather_mc + cnt_off), "f"((float)n) : "memory");
+    return;
+  }
+  for (int d = 0; d < p.gather_n; ++d) {
+    float* o = p.gather_dst[d] + off;
+    if (vec) {
+      float4* o4 = reinterpret_cast<float4*>(o);
+      const float4* s4 = reinterpret_cast<const float4*>(sh);
+      for (int i = tid; i < (floats >> 2); i += kN2Threads) o4[i] = s4[i];
+    } else {
+      for (int i = tid; i < floats; i += kN2Threads) o[i] = sh[i];
+    }
+    if (tid == 0) p.gather_dst[d][cnt_off] = (float)n;
+  }
+}
+
 static size_t align256_(size_t x) { return (x + 255) & ~(size_t)255; }
 
 size_t sort_nms_workspace_bytes(int B, int max_cand, int nc) {
@@ -1400,7 +1467,8 @@ size_t sort_nms_workspace_bytes(int B, int max_cand, int nc) {
 int sort_nms_launch(const uint64_t* cand_key, const int32_t* cand_count, const float* box_dense, int B, int max_cand, int64_t A,
                     int nc, double iou_thres, int rule, int order, int max_det, int max_nms, int max_out, float* det_box,
                     float* det_score, int32_t* det_cls, int32_t* det_anchor, int32_t* det_count, void* workspace,
-                    size_t workspace_bytes, cudaStream_t stream, int32_t* cand_count_out) {
+                    size_t workspace_bytes, cudaStream_t stream, int32_t* cand_count_out, float* const* gather_dst,
+                    float* gather_mc, int gather_n, int gather_rank) {
   if (!cand_key || !cand_count || !box_dense || !det_box || !det_score || !det_cls || !det_anchor || !det_count) {
     set_error("sort_nms: NULL pointer argument");
     return CVPP_ERR_INVALID_ARG;
@@ -1475,6 +1543,29 @@ int sort_nms_launch(const uint64_t* cand_key, const int32_t* cand_count, const f
   p.det_anchor = det_anchor;
   p.det_count = det_count;
   p.cand_count_out = cand_count_out;
+  p.gather_n = 0;
+  p.gather_mc = nullptr;
+  p.gather_rank = 0;
+  if (gather_n > 0) {
+    if (gather_n > CVPP_MAX_PEERS || gather_rank < 0 || gather_rank >= gather_n || (!gather_dst && !gather_mc)) {
+      set_error("sort_nms: bad gather description (n=%d rank=%d)", gather_n, gather_rank);
+      return CVPP_ERR_INVALID_ARG;
+    }
+    if (gather_mc && (reinterpret_cast<uintptr_t>(gather_mc) & 15u)) {
+      set_error("sort_nms: the multicast gather address must be 16-byte aligned");
+      return CVPP_ERR_ALIGNMENT;
+    }
+    p.gather_n = gather_n;
+    p.gather_rank = gather_rank;
+    p.gather_mc = gather_mc;
+    for (int d = 0; d < gather_n && !gather_mc; ++d) {
+      if (!gather_dst[d] || (reinterpret_cast<uintptr_t>(gather_dst[d]) & 15u)) {
+        set_error("sort_nms: gather destination %d is NULL or not 16-byte aligned", d);
+        return CVPP_ERR_INVALID_ARG;
+      }
+      p.gather_dst[d] = gather_dst[d];
+    }
+  }
   // shared memory of the fused path: 28 B per position + 1 bit, 3 ints per class; the selection stage needs
   // 16 KB of histogram inside the 16 B/position box array and 8 B/position of selected keys behind it
   const size_t fixed = (size_t)nc * 12 + 256;
@@ -1491,6 +1582,7 @@ int sort_nms_launch(const uint64_t* cand_key, const int32_t* cand_count, const f
   p.mask_words = (int)(cap_pos / 32);
   size_t smem = cap_pos * 28 + (size_t)p.mask_words * 4 + (size_t)nc * 12;
   if (smem_fb > smem) smem = smem_fb;
+  if (p.gather_n > 0 && (size_t)max_out * 28 > smem) smem = (size_t)max_out * 28;  // staging of the image's rows
   // the fallback sort uses whatever dynamic shared memory the launch has (power-of-two key count)
   int fb_keys_smem = 32;
   while ((size_t)fb_keys_smem * 2 * sizeof(uint64_t) <= smem && fb_keys_smem < 8192) fb_keys_smem <<= 1;

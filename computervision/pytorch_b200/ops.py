@@ -319,8 +319,11 @@ class Yolov8Postprocessor:
                           _ptr(self.ws), self.ws_bytes)
 
     def __call__(self, ls: LevelSet, conf_thres: float, iou_thres: float, rule: int = RULE_TORCHVISION_CPU,
-                 max_nms: int = 30000, reg_max: int = 16, consumed: Optional[torch.cuda.Event] = None) -> Detections:
-        """`consumed` (optional CUDA event) is recorded right after the decode kernel, the last reader of `ls`."""
+                 max_nms: int = 30000, reg_max: int = 16, consumed: Optional[torch.cuda.Event] = None,
+                 gather: Optional[Tuple[Sequence[int], int, int]] = None) -> Detections:
+        """`consumed` (optional CUDA event) is recorded right after the decode kernel, the last reader of `ls`.
+        `gather` = (peer_ptrs, multicast_ptr, rank): the NMS kernel also writes the image's CVPP_ROWS_FULL rows + count into
+        every rank's gather buffer (cvpp_yolov8_postprocess_gather: the all-gather without a third launch)."""
         if ls.B != self.B or ls.A != self.A or ls.C != 4 * reg_max + self.nc:
             raise ValueError("level set does not match the shapes this post-processor was built for")
         dev = self.device
@@ -328,12 +331,21 @@ class Yolov8Postprocessor:
             raise ValueError(f"level set lives on {ls.device}, this post-processor on {dev}")
         if torch.cuda.current_device() != dev.index:
             with torch.cuda.device(dev):
-                return self.__call__(ls, conf_thres, iou_thres, rule, max_nms, reg_max, consumed)
+                return self.__call__(ls, conf_thres, iou_thres, rule, max_nms, reg_max, consumed, gather)
         ev = c_vp(0)
         if consumed is not None:
             if not consumed.cuda_event:          # torch creates the handle lazily, on the first record
                 consumed.record()
             ev = c_vp(consumed.cuda_event)
+        if gather is not None:
+            peer_ptrs, mc_ptr, rank = gather
+            n = len(peer_ptrs)
+            arr = (c_vp * n)(*[int(q) for q in peer_ptrs])
+            check(self._lib.cvpp_yolov8_postprocess_gather(
+                ls.ptr, ls.batch_stride, ls.chan_stride, ls.h, ls.w, ls.stride, ls.n, self.B, self.nc, reg_max,
+                float(conf_thres), float(iou_thres), rule, self.max_det, int(max_nms), self.max_cand, *self._out_args,
+                ev, arr, c_vp(int(mc_ptr or 0)), n, int(rank), c_vp(torch.cuda.current_stream().cuda_stream)))
+            return self.det
         check(self._lib.cvpp_yolov8_postprocess_ev(
             ls.ptr, ls.batch_stride, ls.chan_stride, ls.h, ls.w, ls.stride, ls.n, self.B, self.nc, reg_max,
             float(conf_thres), float(iou_thres), rule, self.max_det, int(max_nms), self.max_cand, *self._out_args,
@@ -390,8 +402,9 @@ class PipelinedPostprocess:
 
     def __init__(self, B: int, A: int, nc: int, device, inputs, conf_thres: float, iou_thres: float,
                  max_det: int = 300, depth: Optional[int] = None, graph: bool = True, gather=None,
-                 use_multicast: bool = True, **post_args):
+                 use_multicast: bool = True, fused_rows: bool = True, **post_args):
         self.use_multicast = bool(use_multicast)
+        self.fused_rows = bool(fused_rows)
         if isinstance(inputs, LevelSet):
             depth = int(depth or 2)
             inputs = [inputs] * depth
@@ -450,9 +463,12 @@ class PipelinedPostprocess:
             s.wait_stream(cur)
 
     def _post_and_gather(self, i: int) -> None:
+        mc = self.gather.multicast_ptr(i) if self.use_multicast else 0
+        if self.fused_rows:   # the NMS kernel writes the rows itself: two launches per step
+            self.posts[i](self.inputs[i], *self.args, consumed=self.consumed[i], gather=(self.gather.peer_ptrs(i), mc, self.gather.rank))
+            return
         det = self.posts[i](self.inputs[i], *self.args, consumed=self.consumed[i])
-        detection_epilogue_allgather(det, ROWS_FULL, self.gather.peer_ptrs(i), self.gather.rank,
-                                     multicast_ptr=(self.gather.multicast_ptr(i) if self.use_multicast else 0))
+        detection_epilogue_allgather(det, ROWS_FULL, self.gather.peer_ptrs(i), self.gather.rank, multicast_ptr=mc)
 
     def submit(self, ready: Optional[torch.cuda.Event] = None, gather: bool = False) -> Detections:
         """gather=True (needs the `gather=` PeerGather of the constructor): the slot's rows + counts are also stored into

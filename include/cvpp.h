@@ -246,6 +246,22 @@ CVPP_API int cvpp_yolov8_postprocess_ev(const float* const* level_ptr, const int
                             void* workspace, size_t workspace_bytes, cvpp_event_t inputs_consumed,
                             cvpp_stream_t stream);
 
+/* cvpp_yolov8_postprocess_ev + the evaluation all-gather with NO extra launch: the CTA of the fused
+ * sort+NMS kernel that finished image b also writes its rows (CVPP_ROWS_FULL: x1, y1, x2, y2, score, class, anchor;
+ * zero rows past the count) and its count into the gather buffer of every rank - peer_dst[d] (peer mappings, HOST array
+ * of n_ranks device pointers) or, when mc_dst is not NULL, ONE multimem.st per 16 bytes to the NVSwitch multicast
+ * address of the same buffer.  Layout and visibility exactly as cvpp_detection_epilogue_allgather
+ * ([n_ranks][B][max_det][7] rows | [n_ranks][B] counts, this rank at `rank`); the local det_* arrays are written too. */
+CVPP_API int cvpp_yolov8_postprocess_gather(const float* const* level_ptr, const int64_t* batch_stride,
+                                            const int64_t* chan_stride, const int* level_h, const int* level_w,
+                                            const float* level_stride, int num_levels, int B, int nc, int reg_max,
+                                            float conf_thres, double iou_thres, int rule, int max_det, int max_nms,
+                                            int max_cand, float* det_box, float* det_score, int32_t* det_cls,
+                                            int32_t* det_anchor, int32_t* det_count, int32_t* cand_count_out,
+                                            void* workspace, size_t workspace_bytes, cvpp_event_t inputs_consumed,
+                                            float* const* peer_dst, float* mc_dst, int n_ranks, int rank,
+                                            cvpp_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * CenterNet decode (kernel 4): heatmap peaks + top-K + box assembly + score mask + optional
  * class-agnostic DIoU-NMS + letterbox inverse, per image.

@@ -85,9 +85,11 @@ class _FakeGather:
         return 0
 
 
-def test_pipelined_postprocess_with_the_gather_in_the_slot_graph():
-    """PipelinedPostprocess(gather=...): decode, NMS and the epilogue + gather stores of a slot replay as ONE CUDA graph
-    (programmatic dependent launches between the kernels).  Every destination buffer must hold, at this rank's place in
+@pytest.mark.parametrize("fused_rows", [True, False])
+def test_pipelined_postprocess_with_the_gather_in_the_slot_graph(fused_rows):
+    """PipelinedPostprocess(gather=...): decode, NMS and the gather stores of a slot replay as ONE CUDA graph - with the rows
+    written by the NMS kernel's own CTAs (fused_rows, cvpp_yolov8_postprocess_gather) or by the epilogue kernel behind a
+    programmatic dependent launch.  Every destination buffer must hold, at this rank's place in
     the slot, exactly the rows the plain epilogue produces from the slot's detections - for every slot, replayed twice."""
     B, A, nc, md, depth, world, rank = 2, 8400, 80, 40, 3, 3, 1
     sets = []
@@ -95,7 +97,7 @@ def test_pipelined_postprocess_with_the_gather_in_the_slot_graph():
         lv = synth.yolov8_head(50 + s, B=B, nc=nc, clustered=True)
         sets.append(ops.make_levels([torch.from_numpy(np.ascontiguousarray(x)).to(DEV) for x in lv], (8.0, 16.0, 32.0)))
     fake = _FakeGather(world, rank, B, md, 7, depth)
-    pipe = ops.PipelinedPostprocess(B, A, nc, torch.device(DEV), sets, 0.05, 0.7, max_det=md, gather=fake)
+    pipe = ops.PipelinedPostprocess(B, A, nc, torch.device(DEV), sets, 0.05, 0.7, max_det=md, gather=fake, fused_rows=fused_rows)
     per = B * md * 7
     for turn in range(2 * depth):
         slot = pipe.next_slot
