@@ -32,8 +32,8 @@ constexpr int kYaStages = 2;
 // CPL = cells per lane: tiles of 32 * CPL cells, chunks of 16 rows x 32 * CPL cells (4 KB at CPL 2, 8 KB at CPL 4).
 // The per-chunk arithmetic is latency-bound per warp (fewer warps are slower for both modes, unlike the YOLOv8
 // kernel), so the default is CPL 2: half the per-thread state and twice the warps.
-constexpr int ya_max_warps(int mode, int cpl) { return cpl == 4 ? (mode == 0 ? 14 : 12) : (mode == 0 ? 24 : 20); }
-constexpr int kYaHitCap = 224;    // V3: per-warp staging of candidate records (12 B each, see V3Stage)
+constexpr int ya_max_warps(int mode, int cpl) { return cpl == 4 ? (mode == 0 ? 14 : 12) : 24; }
+constexpr int kYaHitCap = 160;    // V3: per-warp staging of candidate keys (8 B each, see V3Stage)
 constexpr int kYaMaxLevels = 4;
 constexpr int MODE_V7 = 0;
 constexpr int MODE_V3 = 1;
@@ -182,62 +182,65 @@ __device__ __forceinline__ void ya_tile_info(const YaParams& p, int g, int& b, i
 }
 
 // ---- V3 candidate staging ---------------------------------------------------------------------------
-// A class logit that passes the per-cell cut is pushed as a RECORD (logit, sigmoid(obj), class | cell) into
-// a per-warp shared-memory list with one shared-memory atomic; records are evaluated exactly, 32 at a
-// time at full warp efficiency, when the list fills up or the tile ends, and the surviving keys leave with
-// ONE global atomic per flush.  (First version: exact evaluation + a global atomic per class row; at eval
-// thresholds nearly every 128-cell row has a survivor, so the "rare" path ran for every row: 2.6 ms for
-// 256 images.)
+// Round 2 (the first form pushed a RECORD per passing logit inside the class loop - a divergent region with a shared-memory
+// atomic per (row, cell), 40 per tile, two thirds of them taken at eval thresholds: 30 % of the kernel's instructions were
+// BSSY / BRA / BSYNC / ISETP, 1 630 warp-instructions per 64-cell tile).  Now the class loop only ORs a bit per passing
+// logit into a per-lane mask (no branch); after the chunk's rows, while the chunk is still in the ring stage, the
+// warp pops one bit per lane per round, re-reads that logit from shared memory, evaluates the exact fp32 product at up to
+// 32 hits per round and stages the surviving KEYS per warp; they leave with one global atomic per tile.
 struct V3Stage {
-  float2* rec_x;   // (logit, sigmoid(obj)); reused for the packed keys during a flush
-  uint32_t* rec_m; // class << 8 | cell within the tile
-  int* count;
+  uint64_t* keys;  // [kYaHitCap] per warp
 };
 
-__device__ __forceinline__ void v3_flush(const V3Stage& st, const YaParams& p, int ob, int anchor_base, int a, int cell0,
-                                         int hw) {
+// all lanes; n = staged keys (warp-uniform register)
+__device__ __forceinline__ void v3_flush(const V3Stage& st, const YaParams& p, int ob, int& n) {
   const int lane = threadIdx.x & 31;
   __syncwarp();
-  const int n = *st.count;
   if (n == 0) return;
-  uint64_t* keys = reinterpret_cast<uint64_t*>(st.rec_x);
-  int out_n = 0;
-  for (int base = 0; base < n; base += 32) {
-    const int i = base + lane;
-    bool hit = false;
-    uint64_t key = 0;
-    if (i < n) {
-      const float2 r = st.rec_x[i];
-      const uint32_t m = st.rec_m[i];
-      const float score = fmul(r.y, sigmoid_precise(r.x));  // confidence * class_prob (yolov3_decode.py:49)
-      hit = score >= p.conf_thres;                           // nms.py:60
-      const int anchor = anchor_base + ya_local_index<MODE_V3>(a, cell0 + (int)(m & 0xffu), hw);
-      key = key_pack(m >> 8, __float_as_uint(score), (uint32_t)anchor);
-    }
-    const unsigned mk = __ballot_sync(0xffffffffu, hit);
-    // every record of this batch is in registers; keys are written at or below the batch's own slots
-    if (hit) keys[out_n + __popc(mk & ((1u << lane) - 1u))] = key;
-    out_n += __popc(mk);
-    __syncwarp();
-  }
   int gbase = 0;
-  if (lane == 0 && out_n) gbase = atomicAdd(p.cand_count + ob, out_n);
+  if (lane == 0) gbase = atomicAdd(p.cand_count + ob, n);
   gbase = __shfl_sync(0xffffffffu, gbase, 0);
   uint64_t* dst = p.cand_key + (int64_t)ob * p.max_cand;
-  for (int i = lane; i < out_n; i += 32)
-    if (gbase + i < p.max_cand) dst[gbase + i] = keys[i];
+  for (int i = lane; i < n; i += 32)
+    if (gbase + i < p.max_cand) dst[gbase + i] = st.keys[i];
   __syncwarp();
-  if (lane == 0) *st.count = 0;
+  n = 0;
+}
+
+// exact evaluation of the logits flagged in `hm` (bit r * CPL + k = row r of the staged chunk, cell k of the lane)
+template <int CPL>
+__device__ __forceinline__ void v3_eval_hits(unsigned hm, const float* stage, int tile_a, int c_of_row0, const float (&so)[CPL],
+                                             unsigned& boxed, const V3Stage& st, int& wk_n, const YaParams& p, int ob,
+                                             int anchor_base, int a, int cell0, int hw) {
+  static_assert(CPL == 2, "the V3 hit mask holds 16 rows x 2 cells");
+  const int lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
+  while (__any_sync(0xffffffffu, hm != 0u)) {
+    const bool has = hm != 0u;
+    const int bit = has ? __ffs(hm) - 1 : 0;
+    hm &= hm - 1u;  // (0 stays 0)
+    const int r = bit >> 1, k = bit & 1;
+    const float x = stage[r * tile_a + CPL * lane + k];
+    const float score = fmul(k ? so[1] : so[0], sigmoid_precise(x));  // confidence * class_prob (yolov3_decode.py:49)
+    const bool hit = has && score >= p.conf_thres;                     // nms.py:60
+    const unsigned mk = __ballot_sync(0xffffffffu, hit);
+    if (mk) {
+      if (wk_n + __popc(mk) > kYaHitCap) v3_flush(st, p, ob, wk_n);
+      if (hit) {
+        const int anchor = anchor_base + ya_local_index<MODE_V3>(a, cell0 + CPL * lane + k, hw);
+        st.keys[wk_n + __popc(mk & lt)] = key_pack((uint32_t)(c_of_row0 + r), __float_as_uint(score), (uint32_t)anchor);
+        boxed |= 1u << k;
+      }
+      wk_n += __popc(mk);
+    }
+  }
   __syncwarp();
 }
 
 // class rows [RBEGIN, rows) of one 16-row chunk; FULL: rows == 16 at compile time
 template <int MODE, int CPL, int RBEGIN, bool FULL>
 __device__ __forceinline__ void ya_class_rows(const float (&v)[kYaChunkRows][CPL], int rows, int c_first, float (&best)[CPL],
-                                              int (&arg)[CPL], float (&prev)[CPL], const float (&so)[CPL],
-                                              const float (&cut)[CPL], unsigned& boxed, const V3Stage& st, const YaParams& p, int ob,
-                                              int anchor_base, int a, int cell0, int hw) {
-  const int lane = threadIdx.x & 31;
+                                              int (&arg)[CPL], float (&prev)[CPL], const float (&cut)[CPL], unsigned& hm) {
 #pragma unroll
   for (int r = RBEGIN; r < kYaChunkRows; ++r) {
     if (FULL || r < rows) {
@@ -248,16 +251,7 @@ __device__ __forceinline__ void ya_class_rows(const float (&v)[kYaChunkRows][CPL
         for (int k = 0; k < CPL; ++k) v7_class_step(x[k], c, best[k], arg[k], prev[k]);
       } else {
 #pragma unroll
-        for (int k = 0; k < CPL; ++k) {
-          if (x[k] >= cut[k]) {
-            const int pos = atomicAdd(st.count, 1);
-            st.rec_x[pos] = make_float2(x[k], so[k]);
-            st.rec_m[pos] = ((uint32_t)c << 8) | (uint32_t)(CPL * lane + k);
-            boxed |= 1u << k;
-          }
-        }
-        __syncwarp();
-        if (*st.count > kYaHitCap - CPL * 32) v3_flush(st, p, ob, anchor_base, a, cell0, hw);  // room for one more row
+        for (int k = 0; k < CPL; ++k) hm |= (x[k] >= cut[k]) ? (1u << ((r * CPL + k) & 31)) : 0u;
       }
     }
   }
@@ -291,13 +285,9 @@ yolo_anchor_stream_kernel(const __grid_constant__ YaParams p) {
   float* ring = reinterpret_cast<float*>(smem_raw) + (size_t)warp * (kYaStages * kYaChunkFloats);
   unsigned char* after_rings = smem_raw + (size_t)kYaWarps * kYaStages * kYaChunkFloats * sizeof(float);
   uint64_t* bar = reinterpret_cast<uint64_t*>(after_rings) + warp * kYaStages;
-  V3Stage st;  // V3 only: [rec_x float2 x cap][rec_m u32 x cap] per warp, then the counters
-  {
-    unsigned char* q = after_rings + (size_t)kYaWarps * kYaStages * sizeof(uint64_t);
-    st.rec_x = reinterpret_cast<float2*>(q) + (size_t)warp * kYaHitCap;
-    st.rec_m = reinterpret_cast<uint32_t*>(q + (size_t)kYaWarps * kYaHitCap * sizeof(float2)) + (size_t)warp * kYaHitCap;
-    st.count = reinterpret_cast<int*>(q + (size_t)kYaWarps * kYaHitCap * (sizeof(float2) + sizeof(uint32_t))) + warp;
-  }
+  V3Stage st;  // V3 only: [keys u64 x cap] per warp
+  st.keys = reinterpret_cast<uint64_t*>(after_rings + (size_t)kYaWarps * kYaStages * sizeof(uint64_t)) + (size_t)warp * kYaHitCap;
+  int wk_n = 0;  // V3: keys staged by this warp (warp-uniform)
   const int nc = p.nc;
   const int attrs = 5 + nc;
   const int nchunks = (attrs + kYaChunkRows - 1) / kYaChunkRows;
@@ -306,7 +296,6 @@ yolo_anchor_stream_kernel(const __grid_constant__ YaParams p) {
 #pragma unroll
     for (int s = 0; s < kYaStages; ++s) mbar_init(&bar[s], 1);
     mbar_fence_init();
-    if (MODE == MODE_V3) *st.count = 0;
   }
   __syncwarp();
 
@@ -364,12 +353,13 @@ yolo_anchor_stream_kernel(const __grid_constant__ YaParams p) {
       for (int r = 0; r < kYaChunkRows; ++r) YaVec<CPL>::unpack(src[r * 32], v[r]);
     }
     __syncwarp();
-    if (pq < total_q) issue();
+    if (MODE == MODE_V7 && pq < total_q) issue();  // V3 re-arms the stage after its hits were re-read from it (below)
 
     // rows of this chunk are attributes [16 j, 16 j + 16) of the anchor: 0..4 box/obj, 5.. classes
     const bool active = CPL * lane < nA;
     const int ob = p.merged ? 0 : b;
     const int anchor_base = L.anchor_off + b * L.image_stride;
+    unsigned hm = 0;  // V3: logits of this chunk above the lane's cut, bit r * CPL + k
     if (j == 0) {
 #pragma unroll
       for (int r = 0; r < 5; ++r) {
@@ -390,22 +380,26 @@ yolo_anchor_stream_kernel(const __grid_constant__ YaParams p) {
         }
       }
       if (attrs >= kYaChunkRows)
-        ya_class_rows<MODE, CPL, 5, true>(v, kYaChunkRows, 0, best, arg, prev, so, cut, boxed, st, p, ob, anchor_base, a, cell0, L.hw);
+        ya_class_rows<MODE, CPL, 5, true>(v, kYaChunkRows, 0, best, arg, prev, cut, hm);
       else
-        ya_class_rows<MODE, CPL, 5, false>(v, attrs, 0, best, arg, prev, so, cut, boxed, st, p, ob, anchor_base, a, cell0, L.hw);
+        ya_class_rows<MODE, CPL, 5, false>(v, attrs, 0, best, arg, prev, cut, hm);
     } else if (j < nchunks - 1) {
-      ya_class_rows<MODE, CPL, 0, true>(v, kYaChunkRows, kYaChunkRows * j - 5, best, arg, prev, so, cut, boxed, st, p, ob,
-                                   anchor_base, a, cell0, L.hw);
+      ya_class_rows<MODE, CPL, 0, true>(v, kYaChunkRows, kYaChunkRows * j - 5, best, arg, prev, cut, hm);
     } else {
-      ya_class_rows<MODE, CPL, 0, false>(v, attrs - kYaChunkRows * j, kYaChunkRows * j - 5, best, arg, prev, so, cut, boxed, st, p,
-                                    ob, anchor_base, a, cell0, L.hw);
+      ya_class_rows<MODE, CPL, 0, false>(v, attrs - kYaChunkRows * j, kYaChunkRows * j - 5, best, arg, prev, cut, hm);
+    }
+    if constexpr (MODE == MODE_V3 && CPL == 2) {
+      // class of row 0 of this chunk: rows are attributes 16 j .., classes start at attribute 5
+      v3_eval_hits<CPL>(hm, ring + s * kYaChunkFloats, kYaTileA, kYaChunkRows * j - 5, so, boxed, st, wk_n, p, ob, anchor_base, a,
+                        cell0, L.hw);
+      if (pq < total_q) issue();
     }
 
     if (++j == nchunks) {  // tile complete
       j = 0;
       g += stride_tiles;
       if (MODE == MODE_V3) {
-        v3_flush(st, p, ob, anchor_base, a, cell0, L.hw);
+        v3_flush(st, p, ob, wk_n);
 #pragma unroll
         for (int k = 0; k < CPL; ++k) {
           if (boxed & (1u << k)) {
@@ -603,7 +597,7 @@ static int ya_pick_warps(int mode, int cpl) {
 
 static size_t ya_smem_bytes(int mode, int warps, int cpl) {
   size_t s = (size_t)warps * kYaStages * kYaChunkRows * 32 * cpl * sizeof(float) + (size_t)warps * kYaStages * sizeof(uint64_t);
-  if (mode == MODE_V3) s += (size_t)warps * (kYaHitCap * (sizeof(float2) + sizeof(uint32_t)) + sizeof(int));
+  if (mode == MODE_V3) s += (size_t)warps * kYaHitCap * sizeof(uint64_t);
   return s;
 }
 
@@ -654,7 +648,7 @@ int yolo_anchor_decode_launch(int mode, const float* const* level_ptr, const int
     return CVPP_ERR_ALIGNMENT;
   }
   const bool merged = mode == MODE_V3 && merge_batch;
-  const int cpl = ya_pick_cpl(), tile_a = 32 * cpl;
+  const int cpl = mode == MODE_V3 ? 2 : ya_pick_cpl(), tile_a = 32 * cpl;  // (the V3 hit mask is 16 rows x 2 cells)
   YaLevel lv[kYaMaxLevels];
   bool tma_level[kYaMaxLevels];
   int64_t A = 0;
@@ -755,8 +749,7 @@ int yolo_anchor_decode_launch(int mode, const float* const* level_ptr, const int
   sp.tiles_per_image = tiles;
   sp.total_tiles = tiles * B;
   if (cpl == 4) {
-    if (mode == MODE_V7) return ya_launch_mode<MODE_V7, 4>(sp, sp.num_levels > 0, gp, gen_anchors, B, smem, di, stream);
-    return ya_launch_mode<MODE_V3, 4>(sp, sp.num_levels > 0, gp, gen_anchors, B, smem, di, stream);
+    return ya_launch_mode<MODE_V7, 4>(sp, sp.num_levels > 0, gp, gen_anchors, B, smem, di, stream);
   }
   if (mode == MODE_V7) return ya_launch_mode<MODE_V7, 2>(sp, sp.num_levels > 0, gp, gen_anchors, B, smem, di, stream);
   return ya_launch_mode<MODE_V3, 2>(sp, sp.num_levels > 0, gp, gen_anchors, B, smem, di, stream);

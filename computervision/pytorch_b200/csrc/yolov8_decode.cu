@@ -24,7 +24,9 @@
 //     tiles costs a whole round, so the host picks the warp count that fills the rounds (pick_shape);
 //   * sigmoid is evaluated once per cell (it is monotone); exact first-index tie semantics of
 //     `cls.max(1)` on sigmoid values are restored on a (rare) slow path;
-//   * survivors are compacted with one warp-aggregated atomic per tile into the per-image key list.
+//   * survivors are compacted with one warp-aggregated atomic per tile into the per-image key list (deferring the use
+//     of the atomic's result to the end of the NEXT tile, so that its ~1 us round trip is never waited for, was
+//     measured in round 2: no change - 54.0 us either way - and 14 more registers, so it is not in).
 #include <cuda.h>
 #include <cstdlib>
 
