@@ -290,9 +290,9 @@ __device__ __noinline__ void ct_test_cell(const float* row, int x, int c, float 
 // the bound takes the SLOW PATH: its 3x3 (x, class) window is read back through L1/L2 (the neighbouring
 // columns are +-336 B away) and tested exactly.
 constexpr int kCtThreads = 256;
-constexpr int kCtUnroll = 4;
+constexpr int kCtUnroll = 3;   // (x occupancy 4 CTAs/SM at 64 registers; measured at C3: unroll 2 / 3 / 4 / 6 = 98.1 / 87.7 / 90.6 / 109 us; 3 CTAs x unroll 4 = 94.9)
 
-__global__ void __launch_bounds__(kCtThreads, 3) centernet_tiles_kernel(const __grid_constant__ CnParams p) {
+__global__ void __launch_bounds__(kCtThreads, 4) centernet_tiles_kernel(const __grid_constant__ CnParams p) {
   pdl_trigger();
   pdl_wait();  // the sampled bounds / zeroed lists of centernet_sample_bound_kernel
   __shared__ uint64_t sh_keys[kCtThreads / 32][kCtKeyStage];
