@@ -499,12 +499,16 @@ yolo_anchor_stream_kernel(const __grid_constant__ YaParams p) {
 }
 
 // generic kernel: one thread per anchor, no alignment requirements
+// Units of blockDim.x consecutive anchors of one image, walked grid-stride (the launch uses one CTA per unit).
 template <int MODE>
 __global__ void __launch_bounds__(128) yolo_anchor_generic_kernel(const __grid_constant__ YaParams p, int anchors_in) {
   const int nc = p.nc, attrs = 5 + nc;
-  const int b = blockIdx.y;
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // position among the anchors of the listed levels
   const int lane = threadIdx.x & 31;
+  const int units_per_image = (anchors_in + (int)blockDim.x - 1) / (int)blockDim.x;
+  const int total_units = units_per_image * p.B;
+  for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+  const int b = unit / units_per_image;
+  const int idx = (unit - b * units_per_image) * blockDim.x + threadIdx.x;  // position among the anchors of the listed levels
   const int ob = p.merged ? 0 : b;
   V7Cell o;
   o.cand = false;
@@ -603,7 +607,7 @@ __global__ void __launch_bounds__(128) yolo_anchor_generic_kernel(const __grid_c
   }
   if (MODE == MODE_V7) {
     const unsigned mk = __ballot_sync(0xffffffffu, o.cand);
-    if (mk == 0) return;
+    if (mk == 0) continue;
     int slot0 = 0;
     if (lane == 0) slot0 = atomicAdd(p.cand_count + ob, __popc(mk));
     slot0 = __shfl_sync(0xffffffffu, slot0, 0);
@@ -615,6 +619,7 @@ __global__ void __launch_bounds__(128) yolo_anchor_generic_kernel(const __grid_c
       p.aux_dense[(int64_t)ob * p.A + anchor] = make_float2(o.obj, o.cconf);
     }
   }
+  }  // unit loop
 }
 
 typedef CUresult (*YaEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -665,8 +670,11 @@ static int ya_launch_mode(YaParams& stream_p, bool have_stream, YaParams& gen_p,
     CVPP_CUDA_TRY(cudaGetLastError());
   }
   if (gen_anchors > 0) {
-    dim3 grid((unsigned)((gen_anchors + 127) / 128), (unsigned)B);
-    yolo_anchor_generic_kernel<MODE><<<grid, 128, 0, stream>>>(gen_p, gen_anchors);
+    // One CTA per unit.  (Running this kernel NEXT TO the streaming one - a programmatic dependent of one 64-thread CTA per SM,
+    // which is what fits beside its 768 threads - was measured: 239 us instead of 95; a thread needs ~16 us per anchor, four
+    // dependent batches of DRAM loads, so the level needs the 130 K threads of a launch of its own.)
+    const int units = ((gen_anchors + 127) / 128) * B;
+    yolo_anchor_generic_kernel<MODE><<<(unsigned)units, 128, 0, stream>>>(gen_p, gen_anchors);
     CVPP_CUDA_TRY(cudaGetLastError());
   }
   return CVPP_OK;

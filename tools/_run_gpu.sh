@@ -1,3 +1,2 @@
-for w in 24 22; do CVPP_YA_WARPS=$w timeout 200 python tools/bench_paths.py --only yolov7 --iters 30 2>&1 | cut -c1-130; done
-cp computervision/pytorch_b200/libcvpp_s4.so computervision/pytorch_b200/libcvpp.so
-for w in 10 12 13; do echo "stages 4 warps $w"; CVPP_YA_WARPS=$w timeout 200 python tools/bench_paths.py --only yolov7 --iters 30 2>&1 | cut -c1-130; done
+timeout 900 python -m pytest tests/test_yolov3_gpu.py tests/test_yolov7_gpu.py tests/test_eval_gpu.py tests/test_properties_gpu.py -q -m gpu --timeout=300 2>&1 | tail -3
+timeout 200 python tools/bench_paths.py --only yolov3 --iters 50 2>&1 | cut -c1-230
