@@ -238,10 +238,19 @@ __global__ void __launch_bounds__(kSsdMaxWarps * 32, 1) ssd_stream_kernel(const 
   const int last_slot = warp * gridDim.x + blockIdx.x;
   const int n_tiles = full_rounds + (full_rounds * stride_tiles + last_slot < p.total_tiles ? 1 : 0);
   auto tile_of = [&](int r) { return r * stride_tiles + (r < full_rounds ? first : last_slot); };
+  // g / tiles_per_image without the ~25-instruction integer division (two per tile were 5.6 % of the kernel): float
+  // reciprocal estimate, corrected by at most one (g < 2^24 tiles is checked on the host)
+  const float inv_tpi = 1.0f / (float)p.tiles_per_image;
+  auto image_of = [&](int g) {
+    int b = (int)((float)g * inv_tpi);
+    const int rem = g - b * p.tiles_per_image;
+    b += rem >= p.tiles_per_image ? 1 : (rem < 0 ? -1 : 0);
+    return b;
+  };
   int pr_round = 0;
   auto issue = [&]() {
     const int g = tile_of(pr_round);
-    const int b = g / p.tiles_per_image;
+    const int b = image_of(g);
     const int p0 = (g - b * p.tiles_per_image) * kSsdTile;
     const int rows = min(kSsdTile, P - p0);
     if (lane == 0) {
@@ -258,7 +267,7 @@ __global__ void __launch_bounds__(kSsdMaxWarps * 32, 1) ssd_stream_kernel(const 
   const int grp = lane >> 3, gl = lane & 7;
   for (int r = 0; r < n_tiles; ++r) {
     const int g = tile_of(r);
-    const int b = g / p.tiles_per_image;
+    const int b = image_of(g);
     const int p0 = (g - b * p.tiles_per_image) * kSsdTile;
     const int rows = min(kSsdTile, P - p0);
     const int s = r % kSsdStages;
@@ -271,7 +280,9 @@ __global__ void __launch_bounds__(kSsdMaxWarps * 32, 1) ssd_stream_kernel(const 
     for (int u = 0; u < kSsdTile / 32; ++u) {
       const int row = lane + 32 * u;
       bool cand = false;
-      float cut = INFINITY;
+      float cut = INFINITY, m_exact = 0.0f;
+      uint32_t cmask = 0;
+      float xv_keep[NC1 > 0 ? NC1 : 1];
       if (row < rows) {
         const float* x = x0 + row * nc1;
         float top = -INFINITY;
@@ -281,6 +292,8 @@ __global__ void __launch_bounds__(kSsdMaxWarps * 32, 1) ssd_stream_kernel(const 
           float xv[NC1 > 0 ? NC1 : 1];
 #pragma unroll
           for (int k = 0; k < NC1; ++k) xv[k] = x[k];
+#pragma unroll
+          for (int k = 0; k < NC1; ++k) xv_keep[k] = xv[k];
 #pragma unroll
           for (int k = 1; k < NC1; ++k) top = fmaxf(top, xv[k]);
           m = fmaxf(xv[0], top);
@@ -299,12 +312,21 @@ __global__ void __launch_bounds__(kSsdMaxWarps * 32, 1) ssd_stream_kernel(const 
         }
         cut = p.conf_thres > 0.0f ? m + __logf(p.conf_thres * sum) - 0.02f : -INFINITY;
         cand = top >= cut;
+        m_exact = m;  // fmaxf does not round: phase 1's maximum IS the reference's softmax maximum
+        if (NC1 > 0 && NC1 <= 32) {
+          // classes above the cut, as a bit mask, while the logits are in registers (phase 2 re-scanned the listed priors'
+          // rows with 8 lanes, a ballot and a conditional store per 8 classes: 16 % of the kernel)
+#pragma unroll
+          for (int k = 1; k < (NC1 > 0 ? NC1 : 1); ++k) cmask |= (xv_keep[k] >= cut) ? (1u << k) : 0u;
+        }
       }
       const unsigned mk = __ballot_sync(0xffffffffu, cand);
       if (cand) {
         const int slot = n_list + __popc(mk & lt);
         list[slot] = row;
-        cuts[slot] = cut;
+        if (NC1 > 0 && NC1 <= 32) reinterpret_cast<uint32_t*>(cuts)[slot] = cmask;
+        else cuts[slot] = cut;
+        msum[slot].x = m_exact;
       }
       n_list += __popc(mk);
     }
@@ -356,6 +378,43 @@ __global__ void __launch_bounds__(kSsdMaxWarps * 32, 1) ssd_stream_kernel(const 
       __syncwarp();
       n_pairs = 0;
     };
+    if (NC1 > 0 && NC1 <= 32) {
+      // (a) exact denominators, 8 lanes per listed prior (the maximum comes from phase 1)
+      for (int base = 0; base < n_list; base += 4) {
+        const int i = base + grp;
+        const bool valid = i < n_list;
+        const int row = valid ? list[i] : 0;
+        const float m = valid ? msum[i].x : 0.0f;
+        const float* x = x0 + row * nc1;
+        float sum = 0.0f;
+#pragma unroll
+        for (int k0 = 0; k0 < (NC1 > 0 ? NC1 : 1); k0 += 8)
+          if (k0 + gl < nc1) sum = fadd(sum, expf(fsub(x[k0 + gl], m)));
+        sum = fadd(sum, __shfl_xor_sync(0xffffffffu, sum, 1));
+        sum = fadd(sum, __shfl_xor_sync(0xffffffffu, sum, 2));
+        sum = fadd(sum, __shfl_xor_sync(0xffffffffu, sum, 4));
+        if (valid && gl == 0) msum[i].y = sum;
+      }
+      // (b) the (prior, class) pairs of the masks, compacted across the lanes: lane i owns listed prior i
+      uint32_t my = lane < n_list ? reinterpret_cast<const uint32_t*>(cuts)[lane] : 0u;
+      while (__any_sync(0xffffffffu, my != 0u)) {
+        const int take = min(__popc(my), kSsdPairCap / 32);   // at most 4 per lane per round: a round never overflows the list
+        int incl = take;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const int u = __shfl_up_sync(0xffffffffu, incl, d);
+          if (lane >= d) incl += u;
+        }
+        int pos = incl - take;
+        for (int q = 0; q < take; ++q) {
+          const int c = __ffs(my) - 1;
+          my &= my - 1u;
+          pairs[pos++] = (uint16_t)((lane << 8) | c);
+        }
+        n_pairs = __shfl_sync(0xffffffffu, incl, 31);
+        eval_pairs();
+      }
+    } else {
     for (int base = 0; base < n_list; base += 4) {
       const int i = base + grp;
       const bool valid = i < n_list;
@@ -383,6 +442,7 @@ __global__ void __launch_bounds__(kSsdMaxWarps * 32, 1) ssd_stream_kernel(const 
           n_pairs += __popc(am);
         }
       }
+    }
     }
     if (n_pairs) eval_pairs();
     if (lane < n_list && ((boxed >> lane) & 1u)) {
@@ -436,7 +496,9 @@ int ssd_decode_filter_launch(const float* loc, const float* conf, const float* p
     if (wmax > kSsdMaxWarps) wmax = kSsdMaxWarps;
     const bool aligned = (reinterpret_cast<uintptr_t>(conf) & 15u) == 0 && (((int64_t)P * nc1) & 3) == 0;
     const char* force = getenv("CVPP_SSD_BLOCK_KERNEL");
-    if (aligned && wmax >= 4 && nc <= 255 && !(force && force[0] == '1')) {
+    // (the kernel's reciprocal tile -> image division is exact below 2^24 tiles)
+    const bool few_tiles = (int64_t)((P + kSsdTile - 1) / kSsdTile) * B < (1 << 24);
+    if (aligned && wmax >= 4 && nc <= 255 && few_tiles && !(force && force[0] == '1')) {
       SsdParams sp{};
       sp.loc = reinterpret_cast<const float4*>(loc);
       sp.conf = conf;
