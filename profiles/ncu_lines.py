@@ -35,7 +35,6 @@ rows = list(csv.reader(out.splitlines()))
 hdr = rows[1]
 iex, ismp = hdr.index("Instructions Executed"), hdr.index("# Samples")
 ex = [(int(r[iex]), int(r[ismp] or 0)) for r in rows[2:] if len(r) > iex and r[iex].isdigit()]
-ex = ex[:len(lines)]
 assert len(ex) == len(lines), (len(ex), len(lines), "the report was captured with a different build of the kernel")
 agg, smp = collections.Counter(), collections.Counter()
 for (e, s), ln in zip(ex, lines):
