@@ -81,6 +81,15 @@ __device__ __noinline__ void class_argmax_sigmoid(const float* col, int64_t cs, 
   arg = ba;
 }
 
+// cand_count[0..B) = 0 as a KERNEL (not a memset node): it triggers its dependents at once, so the streaming decode kernel -
+// launched as its programmatic dependent - sets up, issues its first TMA loads and decodes its first tiles while this runs,
+// and only waits (griddepcontrol.wait) before its first candidate append.  One node boundary (~2 us of the bs = 1 latency and
+// of every serial step) leaves the critical path.
+__global__ void __launch_bounds__(256) zero_counts_kernel(int32_t* __restrict__ cnt, int n) {
+  pdl_trigger();
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) cnt[i] = 0;
+}
+
 // warp-aggregated append of one candidate per flagged lane (all 32 lanes must call)
 __device__ __forceinline__ void emit_candidate(bool flag, int b, uint64_t key, int anchor, const float4& box,
                                                const DecodeParams& p) {
@@ -345,6 +354,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) yolov8_decode_stream_kernel
           total += __popc(m[k]);
         }
         if (total) {
+          pdl_wait();  // the counts have been zeroed (zero_counts_kernel, the programmatic predecessor); free after the first time
           int base = 0;
           if (lane == 0) base = atomicAdd(p.cand_count + b, total);
           base = __shfl_sync(0xffffffffu, base, 0);
@@ -499,7 +509,13 @@ static int launch_stream(DecodeParams& p, const DeviceInfo& di, int grid, int wa
   static unsigned long long attr_done = 0;  // one per template instantiation
   int rc = ensure_smem_attr(reinterpret_cast<const void*>(kern), di.max_smem, di.device, &attr_done);
   if (rc != CVPP_OK) return rc;
-  kern<<<grid, warps * 32, smem, stream>>>(p);
+  if (FULL) {
+    kern<<<grid, warps * 32, smem, stream>>>(p);   // ordinary launch: the kernel reads its inputs at once
+  } else {
+    // programmatic dependent of zero_counts_kernel (which was launched normally, i.e. after everything earlier in the stream
+    // had completed, and triggers at once): the inputs may be read before griddepcontrol.wait, the counts may not
+    CVPP_CUDA_TRY(launch_pdl(kern, dim3(grid), dim3(warps * 32), smem, stream, p));
+  }
   return CVPP_OK;
 }
 
@@ -605,8 +621,11 @@ int yolov8_decode_launch(const float* const* level_ptr, const int64_t* batch_str
   p.A = (int)A;
   p.tiles_per_image = tiles;
   p.total_tiles = tiles * B;
-  if (!full) CVPP_CUDA_TRY(cudaMemsetAsync(cand_count, 0, sizeof(int32_t) * (size_t)B, stream));
   if (B == 0) return CVPP_OK;
+  if (!full) {
+    zero_counts_kernel<<<(B + 255) / 256, 256, 0, stream>>>(cand_count, B);
+    CVPP_CUDA_TRY(cudaGetLastError());
+  }
   return full ? launch_decode<true>(p, tma_ok, stream) : launch_decode<false>(p, tma_ok, stream);
 }
 

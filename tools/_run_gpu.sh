@@ -1,7 +1,6 @@
-run() { echo "== $*"; env "$@" timeout 200 python tools/bench_paths.py --only yolov8 --iters 100 2>&1 | cut -c1-120; }
-run A=1
-run CVPP_DECODE_CPL=4
-run CVPP_DECODE_STAGES=3 CVPP_DECODE_WARPS=12
-run CVPP_DECODE_STAGES=3 CVPP_DECODE_WARPS=10
-run CVPP_DECODE_STAGES=2 CVPP_DECODE_WARPS=14
-run CVPP_DECODE_STAGES=2 CVPP_DECODE_WARPS=16
+CVPP_BENCH_BS1_EARLY=1 timeout 600 python bench.py --steps 50 --warmup 5 --no-paths --no-c5 --no-reference-gpu --no-cpu > gpurun_out/r2_w2_bench.json 2>/dev/null
+python - <<PY
+import json
+d=json.loads(open("gpurun_out/r2_w2_bench.json").read().strip().splitlines()[-1])
+print(json.dumps(d["bs1_latency"]))
+PY
