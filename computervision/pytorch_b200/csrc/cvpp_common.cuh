@@ -66,6 +66,22 @@ static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 blo
 }
 #endif
 
+// Counters zeroed by a KERNEL that triggers its dependents at once (instead of a memset node): the filter kernel that follows,
+// launched with launch_pdl(), sets up and streams its first tiles while this runs and calls pdl_wait() only before its first
+// append.  Because this kernel itself is an ordinary launch (it starts after everything earlier in the stream has completed),
+// the dependent may read its INPUTS before pdl_wait(); only the counters must not be touched before it.
+#ifdef __CUDACC__
+static __global__ void __launch_bounds__(256) cvpp_zero_i32_kernel(int32_t* __restrict__ p, int n) {
+  pdl_trigger();
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = 0;
+}
+static inline cudaError_t zero_counts_async(int32_t* p, int n, cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  cvpp_zero_i32_kernel<<<(n + 255) / 256, 256, 0, stream>>>(p, n);
+  return cudaGetLastError();
+}
+#endif
+
 // ---- single-use (streamed) global loads ------------------------------------------------------
 // Inputs that are read exactly once carry an L2 evict-first policy: hundreds of MB of streamed predictions
 // then do not displace what the next kernel needs from L2 (candidate keys, dense boxes, its code).

@@ -339,6 +339,7 @@ __global__ void __launch_bounds__(kSsdMaxWarps * 32, 1) ssd_stream_kernel(const 
     int wk_n = 0;
     auto flush = [&]() {
       __syncwarp();
+      pdl_wait();  // the counts have been zeroed by the programmatic predecessor
       int base = 0;
       if (lane == 0) base = atomicAdd(p.cand_count + b, wk_n);
       base = __shfl_sync(0xffffffffu, base, 0);
@@ -481,7 +482,7 @@ int ssd_decode_filter_launch(const float* loc, const float* conf, const float* p
     set_error("ssd_decode_filter: loc, priors and box_dense must be 16-byte aligned");
     return CVPP_ERR_ALIGNMENT;
   }
-  CVPP_CUDA_TRY(cudaMemsetAsync(cand_count, 0, sizeof(int32_t) * (size_t)B, stream));
+  CVPP_CUDA_TRY(zero_counts_async(cand_count, B, stream));  // the stream kernel is its programmatic dependent (cvpp_common.cuh)
   if (B == 0) return CVPP_OK;
   {
     // streaming kernel: needs 16-byte aligned conf rows per image and tile (bulk copies) and room for >= 4 warps
@@ -537,11 +538,11 @@ int ssd_decode_filter_launch(const float* loc, const float* conf, const float* p
       if (nc1 == 21) {
         rc = ensure_smem_attr(reinterpret_cast<const void*>(ssd_stream_kernel<21>), di.max_smem, di.device, &attr_done21);
         if (rc != CVPP_OK) return rc;
-        ssd_stream_kernel<21><<<grid, warps * 32, per_warp * warps, stream>>>(sp);
+        CVPP_CUDA_TRY(launch_pdl(ssd_stream_kernel<21>, dim3(grid), dim3(warps * 32), per_warp * warps, stream, sp));
       } else {
         rc = ensure_smem_attr(reinterpret_cast<const void*>(ssd_stream_kernel<0>), di.max_smem, di.device, &attr_done);
         if (rc != CVPP_OK) return rc;
-        ssd_stream_kernel<0><<<grid, warps * 32, per_warp * warps, stream>>>(sp);
+        CVPP_CUDA_TRY(launch_pdl(ssd_stream_kernel<0>, dim3(grid), dim3(warps * 32), per_warp * warps, stream, sp));
       }
       CVPP_CUDA_TRY(cudaGetLastError());
       return CVPP_OK;

@@ -210,6 +210,7 @@ __device__ __forceinline__ void v3_flush(const V3Stage& st, const YaParams& p, i
   const int lane = threadIdx.x & 31;
   __syncwarp();
   if (n == 0) return;
+  pdl_wait();  // the counts have been zeroed by the programmatic predecessor
   int gbase = 0;
   if (lane == 0) gbase = atomicAdd(p.cand_count + ob, n);
   gbase = __shfl_sync(0xffffffffu, gbase, 0);
@@ -486,6 +487,7 @@ yolo_anchor_stream_kernel(const __grid_constant__ YaParams p) {
           total += __popc(m[k]);
         }
         if (total) {
+          pdl_wait();  // the counts have been zeroed by the programmatic predecessor
           int base = 0;
           if (lane == 0) base = atomicAdd(p.cand_count + ob, total);
           base = __shfl_sync(0xffffffffu, base, 0);
@@ -677,8 +679,7 @@ static int ya_launch_mode(YaParams& stream_p, bool have_stream, YaParams& gen_p,
     if (rc != CVPP_OK) return rc;
     const int want = (stream_p.total_tiles + kYaWarps - 1) / kYaWarps;
     const int grid = want < di.sms ? want : di.sms;
-    yolo_anchor_stream_kernel<MODE, CPL><<<grid, kYaWarps * 32, smem, stream>>>(stream_p);
-    CVPP_CUDA_TRY(cudaGetLastError());
+    CVPP_CUDA_TRY(launch_pdl(yolo_anchor_stream_kernel<MODE, CPL>, dim3(grid), dim3(kYaWarps * 32), smem, stream, stream_p));
   }
   if (gen_anchors > 0) {
     // One CTA per unit.  (Running this kernel NEXT TO the streaming one - a programmatic dependent of one 64-thread CTA per SM,
@@ -762,7 +763,7 @@ int yolo_anchor_decode_launch(int mode, const float* const* level_ptr, const int
     return CVPP_ERR_UNSUPPORTED;
   }
   const int n_out = merged ? (B > 0 ? 1 : 0) : B;
-  CVPP_CUDA_TRY(cudaMemsetAsync(cand_count, 0, sizeof(int32_t) * (size_t)n_out, stream));
+  CVPP_CUDA_TRY(zero_counts_async(cand_count, n_out, stream));  // the stream kernel is its programmatic dependent (cvpp_common.cuh)
   if (B == 0) return CVPP_OK;
 
   DeviceInfo di;

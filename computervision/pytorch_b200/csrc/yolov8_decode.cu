@@ -81,15 +81,6 @@ __device__ __noinline__ void class_argmax_sigmoid(const float* col, int64_t cs, 
   arg = ba;
 }
 
-// cand_count[0..B) = 0 as a KERNEL (not a memset node): it triggers its dependents at once, so the streaming decode kernel -
-// launched as its programmatic dependent - sets up, issues its first TMA loads and decodes its first tiles while this runs,
-// and only waits (griddepcontrol.wait) before its first candidate append.  One node boundary (~2 us of the bs = 1 latency and
-// of every serial step) leaves the critical path.
-__global__ void __launch_bounds__(256) zero_counts_kernel(int32_t* __restrict__ cnt, int n) {
-  pdl_trigger();
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) cnt[i] = 0;
-}
-
 // warp-aggregated append of one candidate per flagged lane (all 32 lanes must call)
 __device__ __forceinline__ void emit_candidate(bool flag, int b, uint64_t key, int anchor, const float4& box,
                                                const DecodeParams& p) {
@@ -354,7 +345,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) yolov8_decode_stream_kernel
           total += __popc(m[k]);
         }
         if (total) {
-          pdl_wait();  // the counts have been zeroed (zero_counts_kernel, the programmatic predecessor); free after the first time
+          pdl_wait();  // the counts have been zeroed (cvpp_zero_i32_kernel, the programmatic predecessor); free after the first time
           int base = 0;
           if (lane == 0) base = atomicAdd(p.cand_count + b, total);
           base = __shfl_sync(0xffffffffu, base, 0);
@@ -623,8 +614,7 @@ int yolov8_decode_launch(const float* const* level_ptr, const int64_t* batch_str
   p.total_tiles = tiles * B;
   if (B == 0) return CVPP_OK;
   if (!full) {
-    zero_counts_kernel<<<(B + 255) / 256, 256, 0, stream>>>(cand_count, B);
-    CVPP_CUDA_TRY(cudaGetLastError());
+    CVPP_CUDA_TRY(zero_counts_async(cand_count, B, stream));   // (see cvpp_common.cuh: the decode kernel is its programmatic dependent)
   }
   return full ? launch_decode<true>(p, tma_ok, stream) : launch_decode<false>(p, tma_ok, stream);
 }

@@ -561,6 +561,7 @@ __global__ void __launch_bounds__(kHfThreads, 1) yolov8_head_fused_kernel(const 
           if (quarter == 0 && lane == 0) HF_STAMP(6, tile_i);
           const unsigned m = (p.debug & 4) ? 0u : __ballot_sync(0xffffffffu, cand);
           if (m) {
+            pdl_wait();  // the counts have been zeroed by the programmatic predecessor
             int base = 0;
             if (lane == 0) base = atomicAdd(p.cand_count + b, __popc(m));
             base = __shfl_sync(0xffffffffu, base, 0);
@@ -746,7 +747,7 @@ int yolov8_head_fused_launch(const float* const* box_feat, const float* const* c
     return CVPP_ERR_UNSUPPORTED;
   }
   p.A = (int)A;
-  CVPP_CUDA_TRY(cudaMemsetAsync(cand_count, 0, sizeof(int32_t) * (size_t)B, stream));
+  CVPP_CUDA_TRY(zero_counts_async(cand_count, B, stream));  // the kernel below is its programmatic dependent (cvpp_common.cuh)
   if (B == 0) return CVPP_OK;
   for (int l = 0; l < num_levels; ++l) {
     if (!hf_make_tmap(&p.tmap_box[l], box_feat[l], p.lv[l].hw, c2, B) || !hf_make_tmap(&p.tmap_cls[l], cls_feat[l], p.lv[l].hw, c3, B) ||
@@ -788,11 +789,11 @@ int yolov8_head_fused_launch(const float* const* box_feat, const float* const* c
   if (head_out) {
     rc = ensure_smem_attr(reinterpret_cast<const void*>(yolov8_head_fused_kernel<true>), di.max_smem, di.device, &attr_done[1]);
     if (rc != CVPP_OK) return rc;
-    yolov8_head_fused_kernel<true><<<grid, kHfThreads, smem, stream>>>(p);
+    CVPP_CUDA_TRY(launch_pdl(yolov8_head_fused_kernel<true>, dim3(grid), dim3(kHfThreads), smem, stream, p));
   } else {
     rc = ensure_smem_attr(reinterpret_cast<const void*>(yolov8_head_fused_kernel<false>), di.max_smem, di.device, &attr_done[0]);
     if (rc != CVPP_OK) return rc;
-    yolov8_head_fused_kernel<false><<<grid, kHfThreads, smem, stream>>>(p);
+    CVPP_CUDA_TRY(launch_pdl(yolov8_head_fused_kernel<false>, dim3(grid), dim3(kHfThreads), smem, stream, p));
   }
   CVPP_CUDA_TRY(cudaGetLastError());
   return CVPP_OK;
