@@ -1,15 +1,15 @@
 mkdir -p gpurun_out
-rm -f gpurun_out/r2_x1_errors.jsonl
-CVPP_ERR_LOG=gpurun_out/r2_x1_errors.jsonl timeout 1500 python -m pytest tests -q -m gpu --timeout=300 > gpurun_out/r2_x1_gpu_tests.txt 2>&1; tail -2 gpurun_out/r2_x1_gpu_tests.txt
-python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2_x1_smoke.log 2>&1; tail -1 gpurun_out/r2_x1_smoke.log
-timeout 900 python bench.py --steps 50 --warmup 5 > gpurun_out/r2_x1_bench.json 2> gpurun_out/r2_x1_bench.err; tail -2 gpurun_out/r2_x1_bench.err
-timeout 600 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/r2_x1_bench_reference_arm.json 2>> gpurun_out/r2_x1_bench.err
+for n in 8 4 2 1; do
+if [ $n = 1 ]; then
+timeout 600 python bench.py --gpus 1 --steps 50 --warmup 5 --no-paths --no-reference-gpu > gpurun_out/r2_z1_bench_${n}gpu.json 2> gpurun_out/r2_z1_bench_${n}gpu.err
+else
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2953$n bench.py --gpus $n --steps 50 --warmup 5 > gpurun_out/r2_z1_bench_${n}gpu.json 2> gpurun_out/r2_z1_bench_${n}gpu.err
+fi
 python - <<PY
 import json
-d=json.loads(open("gpurun_out/r2_x1_bench.json").read().strip().splitlines()[-1])
-print("value",d['value'],"ms",d['ms_per_step'],"serial",d['serial_ms_per_step'],"bs1",d['bs1_latency']['p50_us'],d['bs1_latency']['floor_us'],"frac",d['roofline']['frac'],"stages",d['stages_ms'],"e2e",d['e2e']['value'], d['e2e']['ceiling']['value'], "cpu", d['cpu_baseline']['value'])
-for p in d['paths']: print(p['path'], p['decode_ms'], p['decode_frac_of_hbm_peak'], p['total_ms'])
-print("c5", d['c5']['images_per_s'], d['c5']['ms_per_step'], d['c5']['decode_ms'], d['c5']['nms_ms'], d['c5']['decode_frac'])
-print("refgpu", d['reference_gpu']['value'], "clocks", d['clocks'])
-r=json.loads(open("gpurun_out/r2_x1_bench_reference_arm.json").read().strip().splitlines()[-1]); print("ref arm", r['value'])
+d=json.loads(open("gpurun_out/r2_z1_bench_${n}gpu.json").read().strip().splitlines()[-1])
+print($n, "value", round(d["value"]), "us/step", round(1e3*d["ms_per_step"],2), "barrier-each", d.get("ms_per_step_barrier_each_step"), "verified", d.get("gather_verified"), "e2e", round(d["e2e"]["value"]), "ceiling", round(d["e2e"]["ceiling"]["value"]), "h2d/gpu", round(d["e2e"]["h2d_GBps_per_gpu"],1))
+c=d["c5"]; print("   c5", round(c["images_per_s"]), c["ms_per_step"], c["compute_ms_per_step"], c["gather_verified"])
 PY
+done
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29539 bench.py --impl reference --gpus 8 --steps 3 --warmup 1 2>/dev/null | cut -c1-160
