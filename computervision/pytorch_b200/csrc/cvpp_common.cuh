@@ -171,20 +171,8 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// try_wait with a suspend-time hint (ns): the thread may sleep in hardware until the phase completes or the hint expires,
-// instead of returning after the (short) default limit - a polling loop around the plain form was 37 % of the instructions
-// the head-fused kernel executed
-__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
-      : "memory");
-  return ok != 0;
-}
+// (mbarrier.try_wait with a suspend-time hint was measured in the head-fused kernel: the polling loops execute just as many
+// instructions - the hardware returns after its own short limit whatever the hint - so the plain form is used.)
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }

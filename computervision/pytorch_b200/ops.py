@@ -398,7 +398,13 @@ class PipelinedPostprocess:
         pipe.join()
 
     A single LevelSet may be passed instead of a list: every slot then reads the SAME buffers (static-input
-    benchmarking only - a real producer could not refill them while another slot's decode is in flight)."""
+    benchmarking only - a real producer could not refill them while another slot's decode is in flight).
+
+    Multi-GPU evaluation: `gather=distributed.PeerGather(...)` (at least `depth` slots) makes `submit(gather=True)` also store
+    the slot's CVPP_ROWS_FULL rows + counts into gather slot `slot` of every rank, from inside the slot's CUDA graph - written
+    by the NMS kernel's own CTAs (`fused_rows=True`, cvpp_yolov8_postprocess_gather: no third launch) or by the epilogue
+    kernel behind a programmatic dependent launch; `use_multicast` picks the NVSwitch multicast address when the gather
+    has one.  Fence with `gather.barrier(slot)` before reading `gather.view(slot)`."""
 
     def __init__(self, B: int, A: int, nc: int, device, inputs, conf_thres: float, iou_thres: float,
                  max_det: int = 300, depth: Optional[int] = None, graph: bool = True, gather=None,
