@@ -141,6 +141,21 @@ __device__ __forceinline__ bool suppresses(const float4& bi, float ai, const flo
   return sup;
 }
 
+// two independent pair tests in one basic block: a warp running these loops is a latency chain (shared-memory load -> min / max
+// -> fma -> compares: ~0.1 instructions per cycle per warp, issue slots half idle), so interleaving two tests gives the
+// scheduler two chains to overlap
+__device__ __forceinline__ void suppresses_x2(const float4& a1, float aa1, const float4& b1, float ab1, const float4& a2, float aa2,
+                                              const float4& b2, float ab2, const SupTest& t, bool& s1, bool& s2) {
+  float i1, u1, i2, u2;
+  inter_union(a1, aa1, b1, ab1, i1, u1);
+  inter_union(a2, aa2, b2, ab2, i2, u2);
+  bool m1, m2;
+  s1 = suppresses_fast(i1, u1, t, m1);
+  s2 = suppresses_fast(i2, u2, t, m2);
+  if (m1) s1 = suppresses_exact(i1, u1, t);
+  if (m2) s2 = suppresses_exact(i2, u2, t);
+}
+
 __device__ __forceinline__ uint32_t seg_mask_of_word(int w, int s, int e) {
   const int lo = max(s - (w << 5), 0), hi = min(e - (w << 5), 32);
   if (hi <= lo) return 0u;
@@ -225,7 +240,25 @@ __device__ __forceinline__ uint32_t resolve_word(int w, int s, int e, const BoxV
   // the earlier box), row = EARLIER boxes that suppress box i (pairs it tested as the later box, i.e. the
   // wrapped rotations).  The greedy replay below combines them, so no per-round routing of verdicts.
   uint32_t col = 0, row = 0;
-  for (int r = 1; r <= rounds; ++r) {
+  int r = 1;
+  for (; r + 1 <= rounds; r += 2) {  // two rotations per iteration (independent tests)
+    const int j1 = (lane + r) & 31, j2 = (lane + r + 1) & 31;
+    const bool p1 = me && ((am >> j1) & 1u) && (r < 16 || lane < 16);
+    const bool p2 = me && ((am >> j2) & 1u) && (r + 1 < 16 || lane < 16);
+    bool s1 = false, s2 = false;
+    if (p1 || p2) {
+      suppresses_x2(bi, ai, bv.load_box(base + j1), bv.load_area(base + j1), bi, ai, bv.load_box(base + j2), bv.load_area(base + j2), t,
+                    s1, s2);
+      s1 = s1 && p1;
+      s2 = s2 && p2;
+    }
+    const uint32_t bit1 = s1 ? (1u << j1) : 0u, bit2 = s2 ? (1u << j2) : 0u;
+    if (j1 > lane) col |= bit1;
+    else row |= bit1;
+    if (j2 > lane) col |= bit2;
+    else row |= bit2;
+  }
+  for (; r <= rounds; ++r) {
     const int j = (lane + r) & 31;
     const bool pair = me && ((am >> j) & 1u) && (r < 16 || lane < 16);
     bool sup = false;
@@ -267,9 +300,18 @@ __device__ __forceinline__ void apply_word(uint32_t am, int w, int w2, int e, co
       const float a2 = bv.load_area((w2 << 5) + lane);
       uint32_t km = am;
       while (km && !sup2) {
-        const int i = __ffs(km) - 1;
+        const int i1 = __ffs(km) - 1;
         km &= km - 1;
-        sup2 = suppresses(bv.load_box((w << 5) + i), bv.load_area((w << 5) + i), b2, a2, t);
+        if (km) {  // two kept boxes per iteration (independent tests)
+          const int i2 = __ffs(km) - 1;
+          km &= km - 1;
+          bool s1, s2;
+          suppresses_x2(bv.load_box((w << 5) + i1), bv.load_area((w << 5) + i1), b2, a2, bv.load_box((w << 5) + i2),
+                        bv.load_area((w << 5) + i2), b2, a2, t, s1, s2);
+          sup2 = s1 || s2;
+        } else {
+          sup2 = suppresses(bv.load_box((w << 5) + i1), bv.load_area((w << 5) + i1), b2, a2, t);
+        }
       }
     }
     sm2 = __ballot_sync(0xffffffffu, sup2);
@@ -284,11 +326,22 @@ __device__ __forceinline__ void apply_word(uint32_t am, int w, int w2, int e, co
     }
     uint32_t lm = live2;
     while (lm) {
-      const int j = __ffs(lm) - 1;
+      const int j1 = __ffs(lm) - 1;
       lm &= lm - 1;
-      bool sup = false;
-      if (kept) sup = suppresses(bi, ai, bv.load_box((w2 << 5) + j), bv.load_area((w2 << 5) + j), t);
-      if (__any_sync(0xffffffffu, sup)) sm2 |= 1u << j;
+      if (lm) {  // two candidates per iteration (independent tests)
+        const int j2 = __ffs(lm) - 1;
+        lm &= lm - 1;
+        bool s1 = false, s2 = false;
+        if (kept)
+          suppresses_x2(bi, ai, bv.load_box((w2 << 5) + j1), bv.load_area((w2 << 5) + j1), bi, ai, bv.load_box((w2 << 5) + j2),
+                        bv.load_area((w2 << 5) + j2), t, s1, s2);
+        if (__any_sync(0xffffffffu, s1)) sm2 |= 1u << j1;
+        if (__any_sync(0xffffffffu, s2)) sm2 |= 1u << j2;
+      } else {
+        bool sup = false;
+        if (kept) sup = suppresses(bi, ai, bv.load_box((w2 << 5) + j1), bv.load_area((w2 << 5) + j1), t);
+        if (__any_sync(0xffffffffu, sup)) sm2 |= 1u << j1;
+      }
     }
   }
   if (lane == 0 && sm2) atomicAnd(&alive[w2], ~sm2);
