@@ -1,7 +1,7 @@
-cp computervision/pytorch_b200/libcvpp.so /tmp/new.so
-for v in new prev new prev; do
-if [ $v = prev ]; then cp computervision/pytorch_b200/libcvpp_prevnms.so computervision/pytorch_b200/libcvpp.so; else cp /tmp/new.so computervision/pytorch_b200/libcvpp.so; fi
-timeout 300 python bench.py --steps 50 --warmup 5 --no-paths --no-c5 --no-reference-gpu --no-cpu 2>/dev/null | python -c "
-import json,sys
-d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('$v','us/step',round(1e3*d['ms_per_step'],2),'serial',round(1e3*d['serial_ms_per_step'],2),'nms',round(1e3*d['stages_ms']['fused_sort_nms'],2),'dec',round(1e3*d['stages_ms']['decode_filter'],2),'bs1',round(d['bs1_latency']['mean_us'],2))"
-done
+# what `gpurun -- 'bash tools/_run_gpu.sh'` runs on the GPU box: the -m gpu suite, smoke(), and both bench arms
+set -x
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -q -m gpu --timeout=300 > gpurun_out/gpu_tests.txt 2>&1; tail -2 gpurun_out/gpu_tests.txt
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+timeout 900 python bench.py --steps 50 --warmup 5 > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -c 400 gpurun_out/bench.json
+timeout 600 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_reference_arm.json 2>> gpurun_out/bench.err; cut -c1-200 gpurun_out/bench_reference_arm.json
